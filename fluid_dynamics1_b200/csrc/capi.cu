@@ -1,0 +1,426 @@
+// capi.cu -- extern "C" surface of libcnavier_b200.so (declared in include/cnavier_b200.h) and the
+// device-resident time stepper that restates the loop body of the reference driver
+// (src/main.c:283-395) on top of the CUDA kernels.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/cnavier_b200.h"
+#include "kernels.h"
+
+namespace cnv {
+size_t total_launches();
+void count_launch(size_t n);
+
+static void require_device()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        std::printf("** Error: no CUDA device visible: the B200 path has no CPU fallback **\n");
+        std::fflush(stdout);
+        std::exit(1);
+    }
+}
+
+// RAII device scratch for the host-staging entry points
+struct DevArray {
+    double *p = nullptr;
+    int nrows, ncols, ld;
+    DevArray(int nr, int nc) : nrows(nr), ncols(nc), ld(round_up(nc, 16))
+    {
+        CNV_CUDA_CHECK(cudaMalloc(&p, sizeof(double) * (size_t)nr * ld));
+        CNV_CUDA_CHECK(cudaMemset(p, 0, sizeof(double) * (size_t)nr * ld));
+    }
+    ~DevArray() { cudaFree(p); }
+    void upload(const double *h, cudaStream_t s = 0)
+    {
+        CNV_CUDA_CHECK(cudaMemcpy2DAsync(p, sizeof(double) * ld, h, sizeof(double) * ncols, sizeof(double) * ncols, nrows,
+                                         cudaMemcpyHostToDevice, s));
+    }
+    void download(double *h, cudaStream_t s = 0) const
+    {
+        CNV_CUDA_CHECK(cudaMemcpy2DAsync(h, sizeof(double) * ncols, p, sizeof(double) * ld, sizeof(double) * ncols, nrows,
+                                         cudaMemcpyDeviceToHost, s));
+        CNV_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+};
+
+// L1 distance kernel for error() (src/poisson.c:34-60): block partials, fixed-order final sum on host
+__global__ void k_l1_distance(const double *__restrict__ a, const double *__restrict__ b, int nrows, int ncols, int ld,
+                              double *__restrict__ partial)
+{
+    double s = 0.0;
+    const size_t n = (size_t)nrows * ld;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x)
+        if ((int)(p % ld) < ncols) s = xadd(s, fabs(xsub(b[p], a[p])));
+    __shared__ double sh[256];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] = xadd(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+}  // namespace cnv
+
+using namespace cnv;
+
+struct cnv_poisson {
+    PoissonSolver *s;
+};
+
+// ---------------------------------------------------------------------------------------------
+struct cnv_sim {
+    Config cfg;
+    int nrows, ncols, ld;
+    double dx, dy, beta, inv_re;
+    FdTable d1x, d1y, d2x, d2y;
+    double *u = nullptr, *v = nullptr, *w = nullptr, *w2 = nullptr;
+    PoissonSolver *ps = nullptr;
+    int psi_buf = 0;
+    double *cont_partial = nullptr, *cont_result = nullptr, *h_cont = nullptr;
+    unsigned *cont_ticket = nullptr;
+    bool diag = true;
+    long long sweeps = 0, passes = 0, steps = 0;
+    cudaStream_t stream = 0;
+};
+
+extern "C" {
+
+const char *cnv_version(void) { return "cnavier-b200 0.1 (sm_100a)"; }
+
+int cnv_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// one process per GPU: select the device for this library's (statically linked) CUDA runtime
+int cnv_set_device(int device)
+{
+    require_device();
+    CNV_CUDA_CHECK(cudaSetDevice(device));
+    return 0;
+}
+int cnv_get_device(void)
+{
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return d;
+}
+void cnv_device_synchronize(void) { CNV_CUDA_CHECK(cudaDeviceSynchronize()); }
+
+unsigned long long cnv_launch_count(void) { return (unsigned long long)total_launches(); }
+
+// src/main.c:134 with the truncated PI of include/poisson.h:9
+double cnv_sor_beta(int nx, int ny) { return 0.5 * (2 / (1 + sin(PI / (nx + 1))) + 2 / (1 + sin(PI / (ny + 1)))); }
+// src/main.c:162, :276: t = 0 .. (int)(tf/dt - 1)
+int cnv_num_steps(double tf, double dt) { return (int)((tf / dt) - 1) + 1; }
+
+int cnv_diff_dense(int n, int order, int deriv, double h, double *D)
+{
+    FdTable t;
+    if (n < order || !fd_make_table(n, order, deriv, h, &t)) return 1;
+    std::memset(D, 0, sizeof(double) * (size_t)n * n);
+    for (int i = 0; i < n; i++) {
+        int start; const FdRow *r;
+        fd_row(t, i, &start, &r);
+        for (int k = 0; k < r->cnt; k++) D[(size_t)i * n + start + k] = r->c[k];
+    }
+    return 0;
+}
+
+int cnv_apply_host(const double *A, int nrows, int ncols, int axis, int deriv, int order, double h, double *out)
+{
+    FdTable t;
+    const int n = axis == 1 ? ncols : nrows;
+    if (n < order || !fd_make_table(n, order, deriv, h, &t)) return 1;
+    require_device();
+    DevArray a(nrows, ncols), o(nrows, ncols);
+    a.upload(A);
+    launch_apply(a.p, nrows, ncols, a.ld, axis, t, o.p, o.ld, 1.0, 0);
+    count_launch(1);
+    CNV_CUDA_CHECK(cudaGetLastError());
+    o.download(out);
+    return 0;
+}
+
+int cnv_euler_host(double *w, const double *dwdx, const double *dwdy, const double *d2wdx2, const double *d2wdy2,
+                   const double *u, const double *v, int nrows, int ncols, double Re, double dt)
+{
+    require_device();
+    const double *src[7] = {w, dwdx, dwdy, d2wdx2, d2wdy2, u, v};
+    std::vector<DevArray *> d;
+    for (int i = 0; i < 7; i++) { d.push_back(new DevArray(nrows, ncols)); d[i]->upload(src[i]); }
+    launch_euler_pointwise(d[0]->p, d[1]->p, d[2]->p, d[3]->p, d[4]->p, d[5]->p, d[6]->p, (size_t)nrows * d[0]->ld,
+                           1. / Re, dt, 0);
+    count_launch(1);
+    CNV_CUDA_CHECK(cudaGetLastError());
+    d[0]->download(w);
+    for (auto *x : d) delete x;
+    return 0;
+}
+
+static int addsub_host(const double *a, const double *b, int nrows, int ncols, double *out, int sub)
+{
+    require_device();
+    DevArray da(nrows, ncols), db(nrows, ncols), dc(nrows, ncols);
+    da.upload(a); db.upload(b);
+    launch_pointwise_addsub(da.p, db.p, dc.p, (size_t)nrows * da.ld, sub, 0);
+    count_launch(1);
+    CNV_CUDA_CHECK(cudaGetLastError());
+    dc.download(out);
+    return 0;
+}
+int cnv_continuity_host(const double *dudx, const double *dvdy, int nrows, int ncols, double *out)
+{
+    return addsub_host(dudx, dvdy, nrows, ncols, out, 0);
+}
+int cnv_vorticity_host(const double *a, const double *b, int nrows, int ncols, double *out)
+{
+    return addsub_host(a, b, nrows, ncols, out, 1);
+}
+
+double cnv_error_host(const double *a, const double *b, int nrows, int ncols)
+{
+    require_device();
+    DevArray da(nrows, ncols), db(nrows, ncols);
+    da.upload(a); db.upload(b);
+    const int nb = 296;
+    double *partial;
+    CNV_CUDA_CHECK(cudaMalloc(&partial, sizeof(double) * nb));
+    k_l1_distance<<<nb, 256>>>(da.p, db.p, nrows, ncols, da.ld, partial);
+    count_launch(1);
+    std::vector<double> h(nb);
+    CNV_CUDA_CHECK(cudaMemcpy(h.data(), partial, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+    cudaFree(partial);
+    double e = 0;
+    for (double x : h) e += x;
+    return e;
+}
+
+// ---- Poisson -----------------------------------------------------------------------------------
+cnv_poisson *cnv_poisson_create(int nrows, int ncols, int T)
+{
+    require_device();
+    return new cnv_poisson{new PoissonSolver(nrows, ncols, T)};
+}
+cnv_poisson *cnv_poisson_create_slab(int nrows, int ncols, int T, int grow0, int gnrows, int own_lo, int own_hi)
+{
+    require_device();
+    return new cnv_poisson{new PoissonSolver(nrows, ncols, T, grow0, gnrows, own_lo, own_hi)};
+}
+void cnv_poisson_destroy(cnv_poisson *p)
+{
+    if (!p) return;
+    delete p->s;
+    delete p;
+}
+void cnv_poisson_set_consts(cnv_poisson *p, double dx, double dy, double beta) { p->s->set_consts(dx, dy, beta); }
+int cnv_poisson_ld(const cnv_poisson *p) { return p->s->ld(); }
+double *cnv_poisson_rhs_ptr(cnv_poisson *p) { return p->s->rhs(); }
+double *cnv_poisson_buf_ptr(cnv_poisson *p, int which) { return p->s->buffer(which & 1); }
+double *cnv_poisson_norms_ptr(cnv_poisson *p) { return p->s->local_norms(); }
+void cnv_poisson_plan_info(const cnv_poisson *p, long long *out)
+{
+    const PassGeom &g = p->s->geom();
+    out[0] = g.WS; out[1] = g.HX; out[2] = g.Wout; out[3] = g.Hout; out[4] = g.nstrips; out[5] = g.nchunks;
+    out[6] = pass_threads(p->s->T(), g.WS); out[7] = (long long)pass_smem_bytes(p->s->T(), g.WS);
+    out[8] = p->s->T(); out[9] = p->s->consts().pow2;
+}
+int cnv_poisson_prepare(cnv_poisson *p, const double *f_dev, int ldf, double fsign, void *stream)
+{
+    const PassGeom &g = p->s->geom();
+    launch_prep_rhs(f_dev, g.nrows, g.ncols, ldf, fsign, p->s->consts().pscale, p->s->rhs(), p->s->buffer(0), p->s->buffer(1),
+                    g.ld, (cudaStream_t)stream);
+    count_launch(1);
+    CNV_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int cnv_poisson_upload(cnv_poisson *p, const double *f_host, double fsign, void *stream)
+{
+    const PassGeom &g = p->s->geom();
+    DevArray f(g.nrows, g.ncols);
+    f.upload(f_host, (cudaStream_t)stream);
+    cnv_poisson_prepare(p, f.p, f.ld, fsign, stream);
+    CNV_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int cnv_poisson_solve(cnv_poisson *p, int itmax, double tol, void *stream, int *k, double *e, int *sweeps, int *passes,
+                      int *result_buf)
+{
+    PoissonResult r = p->s->solve(itmax, tol, (cudaStream_t)stream, result_buf, false);
+    if (k) *k = r.k;
+    if (e) *e = r.e;
+    if (sweeps) *sweeps = r.sweeps;
+    if (passes) *passes = r.passes;
+    return r.status;
+}
+void cnv_poisson_reset(cnv_poisson *p, int itmax, double tol, void *stream) { p->s->reset_ctl(itmax, tol, (cudaStream_t)stream); }
+void cnv_poisson_enqueue(cnv_poisson *p, int npasses, void *stream) { p->s->enqueue_passes(npasses, (cudaStream_t)stream); }
+void cnv_poisson_enqueue_decide(cnv_poisson *p, void *stream) { p->s->enqueue_decide((cudaStream_t)stream); }
+void cnv_poisson_set_distributed(cnv_poisson *p, int on) { p->s->set_distributed(on != 0); }
+void cnv_poisson_state(cnv_poisson *p, void *stream, int *state, double *e)
+{
+    PoissonCtl c = p->s->read_ctl((cudaStream_t)stream);
+    state[0] = c.state; state[1] = c.cur; state[2] = c.sweeps; state[3] = c.passes; state[4] = c.result_k; state[5] = c.redo;
+    if (e) { e[0] = c.result_e; e[1] = c.last_e; }
+}
+int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream)
+{
+    const PassGeom &g = p->s->geom();
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(u_host, sizeof(double) * g.ncols, p->s->buffer(which & 1), sizeof(double) * g.ld,
+                                     sizeof(double) * g.ncols, g.nrows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CNV_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+int cnv_poisson_host(const double *f, int nrows, int ncols, double dx, double dy, int itmax, double tol, double beta, int T,
+                     double *u, int *k, double *e, double *history)
+{
+    require_device();
+    PoissonSolver s(nrows, ncols, T);
+    s.set_consts(dx, dy, beta);
+    DevArray df(nrows, ncols);
+    df.upload(f);
+    int buf = 0;
+    PoissonResult r = s.solve_from(df.p, df.ld, 1.0, itmax, tol, 0, &buf, history != nullptr);
+    CNV_CUDA_CHECK(cudaMemcpy2D(u, sizeof(double) * ncols, s.buffer(buf), sizeof(double) * s.ld(), sizeof(double) * ncols, nrows,
+                                cudaMemcpyDeviceToHost));
+    if (history) CNV_CUDA_CHECK(cudaMemcpy(history, s.history(), sizeof(double) * (size_t)r.sweeps, cudaMemcpyDeviceToHost));
+    if (k) *k = r.k;
+    if (e) *e = r.e;
+    return r.status;
+}
+
+// ---- time stepping -----------------------------------------------------------------------------
+cnv_sim *cnv_sim_create(const Config *cfg, int T)
+{
+    require_device();
+    cnv_sim *s = new cnv_sim;
+    s->cfg = *cfg;
+    s->nrows = cfg->nx;  // first index of every field (initm(nx, ny), src/main.c:178)
+    s->ncols = cfg->ny;
+    s->dx = (double)cfg->Lx / cfg->nx;  // src/main.c:138-139 (not L/(n-1))
+    s->dy = (double)cfg->Ly / cfg->ny;
+    s->beta = cnv_sor_beta(cfg->nx, cfg->ny);
+    s->inv_re = 1. / cfg->Re;
+    if (cfg->poisson_type != 1 && cfg->poisson_type != 2) {
+        std::printf("Error - invalid option for Poisson solver\n");  // src/main.c:359
+        std::exit(1);
+    }
+    const int o = cfg->order;
+    if (s->nrows < o || s->ncols < o || !fd_make_table(s->ncols, o, 1, s->dx, &s->d1x) ||
+        !fd_make_table(s->nrows, o, 1, s->dy, &s->d1y) || !fd_make_table(s->ncols, o, 2, s->dx, &s->d2x) ||
+        !fd_make_table(s->nrows, o, 2, s->dy, &s->d2y)) {
+        std::printf("** Error: valid orders are 2, 4 or 6 **\n");  // src/finitediff.c:150
+        std::exit(1);
+    }
+    s->ps = new PoissonSolver(s->nrows, s->ncols, T);
+    s->ps->set_consts(s->dx, s->dy, cfg->poisson_type == 2 ? s->beta : 1.0);
+    s->ld = s->ps->ld();
+    const size_t bytes = sizeof(double) * (size_t)s->nrows * s->ld;
+    for (double **p : {&s->u, &s->v, &s->w, &s->w2}) {
+        CNV_CUDA_CHECK(cudaMalloc(p, bytes));
+        CNV_CUDA_CHECK(cudaMemset(*p, 0, bytes));
+    }
+    // initial condition: interior u = ui, v = vi; w = psi = 0 (src/main.c:178-181, :214-221)
+    std::vector<double> h((size_t)s->nrows * s->ncols, 0.0);
+    for (int pass = 0; pass < 2; pass++) {
+        const double val = pass == 0 ? cfg->ui : cfg->vi;
+        for (int i = 1; i < s->nrows - 1; i++)
+            for (int j = 1; j < s->ncols - 1; j++) h[(size_t)i * s->ncols + j] = val;
+        CNV_CUDA_CHECK(cudaMemcpy2D(pass == 0 ? s->u : s->v, sizeof(double) * s->ld, h.data(), sizeof(double) * s->ncols,
+                                    sizeof(double) * s->ncols, s->nrows, cudaMemcpyHostToDevice));
+    }
+    CNV_CUDA_CHECK(cudaMalloc(&s->cont_partial, sizeof(double) * 2 * continuity_blocks(s->nrows, s->ncols)));
+    CNV_CUDA_CHECK(cudaMalloc(&s->cont_result, sizeof(double) * 2));
+    CNV_CUDA_CHECK(cudaMalloc(&s->cont_ticket, sizeof(unsigned)));
+    CNV_CUDA_CHECK(cudaMemset(s->cont_ticket, 0, sizeof(unsigned)));
+    CNV_CUDA_CHECK(cudaMallocHost(&s->h_cont, sizeof(double) * 2));
+    return s;
+}
+
+void cnv_sim_destroy(cnv_sim *s)
+{
+    if (!s) return;
+    delete s->ps;
+    cudaFree(s->u); cudaFree(s->v); cudaFree(s->w); cudaFree(s->w2);
+    cudaFree(s->cont_partial); cudaFree(s->cont_result); cudaFree(s->cont_ticket);
+    cudaFreeHost(s->h_cont);
+    delete s;
+}
+
+void cnv_sim_set_diagnostics(cnv_sim *s, int on) { s->diag = on != 0; }
+
+int cnv_sim_step(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, double *cont_min)
+{
+    const Config &c = s->cfg;
+    const double bc[8] = {c.u1, c.u2, c.u3, c.u4, c.v1, c.v2, c.v3, c.v4};
+    cudaStream_t st = s->stream;
+    const size_t bytes = sizeof(double) * (size_t)s->nrows * s->ld;
+    for (int t = 0; t < nsteps; t++) {
+        // BCs + wall vorticity (src/main.c:283-320)
+        launch_ring_bc_vorticity(s->u, s->v, s->w, s->nrows, s->ncols, s->ld, bc, s->d1x, s->d1y, st);
+        // vorticity derivatives + Euler on all points + Poisson right-hand side (:323-348)
+        launch_euler_fused(s->w, s->u, s->v, s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->d2x, s->d2y, s->inv_re, c.dt,
+                           s->ps->consts().pscale, s->w2, s->ps->rhs(), st);
+        std::swap(s->w, s->w2);
+        count_launch(2);
+        // zero initial guess every step (fresh initm in the reference, src/poisson.c:229)
+        CNV_CUDA_CHECK(cudaMemsetAsync(s->ps->buffer(0), 0, bytes, st));
+        PoissonResult r = s->ps->solve(c.poisson_max_it, c.poisson_tol, st, &s->psi_buf, false);
+        s->sweeps += r.sweeps;
+        s->passes += r.passes;
+        if (k) k[t] = r.k;
+        if (e) e[t] = r.e;
+        if (r.status != 0) return t + 1;  // reference: log the error and exit(1), src/poisson.c:280-284
+        // velocities from the streamfunction on all points (:366-383)
+        launch_velocity(s->ps->buffer(s->psi_buf), s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
+        count_launch(1);
+        if (s->diag && (cont_max || cont_min)) {
+            launch_continuity(s->u, s->v, s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
+                              s->cont_result, st);
+            count_launch(1);
+            CNV_CUDA_CHECK(cudaMemcpyAsync(s->h_cont, s->cont_result, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+            CNV_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (cont_max) cont_max[t] = s->h_cont[0];
+            if (cont_min) cont_min[t] = s->h_cont[1];
+        }
+        s->steps++;
+    }
+    CNV_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int cnv_sim_get_fields(cnv_sim *s, double *psi, double *w, double *u, double *v)
+{
+    CNV_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    const double *src[4] = {s->ps->buffer(s->psi_buf), s->w, s->u, s->v};
+    double *dst[4] = {psi, w, u, v};
+    for (int i = 0; i < 4; i++)
+        if (dst[i])
+            CNV_CUDA_CHECK(cudaMemcpy2D(dst[i], sizeof(double) * s->ncols, src[i], sizeof(double) * s->ld,
+                                        sizeof(double) * s->ncols, s->nrows, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int cnv_sim_set_fields(cnv_sim *s, const double *psi, const double *w, const double *u, const double *v)
+{
+    double *dst[4] = {s->ps->buffer(s->psi_buf), s->w, s->u, s->v};
+    const double *src[4] = {psi, w, u, v};
+    for (int i = 0; i < 4; i++)
+        if (src[i])
+            CNV_CUDA_CHECK(cudaMemcpy2D(dst[i], sizeof(double) * s->ld, src[i], sizeof(double) * s->ncols,
+                                        sizeof(double) * s->ncols, s->nrows, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void cnv_sim_counters(cnv_sim *s, long long *out)
+{
+    out[0] = s->sweeps; out[1] = s->passes; out[2] = s->steps;
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+// driver.cc -- cnv_main(): the reference program flow (src/main.c:27-481) on the device-resident path.
+//
+// Same command line (`[config_file] [output_folder]`, --help, --help-config), same config system, same
+// step order, same log-file lines (they are the reference's golden-vector format: the Poisson line
+// src/poisson.c:275, the per-step lines src/main.c:403-414, the header :262-271, the summary :467-473),
+// same exit(1) on Poisson non-convergence, same VTK files (src/utils.c:38-100: ASCII STRUCTURED_POINTS,
+// "%.6lf", one global file counter, append mode).  Fields never leave HBM between steps; VTK output
+// copies them out only at output steps.  GPU-only knobs come from the environment so config files
+// stay reference-compatible:  CNV_NO_VTK=1 suppresses VTK files (large grids),
+// CNV_POISSON_T=<1|2|4|8> temporal block depth.
+#include <sys/stat.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <vector>
+
+#include "../../include/cnavier_b200.h"
+
+namespace {
+
+void log_line(FILE *log, const char *fmt, ...)
+{
+    if (!log) return;
+    va_list ap;
+    va_start(ap, fmt);
+    std::vfprintf(log, fmt, ap);
+    va_end(ap);
+    std::fflush(log);
+}
+
+void make_dir(const std::string &dir)
+{
+    struct stat st;
+    if (stat(dir.c_str(), &st) == -1) {
+        std::string cmd = "mkdir -p \"" + dir + "\"";
+        if (std::system(cmd.c_str()) != 0) std::printf("Warning: could not create %s\n", dir.c_str());
+        std::printf("Created output directory: %s\n", dir.c_str());
+    }
+}
+
+int g_vtk_count = 0;  // one counter across all fields, like the static in src/utils.c:42
+
+void write_vtk(const std::vector<double> &A, int m, int n, const char *title, const std::string &dir)
+{
+    make_dir(dir);
+    char name[512];
+    std::snprintf(name, sizeof name, "%s/%s-1-%d.vtk", dir.c_str(), title, g_vtk_count);
+    FILE *pf = std::fopen(name, "a");
+    if (!pf) {
+        std::printf("\nError while opening file: %s\n", name);
+        std::exit(1);
+    }
+    std::printf("%s\n", name);
+    std::fprintf(pf, "# vtk DataFile Version 2.0\ntest\nASCII\nDATASET STRUCTURED_POINTS\n");
+    std::fprintf(pf, "DIMENSIONS %d %d 1\nORIGIN 0 0 0\nSPACING 1 1 1\nPOINT_DATA %d\n", m, n, m * n);
+    std::fprintf(pf, "SCALARS values float\nLOOKUP_TABLE default");
+    for (int i = 0; i < m; i++) {
+        std::fprintf(pf, "\n");
+        for (int j = 0; j < n; j++) std::fprintf(pf, j == 0 ? "%.6lf" : " %.6lf", A[(size_t)i * n + j]);
+    }
+    std::fclose(pf);
+    g_vtk_count++;
+}
+
+void usage(const char *prog)
+{
+    std::printf("Usage: %s [config_file] [output_folder]\n\nOptions:\n", prog);
+    std::printf("  config_file    Path to configuration file (optional)\n");
+    std::printf("                 If not provided, default values will be used\n");
+    std::printf("  output_folder  Name of output subfolder (optional)\n");
+    std::printf("                 Files will be saved to ./output/[output_folder]/\n");
+    std::printf("                 If not provided, files will be saved to ./output/\n");
+    std::printf("\nConfiguration file format:\n  # Comments start with # or ;\n  parameter_name = value\n");
+    std::printf("\nFor a complete list of parameters, run with --help-config\n");
+}
+
+void help_config()
+{
+    std::printf("Complete list of configuration parameters:\n\n");
+    std::printf("Physical Parameters:\n  Re, Lx, Ly\n");
+    std::printf("\nNumerical Parameters:\n  nx, ny, dt, tf, max_co, order (2|4|6), poisson_max_it, poisson_tol,\n");
+    std::printf("  output_interval, poisson_type (1=no relaxation, 2=SOR)\n");
+    std::printf("\nPerformance Parameters:\n  openmp_enabled (parsed, ignored by the GPU path)\n");
+    std::printf("\nBoundary Conditions:\n  ui, vi, u1, u2, u3, u4, v1, v2, v3, v4\n");
+}
+
+double now_s()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+}  // namespace
+
+extern "C" int cnv_main(int argc, char **argv)
+{
+    Config cfg;
+    std::string output_dir = "./output";
+    const double start_time = now_s();
+    if (argc == 1) {
+        std::printf("No configuration file specified. Using default values.\n");
+        cnv_config_default(&cfg);
+    } else if (argc == 2 || argc == 3) {
+        if (argc == 2 && (!std::strcmp(argv[1], "--help") || !std::strcmp(argv[1], "-h"))) { usage(argv[0]); return 0; }
+        if (argc == 2 && !std::strcmp(argv[1], "--help-config")) { help_config(); return 0; }
+        cnv_config_from_file(argv[1], &cfg);
+        if (argc == 3) {
+            output_dir = std::string("./output/") + argv[2];
+            std::printf("Using output directory: %s\n", output_dir.c_str());
+        }
+    } else {
+        std::printf("Error: Too many arguments.\n");
+        usage(argv[0]);
+        return 1;
+    }
+    cnv_config_print(&cfg);
+    std::printf("\n=== Execution Status ===\nBackend: CUDA (sm_100a), %d device(s) visible\n========================\n\n",
+                cnv_device_count());
+
+    const double beta = cnv_sor_beta(cfg.nx, cfg.ny);
+    std::printf("Poisson SOR parameter: %lf\n", beta);
+    const double dx = (double)cfg.Lx / cfg.nx, dy = (double)cfg.Ly / cfg.ny;
+    const int it_max = (int)((cfg.tf / cfg.dt) - 1);
+    // Courant check exactly as the reference does it: with u1 (src/main.c:165-174)
+    const double r1 = cfg.u1 * cfg.dt / dx, r2 = cfg.u1 * cfg.dt / dy;
+    if (r1 > cfg.max_co || r2 > cfg.max_co) {
+        std::printf("Unstable Solution!\nr1: %lf\nr2: %lf\n", r1, r2);
+        return 1;
+    }
+    if (cfg.poisson_type != 1 && cfg.poisson_type != 2) {
+        std::printf("Error - invalid option for Poisson solver\n");
+        return 1;
+    }
+
+    const char *tenv = std::getenv("CNV_POISSON_T");
+    cnv_sim *sim = cnv_sim_create(&cfg, tenv ? std::atoi(tenv) : 0);
+    const bool no_vtk = std::getenv("CNV_NO_VTK") && std::atoi(std::getenv("CNV_NO_VTK"));
+
+    // log file ./output/logs/<run>.txt (src/main.c:229-273)
+    std::string run_name = "default";
+    const std::string prefix = "./output/";
+    if (output_dir.compare(0, prefix.size(), prefix) == 0 && output_dir.size() > prefix.size())
+        run_name = output_dir.substr(prefix.size());
+    const std::string log_filename = "./output/logs/" + run_name + ".txt";
+    if (std::system("mkdir -p output/logs") != 0) std::printf("Warning: could not create output/logs\n");
+    FILE *log = std::fopen(log_filename.c_str(), "w");
+    if (!log) {
+        std::printf("Warning: Could not create log file %s. Logging to console instead.\n", log_filename.c_str());
+    } else {
+        std::printf("Logging simulation progress to: %s\n", log_filename.c_str());
+        std::fprintf(log, "=== Fluid Dynamics Simulation Log ===\nRun name: %s\nOutput directory: %s\n", run_name.c_str(),
+                     output_dir.c_str());
+        std::fprintf(log, "Reynolds number: %.2f\nGrid size: %dx%d\nTime step: %.6f\nFinal time: %.2f\n", cfg.Re, cfg.nx, cfg.ny,
+                     cfg.dt, cfg.tf);
+        std::fprintf(log, "Max iterations: %d\nOpenMP enabled: %s\n", it_max + 1, cfg.openmp_enabled ? "Yes" : "No");
+        std::fprintf(log, "=====================================\n\n");
+        std::fflush(log);
+    }
+
+    const double sim_start = now_s();
+    std::vector<double> psi, w, u, v;
+    int rc = 0;
+    for (int t = 0; t <= it_max; t++) {
+        const double t0 = now_s();
+        int k = 0;
+        double e = 0, cmax = 0, cmin = 0;
+        const int failed = cnv_sim_step(sim, 1, &k, &e, &cmax, &cmin);
+        if (failed) {
+            log_line(log, "Error: maximum number of iterations achieved for Poisson equation.\n");  // src/poisson.c:280
+            rc = 1;
+            break;
+        }
+        log_line(log, "Poisson equation solved with %d iterations - root-sum-of-squares error: %E\n", k, e);
+        const double t1 = now_s();
+        const double elapsed = t1 - sim_start;
+        log_line(log, "Iteration: %d | ", t);
+        log_line(log, "Time: %lf | ", (double)t * cfg.dt);
+        log_line(log, "Progress: %.2lf%% | ", (double)100 * t / it_max);
+        log_line(log, "Iter time: %.3f s\n", t1 - t0);
+        log_line(log, "Continuity max: %E | ", cmax);
+        log_line(log, "Continuity min: %E | ", cmin);
+        log_line(log, "Elapsed: %.1f s | ", elapsed);
+        if (t > 0) log_line(log, "Est. remaining: %.1f s\n", elapsed / (t + 1) * (it_max - t));
+        else log_line(log, "Est. remaining: -- s\n");
+        if (!no_vtk && cfg.output_interval != 0 && t % cfg.output_interval == 0) {
+            const size_t n = (size_t)cfg.nx * cfg.ny;
+            psi.resize(n); w.resize(n); u.resize(n); v.resize(n);
+            cnv_sim_get_fields(sim, psi.data(), w.data(), u.data(), v.data());
+            write_vtk(psi, cfg.nx, cfg.ny, "stream-function", output_dir);
+            write_vtk(w, cfg.nx, cfg.ny, "vorticity", output_dir);
+            write_vtk(u, cfg.nx, cfg.ny, "x-velocity", output_dir);
+            write_vtk(v, cfg.nx, cfg.ny, "y-velocity", output_dir);
+        }
+    }
+    long long counters[3];
+    cnv_sim_counters(sim, counters);
+    cnv_sim_destroy(sim);
+    if (rc == 0) std::printf("Simulation complete!\n");
+    const double end = now_s();
+    log_line(log, "\n=== Timing Summary ===\n");
+    log_line(log, "Setup time: %.4f seconds\n", sim_start - start_time);
+    log_line(log, "Simulation time: %.2f seconds\n", end - sim_start);
+    log_line(log, "Total program time: %.2f seconds\n", end - start_time);
+    log_line(log, "Average iteration time: %.4f seconds\n", (end - sim_start) / (it_max + 1));
+    log_line(log, "Iterations completed: %d\n", (int)counters[2]);
+    log_line(log, "Poisson sweeps: %lld (%lld passes)\n", counters[0], counters[1]);
+    log_line(log, "======================\n");
+    if (log) {
+        std::fclose(log);
+        std::printf("Log saved to: %s\n", log_filename.c_str());
+    }
+    return rc;
+}

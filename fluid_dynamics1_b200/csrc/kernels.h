@@ -1,0 +1,110 @@
+// kernels.h -- internal C++ interface between the CUDA translation units of libcnavier_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+
+#include "fd_coeffs.h"
+#include "poisson_plan.h"
+
+// The reference reports failures with a message and exit(1) (src/poisson.c:280-284,
+// src/linearalg.c:58-79); CUDA errors follow the same convention.
+#define CNV_CUDA_CHECK(expr)                                                                              \
+    do {                                                                                                  \
+        cudaError_t err__ = (expr);                                                                       \
+        if (err__ != cudaSuccess) {                                                                       \
+            std::printf("** Error: CUDA failure %s at %s:%d (%s) **\n", cudaGetErrorString(err__), __FILE__, \
+                        __LINE__, #expr);                                                                 \
+            std::fflush(stdout);                                                                          \
+            std::exit(1);                                                                                 \
+        }                                                                                                 \
+    } while (0)
+
+namespace cnv {
+
+// ---- stencil_kernels.cu ----
+void launch_apply(const double *A, int nrows, int ncols, int lda, int axis, const FdTable &t, double *out, int ldo,
+                  double scale, cudaStream_t s);
+void launch_ring_bc_vorticity(double *u, double *v, double *w, int nrows, int ncols, int ld, const double bc[8],
+                              const FdTable &d1x, const FdTable &d1y, cudaStream_t s);
+void launch_euler_fused(const double *w, const double *u, const double *v, int nrows, int ncols, int ld, const FdTable &d1x,
+                        const FdTable &d1y, const FdTable &d2x, const FdTable &d2y, double inv_re, double dt, double pscale,
+                        double *w_new, double *rhs, cudaStream_t s);
+void launch_euler_pointwise(double *w, const double *dwdx, const double *dwdy, const double *d2wdx2, const double *d2wdy2,
+                            const double *u, const double *v, size_t n, double inv_re, double dt, cudaStream_t s);
+void launch_pointwise_addsub(const double *a, const double *b, double *out, size_t n, int sub, cudaStream_t s);
+void launch_velocity(const double *psi, int nrows, int ncols, int ldp, const FdTable &d1x, const FdTable &d1y, double *u,
+                     double *v, int ld, cudaStream_t s);
+int continuity_blocks(int nrows, int ncols);
+void launch_continuity(const double *u, const double *v, int nrows, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
+                       double *partial, unsigned *ticket, double *result, cudaStream_t s);
+void launch_prep_rhs(const double *f, int nrows, int ncols, int ldf, double sign, double pscale, double *rhs, double *psi0,
+                     double *psi1, int ld, cudaStream_t s);
+
+// ---- poisson.cu ----
+struct PoissonResult {
+    int status;  // 0 converged, 1 itmax reached (the reference exits the process here)
+    int k;       // logged iteration number = sweeps - 1
+    int sweeps;
+    int passes;
+    double e;    // L1 update norm of the last sweep
+};
+
+// Slab neighbours for the multi-GPU path (see poisson.cu); all zero/NULL on one GPU.
+struct SlabComm;
+
+class PoissonSolver {
+public:
+    // local array of nrows x ncols; rows [own_lo, own_hi) are owned (== all rows on one GPU)
+    PoissonSolver(int nrows, int ncols, int T, int grow0 = 0, int gnrows = -1, int own_lo = 0, int own_hi = -1);
+    ~PoissonSolver();
+    PoissonSolver(const PoissonSolver &) = delete;
+
+    int ld() const { return geom_.ld; }
+    int T() const { return T_; }
+    const PassGeom &geom() const { return geom_; }
+    double *rhs() { return rhs_; }                // device, pitch ld(): pscale * f
+    double *buffer(int i) { return buf_[i]; }     // the two iterate buffers
+    double *history() { return hist_; }
+    size_t launches() const { return launches_; }
+    void set_consts(double dx, double dy, double beta);
+    const RelaxConsts &consts() const { return rc_; }
+
+    // rhs() must hold pscale*f and both buffers the initial iterate (zero ring); runs until
+    // convergence / itmax with the reference's stopping rule and returns the result.
+    // `result_buf` receives the index of the buffer holding psi.
+    PoissonResult solve(int itmax, double tol, cudaStream_t s, int *result_buf, bool keep_history = false);
+    // f (device, pitch ldf) -> prepared rhs + zero initial guess, then solve()
+    PoissonResult solve_from(const double *f, int ldf, double fsign, int itmax, double tol, cudaStream_t s, int *result_buf,
+                             bool keep_history = false);
+    // enqueue `npasses` passes without any host synchronisation (benchmark / graph building block)
+    void enqueue_passes(int npasses, cudaStream_t s);
+    void reset_ctl(int itmax, double tol, cudaStream_t s);
+    PoissonCtl read_ctl(cudaStream_t s);
+
+    // multi-GPU hooks (NCCL path): when set, the last CTA only publishes local norms to
+    // local_norms() and decide_kernel() must be enqueued after the all-reduce.
+    void set_distributed(bool on) { distributed_ = on; }
+    double *local_norms() { return norms_; }
+    void enqueue_decide(cudaStream_t s);
+
+private:
+    int T_;
+    PassGeom geom_;
+    RelaxConsts rc_;
+    double *buf_[2] = {nullptr, nullptr};
+    double *rhs_ = nullptr, *partials_ = nullptr, *hist_ = nullptr, *norms_ = nullptr;
+    int hist_cap_ = 0;
+    PoissonCtl *ctl_ = nullptr, *h_ctl_ = nullptr;
+    cudaEvent_t ev_ = nullptr;
+    int predicted_passes_ = 0;
+    bool distributed_ = false;
+    bool use_hist_ = false;
+    size_t launches_ = 0;
+    size_t smem_ = 0;
+    int threads_ = 0;
+};
+
+}  // namespace cnv

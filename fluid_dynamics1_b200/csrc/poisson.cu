@@ -1,0 +1,304 @@
+// poisson.cu -- streamfunction Poisson solve on the B200: temporally blocked red-black SOR.
+//
+// Replaces src/poisson.c:62-285 (poisson, poisson_SOR, poisson_log, poisson_SOR_log, error) of the
+// reference.  The per-thread phases live in poisson_stream.h (shared with the CPU schedule
+// checker); this file holds the kernel skeleton (cp.async pipeline, barriers, reductions, the
+// device-side stopping logic) and the host-side solver object.
+//
+// Roofline: the un-blocked algorithm moves 24 B per interior cell per sweep (read psi, read f,
+// write psi); one pass of this kernel applies T sweeps for the same 24 B (+ halo overlap), so the
+// HBM bound is 24/T B per cell-update and the kernel becomes shared-memory-bandwidth bound
+// (~56 B of LDS/STS per cell-update) for T >= 2.
+#include <algorithm>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace cnv {
+
+static size_t g_launches = 0;
+size_t total_launches() { return g_launches; }
+void count_launch(size_t n) { g_launches += n; }
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Sums `acc` over the threads of each level group in a fixed order; result in s_e[g].
+__device__ __forceinline__ void group_sums(double *sm, double acc, int g, int kk, int TPG, double *s_e)
+{
+    const int tid = threadIdx.x;
+    __syncthreads();
+    sm[tid] = acc;
+    __syncthreads();
+    double *red2 = sm + blockDim.x;
+    if (kk < 32) {
+        double s = 0.0;
+        for (int m = kk; m < TPG; m += 32) s = xadd(s, sm[g * TPG + m]);
+        red2[g * 32 + kk] = s;
+    }
+    __syncthreads();
+    if (kk == 0) {
+        double s = 0.0;
+        const int lim = TPG < 32 ? TPG : 32;
+        for (int m = 0; m < lim; m++) s = xadd(s, red2[g * 32 + m]);
+        s_e[g] = s;
+    }
+    __syncthreads();
+}
+
+template <int T, bool POW2>
+__global__ void __launch_bounds__(T == 8 ? 768 : 512, 1)
+k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0, double *__restrict__ buf1,
+               const double *__restrict__ rhs, PoissonCtl *ctl, double *__restrict__ partials, double *hist,
+               double *norms_out, const int fused_decide)
+{
+    extern __shared__ double4 sm4[];
+    double *sm = reinterpret_cast<double *>(sm4);
+    __shared__ double s_e[8];
+    __shared__ int s_last;
+
+    if (ctl->state != 0) return;  // solve already finished: later passes of a batch are no-ops
+    const int nsw = pass_sweeps(*ctl, T);
+    const int cur = ctl->cur;
+    const double *__restrict__ in = cur ? buf1 : buf0;
+    double *__restrict__ out = cur ? buf0 : buf1;
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const CtaGeom G = cta_geom(p, blockIdx.x, blockIdx.y);
+    const ThreadCtx t = thread_ctx(p, G, tid);
+    const int TPG = p.WS >> 2;
+    const int kk = tid - t.g * TPG;
+    double acc = 0.0;
+
+    // prologue: kPrefetch rows in flight
+#pragma unroll
+    for (int i = 0; i < kPrefetch; i++) {
+        phase_load<T>(p, G, sm, in, rhs, tid, nthreads, first_step(G) + i);
+        cp_async_commit();
+    }
+    const int rend = last_step<T>(G);
+    for (int r = first_step(G); r <= rend; r++) {
+        cp_async_wait<kPrefetch - 1>();  // row r has landed (this thread's copies) ...
+        __syncthreads();                 // ... and everybody's; previous step's updates are visible
+        phase_load<T>(p, G, sm, in, rhs, tid, nthreads, r + kPrefetch);
+        cp_async_commit();
+        phase_store<T>(p, G, sm, out, tid, nthreads, r - 4 * T);
+        phase_compute<T, POW2>(p, G, rc, sm, t, r, nsw, acc);
+    }
+    cp_async_wait<0>();
+
+    // per-CTA L1 update norms, one per sweep of the pass (level g <-> sweep g+1)
+    group_sums(sm, acc, t.g, kk, TPG, s_e);
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid < T) {
+        partials[(size_t)cta * T + tid] = s_e[tid];
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&ctl->ticket, 1u) == (unsigned)ncta - 1;
+    __syncthreads();
+    if (!s_last) return;
+
+    // last CTA: grid-wide sums in a fixed order, then the stopping decision (src/poisson.c:272-279)
+    __threadfence();
+    double part = 0.0;
+    for (int c = kk; c < ncta; c += TPG) part = xadd(part, __ldcg(&partials[(size_t)c * T + t.g]));
+    group_sums(sm, part, t.g, kk, TPG, s_e);
+    if (tid == 0) {
+        if (fused_decide) {
+            PoissonCtl c = *ctl;
+            decide(c, s_e, nsw, hist);
+            c.ticket = 0;
+            *ctl = c;
+        } else {
+            for (int g = 0; g < T; g++) norms_out[g] = g < nsw ? s_e[g] : 0.0;
+            ctl->ticket = 0;
+        }
+    }
+}
+
+// multi-GPU: stopping decision from all-reduced norms (identical on every rank)
+__global__ void k_decide(PoissonCtl *ctl, const double *norms, int T, double *hist)
+{
+    if (ctl->state != 0) return;
+    PoissonCtl c = *ctl;
+    decide(c, norms, pass_sweeps(c, T), hist);
+    *ctl = c;
+}
+
+__global__ void k_reset_ctl(PoissonCtl *ctl, int itmax, double tol)
+{
+    PoissonCtl c;
+    c.state = itmax > 0 ? 0 : 2;
+    c.cur = 0; c.sweeps = 0; c.redo = 0; c.itmax = itmax; c.result_k = -1; c.ticket = 0; c.passes = 0;
+    c.tol = tol; c.result_e = 0.0; c.last_e = 0.0;
+    *ctl = c;
+}
+
+template <int T, bool POW2>
+static void launch_pass(const PassGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
+                        double *partials, double *hist, double *norms, int fused, int threads, size_t smem, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_pass<T, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    k_poisson_pass<T, POW2><<<dim3(g.nstrips, g.nchunks), threads, smem, s>>>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused);
+}
+
+// ---------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt)
+{
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows, int own_lo, int own_hi)
+{
+    if (gnrows < 0) gnrows = nrows;
+    if (own_hi < 0) own_hi = nrows;
+    if (T <= 0) T = env_int("CNV_POISSON_T", 4);
+    if (T != 1 && T != 2 && T != 4 && T != 8) {
+        std::printf("** Error: temporal block depth must be 1, 2, 4 or 8 **\n");
+        std::exit(1);
+    }
+    if (nrows < 3 || ncols < 3) {
+        std::printf("** Error: invalid parameter **\n");  // src/linearalg.c:58-62 wording
+        std::exit(1);
+    }
+    T_ = T;
+    PlanLimits lim;
+    int dev = 0;
+    cudaDeviceProp prop;
+    CNV_CUDA_CHECK(cudaGetDevice(&dev));
+    CNV_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    lim.num_sms = prop.multiProcessorCount;
+    lim.smem_per_cta = prop.sharedMemPerBlockOptin;
+    lim.smem_per_sm = prop.sharedMemPerMultiprocessor;
+    lim.max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
+    const int ld = round_up(ncols, 16);
+    geom_ = make_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, lim, env_int("CNV_POISSON_WS", 0),
+                      env_int("CNV_POISSON_CHUNKS", 0));
+    if (geom_.WS == 0) {
+        std::printf("** Error: no launch plan for a %dx%d grid **\n", nrows, ncols);
+        std::exit(1);
+    }
+    threads_ = pass_threads(T, geom_.WS);
+    smem_ = pass_smem_bytes(T, geom_.WS);
+    std::memset(&rc_, 0, sizeof rc_);
+    const size_t bytes = (size_t)nrows * ld * sizeof(double);
+    for (int i = 0; i < 2; i++) {
+        CNV_CUDA_CHECK(cudaMalloc(&buf_[i], bytes));
+        CNV_CUDA_CHECK(cudaMemset(buf_[i], 0, bytes));
+    }
+    CNV_CUDA_CHECK(cudaMalloc(&rhs_, bytes));
+    CNV_CUDA_CHECK(cudaMemset(rhs_, 0, bytes));
+    CNV_CUDA_CHECK(cudaMalloc(&partials_, sizeof(double) * (size_t)geom_.nstrips * geom_.nchunks * T));
+    CNV_CUDA_CHECK(cudaMalloc(&norms_, sizeof(double) * 8));
+    CNV_CUDA_CHECK(cudaMemset(norms_, 0, sizeof(double) * 8));
+    CNV_CUDA_CHECK(cudaMalloc(&ctl_, sizeof(PoissonCtl)));
+    CNV_CUDA_CHECK(cudaMemset(ctl_, 0, sizeof(PoissonCtl)));
+    CNV_CUDA_CHECK(cudaMallocHost(&h_ctl_, sizeof(PoissonCtl)));
+    CNV_CUDA_CHECK(cudaEventCreateWithFlags(&ev_, cudaEventDisableTiming));
+}
+
+PoissonSolver::~PoissonSolver()
+{
+    cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(rhs_); cudaFree(partials_); cudaFree(norms_); cudaFree(ctl_);
+    if (hist_) cudaFree(hist_);
+    cudaFreeHost(h_ctl_);
+    cudaEventDestroy(ev_);
+}
+
+void PoissonSolver::set_consts(double dx, double dy, double beta) { rc_ = make_relax_consts(dx, dy, beta); }
+
+void PoissonSolver::reset_ctl(int itmax, double tol, cudaStream_t s)
+{
+    k_reset_ctl<<<1, 1, 0, s>>>(ctl_, itmax, tol);
+    count_launch(1);
+}
+
+PoissonCtl PoissonSolver::read_ctl(cudaStream_t s)
+{
+    CNV_CUDA_CHECK(cudaMemcpyAsync(h_ctl_, ctl_, sizeof(PoissonCtl), cudaMemcpyDeviceToHost, s));
+    CNV_CUDA_CHECK(cudaEventRecord(ev_, s));
+    CNV_CUDA_CHECK(cudaEventSynchronize(ev_));
+    return *h_ctl_;
+}
+
+void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
+{
+    double *hist = use_hist_ ? hist_ : nullptr;
+    const int fused = distributed_ ? 0 : 1;
+    for (int i = 0; i < npasses; i++) {
+#define CNV_PASS(TT)                                                                                                     \
+    if (T_ == TT) {                                                                                                      \
+        if (rc_.pow2)                                                                                                    \
+            launch_pass<TT, true>(geom_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, threads_, smem_, s); \
+        else                                                                                                             \
+            launch_pass<TT, false>(geom_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, threads_, smem_, s); \
+    }
+        CNV_PASS(1) CNV_PASS(2) CNV_PASS(4) CNV_PASS(8)
+#undef CNV_PASS
+    }
+    CNV_CUDA_CHECK(cudaGetLastError());
+    launches_ += npasses;
+    count_launch(npasses);
+}
+
+void PoissonSolver::enqueue_decide(cudaStream_t s)
+{
+    k_decide<<<1, 1, 0, s>>>(ctl_, norms_, T_, use_hist_ ? hist_ : nullptr);
+    count_launch(1);
+}
+
+PoissonResult PoissonSolver::solve(int itmax, double tol, cudaStream_t s, int *result_buf, bool keep_history)
+{
+    if (keep_history && hist_cap_ < itmax) {
+        if (hist_) cudaFree(hist_);
+        CNV_CUDA_CHECK(cudaMalloc(&hist_, sizeof(double) * (size_t)itmax));
+        hist_cap_ = itmax;
+    }
+    use_hist_ = keep_history;
+    reset_ctl(itmax, tol, s);
+    // Sweep counts drift slowly from one time step to the next (the shipped logs move by <= ~10
+    // sweeps per step), so the first batch covers the previous solve's pass count plus one and is
+    // followed by small batches.  Passes enqueued after convergence exit immediately.
+    int batch = predicted_passes_ > 0 ? predicted_passes_ + 1 : 16;
+    const int max_passes = (itmax + T_ - 1) / T_ + 2;
+    int enq = 0;
+    PoissonCtl c;
+    for (;;) {
+        batch = std::max(1, std::min(batch, max_passes + 1 - enq));
+        enqueue_passes(batch, s);
+        enq += batch;
+        c = read_ctl(s);
+        if (c.state != 0) break;
+        if (enq > max_passes + 1) {
+            std::printf("** Error: Poisson state machine did not terminate **\n");
+            std::exit(1);
+        }
+        batch = predicted_passes_ > 0 ? 4 : 16;
+    }
+    predicted_passes_ = c.passes;
+    if (result_buf) *result_buf = c.cur;
+    PoissonResult r;
+    r.status = c.state == 1 ? 0 : 1;
+    r.k = c.result_k;
+    r.sweeps = c.sweeps;
+    r.passes = c.passes;
+    r.e = c.state == 1 ? c.result_e : c.last_e;
+    return r;
+}
+
+PoissonResult PoissonSolver::solve_from(const double *f, int ldf, double fsign, int itmax, double tol, cudaStream_t s,
+                                        int *result_buf, bool keep_history)
+{
+    launch_prep_rhs(f, geom_.nrows, geom_.ncols, ldf, fsign, rc_.pscale, rhs_, buf_[0], buf_[1], geom_.ld, s);
+    count_launch(1);
+    return solve(itmax, tol, s, result_buf, keep_history);
+}
+
+}  // namespace cnv

@@ -1,0 +1,113 @@
+// poisson_plan.h -- host-side planning for the streaming Poisson kernel: relaxation constants
+// (evaluated with the reference's expressions) and the strip/chunk decomposition of one pass.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+#include "poisson_stream.h"
+
+namespace cnv {
+
+inline bool is_pow2_double(double x)
+{
+    int e;
+    return x > 0 && std::frexp(x, &e) == 0.5;
+}
+
+// src/poisson.c:246 constants.  `beta` == 1 reproduces the Gauss-Seidel variants (:85, :198):
+// beta*A/D == A/D and (1-beta)*u0 == +0.
+inline RelaxConsts make_relax_consts(double dx, double dy, double beta)
+{
+    RelaxConsts c;
+    std::memset(&c, 0, sizeof c);
+    c.cxx = dx * dx;
+    c.cyy = dy * dy;
+    c.cf = dx * dx * dy * dy;
+    c.D = 2 * (dx * dx + dy * dy);
+    c.rD = 1.0 / c.D;
+    c.beta = beta;
+    c.omb = 1 - beta;
+    c.pow2 = (dx == dy) && is_pow2_double(dx);
+    c.bb = 0.25 * beta;
+    c.pscale = c.pow2 ? c.cxx : c.cf;
+    // Markstein's correction is exact unless the divisor's significand is all ones
+    uint64_t bits;
+    std::memcpy(&bits, &c.D, 8);
+    c.true_div = ((bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull) || !std::isfinite(c.rD);
+    if (const char *e = std::getenv("CNV_POISSON_GENERAL")) {  // force the literal operation sequence
+        if (std::atoi(e)) { c.pow2 = 0; c.pscale = c.cf; }
+    }
+    if (const char *e = std::getenv("CNV_POISSON_TRUE_DIV")) c.true_div = std::atoi(e) != 0;
+    return c;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+inline size_t pass_smem_bytes(int T, int WS) { return (size_t)ring_rows(T) * slot_stride(WS) * sizeof(double); }
+inline int pass_threads(int T, int WS) { return T * (WS / 4); }
+
+struct PlanLimits {
+    int num_sms = 148;
+    size_t smem_per_cta = 227 * 1024;
+    size_t smem_per_sm = 228 * 1024;
+    int max_threads_per_sm = 2048;
+};
+
+// Choose WS / Hout for `own` = [own_lo, own_hi) rows of an nrows x ncols local array.
+// Cost model: the kernel is bound by shared-memory traffic, proportional to (steps x WS x T) per
+// CTA; CTAs resident on one SM share that bandwidth, and the pass ends with the last wave.
+inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T,
+                          const PlanLimits &lim, int force_ws = 0, int force_chunks = 0)
+{
+    PassGeom best;
+    std::memset(&best, 0, sizeof best);
+    double best_cost = 1e300;
+    const int HX = round_up(2 * T, 4), HY = 2 * T;
+    const int own = own_hi - own_lo;
+    for (int WS = 32; WS <= 2048; WS += 32) {
+        if (force_ws && WS != force_ws) continue;
+        const int Wout = WS - 2 * HX;
+        if (Wout < 4) continue;
+        const int NT = pass_threads(T, WS);
+        if (NT > (T == 8 ? 768 : 512) || (!force_ws && NT < 64 && WS < ncols + 2 * HX)) continue;
+        const size_t smem = pass_smem_bytes(T, WS);
+        if (smem > lim.smem_per_cta) continue;
+        // do not take a strip much wider than the domain needs
+        if (!force_ws && WS - 32 >= ncols + 2 * HX) continue;
+        const int nstrips = (ncols + Wout - 1) / Wout;
+        int occ = (int)(lim.smem_per_sm / (smem + 1024));
+        if (occ > lim.max_threads_per_sm / NT) occ = lim.max_threads_per_sm / NT;
+        if (occ < 1) occ = 1;
+        if (occ > 4) occ = 4;
+        const int slots = lim.num_sms * occ;
+        for (int waves = 1; waves <= 4; waves++) {
+            int nchunks = force_chunks ? force_chunks : (slots * waves) / nstrips;
+            if (nchunks < 1) nchunks = 1;
+            if (nchunks > own) nchunks = own;
+            if (!force_chunks) {  // keep the y-halo overhead (4T rows per chunk) below ~50 %
+                const int max_chunks = own / (8 * T) > 1 ? own / (8 * T) : 1;
+                if (nchunks > max_chunks) nchunks = max_chunks;
+            }
+            int Hout = (own + nchunks - 1) / nchunks;
+            nchunks = (own + Hout - 1) / Hout;
+            const long ctas = (long)nstrips * nchunks;
+            const long nwaves = (ctas + slots - 1) / slots;
+            const int steps = Hout + 2 * HY + 4 * T + 8;  // + fixed per-CTA start-up cost
+            const int resident = ctas < slots ? (int)((ctas + lim.num_sms - 1) / lim.num_sms) : occ;
+            const double cost = (double)nwaves * resident * steps * WS * T;
+            if (cost < best_cost) {
+                best_cost = cost;
+                best.WS = WS; best.HX = HX; best.Wout = Wout; best.Hout = Hout; best.HY = HY;
+                best.nstrips = nstrips; best.nchunks = nchunks;
+            }
+            if (force_chunks) break;
+        }
+    }
+    best.nrows = nrows; best.ncols = ncols; best.ld = ld; best.grow0 = grow0; best.gnrows = gnrows;
+    best.own_lo = own_lo; best.own_hi = own_hi;
+    return best;
+}
+
+}  // namespace cnv

@@ -1,0 +1,121 @@
+/*
+ * cnavier_b200.h -- C ABI of libcnavier_b200.so, the B200 (sm_100a) implementation of cnavier's hot
+ * path.  Plain pointers and sizes only; every entry point names the reference interface it serves.
+ *
+ * Conventions
+ *   - fields are row-major double arrays A[i*ncols + j]; i is the first index of the reference's
+ *     mtrx (A.M[i][j]), j the second.  "host" entry points take HOST buffers and stage them.
+ *   - return value 0 = success unless stated otherwise.  Conditions for which the reference prints a
+ *     message and calls exit(1) (Poisson itmax, invalid order) are reported as non-zero codes here;
+ *     the drop-in layer (cnavier_dropin.h) turns them back into message + exit(1).
+ *   - CUDA failures print "** Error: CUDA failure ... **" and exit(1) (reference convention).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails loudly.
+ */
+#ifndef CNAVIER_B200_H
+#define CNAVIER_B200_H
+
+#include <stddef.h>
+#include "cnavier_dropin.h" /* Config */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *cnv_version(void);
+int cnv_device_count(void);               /* 0 when no CUDA device is visible */
+unsigned long long cnv_launch_count(void); /* kernels launched by this library so far */
+int cnv_set_device(int device);           /* one process per GPU: bind this library to a device */
+int cnv_get_device(void);
+void cnv_device_synchronize(void);
+
+/* ---- scalars of the driver: src/main.c:134 (beta, truncated PI), :162/:276 (step count) ------- */
+double cnv_sor_beta(int nx, int ny);
+int cnv_num_steps(double tf, double dt);
+
+/* ---- finite-difference operators ------------------------------------------------------------
+ * cnv_diff_dense: the dense n x n matrix Diff1 (deriv=1) / Diff2 (deriv=2) returns
+ * (src/finitediff.c:51-153, :178-292).  Host only.  Returns 1 for an order other than 2, 4, 6. */
+int cnv_diff_dense(int n, int order, int deriv, double h, double *D);
+/* cnv_apply_host: matrix-free DX (axis=1, along j) / DY (axis=0, along i) application that replaces
+ * kronecker + reshape + mtrxmul (src/main.c:149-152, :298-304; src/linearalg.c:236-285, :353-408),
+ * bit-identical to the dense route. */
+int cnv_apply_host(const double *A, int nrows, int ncols, int axis, int deriv, int order, double h, double *out);
+
+/* ---- pointwise operators: src/fluiddyn.c:71-102, :126-154, :179-207 -------------------------- */
+int cnv_euler_host(double *w, const double *dwdx, const double *dwdy, const double *d2wdx2, const double *d2wdy2,
+                   const double *u, const double *v, int nrows, int ncols, double Re, double dt);
+int cnv_continuity_host(const double *dudx, const double *dvdy, int nrows, int ncols, double *out);
+int cnv_vorticity_host(const double *a, const double *b, int nrows, int ncols, double *out); /* out = b - a */
+/* L1 distance sum|a-b| over the grid: error(), src/poisson.c:34-60 */
+double cnv_error_host(const double *a, const double *b, int nrows, int ncols);
+
+/* ---- Poisson solve: src/poisson.c:62-285 -------------------------------------------------------
+ * Solves lap(u) = f, zero Dirichlet ring, zero initial guess, red-black ordering ((i+j) even first,
+ * the reference's OpenMP build), stopping at the first sweep whose L1 update norm is < tol.
+ * beta = 1 gives the Gauss-Seidel variants (poisson / poisson_log).
+ * T = temporal block depth (sweeps per HBM pass: 1, 2, 4, 8; 0 = default).
+ * Returns 0 converged, 1 itmax reached (reference: message + exit(1)).
+ * *k = the reference's logged iteration number (sweeps-1), *e = final norm. */
+int cnv_poisson_host(const double *f, int nrows, int ncols, double dx, double dy, int itmax, double tol, double beta,
+                     int T, double *u, int *k, double *e, double *history /* NULL or itmax doubles */);
+
+/* Device-resident solver object (benchmarks, time stepping, multi-GPU). */
+typedef struct cnv_poisson cnv_poisson;
+cnv_poisson *cnv_poisson_create(int nrows, int ncols, int T);
+/* slab of a larger grid: local array rows [0,nrows) = global rows [grow0, grow0+nrows) of gnrows;
+ * rows [own_lo, own_hi) (local indices) are owned, the rest are halo rows (>= 2T deep). */
+cnv_poisson *cnv_poisson_create_slab(int nrows, int ncols, int T, int grow0, int gnrows, int own_lo, int own_hi);
+void cnv_poisson_destroy(cnv_poisson *p);
+void cnv_poisson_set_consts(cnv_poisson *p, double dx, double dy, double beta);
+int cnv_poisson_ld(const cnv_poisson *p);                 /* pitch (doubles) of the device arrays */
+double *cnv_poisson_rhs_ptr(cnv_poisson *p);              /* device: prepared right-hand side */
+double *cnv_poisson_buf_ptr(cnv_poisson *p, int which);   /* device: iterate buffers 0/1 */
+double *cnv_poisson_norms_ptr(cnv_poisson *p);            /* device: T per-sweep norms of the last pass */
+/* out[0..9] = WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, T, pow2-path flag */
+void cnv_poisson_plan_info(const cnv_poisson *p, long long *out);
+/* stage a host right-hand side f (nrows x ncols, dense) and zero the iterate; fsign = -1 solves with -f */
+int cnv_poisson_upload(cnv_poisson *p, const double *f_host, double fsign, void *stream);
+/* same from a device array with pitch ldf */
+int cnv_poisson_prepare(cnv_poisson *p, const double *f_dev, int ldf, double fsign, void *stream);
+/* run to convergence / itmax (synchronises).  Returns 0 / 1 as cnv_poisson_host. */
+int cnv_poisson_solve(cnv_poisson *p, int itmax, double tol, void *stream, int *k, double *e, int *sweeps, int *passes,
+                      int *result_buf);
+/* asynchronous building blocks: reset the device state machine, enqueue passes (each applies up to T
+ * sweeps, no-ops once the state machine has stopped), read the state back (synchronises). */
+void cnv_poisson_reset(cnv_poisson *p, int itmax, double tol, void *stream);
+void cnv_poisson_enqueue(cnv_poisson *p, int npasses, void *stream);
+void cnv_poisson_enqueue_decide(cnv_poisson *p, void *stream);
+void cnv_poisson_set_distributed(cnv_poisson *p, int on);
+/* state[0..5] = state (0 running, 1 converged, 2 itmax), cur buffer, sweeps, passes, k, redo */
+void cnv_poisson_state(cnv_poisson *p, void *stream, int *state, double *e);
+int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream);
+
+/* ---- device-resident time stepping: the loop body of src/main.c:283-395 ---------------------- */
+typedef struct cnv_sim cnv_sim;
+cnv_sim *cnv_sim_create(const Config *cfg, int T);
+void cnv_sim_destroy(cnv_sim *s);
+/* Advances nsteps steps.  k/e/cont_max/cont_min: NULL or arrays of nsteps (per-step Poisson log values
+ * and continuity diagnostic).  Returns 0, or (index of the step whose Poisson solve hit itmax) + 1. */
+int cnv_sim_step(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, double *cont_min);
+int cnv_sim_get_fields(cnv_sim *s, double *psi, double *w, double *u, double *v); /* host, nx*ny each, NULL to skip */
+int cnv_sim_set_fields(cnv_sim *s, const double *psi, const double *w, const double *u, const double *v);
+void cnv_sim_set_diagnostics(cnv_sim *s, int continuity_on);
+/* cumulative counters: [0] Poisson sweeps, [1] Poisson passes, [2] steps */
+void cnv_sim_counters(cnv_sim *s, long long *out);
+
+/* ---- whole driver: restates src/main.c:27-481 on top of the device-resident path ---------------
+ * (same config file, same stdout/log lines, same step order; VTK through printvtk-compatible writer
+ * unless CNV_NO_VTK=1).  Returns the process exit code. */
+int cnv_main(int argc, char **argv);
+
+/* configuration system (src/config.c) under cnv_ names for callers that do not want the
+ * reference-named symbols of the drop-in library */
+void cnv_config_default(Config *out);
+void cnv_config_from_file(const char *filename, Config *out);
+void cnv_config_print(const Config *cfg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNAVIER_B200_H */

@@ -1,0 +1,110 @@
+// stream_emul.cc -- CPU schedule checker for the streaming Poisson kernel.  TEST ONLY.
+//
+// Compiles the kernel's own per-thread phase functions (fluid_dynamics1_b200/csrc/poisson_stream.h)
+// for the host and executes one pass the way the GPU does: CTA by CTA, step by step, with the
+// "threads" of a CTA run in a loop between the points where the kernel has a __syncthreads().
+// It exists so that the tiling / ring buffer / stage skew / halo logic can be compared with the
+// oracle in the CPU test suite (no GPU in the build container).  It is not linked into the
+// product library and is never used as a fallback.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../fluid_dynamics1_b200/csrc/poisson_plan.h"
+
+using namespace cnv;
+
+template <int T, bool POW2>
+static void run_pass(const PassGeom &p, const RelaxConsts &rc, const double *in, const double *rhs, double *out,
+                     int nsw, double *norms)
+{
+    constexpr int R = ring_rows(T);
+    const int NT = pass_threads(T, p.WS);
+    std::vector<double> sm((size_t)R * slot_stride(p.WS));
+    std::vector<double> acc(NT);
+    std::vector<ThreadCtx> ctx(NT);
+    for (int g = 0; g < T; g++) norms[g] = 0.0;
+    for (int by = 0; by < p.nchunks; by++)
+        for (int bx = 0; bx < p.nstrips; bx++) {
+            // poison shared memory so that any read of a row that was never loaded shows up
+            for (auto &x : sm) x = std::nan("");
+            const CtaGeom G = cta_geom(p, bx, by);
+            for (int t = 0; t < NT; t++) { ctx[t] = thread_ctx(p, G, t); acc[t] = 0.0; }
+            for (int rl = first_step(G); rl < first_step(G) + kPrefetch; rl++)
+                for (int t = 0; t < NT; t++) phase_load<T>(p, G, sm.data(), in, rhs, t, NT, rl);
+            for (int r = first_step(G); r <= last_step<T>(G); r++) {
+                // --- barrier ---
+                for (int t = 0; t < NT; t++) phase_load<T>(p, G, sm.data(), in, rhs, t, NT, r + kPrefetch);
+                for (int t = 0; t < NT; t++) phase_store<T>(p, G, sm.data(), out, t, NT, r - 4 * T);
+                for (int t = 0; t < NT; t++) phase_compute<T, POW2>(p, G, rc, sm.data(), ctx[t], r, nsw, acc[t]);
+            }
+            for (int t = 0; t < NT; t++) norms[ctx[t].g] += acc[t];
+        }
+}
+
+extern "C" {
+
+// plan only: returns WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes in out[8]
+void emul_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T, int force_ws,
+               int force_chunks, long *out)
+{
+    PlanLimits lim;
+    PassGeom p = make_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, lim, force_ws, force_chunks);
+    out[0] = p.WS; out[1] = p.HX; out[2] = p.Wout; out[3] = p.Hout; out[4] = p.nstrips; out[5] = p.nchunks;
+    out[6] = pass_threads(T, p.WS); out[7] = (long)pass_smem_bytes(T, p.WS);
+}
+
+// One pass of nsw <= T sweeps.  in/out: nrows x ld; rhs = pscale * f (prepared like the product's
+// prep kernel).  mode: 0 auto (pow2 fast path when exact), 1 force the literal general sequence.
+int emul_pass(int T, int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int force_ws,
+              int force_chunks, double dx, double dy, double beta, int mode, const double *in, const double *f,
+              double *out, int nsw, double *norms)
+{
+    PlanLimits lim;
+    PassGeom p = make_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, lim, force_ws, force_chunks);
+    if (p.WS == 0) return -1;
+    RelaxConsts rc = make_relax_consts(dx, dy, beta);
+    if (mode == 1) { rc.pow2 = 0; rc.pscale = rc.cf; }
+    std::vector<double> rhs((size_t)nrows * ld);
+    for (size_t i = 0; i < rhs.size(); i++) rhs[i] = rc.pscale * f[i];
+#define RUN(TT)                                                                       \
+    if (T == TT) {                                                                    \
+        if (rc.pow2) run_pass<TT, true>(p, rc, in, rhs.data(), out, nsw, norms);      \
+        else run_pass<TT, false>(p, rc, in, rhs.data(), out, nsw, norms);             \
+        return 0;                                                                     \
+    }
+    RUN(1) RUN(2) RUN(4) RUN(8)
+#undef RUN
+    return -2;
+}
+
+// state machine: feed a sequence of per-pass norm vectors, observe the decisions
+void emul_decide(int *ctl_ints, double *ctl_dbls, const double *e, int nsw, double *hist)
+{
+    PoissonCtl c;
+    c.state = ctl_ints[0]; c.cur = ctl_ints[1]; c.sweeps = ctl_ints[2]; c.redo = ctl_ints[3]; c.itmax = ctl_ints[4];
+    c.result_k = ctl_ints[5]; c.passes = ctl_ints[6]; c.ticket = 0;
+    c.tol = ctl_dbls[0]; c.result_e = ctl_dbls[1]; c.last_e = ctl_dbls[2];
+    decide(c, e, nsw, hist);
+    ctl_ints[0] = c.state; ctl_ints[1] = c.cur; ctl_ints[2] = c.sweeps; ctl_ints[3] = c.redo; ctl_ints[5] = c.result_k;
+    ctl_ints[6] = c.passes;
+    ctl_dbls[1] = c.result_e; ctl_dbls[2] = c.last_e;
+}
+int emul_pass_sweeps(int sweeps, int redo, int itmax, int T)
+{
+    PoissonCtl c; std::memset(&c, 0, sizeof c);
+    c.sweeps = sweeps; c.redo = redo; c.itmax = itmax;
+    return pass_sweeps(c, T);
+}
+
+// Markstein division vs hardware division: returns the number of mismatches
+long emul_check_div(double d, const double *a, long n)
+{
+    long bad = 0;
+    const double rd = 1.0 / d;
+    for (long i = 0; i < n; i++)
+        if (xdiv_const(a[i], d, rd) != a[i] / d) bad++;
+    return bad;
+}
+}

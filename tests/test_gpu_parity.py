@@ -1,0 +1,308 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle
+(oracle/cnavier_oracle.c, pinned in test_oracle_pinned.py) and the committed golden fixtures.
+
+Bar: the whole path is fp64 with individually rounded operations in the reference's association
+order, so fields are compared BITWISE wherever the summation order cannot differ; the only quantity
+whose rounding may differ is the L1 convergence norm (a grid-wide sum), checked to 1e-12 relative.
+The north_star tolerance (relative L2 <= 1e-8 on psi, w, u, v) is asserted as well.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2, sine_rhs
+
+pytestmark = pytest.mark.gpu
+
+fd = pytest.importorskip("fluid_dynamics1_b200")
+from oracle import api  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    fd.require_gpu()
+
+
+# ---- stencils ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", [2, 4, 6])
+@pytest.mark.parametrize("shape", [(7, 7), (16, 16), (33, 50), (64, 64), (200, 131)])
+def test_apply_operator_bitwise(port, order, shape):
+    rng = np.random.default_rng(order * 100 + shape[0])
+    A = rng.standard_normal(shape) * 10.0 ** rng.integers(-3, 3, shape)
+    for axis in (0, 1):
+        for deriv in (1, 2):
+            h = 1.0 / shape[axis]
+            got = fd.apply_operator(A, axis, deriv, order, h)
+            assert got.tobytes() == port.apply(A, axis, deriv, order, h).tobytes(), (axis, deriv)
+
+
+def test_apply_operator_bad_order():
+    with pytest.raises(ValueError):
+        fd.apply_operator(np.zeros((8, 8)), 0, 1, 3, 0.1)
+
+
+def test_diff_matrix_vs_oracle(port):
+    for order in (2, 4, 6):
+        for deriv in (1, 2):
+            assert np.array_equal(fd.diff_matrix(12, order, deriv, 0.37), port.diff_dense(12, order, deriv, 0.37))
+
+
+def test_pointwise_bitwise(port):
+    rng = np.random.default_rng(3)
+    a = [rng.standard_normal((37, 53)) for _ in range(7)]
+    assert np.array_equal(fd.euler(*a, 1000.0, 0.005), port.euler(*a, 1000.0, 0.005))
+    assert np.array_equal(fd.continuity(a[0], a[1]), a[0] + a[1])
+    assert np.array_equal(fd.vorticity(a[0], a[1]), a[1] - a[0])           # second minus first (quirk Q18)
+    e = fd.error(a[0], a[1])
+    assert abs(e - np.abs(a[0] - a[1]).sum()) <= 1e-12 * e
+
+
+# ---- Poisson ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T", [1, 2, 4, 8])
+@pytest.mark.parametrize("n", [16, 64, 100, 257])
+def test_poisson_sor_vs_oracle(port, n, T):
+    """Same sweep count, same field bits, same residual (to summation rounding) as the red-black
+    reference build; n=64 is the pow2 fast path, 100 and 257 the general (Markstein division) path."""
+    f = sine_rhs(n)
+    dx = 1.0 / n
+    beta = port.beta(n, n)
+    got = fd.poisson_sor(f, dx, dx, 20000, 1e-3, beta, T=T, history=True)
+    want = port.poisson(f, dx, dx, 20000, 1e-3, beta, redblack=True, history=True)
+    assert got["k"] == want["k"]
+    assert got["u"].tobytes() == want["u"].tobytes()
+    assert abs(got["e"] - want["e"]) <= 1e-12 * want["e"]
+    assert "%E" % got["e"] == "%E" % want["e"]
+    np.testing.assert_allclose(got["history"], want["history"], rtol=1e-12)
+
+
+def test_poisson_sine_golden_counts():
+    import json
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "poisson_sine.json")) as fh:
+        g = json.load(fh)
+    for n in (64, 128, 256):
+        r = fd.poisson_sor(sine_rhs(n), 1.0 / n, 1.0 / n, 20000, 1e-3, fd.sor_beta(n, n))
+        assert r["k"] == g[str(n)]["rb_k"]
+        assert "%.10f" % r["e"] == "%.10f" % g[str(n)]["rb_e"]
+
+
+@pytest.mark.parametrize("shape,dx,dy", [((40, 72), 1 / 40, 1 / 72), ((96, 33), 0.01, 0.013), ((5, 9), 0.2, 0.1)])
+def test_poisson_nonsquare_random_rhs(port, shape, dx, dy):
+    rng = np.random.default_rng(shape[0])
+    f = rng.standard_normal(shape)
+    beta = port.beta(*shape)
+    for T in (1, 4):
+        got = fd.poisson_sor(f, dx, dy, 50000, 1e-6, beta, T=T)
+        want = port.poisson(f, dx, dy, 50000, 1e-6, beta, redblack=True)
+        assert got["k"] == want["k"]
+        assert got["u"].tobytes() == want["u"].tobytes()
+
+
+def test_poisson_gauss_seidel_variant(port):
+    """poisson()/poisson_log(): beta == 1, no relaxation term (src/poisson.c:62-109, 176-222)."""
+    f = sine_rhs(48)
+    got = fd.poisson_sor(f, 1 / 48, 1 / 48, 50000, 1e-3, 1.0)
+    want = port.poisson(f, 1 / 48, 1 / 48, 50000, 1e-3, 1.0, redblack=True, sor=False)
+    assert got["k"] == want["k"]
+    assert np.array_equal(got["u"], want["u"])       # == ignores the sign of zero
+
+
+def test_poisson_itmax(port):
+    """itmax reached: status 1 (the drop-in layer turns it into message + exit(1))."""
+    f = sine_rhs(32)
+    for itmax in (1, 3, 4, 5, 9):
+        r = fd.poisson_sor(f, 1 / 32, 1 / 32, itmax, 1e-12, fd.sor_beta(32, 32), raise_on_itmax=False)
+        assert r["status"] == 1 and r["k"] == itmax - 1
+        u, norms = port.poisson_sweeps(f, 1 / 32, 1 / 32, itmax, port.beta(32, 32))
+        assert r["u"].tobytes() == u.tobytes()
+    with pytest.raises(fd.PoissonNotConverged):
+        fd.poisson_sor(f, 1 / 32, 1 / 32, 5, 1e-12, fd.sor_beta(32, 32))
+
+
+def test_poisson_zero_rhs_and_tiny_grid(port):
+    r = fd.poisson_sor(np.zeros((8, 8)), 0.1, 0.1, 10, 1e-3, 1.5)
+    assert r["k"] == 0 and r["e"] == 0.0 and not r["u"].any()
+    f = np.ones((3, 3))
+    got = fd.poisson_sor(f, 0.5, 0.5, 100, 1e-9, 1.2)
+    want = port.poisson(f, 0.5, 0.5, 100, 1e-9, 1.2, redblack=True)
+    assert got["k"] == want["k"] and np.array_equal(got["u"], want["u"])
+
+
+def test_poisson_every_stop_position(port):
+    """The converged sweep can fall on any position inside a temporal block: sweep through
+    tolerances so that sweeps-1 takes many consecutive values, for every T."""
+    n = 40
+    f = sine_rhs(n)
+    beta = port.beta(n, n)
+    full = port.poisson(f, 1 / n, 1 / n, 5000, 1e-9, beta, redblack=True, history=True)
+    hist = full["history"]
+    for T in (2, 4, 8):
+        for k in range(3, 20):
+            tol = 0.5 * (hist[k] + hist[k - 1]) if hist[k] < hist[k - 1] else None
+            if tol is None:
+                continue
+            got = fd.poisson_sor(f, 1 / n, 1 / n, 5000, tol, beta, T=T)
+            want = port.poisson(f, 1 / n, 1 / n, 5000, tol, beta, redblack=True)
+            assert got["k"] == want["k"] == k, (T, k)
+            assert got["u"].tobytes() == want["u"].tobytes()
+
+
+@pytest.mark.parametrize("n,sweeps", [(1024, 24), (4096, 8)])
+def test_poisson_full_size_fixed_sweeps(port, n, sweeps):
+    """BASELINE sizes: K sweeps of the 1024^2 / 4096^2 cavity grids, bitwise against the oracle
+    (OpenMP red-black) and identical for every temporal block depth."""
+    rng = np.random.default_rng(n)
+    f = rng.standard_normal((n, n))
+    beta = port.beta(n, n)
+    want, norms = port.poisson_sweeps(f, 1 / n, 1 / n, sweeps, beta)
+    for T in (1, 4):
+        s = fd.PoissonSolver(n, n, T)
+        s.set_consts(1 / n, 1 / n, beta)
+        s.upload(f)
+        r = s.solve(sweeps, 0.0)
+        assert r["status"] == 1 and r["sweeps"] == sweeps
+        got = s.download(r["buf"])
+        assert got.tobytes() == want.tobytes(), T
+        assert abs(r["e"] - norms[-1]) <= 1e-11 * norms[-1]
+        s.close()
+
+
+def test_poisson_linearity_property():
+    """Size-independent property at 2048^2: the sweep operator is affine in f with a zero start, so
+    K sweeps on 2f equal twice K sweeps on f exactly (scaling by 2 commutes with rounding)."""
+    n, K = 2048, 16
+    rng = np.random.default_rng(7)
+    f = rng.standard_normal((n, n))
+    s = fd.PoissonSolver(n, n, 4)
+    s.set_consts(1 / n, 1 / n, fd.sor_beta(n, n))
+    s.upload(f)
+    a = s.download(s.solve(K, 0.0)["buf"])
+    s.upload(2 * f)
+    b = s.download(s.solve(K, 0.0)["buf"])
+    assert np.array_equal(b, 2 * a)
+    assert not np.any(a[0]) and not np.any(a[-1]) and not np.any(a[:, 0]) and not np.any(a[:, -1])   # ring stays 0
+    s.close()
+
+
+# ---- whole time steps -----------------------------------------------------------------------------
+def test_default_config_vs_golden_fields_and_logs(golden_logs):
+    """config_default.txt: fields after steps 0, 10, 20 against raw dumps of the reference executable;
+    Poisson log lines against the reference's shipped testRunOMP.txt."""
+    g = load_golden("fields_default_rb.npz")
+    sim = fd.Simulation(dict(api.CONFIG_DEFAULT))
+    done = 0
+    ks, es = [], []
+    for idx, step in enumerate(g["dump_steps"]):
+        r = sim.step(int(step) + 1 - done)
+        done = int(step) + 1
+        assert r["failed_step"] == 0
+        ks += list(r["k"]); es += list(r["e"])
+        f = sim.fields()
+        for name in ("psi", "w", "u", "v"):
+            assert rel_l2(f[name], g[name][idx]) <= 1e-8, (name, step)
+            assert np.array_equal(f[name], g[name][idx]), (name, step, rel_l2(f[name], g[name][idx]))
+    assert ks == golden_logs["testRunOMP"]["k"][:done]
+    assert ["%E" % e for e in es] == golden_logs["testRunOMP"]["e"][:done]
+    r = sim.step(352 - done)                        # the rest of the 352 shipped log lines
+    ks += list(r["k"]); es += list(r["e"])
+    assert ks == golden_logs["testRunOMP"]["k"]
+    assert ["%E" % e for e in es] == golden_logs["testRunOMP"]["e"]
+    assert np.all(np.abs(r["cont_max"]) < 1e-10) and np.all(np.abs(r["cont_min"]) < 1e-10)
+
+
+def test_high_re_config_vs_golden(golden_logs):
+    g = load_golden("fields_highre_rb.npz")
+    sim = fd.Simulation(dict(api.CONFIG_HIGH_RE))
+    r = sim.step(6)
+    f = sim.fields()
+    for name in ("psi", "w", "u", "v"):
+        assert np.array_equal(f[name], g[name][-1]), (name, rel_l2(f[name], g[name][-1]))
+    r2 = sim.step(6)
+    assert list(r["k"]) + list(r2["k"]) == golden_logs["testRunOMPHIGHRES"]["k"]
+    assert ["%E" % e for e in list(r["e"]) + list(r2["e"])] == golden_logs["testRunOMPHIGHRES"]["e"]
+
+
+@pytest.mark.parametrize("order,ptype,n", [(2, 2, 48), (4, 2, 48), (6, 1, 40), (6, 2, 50)])
+def test_steps_vs_oracle_other_orders_and_solver_types(port, order, ptype, n):
+    cfg = dict(api.CONFIG_DEFAULT, nx=n, ny=n, order=order, poisson_type=ptype, poisson_max_it=100000,
+               u1=0.1, u2=-0.2, u3=0.3, v1=0.05, v2=-0.05, v3=0.02, v4=-0.01, ui=0.01, vi=-0.02, dt=0.002)
+    sim = fd.Simulation(cfg)
+    r = sim.step(4)
+    want = port.run(cfg, 4, redblack=True)
+    assert list(r["k"]) == list(want["k"])
+    f = sim.fields()
+    for name in ("psi", "w", "u", "v"):
+        assert np.array_equal(f[name], want[name]), (name, rel_l2(f[name], want[name]))
+
+
+def test_tight_tolerance_vs_lexicographic_reference():
+    """Ordering-independent check: at poisson_tol = 1e-11 the red-black GPU fields agree with the
+    SERIAL (lexicographic) reference executable within the north_star tolerance."""
+    g = load_golden("fields_default_lex_tight.npz")
+    sim = fd.Simulation(dict(api.CONFIG_DEFAULT, poisson_tol=1e-11, poisson_max_it=100000))
+    sim.step(3)
+    f = sim.fields()
+    for name in ("psi", "w", "u", "v"):
+        assert rel_l2(f[name], g[name][-1]) <= 1e-8, name
+
+
+def test_1024_steps_vs_oracle(port):
+    """BASELINE config 3 grid (1024^2, Re 1000): two full time steps against the matrix-free oracle."""
+    cfg = dict(api.CONFIG_DEFAULT, nx=1024, ny=1024, dt=1e-4, poisson_max_it=20000)
+    sim = fd.Simulation(cfg)
+    r = sim.step(2)
+    want = port.run(cfg, 2, redblack=True)
+    assert list(r["k"]) == list(want["k"])
+    f = sim.fields()
+    for name in ("psi", "w", "u", "v"):
+        assert rel_l2(f[name], want[name]) <= 1e-8, name
+        assert np.array_equal(f[name], want[name]), name
+
+
+# ---- the reference's own C signatures (drop-in library) ---------------------------------------------
+def _to_mtrx(D, a):
+    from fluid_dynamics1_b200._lib import Mtrx
+    m = D.initm(a.shape[0], a.shape[1])
+    for i in range(a.shape[0]):
+        C.memmove(m.M[i], a[i].ctypes.data, a.shape[1] * 8)
+    return m
+
+
+def _from_mtrx(m):
+    out = np.empty((m.m, m.n))
+    for i in range(m.m):
+        C.memmove(out[i].ctypes.data, m.M[i], m.n * 8)
+    return out
+
+
+def test_dropin_signatures(port, tmp_path):
+    D = fd.dropin()
+    n = 64
+    f = sine_rhs(n)
+    F = _to_mtrx(D, f)
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    logp = str(tmp_path / "log.txt").encode()
+    fh = libc.fopen(logp, b"w")
+    U = D.poisson_SOR_log(F, 1 / n, 1 / n, 20000, 1e-3, port.beta(n, n), fh)
+    libc.fclose(fh)
+    want = port.poisson(f, 1 / n, 1 / n, 20000, 1e-3, port.beta(n, n), redblack=True)
+    assert np.array_equal(_from_mtrx(U), want["u"])
+    line = open(logp).read()
+    assert line == "Poisson equation solved with %d iterations - root-sum-of-squares error: %E\n" % (want["k"], want["e"])
+    assert abs(D.error(U, F) - np.abs(want["u"] - f).sum()) < 1e-9
+    d1 = D.Diff1(10, 6, 0.1)
+    assert np.array_equal(_from_mtrx(d1), port.diff_dense(10, 6, 1, 0.1))
+    rng = np.random.default_rng(0)
+    arrs = [rng.standard_normal((12, 12)) for _ in range(7)]
+    ms = [_to_mtrx(D, a) for a in arrs]
+    D.euler(*ms, 1000.0, 0.005)
+    assert np.array_equal(_from_mtrx(ms[0]), port.euler(*arrs, 1000.0, 0.005))
+    c = D.continuity(ms[1], ms[2])
+    assert np.array_equal(_from_mtrx(c), arrs[1] + arrs[2])
+    for m in ms + [F, U, d1, c]:
+        D.freem(m)
