@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the cnavier hot path on B200.
+
+Metric (BASELINE.json): Poisson cell-updates/s (and sweeps/s) against the HBM roofline.
+Workload at N GPUs: the 4096^2 Re=1000 lid-driven cavity grid (BASELINE config 4, the configuration
+the north_star target is quoted on; it fits one GPU), slab-decomposed over N GPUs by rows with a
+fixed 4096 x 4096 slab per GPU (weak scaling; `--scaling strong` keeps the total at 4096^2).
+A "step" = one fixed-sweep red-black SOR solve (`--sweeps`, default 256) of lap(psi) = -w from a zero
+initial guess on a synthetic cavity-like vorticity field (zero guess + state reset are inside the
+timed region; no convergence exit: tol = 0, so no work is ever skipped).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                     # the reference's own CPU code (oracle/_ref)
+
+One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for the definitions.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_BYTES_PER_CELL_SWEEP = 24.0  # read psi + read f + write psi
+
+
+def synthetic_vorticity(nrows, ncols, row0=0, total_rows=None, seed=1234):
+    """Deterministic cavity-like vorticity: strong near the moving lid (last row), smooth bulk, plus
+    small-scale noise so that no cell is trivially zero."""
+    total_rows = total_rows or nrows
+    rng = np.random.default_rng(seed + row0)
+    i = (np.arange(row0, row0 + nrows) / total_rows)[:, None]
+    j = (np.arange(ncols) / ncols)[None, :]
+    w = -40.0 * np.exp(-((1 - i) * 30.0)) * np.sin(np.pi * j) + 4.0 * np.sin(2 * np.pi * i) * np.sin(3 * np.pi * j)
+    w += 0.05 * rng.standard_normal((nrows, ncols))
+    return np.ascontiguousarray(w)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.proc = None
+        self.device = device
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import fluid_dynamics1_b200 as fd
+    from fluid_dynamics1_b200 import parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    fd.require_gpu()
+    torch.cuda.set_device(local_rank)
+    L = fd.lib()
+    L.cnv_set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ncols = args.n
+    if args.scaling == "weak":
+        total_rows, rows_per = args.n * world, args.n
+    else:
+        total_rows, rows_per = args.n, args.n // world
+    T, S = args.T, args.sweeps
+    dx = dy = 1.0 / ncols
+    beta = fd.sor_beta(ncols, ncols)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    slab = parallel.SlabPoisson(total_rows, ncols, T, rank, world, stream=sp) if world > 1 else None
+    if slab is None:
+        solver = fd.PoissonSolver(rows_per, ncols, T)
+        solver.set_consts(dx, dy, beta)
+        w_host = synthetic_vorticity(rows_per, ncols)
+        solver.upload(w_host, -1.0, sp)  # f = -w (src/main.c:348)
+        T = solver.T
+        plan = solver.plan
+    else:
+        slab.set_consts(dx, dy, beta)
+        w_host = synthetic_vorticity(slab.own_rows, ncols, slab.row0, total_rows)
+        slab.upload_owned(w_host, -1.0)
+        T = slab.T
+        plan = slab.solver.plan
+    npass = (S + T - 1) // T
+    interior_cells = (total_rows - 2) * (ncols - 2)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step(pass_events=None):
+        """resident-input step: zero guess, reset state machine, S sweeps."""
+        if slab is None:
+            solver.L.cnv_poisson_prepare(solver.h, None, 0, 1.0, sp)  # f == NULL: only zero the iterate buffers
+            solver.reset(S, 0.0, sp)
+            if pass_events is not None:
+                pass_events[0].record(stream)
+            solver.enqueue(npass, sp)
+            if pass_events is not None:
+                pass_events[1].record(stream)
+        else:
+            slab.zero_iterate()
+            slab.reset(S, 0.0)
+            if pass_events is not None:
+                pass_events[0].record(stream)
+            slab.enqueue(npass)
+            if pass_events is not None:
+                pass_events[1].record(stream)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    launches0 = L.cnv_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pass_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev0.record(stream)
+    for k in range(args.steps):
+        one_step(pass_ev[k])
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = L.cnv_launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    pass_ms = sum(a.elapsed_time(b) for a, b in pass_ev)
+    # verify the work really happened
+    st = solver.state(sp) if slab is None else slab.state()
+    assert st["sweeps"] == S and st["state"] == 2, st
+
+    # ---- e2e: host buffers in, host psi out, through the C ABI, copies inside the timed region ----
+    pin_in = torch.from_numpy(w_host).pin_memory()
+    pin_out = torch.empty_like(pin_in).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    in_np, out_np = pin_in.numpy(), pin_out.numpy()
+
+    def e2e_step():
+        if slab is None:
+            solver.upload(in_np, -1.0, sp)           # H2D + rhs preparation + zero guess
+            solver.reset(S, 0.0, sp)
+            solver.enqueue(npass, sp)
+            solver.L.cnv_poisson_download(solver.h, npass & 1, out_np, sp)   # D2H of psi (synchronises)
+        else:
+            slab.upload_owned(in_np, -1.0)
+            slab.reset(S, 0.0)
+            slab.enqueue(npass)
+            slab.download_owned(npass & 1, out_np)
+
+    e2e_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms, pass_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, pass_ms, e2e_ms = t.tolist()
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        value = interior_cells * S * args.steps / (ms * 1e-3)
+        e2e_val = interior_cells * S * args.steps / (e2e_ms * 1e-3)
+        # dominant kernel: k_poisson_pass<T>.  Algorithmic bytes per launch = 24 B x interior cells of this
+        # GPU's slab x sweeps per launch (T); duration = CUDA-event time around the pass launches / count.
+        per_gpu_cells = interior_cells / world
+        launch_s = pass_ms * 1e-3 / (npass * args.steps)
+        achieved = ALGO_BYTES_PER_CELL_SWEEP * per_gpu_cells * T / launch_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "poisson_pass_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": "poisson_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{total_rows}x{ncols} Re=1000 lid-driven cavity, red-black SOR Poisson solve "
+                                   f"(BASELINE config 4 grid{' per GPU' if args.scaling == 'weak' and world > 1 else ''})",
+                       "grid": [total_rows, ncols], "slab_rows_per_gpu": rows_per, "sweeps_per_step": S,
+                       "temporal_block_T": T, "strip_width": plan["WS"], "rows_per_chunk": plan["Hout"],
+                       "ctas": plan["nstrips"] * plan["nchunks"], "arith_path": "pow2-exact" if plan["pow2"] else "general",
+                       "parallelism": f"slab{world}" if world > 1 else "single",
+                       "l2": "inputs larger than L2 (3 x %.0f MB resident arrays per GPU vs 126 MB L2), no flush" %
+                             (rows_per * ncols * 8 / 1e6)},
+            "sweeps_per_s": S * args.steps / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": f"k_poisson_pass<T={T}>",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_SWEEP * per_gpu_cells * T,
+                         "launch_us": launch_s * 1e6,
+                         "note": "temporal blocking: T sweeps per HBM pass, so algorithmic GB/s may exceed the HBM peak"},
+            "e2e": {"value": e2e_val, "unit": "cell-updates/s", "h2d_bytes_per_step": int(w_host.nbytes * world),
+                    "d2h_bytes_per_step": int(w_host.nbytes * world), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(args.n, args.cpu_seconds)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+_CHILD = r"""
+import sys, time, numpy as np
+sys.path.insert(0, {root!r})
+from oracle import api
+R = api.ref()
+n, k = {n}, {k}
+from bench import synthetic_vorticity
+f = -synthetic_vorticity(n, n)
+beta = api.port().beta(n, n)
+print("START", time.time(), flush=True)
+R.poisson(f, 1.0 / n, 1.0 / n, k, 0.0, beta, sor=True)   # never converges (tol = 0): k sweeps, then exit(1)
+"""
+
+
+def ref_sweeps_time(n, k):
+    """Wall time of k red-black sweeps of the UNMODIFIED poisson_SOR_log (oracle/_ref): run in a child
+    process with itmax = k, tol = 0 -- it performs exactly k sweeps and then exit(1)s (src/poisson.c:280-284)."""
+    with tempfile.TemporaryDirectory() as td:
+        p = subprocess.Popen([sys.executable, "-c", _CHILD.format(root=ROOT, n=n, k=k)], stdout=subprocess.PIPE, text=True, cwd=td)
+        start = None
+        for line in p.stdout:
+            if line.startswith("START"):
+                start = float(line.split()[1])
+        p.wait()
+        end = time.time()
+    if start is None or p.returncode != 1:
+        raise RuntimeError("reference child did not run to its itmax exit")
+    return end - start
+
+
+def cpu_sweep_rate(n, seconds, prefer_ref=True):
+    """(cell-updates/s, kind, cores, sample description) of the CPU reference path on this box."""
+    from oracle import api
+    cores = os.cpu_count() or 1
+    port = api.port()
+    f = -synthetic_vorticity(n, n)
+    beta = port.beta(n, n)
+    t0 = time.time()
+    port.poisson_sweeps(f, 1.0 / n, 1.0 / n, 2, beta)
+    per_sweep = (time.time() - t0) / 2
+    k = int(max(2, min(2000, seconds / max(per_sweep, 1e-6))))
+    if prefer_ref and api.ref() is not None:
+        t = ref_sweeps_time(n, k)
+        kind = "reference"
+        what = "unmodified poisson_SOR_log (oracle/_ref, -O2 -fopenmp -DOPENMP_ENABLED, red-black)"
+    else:
+        t0 = time.time()
+        port.poisson_sweeps(f, 1.0 / n, 1.0 / n, k, beta)
+        t = time.time() - t0
+        kind = "port"
+        what = "oracle/cnavier_oracle.c orc_poisson_sweeps (OpenMP red-black)"
+    threads = port.max_threads()
+    return (n - 2) ** 2 * k / t, kind, threads, f"{k} sweeps of the {n}x{n} grid, {what}, {threads} OpenMP threads on {cores} host cores"
+
+
+def cpu_baseline(n, seconds):
+    v, kind, threads, sample = cpu_sweep_rate(n, seconds)
+    return {"value": v, "unit": "cell-updates/s", "cores": threads, "kind": kind, "sample": sample}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    kind = threads = sample = None
+    for i in range(args.warmup + args.steps):
+        v, kind, threads, sample = cpu_sweep_rate(args.n, per_step)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(len(vals) / sum(1.0 / v for v in vals))  # total work / total time
+    total_rows = args.n * args.gpus if args.scaling == "weak" else args.n
+    out = {"impl": "reference", "metric": "poisson_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+           "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"{total_rows}x{args.n} Re=1000 lid-driven cavity, red-black SOR Poisson solve (BASELINE config 4 grid)",
+                      "note": "CPU arm: each step is a bounded sample of sweeps on the 4096x4096 grid; rate is size-independent per cell"},
+           "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": threads, "kind": kind, "sample": sample},
+           "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=4096, help="grid columns (and rows per GPU under weak scaling)")
+    ap.add_argument("--sweeps", type=int, default=256, help="red-black SOR sweeps per step")
+    ap.add_argument("--T", type=int, default=0, help="temporal block depth (0 = library default)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 3)   # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

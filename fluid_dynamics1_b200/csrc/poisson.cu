@@ -140,10 +140,10 @@ template <int T, bool POW2>
 static void launch_pass(const PassGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
                         double *partials, double *hist, double *norms, int fused, int threads, size_t smem, cudaStream_t s)
 {
-    static bool configured = false;
-    if (!configured) {
-        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_pass<T, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+    static size_t configured = 48 * 1024;  // opt in to large dynamic shared memory (static smem counts against the 227 KB)
+    if (smem > configured) {
+        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_pass<T, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
     k_poisson_pass<T, POW2><<<dim3(g.nstrips, g.nchunks), threads, smem, s>>>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused);
 }
@@ -175,7 +175,7 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
     CNV_CUDA_CHECK(cudaGetDevice(&dev));
     CNV_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     lim.num_sms = prop.multiProcessorCount;
-    lim.smem_per_cta = prop.sharedMemPerBlockOptin;
+    lim.smem_per_cta = prop.sharedMemPerBlockOptin - 1024;  // room for the kernel's static shared memory
     lim.smem_per_sm = prop.sharedMemPerMultiprocessor;
     lim.max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
     const int ld = round_up(ncols, 16);

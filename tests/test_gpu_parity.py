@@ -138,14 +138,17 @@ def test_poisson_every_stop_position(port):
     beta = port.beta(n, n)
     full = port.poisson(f, 1 / n, 1 / n, 5000, 1e-9, beta, redblack=True, history=True)
     hist = full["history"]
+    # the SOR update norm first grows, then decays: use stop positions on the decaying tail, where
+    # hist[k] is the first value below the tolerance
+    ks = [k for k in range(1, len(hist)) if hist[k] < hist[:k].min()][:18]
+    assert len(ks) >= 16 and len({k % 8 for k in ks}) == 8
     for T in (2, 4, 8):
-        for k in range(3, 20):
-            tol = 0.5 * (hist[k] + hist[k - 1]) if hist[k] < hist[k - 1] else None
-            if tol is None:
-                continue
+        for k in ks:
+            tol = 0.5 * (hist[k] + hist[:k].min())
             got = fd.poisson_sor(f, 1 / n, 1 / n, 5000, tol, beta, T=T)
             want = port.poisson(f, 1 / n, 1 / n, 5000, tol, beta, redblack=True)
-            assert got["k"] == want["k"] == k, (T, k)
+            assert want["k"] == k
+            assert got["k"] == k, (T, k)
             assert got["u"].tobytes() == want["u"].tobytes()
 
 
