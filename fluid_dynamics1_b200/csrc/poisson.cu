@@ -20,7 +20,6 @@ static size_t g_launches = 0;
 size_t total_launches() { return g_launches; }
 void count_launch(size_t n) { g_launches += n; }
 
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -64,29 +63,25 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     const double *__restrict__ in = cur ? buf1 : buf0;
     double *__restrict__ out = cur ? buf0 : buf1;
 
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int tid = threadIdx.x;
     const CtaGeom G = cta_geom(p, blockIdx.x, blockIdx.y);
-    const ThreadCtx t = thread_ctx(p, G, tid);
+    StreamThread<T> st;
+    stream_init<T>(st, p, G, tid, blockDim.x);
     const int TPG = p.WS >> 2;
-    const int kk = tid - t.g * TPG;
-    double acc = 0.0;
+    const int kk = tid - st.g * TPG;
 
-    // prologue: kPrefetch rows in flight
-#pragma unroll
-    for (int i = 0; i < kPrefetch; i++) {
-        phase_load<T>(p, G, sm, in, rhs, tid, nthreads, first_step(G) + i);
-        cp_async_commit();
-    }
-    const int rend = last_step<T>(G);
-    for (int r = first_step(G); r <= rend; r++) {
+    stream_prologue<T>(st, sm, in, rhs);  // kPrefetch rows in flight
+    for (int r = st.ybase; r <= st.rend; r += 2) {
         cp_async_wait<kPrefetch - 1>();  // row r has landed (this thread's copies) ...
         __syncthreads();                 // ... and everybody's; previous step's updates are visible
-        phase_load<T>(p, G, sm, in, rhs, tid, nthreads, r + kPrefetch);
-        cp_async_commit();
-        phase_store<T>(p, G, sm, out, tid, nthreads, r - 4 * T);
-        phase_compute<T, POW2>(p, G, rc, sm, t, r, nsw, acc);
+        stream_step<T, POW2, 0>(st, rc, sm, in, rhs, out, r, nsw);
+        cp_async_wait<kPrefetch - 1>();
+        __syncthreads();
+        stream_step<T, POW2, 1>(st, rc, sm, in, rhs, out, r + 1, nsw);
     }
     cp_async_wait<0>();
+    const double acc = st.acc;
+    struct { int g; } t = {st.g};
 
     // per-CTA L1 update norms, one per sweep of the pass (level g <-> sweep g+1)
     group_sums(sm, acc, t.g, kk, TPG, s_e);

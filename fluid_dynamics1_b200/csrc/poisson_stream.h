@@ -91,119 +91,201 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+struct dbl2 { double x, y; };
+__device__ __forceinline__ dbl2 lds2(const double *p) { double2 v = *reinterpret_cast<const double2 *>(p); return {v.x, v.y}; }
+__device__ __forceinline__ void sts2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+__device__ __forceinline__ void stg2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 #else
 inline void cp_async8(double *dst, const double *src) { *dst = *src; }
+inline void cp_async_commit() {}
+struct dbl2 { double x, y; };
+inline dbl2 lds2(const double *p) { return {p[0], p[1]}; }
+inline void sts2(double *p, double a, double b) { p[0] = a; p[1] = b; }
+inline void stg2(double *p, double a, double b) { p[0] = a; p[1] = b; }
 #endif
 
-// ---- phase 1: bring local row rl (psi and prepared right-hand side) into its ring slot --------
+// Per-thread state of the streaming pass.  Everything that does not change from step to step is
+// computed once here, so that one step costs only the loads/stores, the arithmetic and a handful
+// of pointer increments: ring-slot offsets advance incrementally (no modulo in the loop), global
+// addresses advance by one pitch per step, and the colour type of a stage is a compile-time
+// parameter of the step (the step loop is unrolled by two).
 template <int T>
-CNV_HD void phase_load(const PassGeom &p, const CtaGeom &G, double *sm, const double *__restrict__ in,
-                       const double *__restrict__ rhs, int tid, int nthreads, int rl)
+struct StreamThread {
+    static constexpr int R = ring_rows(T);
+    static constexpr int NCH = (4 + T - 1) / T;  // (psi|rhs) column pairs this thread copies per row
+    static constexpr int NST = T == 1 ? 2 : 1;   // column pairs this thread writes back per row
+    // uniform
+    int ss, ring;        // slot stride and ring size, in doubles
+    int ybase, rend;     // first / last step; ring slot of row q is (q - ybase) mod R
+    int ylo, yhi, y0, y1;
+    int vlo, vhi;        // rows that may be updated: inside the streamed range and off the Dirichlet ring
+    int ld;
+    int lslot, sslot;    // slot offsets of the row being loaded (r + kPrefetch) / written back (r - 4T)
+    // load
+    long long lsrc[NCH];      // element offset of this thread's chunk in the row being loaded
+    int ldE[NCH], ldO[NCH];   // destination offsets inside a slot
+    int lmode[NCH];           // 0 none, 1 psi, 2 rhs, 3 zero fill (psi side), 4 zero fill (rhs side)
+    // store
+    long long sdst[NST];
+    int skE[NST], skO[NST];
+    bool sact[NST];
+    // compute
+    int g, dq, k0;
+    int o[5];            // slot offsets of rows qtop, qtop-1, .., qtop-4 with qtop = r - dq
+    int aSE, aSO, aPE, aPO;  // array offsets inside a slot, k0 folded in
+    bool vE0, vO0, vE1, vO1, colown;
+    double acc;
+};
+
+CNV_HD int wrap_inc(int off, int ss, int ring) { off += ss; return off >= ring ? off - ring : off; }
+
+template <int T>
+CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G, int tid, int nthreads)
 {
-    constexpr int R = ring_rows(T);
-    if (rl > G.yhi) return;
+    constexpr int R = StreamThread<T>::R;
     const int WP = p.WS >> 1;
-    double *slot = sm + ((rl - G.ylo) % R) * slot_stride(p.WS);
-    const size_t rowoff = (size_t)rl * p.ld;
-    for (int c = tid; c < p.WS; c += nthreads) {
-        const bool isP = c >= WP;
-        const int k = isP ? c - WP : c;
-        const int gc = G.gx0 + 2 * k;
-        double *dE = slot + arr_off(p.WS, isP ? 2 : 0) + k;
-        double *dO = slot + arr_off(p.WS, isP ? 3 : 1) + k;
-        if (gc >= 0 && gc < p.ld) {
-            const double *src = (isP ? rhs : in) + rowoff + gc;
-            cp_async8(dE, src);
-            cp_async8(dO, src + 1);
-        } else {
-            *dE = 0.0;
-            *dO = 0.0;
+    s.ss = slot_stride(p.WS);
+    s.ring = R * s.ss;
+    // start on a step whose stage-0 row has even (global row + 1): the colour type then alternates
+    // with the step parity (PAR in stream_step)
+    s.ybase = G.ylo - ((p.grow0 + G.ylo - 1) & 1);
+    s.rend = G.y1 - 1 + 4 * T;
+    if (((s.rend - s.ybase) & 1) == 0) s.rend++;  // whole pairs of steps
+    s.ylo = G.ylo; s.yhi = G.yhi; s.y0 = G.y0; s.y1 = G.y1;
+    s.vlo = G.ylo + 1 > 1 - p.grow0 ? G.ylo + 1 : 1 - p.grow0;
+    s.vhi = G.yhi - 1 < p.gnrows - 2 - p.grow0 ? G.yhi - 1 : p.gnrows - 2 - p.grow0;
+    s.ld = p.ld;
+    s.lslot = (kPrefetch % R) * s.ss;
+    s.sslot = (((-4 * T) % R + R) % R) * s.ss;
+    for (int j = 0; j < StreamThread<T>::NCH; j++) {
+        const int c = tid + j * nthreads;
+        s.lmode[j] = 0; s.lsrc[j] = 0; s.ldE[j] = 0; s.ldO[j] = 0;
+        if (c < p.WS) {
+            const bool isP = c >= WP;
+            const int k = isP ? c - WP : c;
+            const int gc = G.gx0 + 2 * k;
+            s.ldE[j] = arr_off(p.WS, isP ? 2 : 0) + k;
+            s.ldO[j] = arr_off(p.WS, isP ? 3 : 1) + k;
+            const bool inside = gc >= 0 && gc < p.ld;
+            s.lmode[j] = inside ? (isP ? 2 : 1) : (isP ? 4 : 3);
+            s.lsrc[j] = (long long)(s.ybase + kPrefetch) * p.ld + gc;
         }
     }
-}
-
-// ---- phase 2: write back the finished row qs (all 2T half-sweeps applied) ---------------------
-template <int T>
-CNV_HD void phase_store(const PassGeom &p, const CtaGeom &G, const double *sm, double *__restrict__ out,
-                        int tid, int nthreads, int qs)
-{
-    constexpr int R = ring_rows(T);
-    if (qs < G.y0 || qs >= G.y1) return;
-    const double *slot = sm + ((qs - G.ylo) % R) * slot_stride(p.WS);
-    const double *SE = slot + arr_off(p.WS, 0), *SO = slot + arr_off(p.WS, 1);
     const int kbeg = p.HX >> 1, kend = (p.HX + p.Wout) >> 1;
-    double *orow = out + (size_t)qs * p.ld;
-    for (int k = kbeg + tid; k < kend; k += nthreads) {
+    for (int j = 0; j < StreamThread<T>::NST; j++) {
+        const int k = kbeg + tid + j * nthreads;
         const int gc = G.gx0 + 2 * k;
-        if (gc < p.ld) {
-#if defined(__CUDA_ARCH__)
-            *reinterpret_cast<double2 *>(orow + gc) = make_double2(SE[k], SO[k]);
-#else
-            orow[gc] = SE[k];
-            orow[gc + 1] = SO[k];
-#endif
-        }
+        s.sact[j] = k < kend && gc < p.ld;
+        s.skE[j] = arr_off(p.WS, 0) + k;
+        s.skO[j] = arr_off(p.WS, 1) + k;
+        s.sdst[j] = (long long)(s.ybase - 4 * T) * p.ld + gc;
     }
+    const ThreadCtx t = thread_ctx(p, G, tid);
+    s.g = t.g; s.dq = 4 * t.g; s.k0 = t.k0;
+    for (int j = 0; j < 5; j++) s.o[j] = ((((-s.dq - j) % R) + R) % R) * s.ss;
+    s.aSE = arr_off(p.WS, 0) + t.k0; s.aSO = arr_off(p.WS, 1) + t.k0;
+    s.aPE = arr_off(p.WS, 2) + t.k0; s.aPO = arr_off(p.WS, 3) + t.k0;
+    s.vE0 = t.vmask & 1; s.vO0 = (t.vmask >> 1) & 1; s.vE1 = (t.vmask >> 2) & 1; s.vO1 = (t.vmask >> 3) & 1;
+    s.colown = t.colown;
+    s.acc = 0.0;
 }
 
-// ---- phase 3: this thread's red and black half-row updates of step r --------------------------
-template <int T, bool POW2>
-CNV_HD void phase_compute(const PassGeom &p, const CtaGeom &G, const RelaxConsts &rc, double *sm,
-                          const ThreadCtx &t, int r, int nsw, double &acc)
-{
-    constexpr int R = ring_rows(T);
-    if (t.g >= nsw) return;  // level not active in a shortened pass
-    const int ss = slot_stride(p.WS);
-    const int k0 = t.k0;
-#pragma unroll
-    for (int colour = 0; colour < 2; ++colour) {
-        const int q = r - 1 - 4 * t.g - 2 * colour;
-        if (q <= G.ylo || q >= G.yhi) continue;  // first/last streamed row: never updated
-        const int gq = p.grow0 + q;
-        if (gq < 1 || gq > p.gnrows - 2) continue;  // Dirichlet ring rows stay as loaded
-        // colour 0 = red = (i+j) even (src/poisson.c:247): column parity == row parity
-        const int typeO = (gq + colour) & 1;  // 0: even-column cells, 1: odd-column cells
-        double *s0 = sm + ((q - G.ylo) % R) * ss;
-        const double *sN = sm + ((q + 1 - G.ylo) % R) * ss;
-        const double *sS = sm + ((q - 1 - G.ylo) % R) * ss;
-        const int oA = arr_off(p.WS, typeO), oB = arr_off(p.WS, typeO ^ 1), oP = arr_off(p.WS, 2 + typeO);
-#if defined(__CUDA_ARCH__)
-        const double2 N = *reinterpret_cast<const double2 *>(sN + oA + k0);
-        const double2 S = *reinterpret_cast<const double2 *>(sS + oA + k0);
-        const double2 own = *reinterpret_cast<const double2 *>(s0 + oA + k0);
-        const double2 Pv = *reinterpret_cast<const double2 *>(s0 + oP + k0);
-        const double2 b = *reinterpret_cast<const double2 *>(s0 + oB + k0);
-#else
-        struct d2 { double x, y; };
-        const d2 N = {sN[oA + k0], sN[oA + k0 + 1]}, S = {sS[oA + k0], sS[oA + k0 + 1]};
-        const d2 own = {s0[oA + k0], s0[oA + k0 + 1]}, Pv = {s0[oP + k0], s0[oP + k0 + 1]};
-        const d2 b = {s0[oB + k0], s0[oB + k0 + 1]};
-#endif
-        const double x = s0[oB + k0 + (typeO ? 2 : -1)];
-        // even-column cell of pair k: W = odd[k-1], E = odd[k];  odd-column cell: W = even[k], E = even[k+1]
-        const double W0 = typeO ? b.x : x, E0 = typeO ? b.y : b.x;
-        const double W1 = typeO ? b.y : b.x, E1 = typeO ? x : b.y;
-        double n0 = relax<POW2>(N.x, S.x, E0, W0, own.x, Pv.x, rc);
-        double n1 = relax<POW2>(N.y, S.y, E1, W1, own.y, Pv.y, rc);
-        n0 = (t.vmask >> typeO) & 1 ? n0 : own.x;
-        n1 = (t.vmask >> (2 + typeO)) & 1 ? n1 : own.y;
-#if defined(__CUDA_ARCH__)
-        *reinterpret_cast<double2 *>(s0 + oA + k0) = make_double2(n0, n1);
-#else
-        s0[oA + k0] = n0;
-        s0[oA + k0 + 1] = n1;
-#endif
-        if (t.colown && q >= G.y0 && q < G.y1) {
-            acc = xadd(acc, fabs(xsub(n0, own.x)));
-            acc = xadd(acc, fabs(xsub(n1, own.y)));
-        }
-    }
-}
-
-// first and last step index of a CTA's stream
-CNV_HD int first_step(const CtaGeom &G) { return G.ylo; }
+// copy this thread's chunks of local row rl into ring-slot offset `slot` (cold path for the prologue)
 template <int T>
-CNV_HD int last_step(const CtaGeom &G) { return G.y1 - 1 + 4 * T; }
+CNV_HD void stream_load_row(const StreamThread<T> &s, double *sm, const double *__restrict__ in,
+                            const double *__restrict__ rhs, int slot, const long long *src)
+{
+#pragma unroll
+    for (int j = 0; j < StreamThread<T>::NCH; j++) {
+        const int m = s.lmode[j];
+        if (m == 1 || m == 2) {
+            const double *g = (m == 1 ? in : rhs) + src[j];
+            cp_async8(sm + slot + s.ldE[j], g);
+            cp_async8(sm + slot + s.ldO[j], g + 1);
+        } else if (m >= 3) {
+            sm[slot + s.ldE[j]] = 0.0;
+            sm[slot + s.ldO[j]] = 0.0;
+        }
+    }
+}
+
+// rows ybase .. ybase+kPrefetch-1 (those inside the streamed range), one cp.async group each
+template <int T>
+CNV_HD void stream_prologue(const StreamThread<T> &s, double *sm, const double *__restrict__ in,
+                            const double *__restrict__ rhs)
+{
+    for (int i = 0; i < kPrefetch; i++) {
+        const int rl = s.ybase + i;
+        if (rl >= s.ylo && rl <= s.yhi) {
+            long long src[StreamThread<T>::NCH];
+            for (int j = 0; j < StreamThread<T>::NCH; j++) src[j] = s.lsrc[j] - (long long)(kPrefetch - i) * s.ld;
+            stream_load_row<T>(s, sm, in, rhs, i * s.ss, src);
+        }
+        cp_async_commit();
+    }
+}
+
+// One step of the stream (the caller has waited for row r and passed the CTA barrier):
+// issue the copy of row r+kPrefetch, write back row r-4T, update this thread's red row r-1-dq and
+// black row r-3-dq.  PAR = (global row of the red row + 0) parity bit: 0 -> the red cells of this
+// step are the even-column cells.
+template <int T, bool POW2, int PAR>
+CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, const double *__restrict__ in,
+                        const double *__restrict__ rhs, double *__restrict__ out, int r, int nsw)
+{
+    // ---- load ----
+    if (r + kPrefetch <= s.yhi) stream_load_row<T>(s, sm, in, rhs, s.lslot, s.lsrc);
+    cp_async_commit();
+#pragma unroll
+    for (int j = 0; j < StreamThread<T>::NCH; j++) s.lsrc[j] += s.ld;
+    s.lslot = wrap_inc(s.lslot, s.ss, s.ring);
+    // ---- write back ----
+    {
+        const int qs = r - 4 * T;
+        if (qs >= s.y0 && qs < s.y1) {
+#pragma unroll
+            for (int j = 0; j < StreamThread<T>::NST; j++)
+                if (s.sact[j]) stg2(out + s.sdst[j], sm[s.sslot + s.skE[j]], sm[s.sslot + s.skO[j]]);
+        }
+#pragma unroll
+        for (int j = 0; j < StreamThread<T>::NST; j++) s.sdst[j] += s.ld;
+        s.sslot = wrap_inc(s.sslot, s.ss, s.ring);
+    }
+    // ---- relax ----
+    if (s.g < nsw) {
+        const int qtop = r - s.dq;
+#pragma unroll
+        for (int colour = 0; colour < 2; ++colour) {
+            const int q = qtop - 1 - 2 * colour;
+            if (q >= s.vlo && q <= s.vhi) {
+                // colour 0 = red = (i+j) even (src/poisson.c:247); typeO: the cells are odd-column cells
+                constexpr int dummy = 0; (void)dummy;
+                const bool typeO = (PAR ^ colour) != 0;
+                const int aA = typeO ? s.aSO : s.aSE, aB = typeO ? s.aSE : s.aSO, aP = typeO ? s.aPO : s.aPE;
+                double *s0 = sm + s.o[1 + 2 * colour];
+                const double *sN = sm + s.o[2 * colour], *sS = sm + s.o[2 + 2 * colour];
+                const dbl2 N = lds2(sN + aA), S = lds2(sS + aA), own = lds2(s0 + aA), Pv = lds2(s0 + aP), b = lds2(s0 + aB);
+                const double x = s0[aB + (typeO ? 2 : -1)];
+                // even-column cell of pair k: W = odd[k-1], E = odd[k];  odd-column cell: W = even[k], E = even[k+1]
+                const double W0 = typeO ? b.x : x, E0 = typeO ? b.y : b.x;
+                const double W1 = typeO ? b.y : b.x, E1 = typeO ? x : b.y;
+                double n0 = relax<POW2>(N.x, S.x, E0, W0, own.x, Pv.x, rc);
+                double n1 = relax<POW2>(N.y, S.y, E1, W1, own.y, Pv.y, rc);
+                n0 = (typeO ? s.vO0 : s.vE0) ? n0 : own.x;
+                n1 = (typeO ? s.vO1 : s.vE1) ? n1 : own.y;
+                sts2(s0 + aA, n0, n1);
+                if (s.colown && q >= s.y0 && q < s.y1) {
+                    s.acc = xadd(s.acc, fabs(xsub(n0, own.x)));
+                    s.acc = xadd(s.acc, fabs(xsub(n1, own.y)));
+                }
+            }
+        }
+    }
+    // rows move up by one: rotate the five slot offsets
+    s.o[4] = s.o[3]; s.o[3] = s.o[2]; s.o[2] = s.o[1]; s.o[1] = s.o[0];
+    s.o[0] = wrap_inc(s.o[0], s.ss, s.ring);
+}
 
 // ---- solver state machine (one instance per solve, device resident) ---------------------------
 // Reference semantics (src/poisson.c:234-284): for k = 0..itmax-1 { sweep; e = sum|u-u0|;

@@ -22,24 +22,22 @@ static void run_pass(const PassGeom &p, const RelaxConsts &rc, const double *in,
     constexpr int R = ring_rows(T);
     const int NT = pass_threads(T, p.WS);
     std::vector<double> sm((size_t)R * slot_stride(p.WS));
-    std::vector<double> acc(NT);
-    std::vector<ThreadCtx> ctx(NT);
+    std::vector<StreamThread<T>> st(NT);
     for (int g = 0; g < T; g++) norms[g] = 0.0;
     for (int by = 0; by < p.nchunks; by++)
         for (int bx = 0; bx < p.nstrips; bx++) {
             // poison shared memory so that any read of a row that was never loaded shows up
             for (auto &x : sm) x = std::nan("");
             const CtaGeom G = cta_geom(p, bx, by);
-            for (int t = 0; t < NT; t++) { ctx[t] = thread_ctx(p, G, t); acc[t] = 0.0; }
-            for (int rl = first_step(G); rl < first_step(G) + kPrefetch; rl++)
-                for (int t = 0; t < NT; t++) phase_load<T>(p, G, sm.data(), in, rhs, t, NT, rl);
-            for (int r = first_step(G); r <= last_step<T>(G); r++) {
+            for (int t = 0; t < NT; t++) stream_init<T>(st[t], p, G, t, NT);
+            for (int t = 0; t < NT; t++) stream_prologue<T>(st[t], sm.data(), in, rhs);
+            for (int r = st[0].ybase; r <= st[0].rend; r += 2) {
                 // --- barrier ---
-                for (int t = 0; t < NT; t++) phase_load<T>(p, G, sm.data(), in, rhs, t, NT, r + kPrefetch);
-                for (int t = 0; t < NT; t++) phase_store<T>(p, G, sm.data(), out, t, NT, r - 4 * T);
-                for (int t = 0; t < NT; t++) phase_compute<T, POW2>(p, G, rc, sm.data(), ctx[t], r, nsw, acc[t]);
+                for (int t = 0; t < NT; t++) stream_step<T, POW2, 0>(st[t], rc, sm.data(), in, rhs, out, r, nsw);
+                // --- barrier ---
+                for (int t = 0; t < NT; t++) stream_step<T, POW2, 1>(st[t], rc, sm.data(), in, rhs, out, r + 1, nsw);
             }
-            for (int t = 0; t < NT; t++) norms[ctx[t].g] += acc[t];
+            for (int t = 0; t < NT; t++) norms[st[t].g] += st[t].acc;
         }
 }
 
