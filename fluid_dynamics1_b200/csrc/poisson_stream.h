@@ -6,7 +6,7 @@
 // Algorithm (restates src/poisson.c:238-262, the OpenMP red-black sweep, T sweeps per HBM pass)
 // ---------------------------------------------------------------------------------------------
 // One CTA owns a strip of Wout output columns x Hout output rows and streams rows bottom-up
-// through a ring buffer of R = 4T+PF+1 rows in shared memory.  Each row lives in column-parity
+// through a ring buffer of R = 4T+PF rows in shared memory.  Each row lives in column-parity
 // split form (SE = even columns, SO = odd columns) so that every access of a half-row update is
 // unit stride: for an even-column cell (pair k) N/S are SE[q+-1][k], E/W are SO[q][k], SO[q][k-1].
 // The 2T half-sweeps (red L1, black L1, red L2, ..., black LT) are skewed by 2 rows each:
@@ -14,8 +14,8 @@
 // stage were produced in EARLIER steps, so the 2T stages of one step are independent and one
 // __syncthreads per step suffices; the update is in place (same dependency structure as the
 // reference's in-place sweeps, only the order of independent cell updates changes, so every
-// cell sees bit-identical operands).  Row r-4T is final after step r-1 and is written back at
-// step r.  Dependencies reach 2 cells per sweep, so strips/chunks overlap by 2T halo cells whose
+// cell sees bit-identical operands).  Row r-4T+1 is final once the last level's black stage has
+// processed it, and is written back from registers in that same step.  Dependencies reach 2 cells per sweep, so strips/chunks overlap by 2T halo cells whose
 // (stale-neighbour) results are discarded: the first/last loaded row and column are never
 // updated, and the region of influence of that staleness stays inside the halo.
 // Thread (g, kk) of the CTA owns level g+1 (its red and black stage) and four adjacent columns
@@ -26,7 +26,7 @@
 namespace cnv {
 
 constexpr int kPrefetch = 3;  // rows in flight ahead of the compute front (cp.async groups)
-constexpr int ring_rows(int T) { return 4 * T + kPrefetch + 1; }
+constexpr int ring_rows(int T) { return 4 * T + kPrefetch; }
 
 struct PassGeom {
     // local array: nrows x ncols doubles with pitch ld; row 0 is global row grow0 of gnrows
@@ -110,31 +110,40 @@ inline void stg2(double *p, double a, double b) { p[0] = a; p[1] = b; }
 // of pointer increments: ring-slot offsets advance incrementally (no modulo in the loop), global
 // addresses advance by one pitch per step, and the colour type of a stage is a compile-time
 // parameter of the step (the step loop is unrolled by two).
+//
+// Register-resident column history.  At step r the thread's red row is q = r-1-dq and its black row
+// q-2.  Of the operands of the two updates only four come from shared memory: the row above the red
+// row (N), the red cells themselves (own), the two right-hand sides, plus one neighbour value per
+// colour that belongs to the adjacent thread (x).  Everything else is a value this same thread
+// loaded or produced 1..3 steps ago and still holds:
+//     red:   E/W pair b = N(r-1),  S = N(r-2)
+//     black: own = N(r-3),  N = red result(r-1),  E/W pair = red result(r-2),  S = red result(r-3)
+// (the cells in question are not touched by any other stage in between, see the skew argument above).
 template <int T>
 struct StreamThread {
     static constexpr int R = ring_rows(T);
     static constexpr int NCH = (4 + T - 1) / T;  // (psi|rhs) column pairs this thread copies per row
-    static constexpr int NST = T == 1 ? 2 : 1;   // column pairs this thread writes back per row
     // uniform
     int ss, ring;        // slot stride and ring size, in doubles
     int ybase, rend;     // first / last step; ring slot of row q is (q - ybase) mod R
     int ylo, yhi, y0, y1;
     int vlo, vhi;        // rows that may be updated: inside the streamed range and off the Dirichlet ring
     int ld;
-    int lslot, sslot;    // slot offsets of the row being loaded (r + kPrefetch) / written back (r - 4T)
+    int lslot;           // slot offset of the row being loaded (r + kPrefetch)
     // load
     long long lsrc[NCH];      // element offset of this thread's chunk in the row being loaded
     int ldE[NCH], ldO[NCH];   // destination offsets inside a slot
     int lmode[NCH];           // 0 none, 1 psi, 2 rhs, 3 zero fill (psi side), 4 zero fill (rhs side)
-    // store
-    long long sdst[NST];
-    int skE[NST], skO[NST];
-    bool sact[NST];
+    // write back (threads of the last level only): element offset of columns 4kk.. of the black row
+    long long sdst;
+    bool sact;
     // compute
     int g, dq, k0;
-    int o[5];            // slot offsets of rows qtop, qtop-1, .., qtop-4 with qtop = r - dq
+    int o[4];            // slot offsets of rows qtop, qtop-1, qtop-2, qtop-3 with qtop = r - dq
     int aSE, aSO, aPE, aPO;  // array offsets inside a slot, k0 folded in
     bool vE0, vO0, vE1, vO1, colown;
+    dbl2 h1, h2, h3;     // N loaded 1, 2, 3 steps ago
+    dbl2 r1, r2, r3;     // red results of 1, 2, 3 steps ago
     double acc;
 };
 
@@ -157,7 +166,6 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.vhi = G.yhi - 1 < p.gnrows - 2 - p.grow0 ? G.yhi - 1 : p.gnrows - 2 - p.grow0;
     s.ld = p.ld;
     s.lslot = (kPrefetch % R) * s.ss;
-    s.sslot = (((-4 * T) % R + R) % R) * s.ss;
     for (int j = 0; j < StreamThread<T>::NCH; j++) {
         const int c = tid + j * nthreads;
         s.lmode[j] = 0; s.lsrc[j] = 0; s.ldE[j] = 0; s.ldO[j] = 0;
@@ -172,26 +180,21 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
             s.lsrc[j] = (long long)(s.ybase + kPrefetch) * p.ld + gc;
         }
     }
-    const int kbeg = p.HX >> 1, kend = (p.HX + p.Wout) >> 1;
-    for (int j = 0; j < StreamThread<T>::NST; j++) {
-        const int k = kbeg + tid + j * nthreads;
-        const int gc = G.gx0 + 2 * k;
-        s.sact[j] = k < kend && gc < p.ld;
-        s.skE[j] = arr_off(p.WS, 0) + k;
-        s.skO[j] = arr_off(p.WS, 1) + k;
-        s.sdst[j] = (long long)(s.ybase - 4 * T) * p.ld + gc;
-    }
     const ThreadCtx t = thread_ctx(p, G, tid);
     s.g = t.g; s.dq = 4 * t.g; s.k0 = t.k0;
-    for (int j = 0; j < 5; j++) s.o[j] = ((((-s.dq - j) % R) + R) % R) * s.ss;
+    for (int j = 0; j < 4; j++) s.o[j] = ((((-s.dq - j) % R) + R) % R) * s.ss;
     s.aSE = arr_off(p.WS, 0) + t.k0; s.aSO = arr_off(p.WS, 1) + t.k0;
     s.aPE = arr_off(p.WS, 2) + t.k0; s.aPO = arr_off(p.WS, 3) + t.k0;
     s.vE0 = t.vmask & 1; s.vO0 = (t.vmask >> 1) & 1; s.vE1 = (t.vmask >> 2) & 1; s.vO1 = (t.vmask >> 3) & 1;
     s.colown = t.colown;
+    const int gc4 = G.gx0 + 2 * t.k0;  // first of this thread's four columns
+    s.sact = t.g == T - 1 && t.colown && gc4 >= 0 && gc4 < p.ld;
+    s.sdst = (long long)(s.ybase - 3 - s.dq) * p.ld + gc4;
+    s.h1 = s.h2 = s.h3 = s.r1 = s.r2 = s.r3 = dbl2{0.0, 0.0};
     s.acc = 0.0;
 }
 
-// copy this thread's chunks of local row rl into ring-slot offset `slot` (cold path for the prologue)
+// copy this thread's chunks of local row rl into ring-slot offset `slot`
 template <int T>
 CNV_HD void stream_load_row(const StreamThread<T> &s, double *sm, const double *__restrict__ in,
                             const double *__restrict__ rhs, int slot, const long long *src)
@@ -227,9 +230,11 @@ CNV_HD void stream_prologue(const StreamThread<T> &s, double *sm, const double *
 }
 
 // One step of the stream (the caller has waited for row r and passed the CTA barrier):
-// issue the copy of row r+kPrefetch, write back row r-4T, update this thread's red row r-1-dq and
-// black row r-3-dq.  PAR = (global row of the red row + 0) parity bit: 0 -> the red cells of this
-// step are the even-column cells.
+// issue the copy of row r+kPrefetch, then update this thread's red row r-1-dq and black row r-3-dq;
+// threads of the last level write the finished black row back to global memory.
+// PAR = parity of (global red row): 0 -> the red cells of this step are the even-column cells.
+// The body is branch-free on purpose (loads and arithmetic are unconditional, validity is applied by
+// selects / predicated stores) so that the four cell updates of a step can be interleaved.
 template <int T, bool POW2, int PAR>
 CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, const double *__restrict__ in,
                         const double *__restrict__ rhs, double *__restrict__ out, int r, int nsw)
@@ -240,50 +245,63 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, c
 #pragma unroll
     for (int j = 0; j < StreamThread<T>::NCH; j++) s.lsrc[j] += s.ld;
     s.lslot = wrap_inc(s.lslot, s.ss, s.ring);
-    // ---- write back ----
-    {
-        const int qs = r - 4 * T;
-        if (qs >= s.y0 && qs < s.y1) {
-#pragma unroll
-            for (int j = 0; j < StreamThread<T>::NST; j++)
-                if (s.sact[j]) stg2(out + s.sdst[j], sm[s.sslot + s.skE[j]], sm[s.sslot + s.skO[j]]);
-        }
-#pragma unroll
-        for (int j = 0; j < StreamThread<T>::NST; j++) s.sdst[j] += s.ld;
-        s.sslot = wrap_inc(s.sslot, s.ss, s.ring);
-    }
+
     // ---- relax ----
-    if (s.g < nsw) {
-        const int qtop = r - s.dq;
-#pragma unroll
-        for (int colour = 0; colour < 2; ++colour) {
-            const int q = qtop - 1 - 2 * colour;
-            if (q >= s.vlo && q <= s.vhi) {
-                // colour 0 = red = (i+j) even (src/poisson.c:247); typeO: the cells are odd-column cells
-                constexpr int dummy = 0; (void)dummy;
-                const bool typeO = (PAR ^ colour) != 0;
-                const int aA = typeO ? s.aSO : s.aSE, aB = typeO ? s.aSE : s.aSO, aP = typeO ? s.aPO : s.aPE;
-                double *s0 = sm + s.o[1 + 2 * colour];
-                const double *sN = sm + s.o[2 * colour], *sS = sm + s.o[2 + 2 * colour];
-                const dbl2 N = lds2(sN + aA), S = lds2(sS + aA), own = lds2(s0 + aA), Pv = lds2(s0 + aP), b = lds2(s0 + aB);
-                const double x = s0[aB + (typeO ? 2 : -1)];
-                // even-column cell of pair k: W = odd[k-1], E = odd[k];  odd-column cell: W = even[k], E = even[k+1]
-                const double W0 = typeO ? b.x : x, E0 = typeO ? b.y : b.x;
-                const double W1 = typeO ? b.y : b.x, E1 = typeO ? x : b.y;
-                double n0 = relax<POW2>(N.x, S.x, E0, W0, own.x, Pv.x, rc);
-                double n1 = relax<POW2>(N.y, S.y, E1, W1, own.y, Pv.y, rc);
-                n0 = (typeO ? s.vO0 : s.vE0) ? n0 : own.x;
-                n1 = (typeO ? s.vO1 : s.vE1) ? n1 : own.y;
-                sts2(s0 + aA, n0, n1);
-                if (s.colown && q >= s.y0 && q < s.y1) {
-                    s.acc = xadd(s.acc, fabs(xsub(n0, own.x)));
-                    s.acc = xadd(s.acc, fabs(xsub(n1, own.y)));
-                }
-            }
+    constexpr bool typeR = PAR != 0;  // red cells are the odd-column cells
+    const int aA = typeR ? s.aSO : s.aSE, aB = typeR ? s.aSE : s.aSO;
+    const int aPA = typeR ? s.aPO : s.aPE, aPB = typeR ? s.aPE : s.aPO;
+    const int qtop = r - s.dq, q = qtop - 1, qb = qtop - 3;
+    const bool active = s.g < nsw;
+    // red row q: N from row qtop, own cells, right-hand side, the neighbouring thread's E/W value
+    const dbl2 N = lds2(sm + s.o[0] + aA);
+    const dbl2 own = lds2(sm + s.o[1] + aA);
+    const dbl2 Pr = lds2(sm + s.o[1] + aPA);
+    const double x = sm[s.o[1] + aB + (typeR ? 2 : -1)];
+    const dbl2 Pb = lds2(sm + s.o[3] + aPB);
+    const double xb = sm[s.o[3] + aA + (typeR ? -1 : 2)];
+    const dbl2 b = s.h1, S = s.h2;
+    // even-column cell of pair k: W = odd[k-1], E = odd[k];  odd-column cell: W = even[k], E = even[k+1]
+    double n0 = relax<POW2>(N.x, S.x, typeR ? b.y : b.x, typeR ? b.x : x, own.x, Pr.x, rc);
+    double n1 = relax<POW2>(N.y, S.y, typeR ? x : b.y, typeR ? b.y : b.x, own.y, Pr.y, rc);
+    const bool rowr = active && q >= s.vlo && q <= s.vhi;
+    n0 = rowr && (typeR ? s.vO0 : s.vE0) ? n0 : own.x;
+    n1 = rowr && (typeR ? s.vO1 : s.vE1) ? n1 : own.y;
+    if (q >= s.ylo && q <= s.yhi) sts2(sm + s.o[1] + aA, n0, n1);
+    // black row qb (cells of the other column parity): everything but Pb / xb comes from registers
+    const dbl2 ownb = s.h3, Nb = s.r1, bb = s.r2, Sb = s.r3;
+    double m0 = relax<POW2>(Nb.x, Sb.x, typeR ? bb.x : bb.y, typeR ? xb : bb.x, ownb.x, Pb.x, rc);
+    double m1 = relax<POW2>(Nb.y, Sb.y, typeR ? bb.y : xb, typeR ? bb.x : bb.y, ownb.y, Pb.y, rc);
+    const bool rowb = active && qb >= s.vlo && qb <= s.vhi;
+    m0 = rowb && (typeR ? s.vE0 : s.vO0) ? m0 : ownb.x;
+    m1 = rowb && (typeR ? s.vE1 : s.vO1) ? m1 : ownb.y;
+    if (qb >= s.ylo && qb <= s.yhi) sts2(sm + s.o[3] + aB, m0, m1);
+    // L1 update norm of this level (non-updated cells contribute exactly 0)
+    if (s.colown) {
+        if (q >= s.y0 && q < s.y1) {
+            s.acc = xadd(s.acc, fabs(xsub(n0, own.x)));
+            s.acc = xadd(s.acc, fabs(xsub(n1, own.y)));
+        }
+        if (qb >= s.y0 && qb < s.y1) {
+            s.acc = xadd(s.acc, fabs(xsub(m0, ownb.x)));
+            s.acc = xadd(s.acc, fabs(xsub(m1, ownb.y)));
         }
     }
-    // rows move up by one: rotate the five slot offsets
-    s.o[4] = s.o[3]; s.o[3] = s.o[2]; s.o[2] = s.o[1]; s.o[1] = s.o[0];
+    // ---- write back: the black row of the last level is final; its red cells are r2 ----
+    if (s.sact && qb >= s.y0 && qb < s.y1) {
+        double *dst = out + s.sdst;
+        if (typeR) {  // black cells are the even-column cells
+            stg2(dst, m0, bb.x);
+            stg2(dst + 2, m1, bb.y);
+        } else {
+            stg2(dst, bb.x, m0);
+            stg2(dst + 2, bb.y, m1);
+        }
+    }
+    s.sdst += s.ld;
+    // rows move up by one: rotate histories and slot offsets
+    s.h3 = s.h2; s.h2 = s.h1; s.h1 = N;
+    s.r3 = s.r2; s.r2 = s.r1; s.r1 = dbl2{n0, n1};
+    s.o[3] = s.o[2]; s.o[2] = s.o[1]; s.o[1] = s.o[0];
     s.o[0] = wrap_inc(s.o[0], s.ss, s.ring);
 }
 
