@@ -5,7 +5,7 @@ Metric (BASELINE.json): Poisson cell-updates/s (and sweeps/s) against the HBM ro
 Workload at N GPUs: the 4096^2 Re=1000 lid-driven cavity grid (BASELINE config 4, the configuration
 the north_star target is quoted on; it fits one GPU), slab-decomposed over N GPUs by rows with a
 fixed 4096 x 4096 slab per GPU (weak scaling; `--scaling strong` keeps the total at 4096^2).
-A "step" = one fixed-sweep red-black SOR solve (`--sweeps`, default 256) of lap(psi) = -w from a zero
+A "step" = one fixed-sweep red-black SOR solve (`--sweeps`, default 1024) of lap(psi) = -w from a zero
 initial guess on a synthetic cavity-like vorticity field (zero guess + state reset are inside the
 timed region; no convergence exit: tol = 0, so no work is ever skipped).
 
@@ -69,7 +69,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=4096, help="grid columns (and rows per GPU under weak scaling)")
-    ap.add_argument("--sweeps", type=int, default=256, help="red-black SOR sweeps per step")
+    ap.add_argument("--sweeps", type=int, default=1024, help="red-black SOR sweeps per step")
     ap.add_argument("--T", type=int, default=0, help="temporal block depth (0 = library default)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

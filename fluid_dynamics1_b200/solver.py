@@ -102,6 +102,7 @@ class PoissonSolver:
     """Device-resident solver object (cnv_poisson_*): reusable buffers, asynchronous passes."""
 
     def __init__(self, nrows: int, ncols: int, T: int = 0, slab=None):
+        self.h = None
         _lib.require_gpu()
         self.L = _lib.lib()
         if slab is None:
@@ -159,6 +160,7 @@ class Simulation:
     """Device-resident time stepping: the loop body of the reference driver (src/main.c:283-395)."""
 
     def __init__(self, cfg, T: int = 0):
+        self.h = None
         _lib.require_gpu()
         self.L = _lib.lib()
         if isinstance(cfg, dict):

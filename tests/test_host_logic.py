@@ -1,0 +1,217 @@
+"""CPU tests of the host-side logic and of the kernel's schedule (through the CPU emulator that compiles
+the kernel's own per-thread step function, tests/emul/stream_emul.cc).  No GPU needed."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(ROOT, "tests", "emul", "libstream_emul.so")
+    src = os.path.join(ROOT, "tests", "emul", "stream_emul.cc")
+    hdrs = [os.path.join(ROOT, "fluid_dynamics1_b200", "csrc", h) for h in ("poisson_stream.h", "poisson_plan.h", "exact.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(x) for x in [src] + hdrs):
+        subprocess.run(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", src, "-o", so], check=True)
+    E = C.CDLL(so)
+    E.emul_pass.argtypes = [C.c_int] * 10 + [C.c_double] * 3 + [C.c_int, dp, dp, dp, C.c_int, dp]
+    E.emul_plan.argtypes = [C.c_int] * 10 + [np.ctypeslib.ndpointer(dtype=np.int64)]
+    E.emul_decide.argtypes = [ip, dp, dp, C.c_int, C.c_void_p]
+    E.emul_pass_sweeps.argtypes = [C.c_int] * 4
+    E.emul_check_div.restype = C.c_long
+    E.emul_check_div.argtypes = [C.c_double, dp, C.c_long]
+    return E
+
+
+def _emul_sweeps(E, port, n, m, T, npass, mode, ws=0, ch=0, dx=None, dy=None, seed=0):
+    rng = np.random.default_rng(seed)
+    dx = dx or 1.0 / n
+    dy = dy or 1.0 / m
+    beta = port.beta(n, m)
+    f = rng.standard_normal((n, m))
+    ld = (m + 15) // 16 * 16
+    fp = np.zeros((n, ld))
+    fp[:, :m] = f
+    a, b = np.zeros((n, ld)), np.zeros((n, ld))
+    got_norms = []
+    for _ in range(npass):
+        norms = np.zeros(T)
+        assert E.emul_pass(T, n, m, ld, 0, n, 0, n, ws, ch, dx, dy, beta, mode, a, fp, b, T, norms) == 0
+        a, b = b, a
+        got_norms += list(norms)
+    u, onorms = port.poisson_sweeps(f, dx, dy, T * npass, beta)
+    return a[:, :m], u, np.array(got_norms), onorms
+
+
+@pytest.mark.parametrize("T", [1, 2, 4, 8])
+@pytest.mark.parametrize("shape", [(64, 64), (40, 72), (100, 100), (33, 47)])
+def test_stream_schedule_bitwise_vs_oracle(emul, port, shape, T):
+    """T temporally blocked sweeps per pass == T plain red-black sweeps of the oracle, bit for bit:
+    ring buffer, stage skew, register history, halos, strip/chunk decomposition, both arithmetic paths."""
+    n, m = shape
+    for mode in (0, 1):                               # 0: pow2 fast path where exact, 1: literal general sequence
+        for ws, ch in ((0, 0), (64, 2), (96, 3)):
+            if ws and ws - 2 * max(4, 2 * T) < 4:
+                continue
+            got, want, gn, on = _emul_sweeps(emul, port, n, m, T, 3, mode, ws, ch)
+            assert got.tobytes() == want.tobytes(), (shape, T, mode, ws, ch)
+            np.testing.assert_allclose(gn, on, rtol=1e-13)
+
+
+def test_stream_schedule_nonuniform_spacing(emul, port):
+    got, want, gn, on = _emul_sweeps(emul, port, 50, 38, 4, 2, 0, dx=0.013, dy=0.02)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_planner_properties(emul):
+    for (nrows, ncols) in [(64, 64), (128, 128), (1024, 1024), (4096, 4096), (2064, 16384), (512, 4096), (3, 3), (7, 1000)]:
+        for T in (1, 2, 4, 8):
+            o = np.zeros(8, dtype=np.int64)
+            emul.emul_plan(nrows, ncols, (ncols + 15) // 16 * 16, 0, nrows, 0, nrows, T, 0, 0, o)
+            WS, HX, Wout, Hout, nstrips, nchunks, threads, smem = o
+            assert WS > 0, (nrows, ncols, T)
+            assert WS % 4 == 0 and HX % 4 == 0 and HX >= 2 * T and Wout == WS - 2 * HX
+            assert nstrips * Wout >= ncols and nchunks * Hout >= nrows
+            assert threads == T * WS // 4 and threads <= (768 if T == 8 else 512)
+            assert smem <= 227 * 1024 - 1024
+
+
+def _ctl(itmax, tol):
+    return np.array([0, 0, 0, 0, itmax, -1, 0], dtype=np.int32), np.array([tol, 0.0, 0.0])
+
+
+def test_state_machine_matches_reference_loop(emul):
+    """decide(): stop at the first sweep with e < tol, whatever its position inside a pass (redo when it
+    is not the last sweep of the pass), itmax -> state 2; compared with the reference loop semantics
+    (src/poisson.c:234-284) on random norm sequences."""
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        T = int(rng.choice([1, 2, 4, 8]))
+        itmax = int(rng.integers(1, 40))
+        seq = rng.uniform(0.5, 2.0, size=itmax)
+        if rng.random() < 0.8:
+            seq[int(rng.integers(0, itmax))] = 0.1
+        tol = 0.3
+        want_k = next((k for k in range(itmax) if seq[k] < tol), None)
+        ints, dbls = _ctl(itmax, tol)
+        hist = np.zeros(itmax + 8)
+        base, guard = 0, 0
+        while ints[0] == 0:
+            nsw = emul.emul_pass_sweeps(int(ints[2]), int(ints[3]), itmax, T)
+            assert 1 <= nsw <= T
+            base = int(ints[2])
+            e = np.zeros(8)
+            e[:nsw] = seq[base:base + nsw]
+            cur_before = int(ints[1])
+            emul.emul_decide(ints, dbls, e, nsw, hist.ctypes.data)
+            if ints[3] > 0:                                   # redo requested: the pass input must stay current
+                assert ints[1] == cur_before and ints[2] == base
+            guard += 1
+            assert guard < 100
+        if want_k is None:
+            assert ints[0] == 2 and ints[2] == itmax and ints[5] == itmax - 1
+            assert dbls[2] == seq[itmax - 1]
+        else:
+            assert ints[0] == 1 and ints[5] == want_k and ints[2] == want_k + 1
+            assert dbls[1] == seq[want_k]
+            np.testing.assert_array_equal(hist[:want_k + 1], seq[:want_k + 1])
+
+
+def test_constant_divisor_division_is_correctly_rounded(emul):
+    """exact.h xdiv_const (Markstein correction with rd = RN(1/d)) vs the hardware division."""
+    rng = np.random.default_rng(1)
+    a = np.concatenate([rng.standard_normal(200000) * 10.0 ** rng.integers(-30, 30, 200000),
+                        np.ldexp(rng.integers(1, 2 ** 53, 100000).astype(np.float64), -60)])
+    for d in (2 * (0.01 ** 2 + 0.013 ** 2), 2 * (1 / 100.0 ** 2 + 1 / 100.0 ** 2), 3.0, 1e-7, 0.1, 7.0 / 3.0, 2 * (1.0 / 257 ** 2 * 2)):
+        assert emul.emul_check_div(d, np.ascontiguousarray(a), a.size) == 0, d
+
+
+# ---- the C ABI library: loads on CPU and exports every declared symbol -----------------------------
+def _declared(header, pattern):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return set(re.findall(pattern, txt))
+
+
+def test_cabi_exports_every_declared_symbol():
+    import fluid_dynamics1_b200 as fd
+    from fluid_dynamics1_b200 import _lib
+    L = fd.lib()           # binding resolves every name in CNV_API (AttributeError otherwise)
+    D = fd.dropin()
+    declared = _declared("cnavier_b200.h", r"\b(cnv_[a-z0-9_]+)\s*\(")
+    assert declared == set(_lib.CNV_API), declared ^ set(_lib.CNV_API)
+    for name in declared:
+        assert hasattr(L, name)
+    dropin_decl = _declared("cnavier_dropin.h", r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;")
+    dropin_decl -= {"defined"}
+    assert dropin_decl == set(_lib.DROPIN_API), dropin_decl ^ set(_lib.DROPIN_API)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.DROPIN_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert dropin_decl <= exported, dropin_decl - exported
+    assert L.cnv_device_count() >= 0 and b"sm_100a" in L.cnv_version()
+
+
+def test_cabi_scalars_and_coefficients_on_cpu(port):
+    import fluid_dynamics1_b200 as fd
+    assert fd.sor_beta(64, 64) == port.beta(64, 64)
+    assert fd.num_steps(0.58, 0.005) == 115 and fd.num_steps(20.0, 0.005) == 4000
+    for order in (2, 4, 6):
+        for deriv in (1, 2):
+            for n, h in ((7, 1 / 7), (16, 0.37), (40, 1 / 40)):
+                assert np.array_equal(fd.diff_matrix(n, order, deriv, h), port.diff_dense(n, order, deriv, h))
+    with pytest.raises(ValueError):
+        fd.diff_matrix(8, 5, 1, 0.1)
+
+
+def test_config_system_matches_reference(tmp_path, ref):
+    """Same parse results as the reference's config.c on its shipped files and on the documented quirks."""
+    import fluid_dynamics1_b200 as fd
+    from fluid_dynamics1_b200._lib import Config
+    cases = {
+        "quirks.txt": "# comment\n; other comment\n\nRe = 400.5   # trailing comment dropped\nnx=33\n ny = 35\npoisson_tol = 5E-4\n"
+                      "bogus_key = 3\n   # not a comment: first char is a space\nu4 = 2.5\norder = 4\nv1 = -0.25\ntf = 0.58\n",
+        "default_like.txt": "Re = 1000.0\nLx = 1\nLy = 1\nnx = 64\nny = 64\ndt = 0.005\ntf = 20.0\nmax_co = 1.0\norder = 6\n"
+                            "poisson_max_it = 10000\npoisson_tol = 1E-3\npoisson_type = 2\nopenmp_enabled = 1\noutput_interval = 10\n"
+                            "u4 = 1.0\n",
+        "highre_like.txt": "Re = 5000.0\nnx = 128\nny = 128\ndt = 0.001\ntf = 10.0\nmax_co = 0.5\npoisson_max_it = 15000\n"
+                           "poisson_tol = 5E-4\noutput_interval = 5\n",
+    }
+    assert C.sizeof(Config) == ref.L.ref_config_size()
+    for name, text in cases.items():
+        p = tmp_path / name
+        p.write_text(text)
+        mine = fd.load_config_from_file(str(p))
+        theirs = Config()
+        ref.L.ref_load_config_from_file(str(p).encode(), C.byref(theirs))
+        a, b = mine.as_dict(), theirs.as_dict()
+        a.pop("openmp_enabled"); b.pop("openmp_enabled")          # default differs by build flag only
+        assert a == b, name
+    missing = fd.load_config_from_file(str(tmp_path / "does_not_exist.txt"))       # unreadable file -> defaults
+    d = fd.load_default_config().as_dict()
+    assert missing.as_dict() == d and d["nx"] == 64 and d["u4"] == 1.0 and d["poisson_tol"] == 1e-3
+
+
+def test_no_oracle_or_cpu_fallback_in_product():
+    """The product path never imports / links the oracle and has no CPU compute fallback."""
+    pkg = os.path.join(ROOT, "fluid_dynamics1_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cc", ".h", ".cuh", "Makefile")):
+                txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "oracle" not in txt.lower() or fn == "Makefile" and "oracle" not in txt, (dirpath, fn)
+    out = subprocess.run(["ldd", os.path.join(pkg, "libcnavier_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "cnavier_ref" not in out
+    import fluid_dynamics1_b200 as fd
+    if fd.lib().cnv_device_count() == 0:
+        with pytest.raises(RuntimeError):
+            fd.poisson_sor(np.zeros((8, 8)), 0.1, 0.1, 10, 1e-3)
+        with pytest.raises(RuntimeError):
+            fd.Simulation(fd.load_default_config())
