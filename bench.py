@@ -273,11 +273,34 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(w_host.nbytes * world), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if world == 1:
+            out["stencil_phase"] = stencil_phase(fd, torch, args.n, sp, stream, peak)
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.n, args.cpu_seconds)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stencil_phase(fd, torch, n, sp, stream, peak, reps=20):
+    """The explicit-stencil part of one time step (BCs + wall vorticity, fused derivatives + Euler, velocity
+    recovery, continuity diagnostic) on the same grid: 72 algorithmic bytes per cell per time step
+    (SURVEY.md section 8d).  Reported beside the Poisson number; it is ~0.1 % of a time step at this size."""
+    cfg = fd.config_from_dict(dict(nx=n, ny=n, Re=1000.0, dt=5e-6, poisson_max_it=100000))
+    sim = fd.Simulation(cfg)
+    L = fd.lib()
+    L.cnv_sim_stencil_phase(sim.h, 3, sp)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    L.cnv_sim_stencil_phase(sim.h, reps, sp)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / reps
+    sim.close()
+    gbs = 72.0 * n * n / t / 1e9
+    return {"cell_updates_per_s": n * n / t, "us_per_step": t * 1e6, "algorithmic_bytes_per_cell": 72, "achieved_gbs": gbs,
+            "frac_of_hbm_peak": gbs / peak, "kernels": ["k_ring_bc_vorticity", "k_euler_fused", "k_velocity", "k_continuity"]}
 
 
 # ------------------------------------------------------------------------------------------------

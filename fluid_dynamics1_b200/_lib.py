@@ -80,6 +80,7 @@ CNV_API = {
     "cnv_sim_get_fields": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "cnv_sim_set_fields": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "cnv_sim_set_diagnostics": (None, [_vp, C.c_int]),
+    "cnv_sim_stencil_phase": (None, [_vp, C.c_int, _vp]),
     "cnv_sim_counters": (None, [_vp, C.POINTER(C.c_longlong)]),
     "cnv_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "cnv_config_default": (None, [C.POINTER(Config)]),

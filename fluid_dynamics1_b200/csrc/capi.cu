@@ -395,6 +395,26 @@ int cnv_sim_step(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, do
     return 0;
 }
 
+// Stencil phase only (measurement / profiling): BCs + wall vorticity, fused derivative + Euler, velocity
+// recovery from the current psi, continuity diagnostic -- `reps` times, no Poisson solve.
+void cnv_sim_stencil_phase(cnv_sim *s, int reps, void *stream)
+{
+    const Config &c = s->cfg;
+    const double bc[8] = {c.u1, c.u2, c.u3, c.u4, c.v1, c.v2, c.v3, c.v4};
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int t = 0; t < reps; t++) {
+        launch_ring_bc_vorticity(s->u, s->v, s->w, s->nrows, s->ncols, s->ld, bc, s->d1x, s->d1y, st);
+        launch_euler_fused(s->w, s->u, s->v, s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->d2x, s->d2y, s->inv_re, c.dt,
+                           s->ps->consts().pscale, s->w2, s->ps->rhs(), st);
+        std::swap(s->w, s->w2);
+        launch_velocity(s->ps->buffer(s->psi_buf), s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
+        launch_continuity(s->u, s->v, s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
+                          s->cont_result, st);
+        count_launch(4);
+    }
+    CNV_CUDA_CHECK(cudaGetLastError());
+}
+
 int cnv_sim_get_fields(cnv_sim *s, double *psi, double *w, double *u, double *v)
 {
     CNV_CUDA_CHECK(cudaStreamSynchronize(s->stream));

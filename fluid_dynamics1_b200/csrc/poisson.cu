@@ -47,7 +47,7 @@ __device__ __forceinline__ void group_sums(double *sm, double acc, int g, int kk
 }
 
 template <int T, bool POW2>
-__global__ void __launch_bounds__(T == 8 ? 768 : 512, 1)
+__global__ void __launch_bounds__(pass_max_threads(T), pass_min_ctas(T))
 k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0, double *__restrict__ buf1,
                const double *__restrict__ rhs, PoissonCtl *ctl, double *__restrict__ partials, double *hist,
                double *norms_out, const int fused_decide)
@@ -154,9 +154,9 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
 {
     if (gnrows < 0) gnrows = nrows;
     if (own_hi < 0) own_hi = nrows;
-    if (T <= 0) T = env_int("CNV_POISSON_T", 4);
-    if (T != 1 && T != 2 && T != 4 && T != 8) {
-        std::printf("** Error: temporal block depth must be 1, 2, 4 or 8 **\n");
+    if (T <= 0) T = env_int("CNV_POISSON_T", 8);  // deepest blocking measured best at every size (profiles/)
+    if (T != 1 && T != 2 && T != 4 && T != 6 && T != 8) {
+        std::printf("** Error: temporal block depth must be 1, 2, 4, 6 or 8 **\n");
         std::exit(1);
     }
     if (nrows < 3 || ncols < 3) {
@@ -235,7 +235,7 @@ void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
         else                                                                                                             \
             launch_pass<TT, false>(geom_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, threads_, smem_, s); \
     }
-        CNV_PASS(1) CNV_PASS(2) CNV_PASS(4) CNV_PASS(8)
+        CNV_PASS(1) CNV_PASS(2) CNV_PASS(4) CNV_PASS(6) CNV_PASS(8)
 #undef CNV_PASS
     }
     CNV_CUDA_CHECK(cudaGetLastError());

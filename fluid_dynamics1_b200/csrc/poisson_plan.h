@@ -47,6 +47,10 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 inline size_t pass_smem_bytes(int T, int WS) { return (size_t)ring_rows(T) * slot_stride(WS) * sizeof(double); }
 inline int pass_threads(int T, int WS) { return T * (WS / 4); }
+// Launch bounds of k_poisson_pass<T>: the kernel is latency bound, so registers are capped (<= 85 per
+// thread) to keep 24 warps resident per SM: one 768-thread CTA for deep blocking, two 384-thread CTAs else.
+constexpr int pass_max_threads(int T) { return T >= 6 ? 768 : 384; }
+constexpr int pass_min_ctas(int T) { return T >= 6 ? 1 : 2; }
 
 struct PlanLimits {
     int num_sms = 148;
@@ -56,8 +60,10 @@ struct PlanLimits {
 };
 
 // Choose WS / Hout for `own` = [own_lo, own_hi) rows of an nrows x ncols local array.
-// Cost model: the kernel is bound by shared-memory traffic, proportional to (steps x WS x T) per
-// CTA; CTAs resident on one SM share that bandwidth, and the pass ends with the last wave.
+// Cost model (fitted to B200 measurements, profiles/): the kernel is latency bound, so an SM's throughput
+// grows with its resident warps until ~24; the work of a CTA is (steps x WS x T) cell-updates including
+// halo and pipeline fill/drain; CTAs resident on one SM share it; the pass ends with the last wave, so the
+// CTA count should fill the SM slots (148 x occupancy) as exactly as possible.
 inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T,
                           const PlanLimits &lim, int force_ws = 0, int force_chunks = 0)
 {
@@ -66,41 +72,52 @@ inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, i
     double best_cost = 1e300;
     const int HX = round_up(2 * T, 4), HY = 2 * T;
     const int own = own_hi - own_lo;
-    for (int WS = 32; WS <= 2048; WS += 32) {
-        if (force_ws && WS != force_ws) continue;
+    const int reg_threads = 65536 / 80 / 32 * 32;  // ~80 registers per thread (launch bounds): 800 threads per SM
+    for (int WS = force_ws ? force_ws : 32; WS <= (force_ws ? force_ws : 2048); WS += 32) {
+        if (WS % 4) break;
         const int Wout = WS - 2 * HX;
         if (Wout < 4) continue;
         const int NT = pass_threads(T, WS);
-        if (NT > (T == 8 ? 768 : 512) || (!force_ws && NT < 64 && WS < ncols + 2 * HX)) continue;
+        if (NT > pass_max_threads(T) || (!force_ws && NT < 64 && WS < ncols + 2 * HX)) continue;
         const size_t smem = pass_smem_bytes(T, WS);
         if (smem > lim.smem_per_cta) continue;
         // do not take a strip much wider than the domain needs
         if (!force_ws && WS - 32 >= ncols + 2 * HX) continue;
         const int nstrips = (ncols + Wout - 1) / Wout;
         int occ = (int)(lim.smem_per_sm / (smem + 1024));
+        if (occ > reg_threads / NT) occ = reg_threads / NT;
         if (occ > lim.max_threads_per_sm / NT) occ = lim.max_threads_per_sm / NT;
         if (occ < 1) occ = 1;
-        if (occ > 4) occ = 4;
+        if (occ > 8) occ = 8;
         const int slots = lim.num_sms * occ;
-        for (int waves = 1; waves <= 4; waves++) {
-            int nchunks = force_chunks ? force_chunks : (slots * waves) / nstrips;
-            if (nchunks < 1) nchunks = 1;
-            if (nchunks > own) nchunks = own;
-            if (!force_chunks) {  // keep the y-halo overhead (4T rows per chunk) below ~50 %
-                const int max_chunks = own / (8 * T) > 1 ? own / (8 * T) : 1;
-                if (nchunks > max_chunks) nchunks = max_chunks;
-            }
-            int Hout = (own + nchunks - 1) / nchunks;
-            nchunks = (own + Hout - 1) / Hout;
-            const long ctas = (long)nstrips * nchunks;
-            const long nwaves = (ctas + slots - 1) / slots;
-            const int steps = Hout + 2 * HY + 4 * T + 8;  // + fixed per-CTA start-up cost
-            const int resident = ctas < slots ? (int)((ctas + lim.num_sms - 1) / lim.num_sms) : occ;
-            const double cost = (double)nwaves * resident * steps * WS * T;
-            if (cost < best_cost) {
-                best_cost = cost;
-                best.WS = WS; best.HX = HX; best.Wout = Wout; best.Hout = Hout; best.HY = HY;
-                best.nstrips = nstrips; best.nchunks = nchunks;
+        for (int waves = 1; waves <= 3; waves++) {
+            for (int slack = 0; slack < (force_chunks ? 1 : 3); slack++) {
+                int nchunks = force_chunks ? force_chunks : (slots * waves) / nstrips - slack;
+                if (nchunks < 1) nchunks = 1;
+                if (nchunks > own) nchunks = own;
+                if (!force_chunks) {  // keep the y overhead (halo + pipeline fill: 8T rows per chunk) bounded
+                    const int max_chunks = own / (4 * T) > 1 ? own / (4 * T) : 1;
+                    if (nchunks > max_chunks) nchunks = max_chunks;
+                }
+                const int Hout = (own + nchunks - 1) / nchunks;
+                nchunks = (own + Hout - 1) / Hout;
+                const long ctas = (long)nstrips * nchunks;
+                const long nwaves = (ctas + slots - 1) / slots;
+                const int steps = Hout + 2 * HY + 4 * T + 6;  // + fixed per-CTA start-up cost
+                // CTAs sharing the busiest SM in the last (or only) wave, and its resident warps
+                const long in_last = ctas - (nwaves - 1) * slots;
+                const int resident = (int)((in_last + lim.num_sms - 1) / lim.num_sms);
+                const double warps = resident * NT / 32.0;
+                const double eff = std::pow(warps >= 24.0 ? 1.0 : warps / 24.0, 0.7);
+                const double wave_cost = (double)steps * WS * T;
+                const double full_warps = occ * NT / 32.0;
+                const double full_eff = std::pow(full_warps >= 24.0 ? 1.0 : full_warps / 24.0, 0.7);
+                const double cost = (nwaves - 1) * wave_cost * occ / full_eff + wave_cost * resident / eff;
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best.WS = WS; best.HX = HX; best.Wout = Wout; best.Hout = Hout; best.HY = HY;
+                    best.nstrips = nstrips; best.nchunks = nchunks;
+                }
             }
             if (force_chunks) break;
         }

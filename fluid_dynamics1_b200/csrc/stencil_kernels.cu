@@ -166,46 +166,58 @@ __global__ void k_velocity(const double *__restrict__ psi, int nrows, int ncols,
 
 // ---------------------------------------------------------------------------------------------
 // continuity diagnostic: max and min over the grid of DX u + DY v (src/main.c:387-408).
-// Block partials + last-block final pass in a fixed order (deterministic).
-__global__ void k_continuity(const double *__restrict__ u, const double *__restrict__ v, int nrows, int ncols, int ld,
-                             FdTable d1x, FdTable d1y, double *__restrict__ partial, unsigned *__restrict__ ticket,
-                             double *__restrict__ result)
+// Persistent grid (a few CTAs per SM) looping over 32x8 tiles; block partials, then the last block
+// reduces them in parallel.  max/min are order independent, so the result is deterministic.
+__global__ void __launch_bounds__(256)
+k_continuity(const double *__restrict__ u, const double *__restrict__ v, int nrows, int ncols, int ld,
+             FdTable d1x, FdTable d1y, double *__restrict__ partial, unsigned *__restrict__ ticket,
+             double *__restrict__ result)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
     double mx = -DBL_MAX, mn = DBL_MAX;  // maxel/minel start values, src/linearalg.c:478,514
-    if (i < nrows && j < ncols) {
-        const double *row = u + (size_t)i * ld;
-        const double *col = v + j;
-        const double dudx = fd_apply(d1x, j, [&](int c) { return row[c]; });
-        const double dvdy = fd_apply(d1y, i, [&](int r) { return col[(size_t)r * ld]; });
-        mx = mn = xadd(dudx, dvdy);
-    }
-    __shared__ double smx[32], smn[32];
-    __shared__ bool last;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
-    for (int o = 16; o > 0; o >>= 1) {
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    if ((tid & 31) == 0) { smx[tid >> 5] = mx; smn[tid >> 5] = mn; }
-    __syncthreads();
-    const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-    if (tid == 0) {
-        for (int k = 1; k < (nthr + 31) / 32; k++) { mx = fmax(mx, smx[k]); mn = fmin(mn, smn[k]); }
-        partial[2 * bid] = mx;
-        partial[2 * bid + 1] = mn;
-        __threadfence();
-        last = atomicAdd(ticket, 1u) == (unsigned)nblocks - 1;
-    }
-    __syncthreads();
-    if (last && tid == 0) {
-        __threadfence();
-        mx = -DBL_MAX; mn = DBL_MAX;
-        for (int k = 0; k < nblocks; k++) {
-            mx = fmax(mx, __ldcg(&partial[2 * k]));
-            mn = fmin(mn, __ldcg(&partial[2 * k + 1]));
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tiles_x = (ncols + 31) / 32, tiles_y = (nrows + 7) / 8;
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const int j = (tile % tiles_x) * 32 + tx, i = (tile / tiles_x) * 8 + ty;
+        if (i < nrows && j < ncols) {
+            const double *row = u + (size_t)i * ld;
+            const double *col = v + j;
+            const double dudx = fd_apply(d1x, j, [&](int c) { return row[c]; });
+            const double dvdy = fd_apply(d1y, i, [&](int r) { return col[(size_t)r * ld]; });
+            const double c = xadd(dudx, dvdy);
+            mx = fmax(mx, c);
+            mn = fmin(mn, c);
         }
+    }
+    __shared__ double smx[8], smn[8];
+    __shared__ bool last;
+    auto block_reduce = [&]() {
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        __syncthreads();
+        if (tx == 0) { smx[ty] = mx; smn[ty] = mn; }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int k = 1; k < 8; k++) { mx = fmax(mx, smx[k]); mn = fmin(mn, smn[k]); }
+    };
+    block_reduce();
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = mx;
+        partial[2 * blockIdx.x + 1] = mn;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    mx = -DBL_MAX; mn = DBL_MAX;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) {
+        mx = fmax(mx, __ldcg(&partial[2 * k]));
+        mn = fmin(mn, __ldcg(&partial[2 * k + 1]));
+    }
+    block_reduce();
+    if (threadIdx.x == 0) {
         result[0] = mx;
         result[1] = mn;
         *ticket = 0;
@@ -265,12 +277,15 @@ void launch_velocity(const double *psi, int nrows, int ncols, int ldp, const FdT
     dim3 b(32, 8);
     k_velocity<<<grid2d(nrows, ncols, b), b, 0, s>>>(psi, nrows, ncols, ldp, d1x, d1y, u, v, ld);
 }
-int continuity_blocks(int nrows, int ncols) { return ((ncols + 31) / 32) * ((nrows + 7) / 8); }
+int continuity_blocks(int nrows, int ncols)
+{
+    const int tiles = ((ncols + 31) / 32) * ((nrows + 7) / 8);
+    return tiles < 148 * 8 ? tiles : 148 * 8;
+}
 void launch_continuity(const double *u, const double *v, int nrows, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
                        double *partial, unsigned *ticket, double *result, cudaStream_t s)
 {
-    dim3 b(32, 8);
-    k_continuity<<<grid2d(nrows, ncols, b), b, 0, s>>>(u, v, nrows, ncols, ld, d1x, d1y, partial, ticket, result);
+    k_continuity<<<continuity_blocks(nrows, ncols), 256, 0, s>>>(u, v, nrows, ncols, ld, d1x, d1y, partial, ticket, result);
 }
 void launch_prep_rhs(const double *f, int nrows, int ncols, int ldf, double sign, double pscale, double *rhs, double *psi0,
                      double *psi1, int ld, cudaStream_t s)

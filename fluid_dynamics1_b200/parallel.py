@@ -54,7 +54,7 @@ class SlabPoisson:
         self.torch, self.dist = torch, dist
         self.rank, self.world = rank, world
         self.total_rows, self.ncols = total_rows, ncols
-        T = T or 4
+        T = T or 8
         for r in range(world):
             a, b = slab_bounds(total_rows, world, r)
             if b - a < 2 * T:

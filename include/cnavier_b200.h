@@ -101,6 +101,9 @@ int cnv_sim_step(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, do
 int cnv_sim_get_fields(cnv_sim *s, double *psi, double *w, double *u, double *v); /* host, nx*ny each, NULL to skip */
 int cnv_sim_set_fields(cnv_sim *s, const double *psi, const double *w, const double *u, const double *v);
 void cnv_sim_set_diagnostics(cnv_sim *s, int continuity_on);
+/* measurement hook: the stencil phase only (BCs + wall vorticity, derivatives + Euler, velocity recovery,
+ * continuity diagnostic), `reps` times, asynchronously on `stream`; no Poisson solve */
+void cnv_sim_stencil_phase(cnv_sim *s, int reps, void *stream);
 /* cumulative counters: [0] Poisson sweeps, [1] Poisson passes, [2] steps */
 void cnv_sim_counters(cnv_sim *s, long long *out);
 

@@ -72,7 +72,7 @@ int emul_pass(int T, int nrows, int ncols, int ld, int grow0, int gnrows, int ow
         else run_pass<TT, false>(p, rc, in, rhs.data(), out, nsw, norms);             \
         return 0;                                                                     \
     }
-    RUN(1) RUN(2) RUN(4) RUN(8)
+    RUN(1) RUN(2) RUN(4) RUN(6) RUN(8)
 #undef RUN
     return -2;
 }

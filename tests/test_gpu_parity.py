@@ -309,3 +309,50 @@ def test_dropin_signatures(port, tmp_path):
     assert np.array_equal(_from_mtrx(c), arrs[1] + arrs[2])
     for m in ms + [F, U, d1, c]:
         D.freem(m)
+
+
+# ---- the whole driver (cnv_main / cnavier_b200 executable) against the reference executable -----------
+def test_driver_log_and_vtk_match_reference_executable(tmp_path, golden_logs):
+    """`cnavier_b200 cfg run` vs the unmodified reference binary on the same config file: identical Poisson
+    log lines (also equal to the shipped testRunOMP.txt) and byte-identical VTK files (src/utils.c format,
+    global file counter naming)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(fd._lib.LIB_PATH), "cnavier_b200")
+    cfg = dict(api.CONFIG_DEFAULT, tf=(12 + 0.5) * 0.005, output_interval=5)       # 12 steps, dumps at t = 0, 5, 10
+    mine = tmp_path / "mine"
+    mine.mkdir()
+    api.write_config(cfg, str(mine / "cfg.txt"))
+    r = subprocess.run([exe, "cfg.txt", "run"], cwd=mine, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "Poisson SOR parameter: 1.907826" in r.stdout and "Simulation complete!" in r.stdout
+    log = (mine / "output" / "logs" / "run.txt").read_text()
+    pl = api.parse_poisson_log(log)
+    assert [k for k, _ in pl] == golden_logs["testRunOMP"]["k"][:12]
+    assert [e for _, e in pl] == golden_logs["testRunOMP"]["e"][:12]
+    assert "Iteration: 11 | Time: 0.055000 | Progress: 100.00% |" in log and "Continuity max:" in log
+    vtk = sorted(os.listdir(mine / "output" / "run"))
+    assert len(vtk) == 12 and "stream-function-1-0.vtk" in vtk and "y-velocity-1-11.vtk" in vtk
+    if api.ref_binary() is None:
+        pytest.skip("oracle/_ref not built: VTK byte comparison skipped")
+    theirs = tmp_path / "theirs"
+    theirs.mkdir()
+    api.write_config(cfg, str(theirs / "cfg.txt"))
+    subprocess.run([api.ref_binary(), "cfg.txt", "run"], cwd=theirs, check=True, capture_output=True, timeout=600,
+                   env=dict(os.environ, OMP_NUM_THREADS="8"))
+    for name in vtk:
+        a = (mine / "output" / "run" / name).read_bytes()
+        b = (theirs / "output" / "run" / name).read_bytes()
+        assert a == b, name
+    ref_pl = api.parse_poisson_log((theirs / "output" / "logs" / "run.txt").read_text())
+    assert pl == ref_pl
+
+
+def test_driver_exit_code_on_poisson_itmax(tmp_path):
+    import subprocess
+    exe = os.path.join(os.path.dirname(fd._lib.LIB_PATH), "cnavier_b200")
+    cfg = dict(api.CONFIG_DEFAULT, tf=0.02, poisson_max_it=10)
+    api.write_config(cfg, str(tmp_path / "cfg.txt"))
+    r = subprocess.run([exe, "cfg.txt", "run"], cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, CNV_NO_VTK="1"))
+    assert r.returncode == 1                                                    # reference: exit(1), src/poisson.c:284
+    assert "Error: maximum number of iterations achieved for Poisson equation." in (tmp_path / "output" / "logs" / "run.txt").read_text()
