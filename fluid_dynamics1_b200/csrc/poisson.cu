@@ -66,18 +66,18 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     const int tid = threadIdx.x;
     const CtaGeom G = cta_geom(p, blockIdx.x, blockIdx.y);
     StreamThread<T> st;
-    stream_init<T>(st, p, G, tid, blockDim.x);
+    stream_init<T>(st, p, G, sm, in, rhs, tid, blockDim.x);
     const int TPG = p.WS >> 2;
     const int kk = tid - st.g * TPG;
 
-    stream_prologue<T>(st, sm, in, rhs);  // kPrefetch rows in flight
+    stream_prologue<T>(st, sm);  // kPrefetch rows in flight
     for (int r = st.ybase; r <= st.rend; r += 2) {
         cp_async_wait<kPrefetch - 1>();  // row r has landed (this thread's copies) ...
         __syncthreads();                 // ... and everybody's; previous step's updates are visible
-        stream_step<T, POW2, 0>(st, rc, sm, in, rhs, out, r, nsw);
+        stream_step<T, POW2, 0>(st, rc, sm, out, r, nsw);
         cp_async_wait<kPrefetch - 1>();
         __syncthreads();
-        stream_step<T, POW2, 1>(st, rc, sm, in, rhs, out, r + 1, nsw);
+        stream_step<T, POW2, 1>(st, rc, sm, out, r + 1, nsw);
     }
     cp_async_wait<0>();
     const double acc = st.acc;

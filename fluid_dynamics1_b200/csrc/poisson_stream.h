@@ -16,8 +16,8 @@
 // reference's in-place sweeps, only the order of independent cell updates changes, so every
 // cell sees bit-identical operands).  Row r-4T+1 is final once the last level's black stage has
 // processed it, and is written back from registers in that same step.  Dependencies reach 2 cells per sweep, so strips/chunks overlap by 2T halo cells whose
-// (stale-neighbour) results are discarded: the first/last loaded row and column are never
-// updated, and the region of influence of that staleness stays inside the halo.
+// (stale-neighbour) results are discarded: the first/last loaded row is never updated and the
+// first/last loaded column sees a pad value; the region of influence of either stays inside the halo.
 // Thread (g, kk) of the CTA owns level g+1 (its red and black stage) and four adjacent columns
 // (pairs 2kk, 2kk+1), so its |u - u0| contributions all belong to sweep g+1: one accumulator.
 #pragma once
@@ -76,32 +76,60 @@ CNV_HD ThreadCtx thread_ctx(const PassGeom &p, const CtaGeom &G, int tid)
     t.g = tid / TPG;
     const int kk = tid - t.g * TPG;
     t.k0 = 2 * kk;
+    // A column is protected from updates only if it is a Dirichlet ring column or lies outside the domain.
+    // The first/last column held in shared memory (halo edge of an interior strip) IS updated, from a pad
+    // value: whatever that produces spreads by at most 2 columns per sweep, i.e. stays inside the 2T-column
+    // halo whose results are discarded anyway -- exactly as far as the staleness of a frozen edge would reach.
     t.vmask = 0;
     for (int i = 0; i < 4; i++) {
-        int c = 4 * kk + i, gc = G.gx0 + c;
-        if (c >= 1 && c <= p.WS - 2 && gc >= 1 && gc <= p.ncols - 2) t.vmask |= 1 << i;
+        int gc = G.gx0 + 4 * kk + i;
+        if (gc >= 1 && gc <= p.ncols - 2) t.vmask |= 1 << i;
     }
     t.colown = 4 * kk >= p.HX && 4 * kk < p.HX + p.Wout;
     return t;
 }
 
+// ---- shared-memory accessors.  All ring offsets are BYTE offsets.  On the device they already include
+// the CTA's shared window base, so an access is one 32-bit add + ld.shared/st.shared with no generic
+// address arithmetic; on the host (schedule checker) they are offsets from the emulated array.
+struct dbl2 { double x, y; };
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+__device__ __forceinline__ int smem_base(const double *sm) { return (int)__cvta_generic_to_shared(sm); }
+__device__ __forceinline__ void cp_async8(const double *, int dst, const double *gsrc)
 {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-struct dbl2 { double x, y; };
-__device__ __forceinline__ dbl2 lds2(const double *p) { double2 v = *reinterpret_cast<const double2 *>(p); return {v.x, v.y}; }
-__device__ __forceinline__ void sts2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+__device__ __forceinline__ dbl2 lds2(const double *, int off)
+{
+    dbl2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(off));
+    return v;
+}
+__device__ __forceinline__ double lds1(const double *, int off)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(off));
+    return v;
+}
+__device__ __forceinline__ void sts2(double *, int off, double a, double b)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(off), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void sts1(double *, int off, double a)
+{
+    asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(off), "d"(a) : "memory");
+}
 __device__ __forceinline__ void stg2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 #else
-inline void cp_async8(double *dst, const double *src) { *dst = *src; }
+inline int smem_base(const double *) { return 0; }
+inline double *at(const double *sm, int off) { return reinterpret_cast<double *>(reinterpret_cast<char *>(const_cast<double *>(sm)) + off); }
+inline void cp_async8(const double *sm, int dst, const double *src) { *at(sm, dst) = *src; }
 inline void cp_async_commit() {}
-struct dbl2 { double x, y; };
-inline dbl2 lds2(const double *p) { return {p[0], p[1]}; }
-inline void sts2(double *p, double a, double b) { p[0] = a; p[1] = b; }
+inline dbl2 lds2(const double *sm, int off) { return {at(sm, off)[0], at(sm, off)[1]}; }
+inline double lds1(const double *sm, int off) { return *at(sm, off); }
+inline void sts2(double *sm, int off, double a, double b) { at(sm, off)[0] = a; at(sm, off)[1] = b; }
+inline void sts1(double *sm, int off, double a) { *at(sm, off) = a; }
 inline void stg2(double *p, double a, double b) { p[0] = a; p[1] = b; }
 #endif
 
@@ -124,38 +152,42 @@ struct StreamThread {
     static constexpr int R = ring_rows(T);
     static constexpr int NCH = (4 + T - 1) / T;  // (psi|rhs) column pairs this thread copies per row
     // uniform
-    int ss, ring;        // slot stride and ring size, in doubles
+    int ss, ringend;     // slot stride (bytes); end of the ring (bytes, base included)
     int ybase, rend;     // first / last step; ring slot of row q is (q - ybase) mod R
     int ylo, yhi, y0, y1;
     int vlo, vhi;        // rows that may be updated: inside the streamed range and off the Dirichlet ring
     int ld;
-    int lslot;           // slot offset of the row being loaded (r + kPrefetch)
+    int lslot;           // byte offset of the slot of the row being loaded (r + kPrefetch)
     // load
-    long long lsrc[NCH];      // element offset of this thread's chunk in the row being loaded
-    int ldE[NCH], ldO[NCH];   // destination offsets inside a slot
-    int lmode[NCH];           // 0 none, 1 psi, 2 rhs, 3 zero fill (psi side), 4 zero fill (rhs side)
+    const double *lptr[NCH];  // global address of this thread's chunk in the row being loaded
+    int ldE[NCH], ldO[NCH];   // destination byte offsets inside a slot
+    bool lcopy[NCH], lzero[NCH];
     // write back (threads of the last level only): element offset of columns 4kk.. of the black row
     long long sdst;
     bool sact;
     // compute
     int g, dq, k0;
-    int o[4];            // slot offsets of rows qtop, qtop-1, qtop-2, qtop-3 with qtop = r - dq
-    int aSE, aSO, aPE, aPO;  // array offsets inside a slot, k0 folded in
-    bool vE0, vO0, vE1, vO1, colown;
+    int o[4];            // byte offsets of the slots of rows qtop, qtop-1, qtop-2, qtop-3 (qtop = r - dq)
+    int aSE, aSO, aPE, aPO;  // array byte offsets inside a slot, k0 folded in
+    bool vE0, vO0, vE1, vO1, colown, allvalid;
     dbl2 h1, h2, h3;     // N loaded 1, 2, 3 steps ago
     dbl2 r1, r2, r3;     // red results of 1, 2, 3 steps ago
     double acc;
 };
 
-CNV_HD int wrap_inc(int off, int ss, int ring) { off += ss; return off >= ring ? off - ring : off; }
+// advance a ring offset by one slot; `ringend` = base + R*ss, so wrapping subtracts R*ss
+template <int T>
+CNV_HD int wrap_inc_t(int off, int ss, int ringend) { off += ss; return off >= ringend ? off - StreamThread<T>::R * ss : off; }
 
 template <int T>
-CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G, int tid, int nthreads)
+CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G, const double *sm, const double *in,
+                        const double *rhs, int tid, int nthreads)
 {
     constexpr int R = StreamThread<T>::R;
     const int WP = p.WS >> 1;
-    s.ss = slot_stride(p.WS);
-    s.ring = R * s.ss;
+    const int base = smem_base(sm);
+    s.ss = slot_stride(p.WS) * 8;
+    s.ringend = base + R * s.ss;
     // start on a step whose stage-0 row has even (global row + 1): the colour type then alternates
     // with the step parity (PAR in stream_step)
     s.ybase = G.ylo - ((p.grow0 + G.ylo - 1) & 1);
@@ -165,27 +197,29 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.vlo = G.ylo + 1 > 1 - p.grow0 ? G.ylo + 1 : 1 - p.grow0;
     s.vhi = G.yhi - 1 < p.gnrows - 2 - p.grow0 ? G.yhi - 1 : p.gnrows - 2 - p.grow0;
     s.ld = p.ld;
-    s.lslot = (kPrefetch % R) * s.ss;
+    s.lslot = base + (kPrefetch % R) * s.ss;
     for (int j = 0; j < StreamThread<T>::NCH; j++) {
         const int c = tid + j * nthreads;
-        s.lmode[j] = 0; s.lsrc[j] = 0; s.ldE[j] = 0; s.ldO[j] = 0;
+        s.lcopy[j] = s.lzero[j] = false; s.lptr[j] = in; s.ldE[j] = 0; s.ldO[j] = 0;
         if (c < p.WS) {
             const bool isP = c >= WP;
             const int k = isP ? c - WP : c;
             const int gc = G.gx0 + 2 * k;
-            s.ldE[j] = arr_off(p.WS, isP ? 2 : 0) + k;
-            s.ldO[j] = arr_off(p.WS, isP ? 3 : 1) + k;
+            s.ldE[j] = (arr_off(p.WS, isP ? 2 : 0) + k) * 8;
+            s.ldO[j] = (arr_off(p.WS, isP ? 3 : 1) + k) * 8;
             const bool inside = gc >= 0 && gc < p.ld;
-            s.lmode[j] = inside ? (isP ? 2 : 1) : (isP ? 4 : 3);
-            s.lsrc[j] = (long long)(s.ybase + kPrefetch) * p.ld + gc;
+            s.lcopy[j] = inside;
+            s.lzero[j] = !inside;
+            s.lptr[j] = (isP ? rhs : in) + ((long long)(s.ybase + kPrefetch) * p.ld + (inside ? gc : 0));
         }
     }
     const ThreadCtx t = thread_ctx(p, G, tid);
     s.g = t.g; s.dq = 4 * t.g; s.k0 = t.k0;
-    for (int j = 0; j < 4; j++) s.o[j] = ((((-s.dq - j) % R) + R) % R) * s.ss;
-    s.aSE = arr_off(p.WS, 0) + t.k0; s.aSO = arr_off(p.WS, 1) + t.k0;
-    s.aPE = arr_off(p.WS, 2) + t.k0; s.aPO = arr_off(p.WS, 3) + t.k0;
+    for (int j = 0; j < 4; j++) s.o[j] = base + ((((-s.dq - j) % R) + R) % R) * s.ss;
+    s.aSE = (arr_off(p.WS, 0) + t.k0) * 8; s.aSO = (arr_off(p.WS, 1) + t.k0) * 8;
+    s.aPE = (arr_off(p.WS, 2) + t.k0) * 8; s.aPO = (arr_off(p.WS, 3) + t.k0) * 8;
     s.vE0 = t.vmask & 1; s.vO0 = (t.vmask >> 1) & 1; s.vE1 = (t.vmask >> 2) & 1; s.vO1 = (t.vmask >> 3) & 1;
+    s.allvalid = t.vmask == 15;
     s.colown = t.colown;
     const int gc4 = G.gx0 + 2 * t.k0;  // first of this thread's four columns
     s.sact = t.g == T - 1 && t.colown && gc4 >= 0 && gc4 < p.ld;
@@ -194,37 +228,32 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.acc = 0.0;
 }
 
-// copy this thread's chunks of local row rl into ring-slot offset `slot`
+// copy this thread's chunks of one row into the ring slot at byte offset `slot`; `back` = how many rows
+// before the row lptr[] currently points at (prologue only)
 template <int T>
-CNV_HD void stream_load_row(const StreamThread<T> &s, double *sm, const double *__restrict__ in,
-                            const double *__restrict__ rhs, int slot, const long long *src)
+CNV_HD void stream_load_row(const StreamThread<T> &s, double *sm, int slot, long long back_elems)
 {
 #pragma unroll
     for (int j = 0; j < StreamThread<T>::NCH; j++) {
-        const int m = s.lmode[j];
-        if (m == 1 || m == 2) {
-            const double *g = (m == 1 ? in : rhs) + src[j];
-            cp_async8(sm + slot + s.ldE[j], g);
-            cp_async8(sm + slot + s.ldO[j], g + 1);
-        } else if (m >= 3) {
-            sm[slot + s.ldE[j]] = 0.0;
-            sm[slot + s.ldO[j]] = 0.0;
+        if (s.lcopy[j]) {
+            const double *g = s.lptr[j] - back_elems;
+            cp_async8(sm, slot + s.ldE[j], g);
+            cp_async8(sm, slot + s.ldO[j], g + 1);
+        } else if (s.lzero[j]) {
+            sts1(sm, slot + s.ldE[j], 0.0);
+            sts1(sm, slot + s.ldO[j], 0.0);
         }
     }
 }
 
 // rows ybase .. ybase+kPrefetch-1 (those inside the streamed range), one cp.async group each
 template <int T>
-CNV_HD void stream_prologue(const StreamThread<T> &s, double *sm, const double *__restrict__ in,
-                            const double *__restrict__ rhs)
+CNV_HD void stream_prologue(const StreamThread<T> &s, double *sm)
 {
+    const int base = s.lslot - (kPrefetch % StreamThread<T>::R) * s.ss;
     for (int i = 0; i < kPrefetch; i++) {
         const int rl = s.ybase + i;
-        if (rl >= s.ylo && rl <= s.yhi) {
-            long long src[StreamThread<T>::NCH];
-            for (int j = 0; j < StreamThread<T>::NCH; j++) src[j] = s.lsrc[j] - (long long)(kPrefetch - i) * s.ld;
-            stream_load_row<T>(s, sm, in, rhs, i * s.ss, src);
-        }
+        if (rl >= s.ylo && rl <= s.yhi) stream_load_row<T>(s, sm, base + i * s.ss, (long long)(kPrefetch - i) * s.ld);
         cp_async_commit();
     }
 }
@@ -233,48 +262,54 @@ CNV_HD void stream_prologue(const StreamThread<T> &s, double *sm, const double *
 // issue the copy of row r+kPrefetch, then update this thread's red row r-1-dq and black row r-3-dq;
 // threads of the last level write the finished black row back to global memory.
 // PAR = parity of (global red row): 0 -> the red cells of this step are the even-column cells.
-// The body is branch-free on purpose (loads and arithmetic are unconditional, validity is applied by
-// selects / predicated stores) so that the four cell updates of a step can be interleaved.
+// Loads and arithmetic are unconditional so that the four cell updates of a step interleave; validity
+// (Dirichlet ring, halo edges, pipeline fill/drain) is applied by selects only on the slow path -- threads
+// whose four columns are all updatable take the select-free path whenever both rows are updatable.
 template <int T, bool POW2, int PAR>
-CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, const double *__restrict__ in,
-                        const double *__restrict__ rhs, double *__restrict__ out, int r, int nsw)
+CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, double *__restrict__ out, int r, int nsw)
 {
     // ---- load ----
-    if (r + kPrefetch <= s.yhi) stream_load_row<T>(s, sm, in, rhs, s.lslot, s.lsrc);
+    if (r + kPrefetch <= s.yhi) stream_load_row<T>(s, sm, s.lslot, 0);
     cp_async_commit();
 #pragma unroll
-    for (int j = 0; j < StreamThread<T>::NCH; j++) s.lsrc[j] += s.ld;
-    s.lslot = wrap_inc(s.lslot, s.ss, s.ring);
+    for (int j = 0; j < StreamThread<T>::NCH; j++) s.lptr[j] += s.ld;
+    s.lslot = wrap_inc_t<T>(s.lslot, s.ss, s.ringend);
 
     // ---- relax ----
     constexpr bool typeR = PAR != 0;  // red cells are the odd-column cells
     const int aA = typeR ? s.aSO : s.aSE, aB = typeR ? s.aSE : s.aSO;
     const int aPA = typeR ? s.aPO : s.aPE, aPB = typeR ? s.aPE : s.aPO;
     const int qtop = r - s.dq, q = qtop - 1, qb = qtop - 3;
-    const bool active = s.g < nsw;
     // red row q: N from row qtop, own cells, right-hand side, the neighbouring thread's E/W value
-    const dbl2 N = lds2(sm + s.o[0] + aA);
-    const dbl2 own = lds2(sm + s.o[1] + aA);
-    const dbl2 Pr = lds2(sm + s.o[1] + aPA);
-    const double x = sm[s.o[1] + aB + (typeR ? 2 : -1)];
-    const dbl2 Pb = lds2(sm + s.o[3] + aPB);
-    const double xb = sm[s.o[3] + aA + (typeR ? -1 : 2)];
+    const dbl2 N = lds2(sm, s.o[0] + aA);
+    const dbl2 own = lds2(sm, s.o[1] + aA);
+    const dbl2 Pr = lds2(sm, s.o[1] + aPA);
+    const double x = lds1(sm, s.o[1] + aB + (typeR ? 16 : -8));
+    const dbl2 Pb = lds2(sm, s.o[3] + aPB);
+    const double xb = lds1(sm, s.o[3] + aA + (typeR ? -8 : 16));
     const dbl2 b = s.h1, S = s.h2;
+    const dbl2 ownb = s.h3, Nb = s.r1, bb = s.r2, Sb = s.r3;
     // even-column cell of pair k: W = odd[k-1], E = odd[k];  odd-column cell: W = even[k], E = even[k+1]
     double n0 = relax<POW2>(N.x, S.x, typeR ? b.y : b.x, typeR ? b.x : x, own.x, Pr.x, rc);
     double n1 = relax<POW2>(N.y, S.y, typeR ? x : b.y, typeR ? b.y : b.x, own.y, Pr.y, rc);
-    const bool rowr = active && q >= s.vlo && q <= s.vhi;
-    n0 = rowr && (typeR ? s.vO0 : s.vE0) ? n0 : own.x;
-    n1 = rowr && (typeR ? s.vO1 : s.vE1) ? n1 : own.y;
-    if (q >= s.ylo && q <= s.yhi) sts2(sm + s.o[1] + aA, n0, n1);
     // black row qb (cells of the other column parity): everything but Pb / xb comes from registers
-    const dbl2 ownb = s.h3, Nb = s.r1, bb = s.r2, Sb = s.r3;
     double m0 = relax<POW2>(Nb.x, Sb.x, typeR ? bb.x : bb.y, typeR ? xb : bb.x, ownb.x, Pb.x, rc);
     double m1 = relax<POW2>(Nb.y, Sb.y, typeR ? bb.y : xb, typeR ? bb.x : bb.y, ownb.y, Pb.y, rc);
-    const bool rowb = active && qb >= s.vlo && qb <= s.vhi;
-    m0 = rowb && (typeR ? s.vE0 : s.vO0) ? m0 : ownb.x;
-    m1 = rowb && (typeR ? s.vE1 : s.vO1) ? m1 : ownb.y;
-    if (qb >= s.ylo && qb <= s.yhi) sts2(sm + s.o[3] + aB, m0, m1);
+    if (s.allvalid && s.g < nsw && qb >= s.vlo && q <= s.vhi) {
+        // fast path: all four cells updatable (rows q, qb are inside the streamed range by construction)
+        sts2(sm, s.o[1] + aA, n0, n1);
+        sts2(sm, s.o[3] + aB, m0, m1);
+    } else {
+        const bool active = s.g < nsw;
+        const bool rowr = active && q >= s.vlo && q <= s.vhi;
+        const bool rowb = active && qb >= s.vlo && qb <= s.vhi;
+        n0 = (rowr & (typeR ? s.vO0 : s.vE0)) ? n0 : own.x;
+        n1 = (rowr & (typeR ? s.vO1 : s.vE1)) ? n1 : own.y;
+        m0 = (rowb & (typeR ? s.vE0 : s.vO0)) ? m0 : ownb.x;
+        m1 = (rowb & (typeR ? s.vE1 : s.vO1)) ? m1 : ownb.y;
+        if (q >= s.ylo && q <= s.yhi) sts2(sm, s.o[1] + aA, n0, n1);
+        if (qb >= s.ylo && qb <= s.yhi) sts2(sm, s.o[3] + aB, m0, m1);
+    }
     // L1 update norm of this level (non-updated cells contribute exactly 0)
     if (s.colown) {
         if (q >= s.y0 && q < s.y1) {
@@ -302,7 +337,7 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, c
     s.h3 = s.h2; s.h2 = s.h1; s.h1 = N;
     s.r3 = s.r2; s.r2 = s.r1; s.r1 = dbl2{n0, n1};
     s.o[3] = s.o[2]; s.o[2] = s.o[1]; s.o[1] = s.o[0];
-    s.o[0] = wrap_inc(s.o[0], s.ss, s.ring);
+    s.o[0] = wrap_inc_t<T>(s.o[0], s.ss, s.ringend);
 }
 
 // ---- solver state machine (one instance per solve, device resident) ---------------------------

@@ -29,13 +29,13 @@ static void run_pass(const PassGeom &p, const RelaxConsts &rc, const double *in,
             // poison shared memory so that any read of a row that was never loaded shows up
             for (auto &x : sm) x = std::nan("");
             const CtaGeom G = cta_geom(p, bx, by);
-            for (int t = 0; t < NT; t++) stream_init<T>(st[t], p, G, t, NT);
-            for (int t = 0; t < NT; t++) stream_prologue<T>(st[t], sm.data(), in, rhs);
+            for (int t = 0; t < NT; t++) stream_init<T>(st[t], p, G, sm.data(), in, rhs, t, NT);
+            for (int t = 0; t < NT; t++) stream_prologue<T>(st[t], sm.data());
             for (int r = st[0].ybase; r <= st[0].rend; r += 2) {
                 // --- barrier ---
-                for (int t = 0; t < NT; t++) stream_step<T, POW2, 0>(st[t], rc, sm.data(), in, rhs, out, r, nsw);
+                for (int t = 0; t < NT; t++) stream_step<T, POW2, 0>(st[t], rc, sm.data(), out, r, nsw);
                 // --- barrier ---
-                for (int t = 0; t < NT; t++) stream_step<T, POW2, 1>(st[t], rc, sm.data(), in, rhs, out, r + 1, nsw);
+                for (int t = 0; t < NT; t++) stream_step<T, POW2, 1>(st[t], rc, sm.data(), out, r + 1, nsw);
             }
             for (int t = 0; t < NT; t++) norms[st[t].g] += st[t].acc;
         }

@@ -356,3 +356,28 @@ def test_driver_exit_code_on_poisson_itmax(tmp_path):
                        env=dict(os.environ, CNV_NO_VTK="1"))
     assert r.returncode == 1                                                    # reference: exit(1), src/poisson.c:284
     assert "Error: maximum number of iterations achieved for Poisson equation." in (tmp_path / "output" / "logs" / "run.txt").read_text()
+
+
+def test_unmodified_reference_main_drives_gpu_path(tmp_path, golden_logs):
+    """INTEGRATION.md route 1: the reference's UNMODIFIED main.c + utils.c linked against
+    libcnavier_dropin.so (instead of its own poisson.c / fluiddyn.c / finitediff.c / config.c / linearalg.c):
+    the reference driver itself runs the GPU Poisson solve and Euler update.  Same log lines as its shipped
+    testRunOMP.txt, same fields as the reference executable's raw dumps."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(fd._lib.LIB_PATH)), "oracle", "_ref", "cnavier_main_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/cnavier_main_dropin not built (needs /root/reference at build time)")
+    cfg = dict(api.CONFIG_DEFAULT, tf=(11 + 0.5) * 0.005, output_interval=10)      # 11 steps, dumps at t = 0, 10
+    api.write_config(cfg, str(tmp_path / "cfg.txt"))
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    r = subprocess.run([exe, "cfg.txt", "run"], cwd=tmp_path, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, CNAVIER_DUMP_DIR=str(dump), CNAVIER_DUMP_ONLY="1"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    pl = api.parse_poisson_log((tmp_path / "output" / "logs" / "run.txt").read_text())
+    assert [k for k, _ in pl] == golden_logs["testRunOMP"]["k"][:11]
+    assert [e for _, e in pl] == golden_logs["testRunOMP"]["e"][:11]
+    g = load_golden("fields_default_rb.npz")
+    for title, key in (("stream-function", "psi"), ("vorticity", "w"), ("x-velocity", "u"), ("y-velocity", "v")):
+        got = np.fromfile(dump / (title + ".f64")).reshape(-1, 64, 64)
+        assert np.array_equal(got[0], g[key][0]) and np.array_equal(got[1], g[key][1]), key
