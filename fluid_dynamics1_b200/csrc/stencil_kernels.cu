@@ -15,6 +15,7 @@
 // to the reference's dense route.
 #include <cfloat>
 #include <cstdio>
+#include <type_traits>
 
 #include "kernels.h"
 
@@ -80,53 +81,158 @@ __global__ void k_ring_bc_vorticity(double *__restrict__ u, double *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tiled stencil machinery.  A CTA of 256 threads (64 x 4) owns a 64 x 32 tile; the operand field is
+// staged once in shared memory with a halo of 3 (order 6 reach), so HBM sees each value ~1.3 times.
+// Thread (tx, ty) walks 8 rows of column tx.  Interior cells (>= half cells away from every wall, the
+// overwhelming majority) use the unrolled interior row with its coefficients in registers; cells
+// within `half` of a wall take the generic closure rows (fd_apply).  Both accumulate in ascending
+// column order from +0.0 with separately rounded products (fd_coeffs.h), so results do not depend on
+// the path taken.
+constexpr int TW = 64, TH = 32, THALO = 3, TROWS = TH / 4;
+constexpr int TPITCH = TW + 2 * THALO + 1;
+
+struct Tile {
+    double v[TH + 2 * THALO][TPITCH];
+};
+
+// Each of the 8 warps takes tile rows warp, warp+8, ...; a lane takes columns lane, lane+32, lane+64.  All
+// (up to 15) global loads of a thread are issued before the first shared-memory store, so they are in flight
+// together (the loop is fully unrolled; out-of-domain elements read as 0 without touching memory).
+__device__ __forceinline__ void tile_load(Tile &t, const double *__restrict__ A, int i0, int j0, int nrows, int ncols, int ld)
+{
+    constexpr int NR = (TH + 2 * THALO + 7) / 8, NC = (TW + 2 * THALO + 31) / 32;
+    const int lane = threadIdx.x & 31, warp = (threadIdx.y * blockDim.x + threadIdx.x) >> 5;
+    double buf[NR][NC];
+#pragma unroll
+    for (int a = 0; a < NR; a++) {
+        const int li = warp + 8 * a, gi = i0 - THALO + li;
+        const bool rowok = li < TH + 2 * THALO && gi >= 0 && gi < nrows;
+        const double *row = A + (size_t)(rowok ? gi : 0) * ld + (j0 - THALO);
+#pragma unroll
+        for (int b = 0; b < NC; b++) {
+            const int lj = lane + 32 * b, gj = j0 - THALO + lj;
+            buf[a][b] = (rowok && lj < TW + 2 * THALO && gj >= 0 && gj < ncols) ? row[lj] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < NR; a++) {
+        const int li = warp + 8 * a;
+#pragma unroll
+        for (int b = 0; b < NC; b++) {
+            const int lj = lane + 32 * b;
+            if (li < TH + 2 * THALO && lj < TW + 2 * THALO) t.v[li][lj] = buf[a][b];
+        }
+    }
+}
+
+// interior row: sum_k c[k] * x(k - HALF), ascending
+template <int HALF, class Load>
+__device__ __forceinline__ double fd_interior(const double (&c)[7], Load x)
+{
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k <= 2 * HALF; k++) sum = xadd(sum, xmul(c[k], x(k - HALF)));
+    return sum;
+}
+
+// Register windows: win[0..6] = the operand at offsets -3..+3 along the differentiated axis.
+// Interior cells (>= HALF away from both walls) use the unrolled interior row on the window; cells within
+// HALF of a wall take the generic closure rows (fd_apply) reading the tile.
+template <int HALF>
+__device__ __forceinline__ double win_deriv(const double (&c)[7], const double (&win)[7])
+{
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k <= 2 * HALF; k++) sum = xadd(sum, xmul(c[k], win[THALO - HALF + k]));
+    return sum;
+}
+template <int HALF, bool INTERIOR>
+__device__ __forceinline__ double tile_dx(const Tile &t, const FdTable &tab, const double (&c)[7], const double (&win)[7],
+                                          int li, int j, int j0)
+{
+    if (INTERIOR || (j >= HALF && j < tab.n - HALF)) return win_deriv<HALF>(c, win);
+    return fd_apply(tab, j, [&](int col) { return t.v[li][col - j0 + THALO]; });
+}
+template <int HALF, bool INTERIOR>
+__device__ __forceinline__ double tile_dy(const Tile &t, const FdTable &tab, const double (&c)[7], const double (&win)[7],
+                                          int lj, int i, int i0)
+{
+    if (INTERIOR || (i >= HALF && i < tab.n - HALF)) return win_deriv<HALF>(c, win);
+    return fd_apply(tab, i, [&](int row) { return t.v[row - i0 + THALO][lj]; });
+}
+// a tile whose cells are all >= 3 away from every wall needs no closure rows at all (uniform per CTA):
+// the kernels run a branch-free body for those tiles and the general body for the perimeter tiles
+__device__ __forceinline__ bool tile_is_interior(int i0, int j0, int nrows, int ncols)
+{
+    return i0 >= THALO && j0 >= THALO && i0 + TH <= nrows - THALO && j0 + TW <= ncols - THALO;
+}
+// x window of row li around column lj; y window start (rows li-3..li+3) and slide by one row
+__device__ __forceinline__ void win_x(const Tile &t, int li, int lj, double (&w)[7])
+{
+#pragma unroll
+    for (int d = 0; d < 7; d++) w[d] = t.v[li][lj - THALO + d];
+}
+__device__ __forceinline__ void win_y_init(const Tile &t, int li, int lj, double (&w)[7])
+{
+#pragma unroll
+    for (int d = 0; d < 7; d++) w[d] = t.v[li - THALO + d][lj];
+}
+__device__ __forceinline__ void win_y_slide(const Tile &t, int li, int lj, double (&w)[7])
+{
+#pragma unroll
+    for (int d = 0; d < 6; d++) w[d] = w[d + 1];
+    w[6] = t.v[li + THALO][lj];
+}
+__device__ __forceinline__ void load_coefs(const FdTable &t, double (&c)[7])
+{
+#pragma unroll
+    for (int k = 0; k < 7; k++) c[k] = t.interior.c[k];
+}
+
 // w_new = (-u*dwdx - v*dwdy + (1/Re)*(d2wdx2 + d2wdy2))*dt + w on ALL points (ring included),
 // src/fluiddyn.c:87.  Also emits rhs = pscale * (-w_new): the reference flips the sign of w in place
 // around the Poisson call (invsig, src/main.c:348,363) and the solver multiplies f by
 // dx*dx*dy*dy (src/poisson.c:246); the product is rounded once either way.
-//
-// Tile: 32 x 8 outputs per CTA staged in shared memory with a halo of 3 (order 6), so every w value
-// is read from HBM/L2 once per tile instead of 13 times.
-constexpr int ETX = 32, ETY = 8, EH = 3;
-
-__global__ void __launch_bounds__(ETX *ETY)
+template <int HALF>
+__global__ void __launch_bounds__(256)
 k_euler_fused(const double *__restrict__ w, const double *__restrict__ u, const double *__restrict__ v, int nrows, int ncols,
-              int ld, FdTable d1x, FdTable d1y, FdTable d2x, FdTable d2y, double inv_re, double dt, double pscale,
-              double *__restrict__ w_new, double *__restrict__ rhs)
+              int ld, const FdTable d1x, const FdTable d1y, const FdTable d2x, const FdTable d2y, double inv_re, double dt,
+              double pscale, double *__restrict__ w_new, double *__restrict__ rhs)
 {
-    __shared__ double tile[ETY + 2 * EH][ETX + 2 * EH + 1];
-    const int j0 = blockIdx.x * ETX, i0 = blockIdx.y * ETY;
-    for (int t = threadIdx.y * ETX + threadIdx.x; t < (ETY + 2 * EH) * (ETX + 2 * EH); t += ETX * ETY) {
-        const int li = t / (ETX + 2 * EH), lj = t - li * (ETX + 2 * EH);
-        const int gi = i0 - EH + li, gj = j0 - EH + lj;
-        tile[li][lj] = (gi >= 0 && gi < nrows && gj >= 0 && gj < ncols) ? w[(size_t)gi * ld + gj] : 0.0;
-    }
+    __shared__ Tile tw;
+    const int j0 = blockIdx.x * TW, i0 = blockIdx.y * TH;
+    tile_load(tw, w, i0, j0, nrows, ncols, ld);
+    double c1x[7], c1y[7], c2x[7], c2y[7];
+    load_coefs(d1x, c1x); load_coefs(d1y, c1y); load_coefs(d2x, c2x); load_coefs(d2y, c2y);
     __syncthreads();
-    const int j = j0 + threadIdx.x, i = i0 + threadIdx.y;
-    if (i >= nrows || j >= ncols) return;
-    // closure rows near the walls reach up to 4 cells away from the wall: outside the tile halo only
-    // when the cell itself is within 3 cells of the wall, where the tile still covers the operands
-    // if they lie inside [i0-3, i0+ETY+3) -- otherwise read global memory.
-    auto wx = [&](int c) {
-        const int lj = c - (j0 - EH);
-        return (lj >= 0 && lj < ETX + 2 * EH) ? tile[threadIdx.y + EH][lj] : w[(size_t)i * ld + c];
+    const int j = j0 + threadIdx.x, lj = threadIdx.x + THALO;
+    if (j >= ncols) return;
+    auto body = [&](auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
+        double wy[7], wx[7];
+        win_y_init(tw, threadIdx.y * TROWS + THALO, lj, wy);
+#pragma unroll
+        for (int rr = 0; rr < TROWS; rr++) {
+            const int i = i0 + threadIdx.y * TROWS + rr, li = threadIdx.y * TROWS + rr + THALO;
+            if (!INTERIOR && i >= nrows) break;
+            if (rr > 0) win_y_slide(tw, li, lj, wy);
+            win_x(tw, li, lj, wx);
+            const double dwdx = tile_dx<HALF, INTERIOR>(tw, d1x, c1x, wx, li, j, j0);
+            const double dwdy = tile_dy<HALF, INTERIOR>(tw, d1y, c1y, wy, lj, i, i0);
+            const double d2wdx2 = tile_dx<HALF, INTERIOR>(tw, d2x, c2x, wx, li, j, j0);
+            const double d2wdy2 = tile_dy<HALF, INTERIOR>(tw, d2y, c2y, wy, lj, i, i0);
+            const size_t p = (size_t)i * ld + j;
+            const double uu = u[p], vv = v[p], w0 = wx[THALO];
+            // (((-u)*dwdx - v*dwdy) + (1/Re)*(d2wdx2+d2wdy2)) * dt + w
+            const double conv = xsub(xmul(-uu, dwdx), xmul(vv, dwdy));
+            const double diff = xmul(inv_re, xadd(d2wdx2, d2wdy2));
+            const double wn = xadd(xmul(xadd(conv, diff), dt), w0);
+            w_new[p] = wn;
+            if (rhs) rhs[p] = xmul(pscale, -wn);
+        }
     };
-    auto wy = [&](int r) {
-        const int li = r - (i0 - EH);
-        return (li >= 0 && li < ETY + 2 * EH) ? tile[li][threadIdx.x + EH] : w[(size_t)r * ld + j];
-    };
-    const double dwdx = fd_apply(d1x, j, wx);
-    const double dwdy = fd_apply(d1y, i, wy);
-    const double d2wdx2 = fd_apply(d2x, j, wx);
-    const double d2wdy2 = fd_apply(d2y, i, wy);
-    const size_t p = (size_t)i * ld + j;
-    const double uu = u[p], vv = v[p], w0 = tile[threadIdx.y + EH][threadIdx.x + EH];
-    // (((-u)*dwdx - v*dwdy) + (1/Re)*(d2wdx2+d2wdy2)) * dt + w
-    const double conv = xsub(xmul(-uu, dwdx), xmul(vv, dwdy));
-    const double diff = xmul(inv_re, xadd(d2wdx2, d2wdy2));
-    const double wn = xadd(xmul(xadd(conv, diff), dt), w0);
-    w_new[p] = wn;
-    if (rhs) rhs[p] = xmul(pscale, -wn);
+    if (tile_is_interior(i0, j0, nrows, ncols)) body(std::true_type{});
+    else body(std::false_type{});
 }
 
 // pointwise form behind the drop-in euler() signature (derivatives supplied by the caller)
@@ -150,74 +256,111 @@ __global__ void k_pointwise_addsub(const double *__restrict__ a, const double *_
 
 // ---------------------------------------------------------------------------------------------
 // u = DY psi ; v = -(DX psi) on all points, ring included (src/main.c:366-383)
-__global__ void k_velocity(const double *__restrict__ psi, int nrows, int ncols, int ldp, FdTable d1x, FdTable d1y,
-                           double *__restrict__ u, double *__restrict__ v, int ld)
+template <int HALF>
+__global__ void __launch_bounds__(256)
+k_velocity(const double *__restrict__ psi, int nrows, int ncols, int ldp, const FdTable d1x, const FdTable d1y,
+           double *__restrict__ u, double *__restrict__ v, int ld)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= nrows || j >= ncols) return;
-    const double *row = psi + (size_t)i * ldp;
-    const double *col = psi + j;
-    const double dpdx = fd_apply(d1x, j, [&](int c) { return row[c]; });
-    const double dpdy = fd_apply(d1y, i, [&](int r) { return col[(size_t)r * ldp]; });
-    u[(size_t)i * ld + j] = dpdy;
-    v[(size_t)i * ld + j] = -dpdx;
+    __shared__ Tile tp;
+    const int j0 = blockIdx.x * TW, i0 = blockIdx.y * TH;
+    tile_load(tp, psi, i0, j0, nrows, ncols, ldp);
+    double c1x[7], c1y[7];
+    load_coefs(d1x, c1x); load_coefs(d1y, c1y);
+    __syncthreads();
+    const int j = j0 + threadIdx.x, lj = threadIdx.x + THALO;
+    if (j >= ncols) return;
+    auto body = [&](auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
+        double wy[7], wx[7];
+        win_y_init(tp, threadIdx.y * TROWS + THALO, lj, wy);
+#pragma unroll
+        for (int rr = 0; rr < TROWS; rr++) {
+            const int i = i0 + threadIdx.y * TROWS + rr, li = threadIdx.y * TROWS + rr + THALO;
+            if (!INTERIOR && i >= nrows) break;
+            if (rr > 0) win_y_slide(tp, li, lj, wy);
+            win_x(tp, li, lj, wx);
+            const double dpdx = tile_dx<HALF, INTERIOR>(tp, d1x, c1x, wx, li, j, j0);
+            const double dpdy = tile_dy<HALF, INTERIOR>(tp, d1y, c1y, wy, lj, i, i0);
+            u[(size_t)i * ld + j] = dpdy;
+            v[(size_t)i * ld + j] = -dpdx;
+        }
+    };
+    if (tile_is_interior(i0, j0, nrows, ncols)) body(std::true_type{});
+    else body(std::false_type{});
 }
 
 // ---------------------------------------------------------------------------------------------
 // continuity diagnostic: max and min over the grid of DX u + DY v (src/main.c:387-408).
-// Persistent grid (a few CTAs per SM) looping over 32x8 tiles; block partials, then the last block
-// reduces them in parallel.  max/min are order independent, so the result is deterministic.
+// One 64 x 32 tile per CTA (u and v staged with halos); block partials, then the last block reduces them
+// in parallel.  max/min are order independent, so the result is deterministic.
+template <int HALF>
 __global__ void __launch_bounds__(256)
 k_continuity(const double *__restrict__ u, const double *__restrict__ v, int nrows, int ncols, int ld,
-             FdTable d1x, FdTable d1y, double *__restrict__ partial, unsigned *__restrict__ ticket,
+             const FdTable d1x, const FdTable d1y, double *__restrict__ partial, unsigned *__restrict__ ticket,
              double *__restrict__ result)
 {
+    __shared__ Tile tu, tv;
     double mx = -DBL_MAX, mn = DBL_MAX;  // maxel/minel start values, src/linearalg.c:478,514
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int tiles_x = (ncols + 31) / 32, tiles_y = (nrows + 7) / 8;
-    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
-        const int j = (tile % tiles_x) * 32 + tx, i = (tile / tiles_x) * 8 + ty;
-        if (i < nrows && j < ncols) {
-            const double *row = u + (size_t)i * ld;
-            const double *col = v + j;
-            const double dudx = fd_apply(d1x, j, [&](int c) { return row[c]; });
-            const double dvdy = fd_apply(d1y, i, [&](int r) { return col[(size_t)r * ld]; });
+    const int j0 = blockIdx.x * TW, i0 = blockIdx.y * TH;
+    tile_load(tu, u, i0, j0, nrows, ncols, ld);
+    tile_load(tv, v, i0, j0, nrows, ncols, ld);
+    double c1x[7], c1y[7];
+    load_coefs(d1x, c1x); load_coefs(d1y, c1y);
+    __syncthreads();
+    const int j = j0 + threadIdx.x, lj = threadIdx.x + THALO;
+    auto body = [&](auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
+        double wy[7], wx[7];
+        win_y_init(tv, threadIdx.y * TROWS + THALO, lj, wy);
+#pragma unroll
+        for (int rr = 0; rr < TROWS; rr++) {
+            const int i = i0 + threadIdx.y * TROWS + rr, li = threadIdx.y * TROWS + rr + THALO;
+            if (!INTERIOR && i >= nrows) break;
+            if (rr > 0) win_y_slide(tv, li, lj, wy);
+            win_x(tu, li, lj, wx);
+            const double dudx = tile_dx<HALF, INTERIOR>(tu, d1x, c1x, wx, li, j, j0);
+            const double dvdy = tile_dy<HALF, INTERIOR>(tv, d1y, c1y, wy, lj, i, i0);
             const double c = xadd(dudx, dvdy);
             mx = fmax(mx, c);
             mn = fmin(mn, c);
         }
+    };
+    if (j < ncols) {
+        if (tile_is_interior(i0, j0, nrows, ncols)) body(std::true_type{});
+        else body(std::false_type{});
     }
     __shared__ double smx[8], smn[8];
     __shared__ bool last;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, wid = tid >> 5;
     auto block_reduce = [&]() {
         for (int o = 16; o > 0; o >>= 1) {
             mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         }
         __syncthreads();
-        if (tx == 0) { smx[ty] = mx; smn[ty] = mn; }
+        if (lane == 0) { smx[wid] = mx; smn[wid] = mn; }
         __syncthreads();
-        if (threadIdx.x == 0)
+        if (tid == 0)
             for (int k = 1; k < 8; k++) { mx = fmax(mx, smx[k]); mn = fmin(mn, smn[k]); }
     };
     block_reduce();
-    if (threadIdx.x == 0) {
-        partial[2 * blockIdx.x] = mx;
-        partial[2 * blockIdx.x + 1] = mn;
+    const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+        partial[2 * bid] = mx;
+        partial[2 * bid + 1] = mn;
         __threadfence();
-        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        last = atomicAdd(ticket, 1u) == (unsigned)nblocks - 1;
     }
     __syncthreads();
     if (!last) return;
     __threadfence();
     mx = -DBL_MAX; mn = DBL_MAX;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) {
+    for (int k = tid; k < nblocks; k += 256) {
         mx = fmax(mx, __ldcg(&partial[2 * k]));
         mn = fmin(mn, __ldcg(&partial[2 * k + 1]));
     }
     block_reduce();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         result[0] = mx;
         result[1] = mn;
         *ticket = 0;
@@ -253,13 +396,22 @@ void launch_ring_bc_vorticity(double *u, double *v, double *w, int nrows, int nc
     const int n = 2 * ncols + 2 * nrows;
     k_ring_bc_vorticity<<<(n + 127) / 128, 128, 0, s>>>(u, v, w, nrows, ncols, ld, b, d1x, d1y);
 }
+static inline dim3 tile_grid(int nrows, int ncols) { return dim3((ncols + TW - 1) / TW, (nrows + TH - 1) / TH); }
+#define CNV_BY_HALF(half, CALL)             \
+    do {                                    \
+        if ((half) == 1) { CALL(1); }       \
+        else if ((half) == 2) { CALL(2); }  \
+        else { CALL(3); }                   \
+    } while (0)
+
 void launch_euler_fused(const double *w, const double *u, const double *v, int nrows, int ncols, int ld, const FdTable &d1x,
                         const FdTable &d1y, const FdTable &d2x, const FdTable &d2y, double inv_re, double dt, double pscale,
                         double *w_new, double *rhs, cudaStream_t s)
 {
-    dim3 b(ETX, ETY);
-    k_euler_fused<<<grid2d(nrows, ncols, b), b, 0, s>>>(w, u, v, nrows, ncols, ld, d1x, d1y, d2x, d2y, inv_re, dt, pscale,
-                                                        w_new, rhs);
+    const dim3 b(TW, 4), g = tile_grid(nrows, ncols);
+#define CALL(H) k_euler_fused<H><<<g, b, 0, s>>>(w, u, v, nrows, ncols, ld, d1x, d1y, d2x, d2y, inv_re, dt, pscale, w_new, rhs)
+    CNV_BY_HALF(d1x.half, CALL);
+#undef CALL
 }
 void launch_euler_pointwise(double *w, const double *dwdx, const double *dwdy, const double *d2wdx2, const double *d2wdy2,
                             const double *u, const double *v, size_t n, double inv_re, double dt, cudaStream_t s)
@@ -274,18 +426,19 @@ void launch_pointwise_addsub(const double *a, const double *b, double *out, size
 void launch_velocity(const double *psi, int nrows, int ncols, int ldp, const FdTable &d1x, const FdTable &d1y, double *u,
                      double *v, int ld, cudaStream_t s)
 {
-    dim3 b(32, 8);
-    k_velocity<<<grid2d(nrows, ncols, b), b, 0, s>>>(psi, nrows, ncols, ldp, d1x, d1y, u, v, ld);
+    const dim3 b(TW, 4), g = tile_grid(nrows, ncols);
+#define CALL(H) k_velocity<H><<<g, b, 0, s>>>(psi, nrows, ncols, ldp, d1x, d1y, u, v, ld)
+    CNV_BY_HALF(d1x.half, CALL);
+#undef CALL
 }
-int continuity_blocks(int nrows, int ncols)
-{
-    const int tiles = ((ncols + 31) / 32) * ((nrows + 7) / 8);
-    return tiles < 148 * 8 ? tiles : 148 * 8;
-}
+int continuity_blocks(int nrows, int ncols) { return ((ncols + TW - 1) / TW) * ((nrows + TH - 1) / TH); }
 void launch_continuity(const double *u, const double *v, int nrows, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
                        double *partial, unsigned *ticket, double *result, cudaStream_t s)
 {
-    k_continuity<<<continuity_blocks(nrows, ncols), 256, 0, s>>>(u, v, nrows, ncols, ld, d1x, d1y, partial, ticket, result);
+    const dim3 b(TW, 4), g = tile_grid(nrows, ncols);
+#define CALL(H) k_continuity<H><<<g, b, 0, s>>>(u, v, nrows, ncols, ld, d1x, d1y, partial, ticket, result)
+    CNV_BY_HALF(d1x.half, CALL);
+#undef CALL
 }
 void launch_prep_rhs(const double *f, int nrows, int ncols, int ldf, double sign, double pscale, double *rhs, double *psi0,
                      double *psi1, int ld, cudaStream_t s)
