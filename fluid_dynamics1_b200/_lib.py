@@ -75,6 +75,12 @@ CNV_API = {
     "cnv_poisson_state": (None, [_vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "cnv_poisson_download": (C.c_int, [_vp, C.c_int, _dp, _vp]),
     "cnv_sim_create": (_vp, [C.POINTER(Config), C.c_int]),
+    "cnv_sim_create_slab": (_vp, [C.POINTER(Config), C.c_int, C.c_int, C.c_int]),
+    "cnv_sim_layout": (None, [_vp, C.POINTER(C.c_int)]),
+    "cnv_sim_poisson": (_vp, [_vp]),
+    "cnv_sim_field_ptr": (_vp, [_vp, C.c_int]),
+    "cnv_sim_set_psi_buf": (None, [_vp, C.c_int]),
+    "cnv_sim_phase": (None, [_vp, C.c_int, _vp]),
     "cnv_sim_destroy": (None, [_vp]),
     "cnv_sim_step": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
     "cnv_sim_get_fields": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),

@@ -73,7 +73,9 @@ struct cnv_poisson {
 // ---------------------------------------------------------------------------------------------
 struct cnv_sim {
     Config cfg;
-    int nrows, ncols, ld;
+    int nrows, ncols, ld;  // nrows = rows of the LOCAL arrays (== cfg.nx on one GPU)
+    RowMap map;            // slab geometry (single GPU: the whole grid is owned)
+    cnv_poisson ph{nullptr};  // non-owning view of `ps` for the C ABI
     double dx, dy, beta, inv_re;
     FdTable d1x, d1y, d2x, d2y;
     double *u = nullptr, *v = nullptr, *w = nullptr, *w2 = nullptr;
@@ -296,12 +298,12 @@ int cnv_poisson_host(const double *f, int nrows, int ncols, double dx, double dy
 }
 
 // ---- time stepping -----------------------------------------------------------------------------
-cnv_sim *cnv_sim_create(const Config *cfg, int T)
+static cnv_sim *sim_create(const Config *cfg, int T, int rank, int world)
 {
     require_device();
     cnv_sim *s = new cnv_sim;
     s->cfg = *cfg;
-    s->nrows = cfg->nx;  // first index of every field (initm(nx, ny), src/main.c:178)
+    const int gn = cfg->nx;  // global rows: first index of every field (initm(nx, ny), src/main.c:178)
     s->ncols = cfg->ny;
     s->dx = (double)cfg->Lx / cfg->nx;  // src/main.c:138-139 (not L/(n-1))
     s->dy = (double)cfg->Ly / cfg->ny;
@@ -312,35 +314,111 @@ cnv_sim *cnv_sim_create(const Config *cfg, int T)
         std::exit(1);
     }
     const int o = cfg->order;
-    if (s->nrows < o || s->ncols < o || !fd_make_table(s->ncols, o, 1, s->dx, &s->d1x) ||
-        !fd_make_table(s->nrows, o, 1, s->dy, &s->d1y) || !fd_make_table(s->ncols, o, 2, s->dx, &s->d2x) ||
-        !fd_make_table(s->nrows, o, 2, s->dy, &s->d2y)) {
+    if (gn < o || s->ncols < o || !fd_make_table(s->ncols, o, 1, s->dx, &s->d1x) ||
+        !fd_make_table(gn, o, 1, s->dy, &s->d1y) || !fd_make_table(s->ncols, o, 2, s->dx, &s->d2x) ||
+        !fd_make_table(gn, o, 2, s->dy, &s->d2y)) {
         std::printf("** Error: valid orders are 2, 4 or 6 **\n");  // src/finitediff.c:150
         std::exit(1);
     }
-    s->ps = new PoissonSolver(s->nrows, s->ncols, T);
+    // slab of rows [r0, r1) with 2T halo rows on interior edges (>= 3 = the order-6 stencil reach)
+    if (T <= 0) T = std::getenv("CNV_POISSON_T") ? std::atoi(std::getenv("CNV_POISSON_T")) : 8;
+    if (world > 1 && T < 2) {
+        std::printf("** Error: slab decomposition needs a temporal block depth >= 2 (halo >= 3 rows) **\n");
+        std::exit(1);
+    }
+    const int base = gn / world, rem = gn % world;
+    const int r0 = rank * base + (rank < rem ? rank : rem), r1 = r0 + base + (rank < rem ? 1 : 0);
+    const int hlo = rank > 0 ? 2 * T : 0, hhi = rank < world - 1 ? 2 * T : 0;
+    s->map.grow0 = r0 - hlo;
+    s->map.nloc = (r1 - r0) + hlo + hhi;
+    s->map.gnrows = gn;
+    s->map.own_lo = hlo;
+    s->map.own_hi = hlo + (r1 - r0);
+    s->nrows = s->map.nloc;
+    s->ps = new PoissonSolver(s->map.nloc, s->ncols, T, s->map.grow0, gn, s->map.own_lo, s->map.own_hi);
     s->ps->set_consts(s->dx, s->dy, cfg->poisson_type == 2 ? s->beta : 1.0);
+    s->ps->set_distributed(world > 1);
+    s->ph.s = s->ps;
     s->ld = s->ps->ld();
     const size_t bytes = sizeof(double) * (size_t)s->nrows * s->ld;
     for (double **p : {&s->u, &s->v, &s->w, &s->w2}) {
         CNV_CUDA_CHECK(cudaMalloc(p, bytes));
         CNV_CUDA_CHECK(cudaMemset(*p, 0, bytes));
     }
-    // initial condition: interior u = ui, v = vi; w = psi = 0 (src/main.c:178-181, :214-221)
+    // initial condition: interior u = ui, v = vi; w = psi = 0 (src/main.c:178-181, :214-221); halo rows included
     std::vector<double> h((size_t)s->nrows * s->ncols, 0.0);
     for (int pass = 0; pass < 2; pass++) {
         const double val = pass == 0 ? cfg->ui : cfg->vi;
-        for (int i = 1; i < s->nrows - 1; i++)
-            for (int j = 1; j < s->ncols - 1; j++) h[(size_t)i * s->ncols + j] = val;
+        for (int li = 0; li < s->nrows; li++) {
+            const int gi = s->map.grow0 + li;
+            if (gi < 1 || gi > gn - 2) continue;
+            for (int j = 1; j < s->ncols - 1; j++) h[(size_t)li * s->ncols + j] = val;
+        }
         CNV_CUDA_CHECK(cudaMemcpy2D(pass == 0 ? s->u : s->v, sizeof(double) * s->ld, h.data(), sizeof(double) * s->ncols,
                                     sizeof(double) * s->ncols, s->nrows, cudaMemcpyHostToDevice));
     }
-    CNV_CUDA_CHECK(cudaMalloc(&s->cont_partial, sizeof(double) * 2 * continuity_blocks(s->nrows, s->ncols)));
+    CNV_CUDA_CHECK(cudaMalloc(&s->cont_partial, sizeof(double) * 2 * continuity_blocks(s->map.own_hi - s->map.own_lo, s->ncols)));
     CNV_CUDA_CHECK(cudaMalloc(&s->cont_result, sizeof(double) * 2));
     CNV_CUDA_CHECK(cudaMalloc(&s->cont_ticket, sizeof(unsigned)));
     CNV_CUDA_CHECK(cudaMemset(s->cont_ticket, 0, sizeof(unsigned)));
     CNV_CUDA_CHECK(cudaMallocHost(&s->h_cont, sizeof(double) * 2));
     return s;
+}
+
+cnv_sim *cnv_sim_create(const Config *cfg, int T) { return sim_create(cfg, T, 0, 1); }
+cnv_sim *cnv_sim_create_slab(const Config *cfg, int T, int rank, int world) { return sim_create(cfg, T, rank, world); }
+
+// out[0..7] = grow0, nloc, own_lo, own_hi, ld, ncols, T, global rows
+void cnv_sim_layout(const cnv_sim *s, int *out)
+{
+    out[0] = s->map.grow0; out[1] = s->map.nloc; out[2] = s->map.own_lo; out[3] = s->map.own_hi;
+    out[4] = s->ld; out[5] = s->ncols; out[6] = s->ps->T(); out[7] = s->map.gnrows;
+}
+cnv_poisson *cnv_sim_poisson(cnv_sim *s) { return &s->ph; }
+// device pointers of the slab-local fields: 0 u, 1 v, 2 w, 3 continuity result (max, min)
+double *cnv_sim_field_ptr(cnv_sim *s, int which)
+{
+    switch (which) {
+    case 0: return s->u;
+    case 1: return s->v;
+    case 2: return s->w;
+    case 3: return s->cont_result;
+    default: return nullptr;
+    }
+}
+void cnv_sim_set_psi_buf(cnv_sim *s, int which) { s->psi_buf = which & 1; }
+
+// One phase of a time step, asynchronously on `stream` (multi-GPU orchestration interleaves halo exchanges):
+//   0  BCs + wall vorticity on owned ring cells        (needs u, v halos)
+//   1  derivatives + Euler + Poisson right-hand side    (needs w halos); w <- w_new
+//   2  velocities from psi (buffer set by cnv_sim_set_psi_buf; needs psi halos)
+//   3  continuity max/min over the owned rows            (needs u, v halos) -> field_ptr(3)
+void cnv_sim_phase(cnv_sim *s, int phase, void *stream)
+{
+    const Config &c = s->cfg;
+    const double bc[8] = {c.u1, c.u2, c.u3, c.u4, c.v1, c.v2, c.v3, c.v4};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (phase) {
+    case 0:
+        launch_ring_bc_vorticity(s->u, s->v, s->w, s->map, s->ncols, s->ld, bc, s->d1x, s->d1y, st);
+        break;
+    case 1:
+        launch_euler_fused(s->w, s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->d2x, s->d2y, s->inv_re, c.dt,
+                           s->ps->consts().pscale, s->w2, s->ps->rhs(), st);
+        std::swap(s->w, s->w2);
+        break;
+    case 2:
+        launch_velocity(s->ps->buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
+        break;
+    case 3:
+        launch_continuity(s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
+                          s->cont_result, st);
+        break;
+    default:
+        return;
+    }
+    count_launch(1);
+    CNV_CUDA_CHECK(cudaGetLastError());
 }
 
 void cnv_sim_destroy(cnv_sim *s)
@@ -363,9 +441,9 @@ int cnv_sim_step(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, do
     const size_t bytes = sizeof(double) * (size_t)s->nrows * s->ld;
     for (int t = 0; t < nsteps; t++) {
         // BCs + wall vorticity (src/main.c:283-320)
-        launch_ring_bc_vorticity(s->u, s->v, s->w, s->nrows, s->ncols, s->ld, bc, s->d1x, s->d1y, st);
+        launch_ring_bc_vorticity(s->u, s->v, s->w, s->map, s->ncols, s->ld, bc, s->d1x, s->d1y, st);
         // vorticity derivatives + Euler on all points + Poisson right-hand side (:323-348)
-        launch_euler_fused(s->w, s->u, s->v, s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->d2x, s->d2y, s->inv_re, c.dt,
+        launch_euler_fused(s->w, s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->d2x, s->d2y, s->inv_re, c.dt,
                            s->ps->consts().pscale, s->w2, s->ps->rhs(), st);
         std::swap(s->w, s->w2);
         count_launch(2);
@@ -378,10 +456,10 @@ int cnv_sim_step(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, do
         if (e) e[t] = r.e;
         if (r.status != 0) return t + 1;  // reference: log the error and exit(1), src/poisson.c:280-284
         // velocities from the streamfunction on all points (:366-383)
-        launch_velocity(s->ps->buffer(s->psi_buf), s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
+        launch_velocity(s->ps->buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
         count_launch(1);
         if (s->diag && (cont_max || cont_min)) {
-            launch_continuity(s->u, s->v, s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
+            launch_continuity(s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
                               s->cont_result, st);
             count_launch(1);
             CNV_CUDA_CHECK(cudaMemcpyAsync(s->h_cont, s->cont_result, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
@@ -403,12 +481,12 @@ void cnv_sim_stencil_phase(cnv_sim *s, int reps, void *stream)
     const double bc[8] = {c.u1, c.u2, c.u3, c.u4, c.v1, c.v2, c.v3, c.v4};
     cudaStream_t st = (cudaStream_t)stream;
     for (int t = 0; t < reps; t++) {
-        launch_ring_bc_vorticity(s->u, s->v, s->w, s->nrows, s->ncols, s->ld, bc, s->d1x, s->d1y, st);
-        launch_euler_fused(s->w, s->u, s->v, s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->d2x, s->d2y, s->inv_re, c.dt,
+        launch_ring_bc_vorticity(s->u, s->v, s->w, s->map, s->ncols, s->ld, bc, s->d1x, s->d1y, st);
+        launch_euler_fused(s->w, s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->d2x, s->d2y, s->inv_re, c.dt,
                            s->ps->consts().pscale, s->w2, s->ps->rhs(), st);
         std::swap(s->w, s->w2);
-        launch_velocity(s->ps->buffer(s->psi_buf), s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
-        launch_continuity(s->u, s->v, s->nrows, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
+        launch_velocity(s->ps->buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
+        launch_continuity(s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
                           s->cont_result, st);
         count_launch(4);
     }

@@ -24,21 +24,27 @@
 
 namespace cnv {
 
+// A slab of a row-decomposed grid: the local array has nloc rows, local row 0 is global row grow0 of
+// gnrows; rows [own_lo, own_hi) (local) are owned, the others are halo rows.  Single GPU: {n, 0, n, 0, n}.
+struct RowMap {
+    int nloc, grow0, gnrows, own_lo, own_hi;
+};
+
 // ---- stencil_kernels.cu ----
 void launch_apply(const double *A, int nrows, int ncols, int lda, int axis, const FdTable &t, double *out, int ldo,
                   double scale, cudaStream_t s);
-void launch_ring_bc_vorticity(double *u, double *v, double *w, int nrows, int ncols, int ld, const double bc[8],
+void launch_ring_bc_vorticity(double *u, double *v, double *w, const RowMap &m, int ncols, int ld, const double bc[8],
                               const FdTable &d1x, const FdTable &d1y, cudaStream_t s);
-void launch_euler_fused(const double *w, const double *u, const double *v, int nrows, int ncols, int ld, const FdTable &d1x,
+void launch_euler_fused(const double *w, const double *u, const double *v, const RowMap &m, int ncols, int ld, const FdTable &d1x,
                         const FdTable &d1y, const FdTable &d2x, const FdTable &d2y, double inv_re, double dt, double pscale,
                         double *w_new, double *rhs, cudaStream_t s);
 void launch_euler_pointwise(double *w, const double *dwdx, const double *dwdy, const double *d2wdx2, const double *d2wdy2,
                             const double *u, const double *v, size_t n, double inv_re, double dt, cudaStream_t s);
 void launch_pointwise_addsub(const double *a, const double *b, double *out, size_t n, int sub, cudaStream_t s);
-void launch_velocity(const double *psi, int nrows, int ncols, int ldp, const FdTable &d1x, const FdTable &d1y, double *u,
+void launch_velocity(const double *psi, const RowMap &m, int ncols, int ldp, const FdTable &d1x, const FdTable &d1y, double *u,
                      double *v, int ld, cudaStream_t s);
 int continuity_blocks(int nrows, int ncols);
-void launch_continuity(const double *u, const double *v, int nrows, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
+void launch_continuity(const double *u, const double *v, const RowMap &m, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
                        double *partial, unsigned *ticket, double *result, cudaStream_t s);
 void launch_prep_rhs(const double *f, int nrows, int ncols, int ldf, double sign, double pscale, double *rhs, double *psi0,
                      double *psi1, int ld, cudaStream_t s);

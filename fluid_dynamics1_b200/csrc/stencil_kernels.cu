@@ -43,41 +43,45 @@ __global__ void k_apply(const double *__restrict__ A, int nrows, int ncols, int 
 struct BcValues { double u1, u2, u3, u4, v1, v2, v3, v4; };
 
 // value of u / v after the reference's BC loops (rows first, then columns => corners take the
-// column values u1/u2, v1/v2; src/main.c:283-296)
-__device__ __forceinline__ double bc_u(const double *u, int ld, int nrows, int ncols, const BcValues &b, int i, int j)
+// column values u1/u2, v1/v2; src/main.c:283-296).  gi = GLOBAL row; the arrays are slab-local.
+__device__ __forceinline__ double bc_u(const double *u, int ld, const RowMap &m, int ncols, const BcValues &b, int gi, int j)
 {
     if (j == 0) return b.u1;
     if (j == ncols - 1) return b.u2;
-    if (i == 0) return b.u3;
-    if (i == nrows - 1) return b.u4;
-    return u[(size_t)i * ld + j];
+    if (gi == 0) return b.u3;
+    if (gi == m.gnrows - 1) return b.u4;
+    return u[(size_t)(gi - m.grow0) * ld + j];
 }
-__device__ __forceinline__ double bc_v(const double *v, int ld, int nrows, int ncols, const BcValues &b, int i, int j)
+__device__ __forceinline__ double bc_v(const double *v, int ld, const RowMap &m, int ncols, const BcValues &b, int gi, int j)
 {
     if (j == 0) return b.v1;
     if (j == ncols - 1) return b.v2;
-    if (i == 0) return b.v3;
-    if (i == nrows - 1) return b.v4;
-    return v[(size_t)i * ld + j];
+    if (gi == 0) return b.v3;
+    if (gi == m.gnrows - 1) return b.v4;
+    return v[(size_t)(gi - m.grow0) * ld + j];
 }
 
-// one thread per ring cell: [0,ncols) bottom row, [ncols,2ncols) top row, then the two columns
-__global__ void k_ring_bc_vorticity(double *__restrict__ u, double *__restrict__ v, double *__restrict__ w, int nrows,
+// one thread per ring cell of the GLOBAL grid: [0,ncols) bottom row, [ncols,2ncols) top row, then the two
+// columns; a slab handles the cells whose row it owns
+__global__ void k_ring_bc_vorticity(double *__restrict__ u, double *__restrict__ v, double *__restrict__ w, RowMap m,
                                     int ncols, int ld, BcValues b, FdTable d1x, FdTable d1y)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nrows = m.gnrows;
     int i, j;
     if (idx < ncols) { i = 0; j = idx; }
     else if (idx < 2 * ncols) { i = nrows - 1; j = idx - ncols; }
     else if (idx < 2 * ncols + nrows) { i = idx - 2 * ncols; j = 0; }
     else if (idx < 2 * ncols + 2 * nrows) { i = idx - 2 * ncols - nrows; j = ncols - 1; }
     else return;
-    const double dvdx = fd_apply(d1x, j, [&](int c) { return bc_v(v, ld, nrows, ncols, b, i, c); });
-    const double dudy = fd_apply(d1y, i, [&](int r) { return bc_u(u, ld, nrows, ncols, b, r, j); });
-    const size_t p = (size_t)i * ld + j;
+    const int li = i - m.grow0;
+    if (li < m.own_lo || li >= m.own_hi) return;
+    const double dvdx = fd_apply(d1x, j, [&](int c) { return bc_v(v, ld, m, ncols, b, i, c); });
+    const double dudy = fd_apply(d1y, i, [&](int r) { return bc_u(u, ld, m, ncols, b, r, j); });
+    const size_t p = (size_t)li * ld + j;
     w[p] = xsub(dvdx, dudy);
-    u[p] = bc_u(u, ld, nrows, ncols, b, i, j);
-    v[p] = bc_v(v, ld, nrows, ncols, b, i, j);
+    u[p] = bc_u(u, ld, m, ncols, b, i, j);
+    v[p] = bc_v(v, ld, m, ncols, b, i, j);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -153,18 +157,20 @@ __device__ __forceinline__ double tile_dx(const Tile &t, const FdTable &tab, con
     if (INTERIOR || (j >= HALF && j < tab.n - HALF)) return win_deriv<HALF>(c, win);
     return fd_apply(tab, j, [&](int col) { return t.v[li][col - j0 + THALO]; });
 }
+// i = GLOBAL row of the cell, gi0 = global row of the tile's first row
 template <int HALF, bool INTERIOR>
 __device__ __forceinline__ double tile_dy(const Tile &t, const FdTable &tab, const double (&c)[7], const double (&win)[7],
-                                          int lj, int i, int i0)
+                                          int lj, int i, int gi0)
 {
     if (INTERIOR || (i >= HALF && i < tab.n - HALF)) return win_deriv<HALF>(c, win);
-    return fd_apply(tab, i, [&](int row) { return t.v[row - i0 + THALO][lj]; });
+    return fd_apply(tab, i, [&](int row) { return t.v[row - gi0 + THALO][lj]; });
 }
 // a tile whose cells are all >= 3 away from every wall needs no closure rows at all (uniform per CTA):
 // the kernels run a branch-free body for those tiles and the general body for the perimeter tiles
-__device__ __forceinline__ bool tile_is_interior(int i0, int j0, int nrows, int ncols)
+__device__ __forceinline__ bool tile_is_interior(int i0, int j0, const RowMap &m, int ncols)
 {
-    return i0 >= THALO && j0 >= THALO && i0 + TH <= nrows - THALO && j0 + TW <= ncols - THALO;
+    const int gi0 = m.grow0 + i0;
+    return gi0 >= THALO && j0 >= THALO && gi0 + TH <= m.gnrows - THALO && i0 + TH <= m.own_hi && j0 + TW <= ncols - THALO;
 }
 // x window of row li around column lj; y window start (rows li-3..li+3) and slide by one row
 __device__ __forceinline__ void win_x(const Tile &t, int li, int lj, double (&w)[7])
@@ -195,13 +201,13 @@ __device__ __forceinline__ void load_coefs(const FdTable &t, double (&c)[7])
 // dx*dx*dy*dy (src/poisson.c:246); the product is rounded once either way.
 template <int HALF>
 __global__ void __launch_bounds__(256)
-k_euler_fused(const double *__restrict__ w, const double *__restrict__ u, const double *__restrict__ v, int nrows, int ncols,
+k_euler_fused(const double *__restrict__ w, const double *__restrict__ u, const double *__restrict__ v, RowMap m, int ncols,
               int ld, const FdTable d1x, const FdTable d1y, const FdTable d2x, const FdTable d2y, double inv_re, double dt,
               double pscale, double *__restrict__ w_new, double *__restrict__ rhs)
 {
     __shared__ Tile tw;
-    const int j0 = blockIdx.x * TW, i0 = blockIdx.y * TH;
-    tile_load(tw, w, i0, j0, nrows, ncols, ld);
+    const int j0 = blockIdx.x * TW, i0 = m.own_lo + blockIdx.y * TH, gi0 = m.grow0 + i0;
+    tile_load(tw, w, i0, j0, m.nloc, ncols, ld);
     double c1x[7], c1y[7], c2x[7], c2y[7];
     load_coefs(d1x, c1x); load_coefs(d1y, c1y); load_coefs(d2x, c2x); load_coefs(d2y, c2y);
     __syncthreads();
@@ -214,13 +220,13 @@ k_euler_fused(const double *__restrict__ w, const double *__restrict__ u, const 
 #pragma unroll
         for (int rr = 0; rr < TROWS; rr++) {
             const int i = i0 + threadIdx.y * TROWS + rr, li = threadIdx.y * TROWS + rr + THALO;
-            if (!INTERIOR && i >= nrows) break;
+            if (!INTERIOR && i >= m.own_hi) break;
             if (rr > 0) win_y_slide(tw, li, lj, wy);
             win_x(tw, li, lj, wx);
             const double dwdx = tile_dx<HALF, INTERIOR>(tw, d1x, c1x, wx, li, j, j0);
-            const double dwdy = tile_dy<HALF, INTERIOR>(tw, d1y, c1y, wy, lj, i, i0);
+            const double dwdy = tile_dy<HALF, INTERIOR>(tw, d1y, c1y, wy, lj, m.grow0 + i, gi0);
             const double d2wdx2 = tile_dx<HALF, INTERIOR>(tw, d2x, c2x, wx, li, j, j0);
-            const double d2wdy2 = tile_dy<HALF, INTERIOR>(tw, d2y, c2y, wy, lj, i, i0);
+            const double d2wdy2 = tile_dy<HALF, INTERIOR>(tw, d2y, c2y, wy, lj, m.grow0 + i, gi0);
             const size_t p = (size_t)i * ld + j;
             const double uu = u[p], vv = v[p], w0 = wx[THALO];
             // (((-u)*dwdx - v*dwdy) + (1/Re)*(d2wdx2+d2wdy2)) * dt + w
@@ -231,7 +237,7 @@ k_euler_fused(const double *__restrict__ w, const double *__restrict__ u, const 
             if (rhs) rhs[p] = xmul(pscale, -wn);
         }
     };
-    if (tile_is_interior(i0, j0, nrows, ncols)) body(std::true_type{});
+    if (tile_is_interior(i0, j0, m, ncols)) body(std::true_type{});
     else body(std::false_type{});
 }
 
@@ -258,12 +264,12 @@ __global__ void k_pointwise_addsub(const double *__restrict__ a, const double *_
 // u = DY psi ; v = -(DX psi) on all points, ring included (src/main.c:366-383)
 template <int HALF>
 __global__ void __launch_bounds__(256)
-k_velocity(const double *__restrict__ psi, int nrows, int ncols, int ldp, const FdTable d1x, const FdTable d1y,
+k_velocity(const double *__restrict__ psi, RowMap m, int ncols, int ldp, const FdTable d1x, const FdTable d1y,
            double *__restrict__ u, double *__restrict__ v, int ld)
 {
     __shared__ Tile tp;
-    const int j0 = blockIdx.x * TW, i0 = blockIdx.y * TH;
-    tile_load(tp, psi, i0, j0, nrows, ncols, ldp);
+    const int j0 = blockIdx.x * TW, i0 = m.own_lo + blockIdx.y * TH, gi0 = m.grow0 + i0;
+    tile_load(tp, psi, i0, j0, m.nloc, ncols, ldp);
     double c1x[7], c1y[7];
     load_coefs(d1x, c1x); load_coefs(d1y, c1y);
     __syncthreads();
@@ -276,16 +282,16 @@ k_velocity(const double *__restrict__ psi, int nrows, int ncols, int ldp, const 
 #pragma unroll
         for (int rr = 0; rr < TROWS; rr++) {
             const int i = i0 + threadIdx.y * TROWS + rr, li = threadIdx.y * TROWS + rr + THALO;
-            if (!INTERIOR && i >= nrows) break;
+            if (!INTERIOR && i >= m.own_hi) break;
             if (rr > 0) win_y_slide(tp, li, lj, wy);
             win_x(tp, li, lj, wx);
             const double dpdx = tile_dx<HALF, INTERIOR>(tp, d1x, c1x, wx, li, j, j0);
-            const double dpdy = tile_dy<HALF, INTERIOR>(tp, d1y, c1y, wy, lj, i, i0);
+            const double dpdy = tile_dy<HALF, INTERIOR>(tp, d1y, c1y, wy, lj, m.grow0 + i, gi0);
             u[(size_t)i * ld + j] = dpdy;
             v[(size_t)i * ld + j] = -dpdx;
         }
     };
-    if (tile_is_interior(i0, j0, nrows, ncols)) body(std::true_type{});
+    if (tile_is_interior(i0, j0, m, ncols)) body(std::true_type{});
     else body(std::false_type{});
 }
 
@@ -295,15 +301,15 @@ k_velocity(const double *__restrict__ psi, int nrows, int ncols, int ldp, const 
 // in parallel.  max/min are order independent, so the result is deterministic.
 template <int HALF>
 __global__ void __launch_bounds__(256)
-k_continuity(const double *__restrict__ u, const double *__restrict__ v, int nrows, int ncols, int ld,
+k_continuity(const double *__restrict__ u, const double *__restrict__ v, RowMap m, int ncols, int ld,
              const FdTable d1x, const FdTable d1y, double *__restrict__ partial, unsigned *__restrict__ ticket,
              double *__restrict__ result)
 {
     __shared__ Tile tu, tv;
     double mx = -DBL_MAX, mn = DBL_MAX;  // maxel/minel start values, src/linearalg.c:478,514
-    const int j0 = blockIdx.x * TW, i0 = blockIdx.y * TH;
-    tile_load(tu, u, i0, j0, nrows, ncols, ld);
-    tile_load(tv, v, i0, j0, nrows, ncols, ld);
+    const int j0 = blockIdx.x * TW, i0 = m.own_lo + blockIdx.y * TH, gi0 = m.grow0 + i0;
+    tile_load(tu, u, i0, j0, m.nloc, ncols, ld);
+    tile_load(tv, v, i0, j0, m.nloc, ncols, ld);
     double c1x[7], c1y[7];
     load_coefs(d1x, c1x); load_coefs(d1y, c1y);
     __syncthreads();
@@ -315,18 +321,18 @@ k_continuity(const double *__restrict__ u, const double *__restrict__ v, int nro
 #pragma unroll
         for (int rr = 0; rr < TROWS; rr++) {
             const int i = i0 + threadIdx.y * TROWS + rr, li = threadIdx.y * TROWS + rr + THALO;
-            if (!INTERIOR && i >= nrows) break;
+            if (!INTERIOR && i >= m.own_hi) break;
             if (rr > 0) win_y_slide(tv, li, lj, wy);
             win_x(tu, li, lj, wx);
             const double dudx = tile_dx<HALF, INTERIOR>(tu, d1x, c1x, wx, li, j, j0);
-            const double dvdy = tile_dy<HALF, INTERIOR>(tv, d1y, c1y, wy, lj, i, i0);
+            const double dvdy = tile_dy<HALF, INTERIOR>(tv, d1y, c1y, wy, lj, m.grow0 + i, gi0);
             const double c = xadd(dudx, dvdy);
             mx = fmax(mx, c);
             mn = fmin(mn, c);
         }
     };
     if (j < ncols) {
-        if (tile_is_interior(i0, j0, nrows, ncols)) body(std::true_type{});
+        if (tile_is_interior(i0, j0, m, ncols)) body(std::true_type{});
         else body(std::false_type{});
     }
     __shared__ double smx[8], smn[8];
@@ -389,14 +395,14 @@ void launch_apply(const double *A, int nrows, int ncols, int lda, int axis, cons
     dim3 b(32, 8);
     k_apply<<<grid2d(nrows, ncols, b), b, 0, s>>>(A, nrows, ncols, lda, axis, t, out, ldo, scale);
 }
-void launch_ring_bc_vorticity(double *u, double *v, double *w, int nrows, int ncols, int ld, const double bc[8],
+void launch_ring_bc_vorticity(double *u, double *v, double *w, const RowMap &m, int ncols, int ld, const double bc[8],
                               const FdTable &d1x, const FdTable &d1y, cudaStream_t s)
 {
     BcValues b{bc[0], bc[1], bc[2], bc[3], bc[4], bc[5], bc[6], bc[7]};
-    const int n = 2 * ncols + 2 * nrows;
-    k_ring_bc_vorticity<<<(n + 127) / 128, 128, 0, s>>>(u, v, w, nrows, ncols, ld, b, d1x, d1y);
+    const int n = 2 * ncols + 2 * m.gnrows;
+    k_ring_bc_vorticity<<<(n + 127) / 128, 128, 0, s>>>(u, v, w, m, ncols, ld, b, d1x, d1y);
 }
-static inline dim3 tile_grid(int nrows, int ncols) { return dim3((ncols + TW - 1) / TW, (nrows + TH - 1) / TH); }
+static inline dim3 tile_grid(const RowMap &m, int ncols) { return dim3((ncols + TW - 1) / TW, (m.own_hi - m.own_lo + TH - 1) / TH); }
 #define CNV_BY_HALF(half, CALL)             \
     do {                                    \
         if ((half) == 1) { CALL(1); }       \
@@ -404,12 +410,12 @@ static inline dim3 tile_grid(int nrows, int ncols) { return dim3((ncols + TW - 1
         else { CALL(3); }                   \
     } while (0)
 
-void launch_euler_fused(const double *w, const double *u, const double *v, int nrows, int ncols, int ld, const FdTable &d1x,
+void launch_euler_fused(const double *w, const double *u, const double *v, const RowMap &m, int ncols, int ld, const FdTable &d1x,
                         const FdTable &d1y, const FdTable &d2x, const FdTable &d2y, double inv_re, double dt, double pscale,
                         double *w_new, double *rhs, cudaStream_t s)
 {
-    const dim3 b(TW, 4), g = tile_grid(nrows, ncols);
-#define CALL(H) k_euler_fused<H><<<g, b, 0, s>>>(w, u, v, nrows, ncols, ld, d1x, d1y, d2x, d2y, inv_re, dt, pscale, w_new, rhs)
+    const dim3 b(TW, 4), g = tile_grid(m, ncols);
+#define CALL(H) k_euler_fused<H><<<g, b, 0, s>>>(w, u, v, m, ncols, ld, d1x, d1y, d2x, d2y, inv_re, dt, pscale, w_new, rhs)
     CNV_BY_HALF(d1x.half, CALL);
 #undef CALL
 }
@@ -423,20 +429,20 @@ void launch_pointwise_addsub(const double *a, const double *b, double *out, size
 {
     k_pointwise_addsub<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, s>>>(a, b, out, n, sub);
 }
-void launch_velocity(const double *psi, int nrows, int ncols, int ldp, const FdTable &d1x, const FdTable &d1y, double *u,
+void launch_velocity(const double *psi, const RowMap &m, int ncols, int ldp, const FdTable &d1x, const FdTable &d1y, double *u,
                      double *v, int ld, cudaStream_t s)
 {
-    const dim3 b(TW, 4), g = tile_grid(nrows, ncols);
-#define CALL(H) k_velocity<H><<<g, b, 0, s>>>(psi, nrows, ncols, ldp, d1x, d1y, u, v, ld)
+    const dim3 b(TW, 4), g = tile_grid(m, ncols);
+#define CALL(H) k_velocity<H><<<g, b, 0, s>>>(psi, m, ncols, ldp, d1x, d1y, u, v, ld)
     CNV_BY_HALF(d1x.half, CALL);
 #undef CALL
 }
 int continuity_blocks(int nrows, int ncols) { return ((ncols + TW - 1) / TW) * ((nrows + TH - 1) / TH); }
-void launch_continuity(const double *u, const double *v, int nrows, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
+void launch_continuity(const double *u, const double *v, const RowMap &m, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
                        double *partial, unsigned *ticket, double *result, cudaStream_t s)
 {
-    const dim3 b(TW, 4), g = tile_grid(nrows, ncols);
-#define CALL(H) k_continuity<H><<<g, b, 0, s>>>(u, v, nrows, ncols, ld, d1x, d1y, partial, ticket, result)
+    const dim3 b(TW, 4), g = tile_grid(m, ncols);
+#define CALL(H) k_continuity<H><<<g, b, 0, s>>>(u, v, m, ncols, ld, d1x, d1y, partial, ticket, result)
     CNV_BY_HALF(d1x.half, CALL);
 #undef CALL
 }

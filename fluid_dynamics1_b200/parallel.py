@@ -48,7 +48,7 @@ class _DevView:
 
 
 class SlabPoisson:
-    def __init__(self, total_rows: int, ncols: int, T: int, rank: int, world: int, stream=None):
+    def __init__(self, total_rows: int, ncols: int, T: int, rank: int, world: int, stream=None, handle=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -62,7 +62,7 @@ class SlabPoisson:
         self.grow0, self.nrows, self.own_lo, self.own_hi, self.hlo, self.hhi = slab_layout(total_rows, world, rank, T)
         self.row0 = self.grow0 + self.own_lo
         self.own_rows = self.own_hi - self.own_lo
-        self.solver = PoissonSolver(self.nrows, ncols, T, slab=(self.grow0, total_rows, self.own_lo, self.own_hi))
+        self.solver = PoissonSolver(self.nrows, ncols, T, slab=(self.grow0, total_rows, self.own_lo, self.own_hi), handle=handle)
         self.T = self.solver.T
         self.H = 2 * self.T
         self.L = self.solver.L
@@ -81,16 +81,17 @@ class SlabPoisson:
     def set_consts(self, dx, dy, beta):
         self.solver.set_consts(dx, dy, beta)
 
-    def exchange_halos(self, t):
-        """2T boundary rows of tensor `t` (local array, pitch ld) to/from both slab neighbours."""
+    def exchange_halos(self, t, depth=None):
+        """`depth` (default 2T) boundary rows of tensor `t` (local array, pitch ld) to/from both slab neighbours."""
         dist, H = self.dist, self.H
+        d = H if depth is None else depth
         ops = []
         if self.rank > 0:  # lower neighbour: my first owned rows -> its high halo; its last owned rows -> my low halo
-            ops.append(dist.P2POp(dist.isend, t[self.own_lo:self.own_lo + H], self.rank - 1))
-            ops.append(dist.P2POp(dist.irecv, t[0:H], self.rank - 1))
+            ops.append(dist.P2POp(dist.isend, t[self.own_lo:self.own_lo + d], self.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, t[self.own_lo - d:self.own_lo], self.rank - 1))
         if self.rank < self.world - 1:
-            ops.append(dist.P2POp(dist.isend, t[self.own_hi - H:self.own_hi], self.rank + 1))
-            ops.append(dist.P2POp(dist.irecv, t[self.own_hi:self.own_hi + H], self.rank + 1))
+            ops.append(dist.P2POp(dist.isend, t[self.own_hi - d:self.own_hi], self.rank + 1))
+            ops.append(dist.P2POp(dist.irecv, t[self.own_hi:self.own_hi + d], self.rank + 1))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
@@ -164,3 +165,93 @@ class SlabPoisson:
             return torch.cat(parts).cpu().numpy()
         dist.send(mine, 0)
         return None
+
+
+class SlabSimulation:
+    """Slab-decomposed time stepping (the loop body of src/main.c:283-395) over the GPUs of one node.
+
+    Each rank owns a contiguous block of rows of every field (u, v, w, psi, rhs) plus 2T halo rows per interior
+    edge; closures and boundary conditions use GLOBAL row indices, so the fields are bit-identical to the
+    single-GPU run.  Per step: phase 0 (BCs + wall vorticity) -> exchange w (3 rows) -> phase 1 (derivatives +
+    Euler + rhs) -> exchange rhs (2T rows) -> distributed Poisson solve -> exchange psi (3 rows) -> phase 2
+    (velocities) -> exchange u, v (3 rows) -> phase 3 (continuity) -> all-reduce(max) / all-reduce(min)."""
+
+    STENCIL_HALO = 3  # reach of the order-6 stencils
+
+    def __init__(self, cfg, rank: int, world: int, T: int = 0, stream=None):
+        import torch
+        import torch.distributed as dist
+        from .config import config_from_dict
+        self.torch, self.dist = torch, dist
+        _lib.require_gpu()
+        self.L = _lib.lib()
+        if isinstance(cfg, dict):
+            cfg = config_from_dict(cfg)
+        self.cfg, self.rank, self.world, self.stream = cfg, rank, world, stream
+        self.h = self.L.cnv_sim_create_slab(C.byref(cfg), T, rank, world)
+        lay = (C.c_int * 8)()
+        self.L.cnv_sim_layout(self.h, lay)
+        self.grow0, self.nloc, self.own_lo, self.own_hi, self.ld, self.ncols, self.T, self.gnrows = list(lay)
+        self.poisson = SlabPoisson(self.gnrows, self.ncols, self.T, rank, world, stream=stream,
+                                   handle=self.L.cnv_sim_poisson(self.h))
+        assert (self.poisson.grow0, self.poisson.nrows, self.poisson.own_lo, self.poisson.own_hi) == \
+               (self.grow0, self.nloc, self.own_lo, self.own_hi)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        self.cont = torch.as_tensor(_DevView(self.L.cnv_sim_field_ptr(self.h, 3), (2,)), device=dev)
+        self.psi_buf = 0
+
+    def close(self):
+        if self.h:
+            self.poisson.solver.close()
+            self.L.cnv_sim_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _field(self, which):
+        # w's buffer swaps every step, so views are taken fresh
+        return self.torch.as_tensor(_DevView(self.L.cnv_sim_field_ptr(self.h, which), (self.nloc, self.ld)), device=self.dev)
+
+    def step(self, nsteps=1, diagnostics=True):
+        L, P, H3 = self.L, self.poisson, self.STENCIL_HALO
+        ks, es, cmax, cmin = [], [], [], []
+        for _ in range(nsteps):
+            L.cnv_sim_phase(self.h, 0, self.stream)
+            P.exchange_halos(self._field(2), H3)
+            L.cnv_sim_phase(self.h, 1, self.stream)
+            P.exchange_halos(P.rhs)                       # 2T rows: the solver recomputes its halo
+            r = P.solve(self.cfg.poisson_max_it, self.cfg.poisson_tol)
+            ks.append(r["k"]); es.append(r["e"])
+            if r["status"] != 0:
+                return dict(failed_step=len(ks), k=ks, e=es, cont_max=cmax, cont_min=cmin)
+            self.psi_buf = r["buf"]
+            L.cnv_sim_set_psi_buf(self.h, self.psi_buf)
+            P.exchange_halos(P.bufs[self.psi_buf], H3)    # (a "redo" pass leaves the result's halos stale)
+            L.cnv_sim_phase(self.h, 2, self.stream)
+            P.exchange_halos(self._field(0), H3)
+            P.exchange_halos(self._field(1), H3)
+            if diagnostics:
+                L.cnv_sim_phase(self.h, 3, self.stream)
+                mx, mn = self.cont[0:1].clone(), self.cont[1:2].clone()
+                self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX)
+                self.dist.all_reduce(mn, op=self.dist.ReduceOp.MIN)
+                cmax.append(float(mx.item())); cmin.append(float(mn.item()))
+        return dict(failed_step=0, k=ks, e=es, cont_max=cmax, cont_min=cmin)
+
+    def gather_fields(self):
+        """psi, w, u, v of the whole grid on rank 0 (None elsewhere)."""
+        out = {}
+        srcs = {"psi": self.poisson.bufs[self.psi_buf], "w": self._field(2), "u": self._field(0), "v": self._field(1)}
+        for name, t in srcs.items():
+            mine = t[self.own_lo:self.own_hi, :self.ncols].contiguous()
+            sizes = [slab_bounds(self.gnrows, self.world, r) for r in range(self.world)]
+            if self.rank == 0:
+                parts = [self.torch.empty((b - a, self.ncols), dtype=self.torch.float64, device=self.dev) for a, b in sizes]
+                parts[0].copy_(mine)
+                for r in range(1, self.world):
+                    self.dist.recv(parts[r], r)
+                out[name] = self.torch.cat(parts).cpu().numpy()
+            else:
+                self.dist.send(mine, 0)
+        return out if self.rank == 0 else None

@@ -101,11 +101,14 @@ def poisson_sor(f, dx: float, dy: float, itmax: int, tol: float, beta: float = 1
 class PoissonSolver:
     """Device-resident solver object (cnv_poisson_*): reusable buffers, asynchronous passes."""
 
-    def __init__(self, nrows: int, ncols: int, T: int = 0, slab=None):
+    def __init__(self, nrows: int, ncols: int, T: int = 0, slab=None, handle=None):
         self.h = None
+        self.owned = handle is None
         _lib.require_gpu()
         self.L = _lib.lib()
-        if slab is None:
+        if handle is not None:            # view of a solver owned by a cnv_sim
+            self.h = handle
+        elif slab is None:
             self.h = self.L.cnv_poisson_create(nrows, ncols, T)
         else:
             grow0, gnrows, own_lo, own_hi = slab
@@ -119,9 +122,9 @@ class PoissonSolver:
         self.ld = self.L.cnv_poisson_ld(self.h)
 
     def close(self):
-        if self.h:
+        if self.h and self.owned:
             self.L.cnv_poisson_destroy(self.h)
-            self.h = None
+        self.h = None
 
     __del__ = close
 

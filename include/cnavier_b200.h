@@ -94,6 +94,16 @@ int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream
 /* ---- device-resident time stepping: the loop body of src/main.c:283-395 ---------------------- */
 typedef struct cnv_sim cnv_sim;
 cnv_sim *cnv_sim_create(const Config *cfg, int T);
+/* Multi-GPU: this process' slab (rank of world) of the row-decomposed grid; local arrays carry 2T halo rows on
+ * interior edges.  The caller orchestrates a step as cnv_sim_phase() calls interleaved with halo exchanges
+ * (fluid_dynamics1_b200/parallel.py: SlabSimulation); cnv_sim_step() is for world == 1 only. */
+cnv_sim *cnv_sim_create_slab(const Config *cfg, int T, int rank, int world);
+void cnv_sim_layout(const cnv_sim *s, int *out); /* grow0, nloc, own_lo, own_hi, ld, ncols, T, global rows */
+cnv_poisson *cnv_sim_poisson(cnv_sim *s);        /* the simulation's solver object (not owned by the caller) */
+double *cnv_sim_field_ptr(cnv_sim *s, int which); /* device: 0 u, 1 v, 2 w, 3 continuity (max, min) */
+void cnv_sim_set_psi_buf(cnv_sim *s, int which);
+/* phase 0 BCs + wall vorticity | 1 derivatives + Euler + rhs | 2 velocities from psi | 3 continuity max/min */
+void cnv_sim_phase(cnv_sim *s, int phase, void *stream);
 void cnv_sim_destroy(cnv_sim *s);
 /* Advances nsteps steps.  k/e/cont_max/cont_min: NULL or arrays of nsteps (per-step Poisson log values
  * and continuity diagnostic).  Returns 0, or (index of the step whose Poisson solve hit itmax) + 1. */
