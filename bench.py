@@ -57,9 +57,11 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is
+    started before the warm-up (nvidia-smi needs a moment to produce its first line); samples are selected by
+    their timestamps against the wall-clock window of the timed region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device=0):
@@ -78,30 +80,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        sm, mx, reasons, power = [], [], set(), []
+        for stamp, ln in self.lines:
+            if t0 is not None and not (t0 - 0.03 <= stamp <= t1 + 0.08):
+                continue
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[2])); mx.append(float(f[3])); power.append(float(f[4]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": float(np.median(power)) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -177,22 +182,24 @@ def run_gpu(args):
             if pass_events is not None:
                 pass_events[1].record(stream)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         one_step()
     barrier()
     launches0 = L.cnv_launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pass_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    wall0 = time.time()
     ev0.record(stream)
     for k in range(args.steps):
         one_step(pass_ev[k])
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     launches = L.cnv_launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
     pass_ms = sum(a.elapsed_time(b) for a, b in pass_ev)
@@ -391,7 +398,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=4096, help="grid columns (and rows per GPU under weak scaling)")

@@ -243,11 +243,15 @@ int cnv_poisson_prepare(cnv_poisson *p, const double *f_dev, int ldf, double fsi
 }
 int cnv_poisson_upload(cnv_poisson *p, const double *f_host, double fsign, void *stream)
 {
+    // host f -> the solver's rhs array (pitched) with one 2-D copy, then scaled in place; no staging allocation
     const PassGeom &g = p->s->geom();
-    DevArray f(g.nrows, g.ncols);
-    f.upload(f_host, (cudaStream_t)stream);
-    cnv_poisson_prepare(p, f.p, f.ld, fsign, stream);
-    CNV_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(p->s->rhs(), sizeof(double) * g.ld, f_host, sizeof(double) * g.ncols,
+                                     sizeof(double) * g.ncols, g.nrows, cudaMemcpyHostToDevice, st));
+    launch_prep_rhs(p->s->rhs(), g.nrows, g.ncols, g.ld, fsign, p->s->consts().pscale, p->s->rhs(), p->s->buffer(0),
+                    p->s->buffer(1), g.ld, st);
+    count_launch(1);
+    CNV_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 int cnv_poisson_solve(cnv_poisson *p, int itmax, double tol, void *stream, int *k, double *e, int *sweeps, int *passes,

@@ -374,8 +374,9 @@ k_continuity(const double *__restrict__ u, const double *__restrict__ v, RowMap 
 }
 
 // rhs = pscale * (sign * f), psi0 = 0: prologue of a stand-alone Poisson solve
-__global__ void k_prep_rhs(const double *__restrict__ f, int nrows, int ncols, int ldf, double sign, double pscale,
-                           double *__restrict__ rhs, double *__restrict__ psi0, double *__restrict__ psi1, int ld)
+// (f may alias rhs with ldf == ld: the host-buffer upload copies straight into rhs and scales in place)
+__global__ void k_prep_rhs(const double *f, int nrows, int ncols, int ldf, double sign, double pscale,
+                           double *rhs, double *__restrict__ psi0, double *__restrict__ psi1, int ld)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y;

@@ -381,3 +381,20 @@ def test_unmodified_reference_main_drives_gpu_path(tmp_path, golden_logs):
     for title, key in (("stream-function", "psi"), ("vorticity", "w"), ("x-velocity", "u"), ("y-velocity", "v")):
         got = np.fromfile(dump / (title + ".f64")).reshape(-1, 64, 64)
         assert np.array_equal(got[0], g[key][0]) and np.array_equal(got[1], g[key][1]), key
+
+
+def test_poisson_weak_scaling_slab_shape_fixed_sweeps(port):
+    """BASELINE config 5 per-GPU shape (2048 owned rows of a 16384-wide grid): 8 sweeps, bitwise vs the oracle."""
+    nr, nc, sweeps = 2064, 16384, 8
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal((nr, nc))
+    beta = port.beta(nc, nc)
+    want, norms = port.poisson_sweeps(f, 1 / nc, 1 / nc, sweeps, beta)
+    s = fd.PoissonSolver(nr, nc, 0)
+    s.set_consts(1 / nc, 1 / nc, beta)
+    s.upload(f)
+    r = s.solve(sweeps, 0.0)
+    got = s.download(r["buf"])
+    assert r["sweeps"] == sweeps and got.tobytes() == want.tobytes()
+    assert abs(r["e"] - norms[-1]) <= 1e-11 * norms[-1]
+    s.close()
