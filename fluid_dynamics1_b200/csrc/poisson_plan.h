@@ -47,9 +47,10 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 inline size_t pass_smem_bytes(int T, int WS) { return (size_t)ring_rows(T) * slot_stride(WS) * sizeof(double); }
 inline int pass_threads(int T, int WS) { return T * (WS / 4); }
-// Launch bounds of k_poisson_pass<T>: the kernel is latency bound, so registers are capped (<= 85 per
-// thread) to keep 24 warps resident per SM: one 768-thread CTA for deep blocking, two 384-thread CTAs else.
-constexpr int pass_max_threads(int T) { return T >= 6 ? 768 : 384; }
+// Launch bounds of k_poisson_pass<T>: the kernel is latency bound, so registers are capped (<= 102 per
+// thread: column history + software-pipelined operands) to keep 20 warps resident per SM: one 640-thread CTA
+// for deep blocking, two 320-thread CTAs otherwise.
+constexpr int pass_max_threads(int T) { return T >= 6 ? 640 : 320; }
 constexpr int pass_min_ctas(int T) { return T >= 6 ? 1 : 2; }
 
 struct PlanLimits {
@@ -72,7 +73,7 @@ inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, i
     double best_cost = 1e300;
     const int HX = round_up(2 * T, 4), HY = 2 * T;
     const int own = own_hi - own_lo;
-    const int reg_threads = 65536 / 80 / 32 * 32;  // ~80 registers per thread (launch bounds): 800 threads per SM
+    const int reg_threads = 65536 / 102 / 32 * 32;  // <= 102 registers per thread (launch bounds): 640 threads per SM
     for (int WS = force_ws ? force_ws : 32; WS <= (force_ws ? force_ws : 2048); WS += 32) {
         if (WS % 4) break;
         const int Wout = WS - 2 * HX;

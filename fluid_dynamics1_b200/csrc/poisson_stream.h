@@ -172,6 +172,8 @@ struct StreamThread {
     bool vE0, vO0, vE1, vO1, colown, allvalid;
     dbl2 h1, h2, h3;     // N loaded 1, 2, 3 steps ago
     dbl2 r1, r2, r3;     // red results of 1, 2, 3 steps ago
+    dbl2 pf_own, pf_Pr, pf_Pb;  // operands of THIS step, loaded during the previous step (software pipelining)
+    double pf_x, pf_xb;
     double acc;
 };
 
@@ -225,6 +227,8 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.sact = t.g == T - 1 && t.colown && gc4 >= 0 && gc4 < p.ld;
     s.sdst = (long long)(s.ybase - 3 - s.dq) * p.ld + gc4;
     s.h1 = s.h2 = s.h3 = s.r1 = s.r2 = s.r3 = dbl2{0.0, 0.0};
+    s.pf_own = s.pf_Pr = s.pf_Pb = dbl2{0.0, 0.0};
+    s.pf_x = s.pf_xb = 0.0;
     s.acc = 0.0;
 }
 
@@ -280,13 +284,11 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
     const int aA = typeR ? s.aSO : s.aSE, aB = typeR ? s.aSE : s.aSO;
     const int aPA = typeR ? s.aPO : s.aPE, aPB = typeR ? s.aPE : s.aPO;
     const int qtop = r - s.dq, q = qtop - 1, qb = qtop - 3;
-    // red row q: N from row qtop, own cells, right-hand side, the neighbouring thread's E/W value
+    // red row q: only N (row qtop, written by the level below during the PREVIOUS step) must be read after this
+    // step's barrier; the other operands were prefetched during the previous step (see the end of this function)
     const dbl2 N = lds2(sm, s.o[0] + aA);
-    const dbl2 own = lds2(sm, s.o[1] + aA);
-    const dbl2 Pr = lds2(sm, s.o[1] + aPA);
-    const double x = lds1(sm, s.o[1] + aB + (typeR ? 16 : -8));
-    const dbl2 Pb = lds2(sm, s.o[3] + aPB);
-    const double xb = lds1(sm, s.o[3] + aA + (typeR ? -8 : 16));
+    const dbl2 own = s.pf_own, Pr = s.pf_Pr, Pb = s.pf_Pb;
+    const double x = s.pf_x, xb = s.pf_xb;
     const dbl2 b = s.h1, S = s.h2;
     const dbl2 ownb = s.h3, Nb = s.r1, bb = s.r2, Sb = s.r3;
     // even-column cell of pair k: W = odd[k-1], E = odd[k];  odd-column cell: W = even[k], E = even[k+1]
@@ -338,6 +340,20 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
     s.r3 = s.r2; s.r2 = s.r1; s.r1 = dbl2{n0, n1};
     s.o[3] = s.o[2]; s.o[2] = s.o[1]; s.o[1] = s.o[0];
     s.o[0] = wrap_inc_t<T>(s.o[0], s.ss, s.ringend);
+    // ---- software pipelining: operands of the NEXT step that nobody writes during this one ----
+    // next red row = this step's row qtop (its red cells carry the level below since >= 3 steps, its black
+    // cells since the previous step; rhs is static); next black row = this step's row q-1 (its red cells were
+    // written by this level during the previous step).  The colour type flips with the step parity.
+    {
+        constexpr bool tN = !typeR;
+        const int nA = tN ? s.aSO : s.aSE, nB = tN ? s.aSE : s.aSO;
+        const int nPA = tN ? s.aPO : s.aPE, nPB = tN ? s.aPE : s.aPO;
+        s.pf_own = lds2(sm, s.o[1] + nA);
+        s.pf_Pr = lds2(sm, s.o[1] + nPA);
+        s.pf_x = lds1(sm, s.o[1] + nB + (tN ? 16 : -8));
+        s.pf_Pb = lds2(sm, s.o[3] + nPB);
+        s.pf_xb = lds1(sm, s.o[3] + nA + (tN ? -8 : 16));
+    }
 }
 
 // ---- solver state machine (one instance per solve, device resident) ---------------------------

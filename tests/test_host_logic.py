@@ -80,7 +80,7 @@ def test_planner_properties(emul):
             assert WS > 0, (nrows, ncols, T)
             assert WS % 4 == 0 and HX % 4 == 0 and HX >= 2 * T and Wout == WS - 2 * HX
             assert nstrips * Wout >= ncols and nchunks * Hout >= nrows
-            assert threads == T * WS // 4 and threads <= (768 if T >= 6 else 384)
+            assert threads == T * WS // 4 and threads <= (640 if T >= 6 else 320)
             assert smem <= 227 * 1024 - 1024
 
 
