@@ -72,10 +72,10 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
 
     stream_prologue<T>(st, sm);  // kPrefetch rows in flight
     for (int r = st.ybase; r <= st.rend; r += 2) {
-        cp_async_wait<kPrefetch - 1>();  // row r has landed (this thread's copies) ...
+        cp_async_wait<kPrefetch - 1 - kLand>();  // row r (+kLand) has landed (this thread's copies) ...
         __syncthreads();                 // ... and everybody's; previous step's updates are visible
         stream_step<T, POW2, 0>(st, rc, sm, out, r, nsw);
-        cp_async_wait<kPrefetch - 1>();
+        cp_async_wait<kPrefetch - 1 - kLand>();
         __syncthreads();
         stream_step<T, POW2, 1>(st, rc, sm, out, r + 1, nsw);
     }

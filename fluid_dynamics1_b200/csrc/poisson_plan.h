@@ -104,7 +104,7 @@ inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, i
                 nchunks = (own + Hout - 1) / Hout;
                 const long ctas = (long)nstrips * nchunks;
                 const long nwaves = (ctas + slots - 1) / slots;
-                const int steps = Hout + 2 * HY + 4 * T + 6;  // + fixed per-CTA start-up cost
+                const int steps = Hout + 2 * HY + kSkew * T + 6;  // halo + pipeline fill + fixed per-CTA start-up cost
                 // CTAs sharing the busiest SM in the last (or only) wave, and its resident warps
                 const long in_last = ctas - (nwaves - 1) * slots;
                 const int resident = (int)((in_last + lim.num_sms - 1) / lim.num_sms);

@@ -6,15 +6,15 @@
 // Algorithm (restates src/poisson.c:238-262, the OpenMP red-black sweep, T sweeps per HBM pass)
 // ---------------------------------------------------------------------------------------------
 // One CTA owns a strip of Wout output columns x Hout output rows and streams rows bottom-up
-// through a ring buffer of R = 4T+PF rows in shared memory.  Each row lives in column-parity
+// through a ring buffer of R = kSkew*T+PF-1 rows in shared memory.  Each row lives in column-parity
 // split form (SE = even columns, SO = odd columns) so that every access of a half-row update is
 // unit stride: for an even-column cell (pair k) N/S are SE[q+-1][k], E/W are SO[q][k], SO[q][k-1].
-// The 2T half-sweeps (red L1, black L1, red L2, ..., black LT) are skewed by 2 rows each:
-// at step r (row r has just landed) stage sigma updates row r-1-2*sigma.  All inputs of every
+// The 2T half-sweeps (red L1, black L1, red L2, ..., black LT) are skewed: at step r level g updates its
+// red row r-1-kSkew*g and its black row two rows below (kSkew = 4 would be 2 rows per half-sweep).  All inputs of every
 // stage were produced in EARLIER steps, so the 2T stages of one step are independent and one
 // __syncthreads per step suffices; the update is in place (same dependency structure as the
 // reference's in-place sweeps, only the order of independent cell updates changes, so every
-// cell sees bit-identical operands).  Row r-4T+1 is final once the last level's black stage has
+// cell sees bit-identical operands).  A row is final once the last level's black stage has
 // processed it, and is written back from registers in that same step.  Dependencies reach 2 cells per sweep, so strips/chunks overlap by 2T halo cells whose
 // (stale-neighbour) results are discarded: the first/last loaded row is never updated and the
 // first/last loaded column sees a pad value; the region of influence of either stays inside the halo.
@@ -26,7 +26,12 @@
 namespace cnv {
 
 constexpr int kPrefetch = 3;  // rows in flight ahead of the compute front (cp.async groups)
-constexpr int ring_rows(int T) { return 4 * T + kPrefetch; }
+// Rows between consecutive levels.  4 is the minimum (red + black stage, 2 rows each); with 5 every shared
+// (even) every shared-memory operand of step r+1 -- including the row above the red row -- is already final during step r, so
+// all operand loads are issued one step ahead (software pipelining) and none waits behind the barrier.
+constexpr int kSkew = 4;  // even (compile-time colour parity).  6 = full operand prefetch: measured slower (larger ring, fewer threads)
+constexpr int kLand = kSkew > 4 ? 1 : 0;  // input rows must have landed this many steps early
+constexpr int ring_rows(int T) { return kSkew * T + kPrefetch - (kSkew > 4 ? 1 : 0); }
 
 struct PassGeom {
     // local array: nrows x ncols doubles with pitch ld; row 0 is global row grow0 of gnrows
@@ -172,7 +177,7 @@ struct StreamThread {
     bool vE0, vO0, vE1, vO1, colown, allvalid;
     dbl2 h1, h2, h3;     // N loaded 1, 2, 3 steps ago
     dbl2 r1, r2, r3;     // red results of 1, 2, 3 steps ago
-    dbl2 pf_own, pf_Pr, pf_Pb;  // operands of THIS step, loaded during the previous step (software pipelining)
+    dbl2 pf_N, pf_own, pf_Pr, pf_Pb;  // operands of THIS step, loaded during the previous step (software pipelining)
     double pf_x, pf_xb;
     double acc;
 };
@@ -192,8 +197,10 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.ringend = base + R * s.ss;
     // start on a step whose stage-0 row has even (global row + 1): the colour type then alternates
     // with the step parity (PAR in stream_step)
-    s.ybase = G.ylo - ((p.grow0 + G.ylo - 1) & 1);
-    s.rend = G.y1 - 1 + 4 * T;
+    // (with full operand prefetch the stream starts kLand steps early: the operands of the first streamed row
+    // are loaded one step before they are used)
+    s.ybase = G.ylo - kLand - ((p.grow0 + G.ylo - kLand - 1) & 1);
+    s.rend = G.y1 + 2 + kSkew * (T - 1);  // the last level's black stage reaches row y1-1
     if (((s.rend - s.ybase) & 1) == 0) s.rend++;  // whole pairs of steps
     s.ylo = G.ylo; s.yhi = G.yhi; s.y0 = G.y0; s.y1 = G.y1;
     s.vlo = G.ylo + 1 > 1 - p.grow0 ? G.ylo + 1 : 1 - p.grow0;
@@ -216,7 +223,7 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
         }
     }
     const ThreadCtx t = thread_ctx(p, G, tid);
-    s.g = t.g; s.dq = 4 * t.g; s.k0 = t.k0;
+    s.g = t.g; s.dq = kSkew * t.g; s.k0 = t.k0;
     for (int j = 0; j < 4; j++) s.o[j] = base + ((((-s.dq - j) % R) + R) % R) * s.ss;
     s.aSE = (arr_off(p.WS, 0) + t.k0) * 8; s.aSO = (arr_off(p.WS, 1) + t.k0) * 8;
     s.aPE = (arr_off(p.WS, 2) + t.k0) * 8; s.aPO = (arr_off(p.WS, 3) + t.k0) * 8;
@@ -227,7 +234,7 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.sact = t.g == T - 1 && t.colown && gc4 >= 0 && gc4 < p.ld;
     s.sdst = (long long)(s.ybase - 3 - s.dq) * p.ld + gc4;
     s.h1 = s.h2 = s.h3 = s.r1 = s.r2 = s.r3 = dbl2{0.0, 0.0};
-    s.pf_own = s.pf_Pr = s.pf_Pb = dbl2{0.0, 0.0};
+    s.pf_N = s.pf_own = s.pf_Pr = s.pf_Pb = dbl2{0.0, 0.0};
     s.pf_x = s.pf_xb = 0.0;
     s.acc = 0.0;
 }
@@ -284,9 +291,9 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
     const int aA = typeR ? s.aSO : s.aSE, aB = typeR ? s.aSE : s.aSO;
     const int aPA = typeR ? s.aPO : s.aPE, aPB = typeR ? s.aPE : s.aPO;
     const int qtop = r - s.dq, q = qtop - 1, qb = qtop - 3;
-    // red row q: only N (row qtop, written by the level below during the PREVIOUS step) must be read after this
-    // step's barrier; the other operands were prefetched during the previous step (see the end of this function)
-    const dbl2 N = lds2(sm, s.o[0] + aA);
+    // every operand was loaded during the previous step (see the end of this function); with kSkew == 4 the row
+    // above the red row is written by the level below during the previous step and must be read now
+    const dbl2 N = kSkew > 4 ? s.pf_N : lds2(sm, s.o[0] + aA);
     const dbl2 own = s.pf_own, Pr = s.pf_Pr, Pb = s.pf_Pb;
     const double x = s.pf_x, xb = s.pf_xb;
     const dbl2 b = s.h1, S = s.h2;
@@ -348,6 +355,7 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         constexpr bool tN = !typeR;
         const int nA = tN ? s.aSO : s.aSE, nB = tN ? s.aSE : s.aSO;
         const int nPA = tN ? s.aPO : s.aPE, nPB = tN ? s.aPE : s.aPO;
+        if (kSkew > 4) s.pf_N = lds2(sm, s.o[0] + nA);
         s.pf_own = lds2(sm, s.o[1] + nA);
         s.pf_Pr = lds2(sm, s.o[1] + nPA);
         s.pf_x = lds1(sm, s.o[1] + nB + (tN ? 16 : -8));
