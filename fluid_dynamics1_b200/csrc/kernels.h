@@ -49,6 +49,20 @@ void launch_continuity(const double *u, const double *v, const RowMap &m, int nc
 void launch_prep_rhs(const double *f, int nrows, int ncols, int ldf, double sign, double pscale, double *rhs, double *psi0,
                      double *psi1, int ld, cudaStream_t s);
 
+// ---- poisson_resident.cu: whole solve in one launch for small grids (thread-block cluster + DSMEM) ----
+struct ResidentGeom {
+    int nrows, ncols, ld;
+    int KP;   // column pairs per row = ceil(ncols / 2)
+    int PK;   // shared row pitch (doubles) = KP + 2 (one pad each side for the k-1 / k+1 neighbour)
+    int RPC;  // rows per CTA
+    int RPB;  // rows covered by one "m" step of the CTA = kResThreads / KP (even)
+    int C;    // cluster size
+};
+
+bool resident_plan(int nrows, int ncols, int ld, size_t smem_limit, ResidentGeom *g, size_t *smem);
+void launch_resident(const ResidentGeom &g, size_t smem, const RelaxConsts &rc, const double *psi0, const double *rhs, double *out,
+                     PoissonCtl *ctl, double *hist, int itmax, double tol, cudaStream_t s);
+
 // ---- poisson.cu ----
 struct PoissonResult {
     int status;  // 0 converged, 1 itmax reached (the reference exits the process here)
@@ -111,6 +125,7 @@ private:
     size_t launches_ = 0;
     size_t smem_ = 0;
     int threads_ = 0;
+    size_t smem_optin_ = 0;
 };
 
 }  // namespace cnv

@@ -171,6 +171,7 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
     CNV_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     lim.num_sms = prop.multiProcessorCount;
     lim.smem_per_cta = prop.sharedMemPerBlockOptin - 1024;  // room for the kernel's static shared memory
+    smem_optin_ = lim.smem_per_cta;
     lim.smem_per_sm = prop.sharedMemPerMultiprocessor;
     lim.max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
     const int ld = round_up(ncols, 16);
@@ -258,6 +259,25 @@ PoissonResult PoissonSolver::solve(int itmax, double tol, cudaStream_t s, int *r
     }
     use_hist_ = keep_history;
     reset_ctl(itmax, tol, s);
+    // Small grids: the whole solve (all sweeps + the convergence test after each) in one cluster launch with psi
+    // resident in shared memory (poisson_resident.cu).  Same arithmetic, same red-black order -> same bits.
+    ResidentGeom rg;
+    size_t rsmem = 0;
+    if (!distributed_ && geom_.grow0 == 0 && geom_.gnrows == geom_.nrows && geom_.own_lo == 0 && geom_.own_hi == geom_.nrows &&
+        itmax > 0 && resident_plan(geom_.nrows, geom_.ncols, geom_.ld, smem_optin_, &rg, &rsmem)) {
+        launch_resident(rg, rsmem, rc_, buf_[0], rhs_, buf_[1], ctl_, use_hist_ ? hist_ : nullptr, itmax, tol, s);
+        launches_ += 1;
+        count_launch(1);
+        PoissonCtl c = read_ctl(s);
+        if (result_buf) *result_buf = c.cur;
+        PoissonResult r;
+        r.status = c.state == 1 ? 0 : 1;
+        r.k = c.result_k;
+        r.sweeps = c.sweeps;
+        r.passes = c.passes;
+        r.e = c.result_e;
+        return r;
+    }
     // Sweep counts drift slowly from one time step to the next (the shipped logs move by <= ~10
     // sweeps per step), so the first batch covers the previous solve's pass count plus one and is
     // followed by small batches.  Passes enqueued after convergence exit immediately.

@@ -25,6 +25,14 @@ def _gpu():
     fd.require_gpu()
 
 
+@pytest.fixture(params=["resident", "stream"])
+def small_grid_path(request, monkeypatch):
+    """Small grids (<= ~360^2) are solved by the shared-memory-resident cluster kernel by default; the same
+    tests also run with it disabled so the streaming kernel stays covered at small sizes."""
+    monkeypatch.setenv("CNV_POISSON_RESIDENT", "2" if request.param == "resident" else "0")  # 2 = force (clusters too)
+    return request.param
+
+
 # ---- stencils ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("order", [2, 4, 6])
 @pytest.mark.parametrize("shape", [(7, 7), (16, 16), (33, 50), (64, 64), (200, 131)])
@@ -62,7 +70,7 @@ def test_pointwise_bitwise(port):
 # ---- Poisson ------------------------------------------------------------------------------------
 @pytest.mark.parametrize("T", [1, 2, 4, 8])
 @pytest.mark.parametrize("n", [16, 64, 100, 257])
-def test_poisson_sor_vs_oracle(port, n, T):
+def test_poisson_sor_vs_oracle(port, n, T, small_grid_path):
     """Same sweep count, same field bits, same residual (to summation rounding) as the red-black
     reference build; n=64 is the pow2 fast path, 100 and 257 the general (Markstein division) path."""
     f = sine_rhs(n)
@@ -89,7 +97,7 @@ def test_poisson_sine_golden_counts():
 
 
 @pytest.mark.parametrize("shape,dx,dy", [((40, 72), 1 / 40, 1 / 72), ((96, 33), 0.01, 0.013), ((5, 9), 0.2, 0.1)])
-def test_poisson_nonsquare_random_rhs(port, shape, dx, dy):
+def test_poisson_nonsquare_random_rhs(port, shape, dx, dy, small_grid_path):
     rng = np.random.default_rng(shape[0])
     f = rng.standard_normal(shape)
     beta = port.beta(*shape)
@@ -100,7 +108,7 @@ def test_poisson_nonsquare_random_rhs(port, shape, dx, dy):
         assert got["u"].tobytes() == want["u"].tobytes()
 
 
-def test_poisson_gauss_seidel_variant(port):
+def test_poisson_gauss_seidel_variant(port, small_grid_path):
     """poisson()/poisson_log(): beta == 1, no relaxation term (src/poisson.c:62-109, 176-222)."""
     f = sine_rhs(48)
     got = fd.poisson_sor(f, 1 / 48, 1 / 48, 50000, 1e-3, 1.0)
@@ -109,7 +117,7 @@ def test_poisson_gauss_seidel_variant(port):
     assert np.array_equal(got["u"], want["u"])       # == ignores the sign of zero
 
 
-def test_poisson_itmax(port):
+def test_poisson_itmax(port, small_grid_path):
     """itmax reached: status 1 (the drop-in layer turns it into message + exit(1))."""
     f = sine_rhs(32)
     for itmax in (1, 3, 4, 5, 9):
@@ -121,7 +129,7 @@ def test_poisson_itmax(port):
         fd.poisson_sor(f, 1 / 32, 1 / 32, 5, 1e-12, fd.sor_beta(32, 32))
 
 
-def test_poisson_zero_rhs_and_tiny_grid(port):
+def test_poisson_zero_rhs_and_tiny_grid(port, small_grid_path):
     r = fd.poisson_sor(np.zeros((8, 8)), 0.1, 0.1, 10, 1e-3, 1.5)
     assert r["k"] == 0 and r["e"] == 0.0 and not r["u"].any()
     f = np.ones((3, 3))
@@ -130,7 +138,7 @@ def test_poisson_zero_rhs_and_tiny_grid(port):
     assert got["k"] == want["k"] and np.array_equal(got["u"], want["u"])
 
 
-def test_poisson_every_stop_position(port):
+def test_poisson_every_stop_position(port, small_grid_path):
     """The converged sweep can fall on any position inside a temporal block: sweep through
     tolerances so that sweeps-1 takes many consecutive values, for every T."""
     n = 40
@@ -190,7 +198,7 @@ def test_poisson_linearity_property():
 
 
 # ---- whole time steps -----------------------------------------------------------------------------
-def test_default_config_vs_golden_fields_and_logs(golden_logs):
+def test_default_config_vs_golden_fields_and_logs(golden_logs, small_grid_path):
     """config_default.txt: fields after steps 0, 10, 20 against raw dumps of the reference executable;
     Poisson log lines against the reference's shipped testRunOMP.txt."""
     g = load_golden("fields_default_rb.npz")
@@ -215,7 +223,7 @@ def test_default_config_vs_golden_fields_and_logs(golden_logs):
     assert np.all(np.abs(r["cont_max"]) < 1e-10) and np.all(np.abs(r["cont_min"]) < 1e-10)
 
 
-def test_high_re_config_vs_golden(golden_logs):
+def test_high_re_config_vs_golden(golden_logs, small_grid_path):
     g = load_golden("fields_highre_rb.npz")
     sim = fd.Simulation(dict(api.CONFIG_HIGH_RE))
     r = sim.step(6)
@@ -228,7 +236,7 @@ def test_high_re_config_vs_golden(golden_logs):
 
 
 @pytest.mark.parametrize("order,ptype,n", [(2, 2, 48), (4, 2, 48), (6, 1, 40), (6, 2, 50)])
-def test_steps_vs_oracle_other_orders_and_solver_types(port, order, ptype, n):
+def test_steps_vs_oracle_other_orders_and_solver_types(port, order, ptype, n, small_grid_path):
     cfg = dict(api.CONFIG_DEFAULT, nx=n, ny=n, order=order, poisson_type=ptype, poisson_max_it=100000,
                u1=0.1, u2=-0.2, u3=0.3, v1=0.05, v2=-0.05, v3=0.02, v4=-0.01, ui=0.01, vi=-0.02, dt=0.002)
     sim = fd.Simulation(cfg)
