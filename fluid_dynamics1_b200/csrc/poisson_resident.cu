@@ -17,7 +17,7 @@
 //     order by every CTA, so all CTAs take the same stop decision (first sweep with e < tol, src/poisson.c:273).
 // Cell updates use exact.h::relax, i.e. the same separately rounded operation sequence as everywhere else;
 // the red-black order makes the result independent of how the rows are split: fields are bit-identical to the
-// streaming kernel and to the oracle.
+// streaming kernel and to the reference.
 #include <cooperative_groups.h>
 
 #include "kernels.h"
