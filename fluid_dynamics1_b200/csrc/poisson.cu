@@ -67,7 +67,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     const CtaGeom G = cta_geom(p, blockIdx.x, blockIdx.y);
     StreamThread<T> st;
     stream_init<T>(st, p, G, sm, in, rhs, tid, blockDim.x);
-    const int TPG = p.WS >> 2;
+    const int TPG = p.WS / (2 * kPairs);
     const int kk = tid - st.g * TPG;
 
     stream_prologue<T>(st, sm);  // kPrefetch rows in flight

@@ -46,7 +46,7 @@ inline RelaxConsts make_relax_consts(double dx, double dy, double beta)
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 inline size_t pass_smem_bytes(int T, int WS) { return (size_t)ring_rows(T) * slot_stride(WS) * sizeof(double); }
-inline int pass_threads(int T, int WS) { return T * (WS / 4); }
+inline int pass_threads(int T, int WS) { return T * (WS / (2 * kPairs)); }
 // Launch bounds of k_poisson_pass<T>: the kernel is latency bound, so registers are capped (<= 102 per
 // thread: column history + software-pipelined operands) to keep 20 warps resident per SM: one 640-thread CTA
 // for deep blocking, two 320-thread CTAs otherwise.
@@ -71,11 +71,11 @@ inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, i
     PassGeom best;
     std::memset(&best, 0, sizeof best);
     double best_cost = 1e300;
-    const int HX = round_up(2 * T, 4), HY = 2 * T;
+    const int HX = round_up(2 * T, 2 * kPairs), HY = 2 * T;  // a thread's columns are all inside or all outside the halo
     const int own = own_hi - own_lo;
     const int reg_threads = 65536 / 102 / 32 * 32;  // <= 102 registers per thread (launch bounds): 640 threads per SM
     for (int WS = force_ws ? force_ws : 32; WS <= (force_ws ? force_ws : 2048); WS += 32) {
-        if (WS % 4) break;
+        if (WS % (2 * kPairs)) break;
         const int Wout = WS - 2 * HX;
         if (Wout < 4) continue;
         const int NT = pass_threads(T, WS);

@@ -31,6 +31,10 @@ constexpr int kPrefetch = 3;  // rows in flight ahead of the compute front (cp.a
 // all operand loads are issued one step ahead (software pipelining) and none waits behind the barrier.
 constexpr int kSkew = 4;  // even (compile-time colour parity).  6 = full operand prefetch: measured slower (larger ring, fewer threads)
 constexpr int kLand = kSkew > 4 ? 1 : 0;  // input rows must have landed this many steps early
+// Column pairs per thread (a thread owns 2*kPairs adjacent columns).  More pairs = more independent
+// cell updates in flight per thread (fp64 latency) and less per-cell overhead, at the price of registers.
+constexpr int kPairs = 2;  // 4 measured slower on B200 (128 registers + spills, 12 warps/SM: 47 vs 36 us/sweep at 4096^2)
+static_assert(kPairs % 2 == 0, "pairs are moved as 16-byte vectors");
 constexpr int ring_rows(int T) { return kSkew * T + kPrefetch - (kSkew > 4 ? 1 : 0); }
 
 struct PassGeom {
@@ -69,28 +73,28 @@ CNV_HD int arr_off(int WS, int which) { return which * (WS / 2 + 4) + 2; }  // 0
 
 struct ThreadCtx {
     int g;        // level index (sweep g+1 of the pass)
-    int k0;       // first of the two column pairs
-    int vmask;    // bit i: smem col 4kk+i is updatable; cols = (E k0, O k0, E k0+1, O k0+1)
-    bool colown;  // the four columns belong to the strip's output range
+    int k0;       // first of this thread's kPairs column pairs
+    int vmask;    // bit 2p / 2p+1: the even / odd column of pair k0+p is updatable
+    bool colown;  // the thread's columns belong to the strip's output range
 };
 
 CNV_HD ThreadCtx thread_ctx(const PassGeom &p, const CtaGeom &G, int tid)
 {
     ThreadCtx t;
-    const int TPG = p.WS >> 2;
+    const int TPG = p.WS / (2 * kPairs);
     t.g = tid / TPG;
     const int kk = tid - t.g * TPG;
-    t.k0 = 2 * kk;
+    t.k0 = kPairs * kk;
     // A column is protected from updates only if it is a Dirichlet ring column or lies outside the domain.
     // The first/last column held in shared memory (halo edge of an interior strip) IS updated, from a pad
     // value: whatever that produces spreads by at most 2 columns per sweep, i.e. stays inside the 2T-column
     // halo whose results are discarded anyway -- exactly as far as the staleness of a frozen edge would reach.
     t.vmask = 0;
-    for (int i = 0; i < 4; i++) {
-        int gc = G.gx0 + 4 * kk + i;
+    for (int i = 0; i < 2 * kPairs; i++) {
+        int gc = G.gx0 + 2 * t.k0 + i;
         if (gc >= 1 && gc <= p.ncols - 2) t.vmask |= 1 << i;
     }
-    t.colown = 4 * kk >= p.HX && 4 * kk < p.HX + p.Wout;
+    t.colown = 2 * t.k0 >= p.HX && 2 * t.k0 < p.HX + p.Wout;
     return t;
 }
 
@@ -138,6 +142,28 @@ inline void sts1(double *sm, int off, double a) { *at(sm, off) = a; }
 inline void stg2(double *p, double a, double b) { p[0] = a; p[1] = b; }
 #endif
 
+// kPairs doubles of one parity array (pairs k0 .. k0+kPairs-1), moved as 16-byte vectors
+struct vecP { double v[kPairs]; };
+CNV_HD vecP ldsP(const double *sm, int off)
+{
+    vecP r;
+#pragma unroll
+    for (int i = 0; i < kPairs; i += 2) { const dbl2 t = lds2(sm, off + 8 * i); r.v[i] = t.x; r.v[i + 1] = t.y; }
+    return r;
+}
+CNV_HD void stsP(double *sm, int off, const vecP &a)
+{
+#pragma unroll
+    for (int i = 0; i < kPairs; i += 2) sts2(sm, off + 8 * i, a.v[i], a.v[i + 1]);
+}
+CNV_HD vecP zeroP()
+{
+    vecP r;
+#pragma unroll
+    for (int i = 0; i < kPairs; i++) r.v[i] = 0.0;
+    return r;
+}
+
 // Per-thread state of the streaming pass.  Everything that does not change from step to step is
 // computed once here, so that one step costs only the loads/stores, the arithmetic and a handful
 // of pointer increments: ring-slot offsets advance incrementally (no modulo in the loop), global
@@ -155,7 +181,7 @@ inline void stg2(double *p, double a, double b) { p[0] = a; p[1] = b; }
 template <int T>
 struct StreamThread {
     static constexpr int R = ring_rows(T);
-    static constexpr int NCH = (4 + T - 1) / T;  // (psi|rhs) column pairs this thread copies per row
+    static constexpr int NCH = (2 * kPairs + T - 1) / T;  // (psi|rhs) column pairs this thread copies per row
     // uniform
     int ss, ringend;     // slot stride (bytes); end of the ring (bytes, base included)
     int ybase, rend;     // first / last step; ring slot of row q is (q - ybase) mod R
@@ -167,17 +193,18 @@ struct StreamThread {
     const double *lptr[NCH];  // global address of this thread's chunk in the row being loaded
     int ldE[NCH], ldO[NCH];   // destination byte offsets inside a slot
     bool lcopy[NCH], lzero[NCH];
-    // write back (threads of the last level only): element offset of columns 4kk.. of the black row
+    // write back (threads of the last level only): element offset of the thread's first column in the black row
     long long sdst;
     bool sact;
     // compute
     int g, dq, k0;
     int o[4];            // byte offsets of the slots of rows qtop, qtop-1, qtop-2, qtop-3 (qtop = r - dq)
     int aSE, aSO, aPE, aPO;  // array byte offsets inside a slot, k0 folded in
-    bool vE0, vO0, vE1, vO1, colown, allvalid;
-    dbl2 h1, h2, h3;     // N loaded 1, 2, 3 steps ago
-    dbl2 r1, r2, r3;     // red results of 1, 2, 3 steps ago
-    dbl2 pf_N, pf_own, pf_Pr, pf_Pb;  // operands of THIS step, loaded during the previous step (software pipelining)
+    int vmask;           // bit 2p / 2p+1: even / odd column of pair k0+p updatable
+    bool colown, allvalid;
+    vecP h1, h2, h3;     // N loaded 1, 2, 3 steps ago
+    vecP r1, r2, r3;     // red results of 1, 2, 3 steps ago
+    vecP pf_N, pf_own, pf_Pr, pf_Pb;  // operands of THIS step, loaded during the previous step (software pipelining)
     double pf_x, pf_xb;
     double acc;
 };
@@ -227,14 +254,14 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     for (int j = 0; j < 4; j++) s.o[j] = base + ((((-s.dq - j) % R) + R) % R) * s.ss;
     s.aSE = (arr_off(p.WS, 0) + t.k0) * 8; s.aSO = (arr_off(p.WS, 1) + t.k0) * 8;
     s.aPE = (arr_off(p.WS, 2) + t.k0) * 8; s.aPO = (arr_off(p.WS, 3) + t.k0) * 8;
-    s.vE0 = t.vmask & 1; s.vO0 = (t.vmask >> 1) & 1; s.vE1 = (t.vmask >> 2) & 1; s.vO1 = (t.vmask >> 3) & 1;
-    s.allvalid = t.vmask == 15;
+    s.vmask = t.vmask;
+    s.allvalid = t.vmask == (1 << (2 * kPairs)) - 1;
     s.colown = t.colown;
-    const int gc4 = G.gx0 + 2 * t.k0;  // first of this thread's four columns
+    const int gc4 = G.gx0 + 2 * t.k0;  // first of this thread's columns
     s.sact = t.g == T - 1 && t.colown && gc4 >= 0 && gc4 < p.ld;
     s.sdst = (long long)(s.ybase - 3 - s.dq) * p.ld + gc4;
-    s.h1 = s.h2 = s.h3 = s.r1 = s.r2 = s.r3 = dbl2{0.0, 0.0};
-    s.pf_N = s.pf_own = s.pf_Pr = s.pf_Pb = dbl2{0.0, 0.0};
+    s.h1 = s.h2 = s.h3 = s.r1 = s.r2 = s.r3 = zeroP();
+    s.pf_N = s.pf_own = s.pf_Pr = s.pf_Pb = zeroP();
     s.pf_x = s.pf_xb = 0.0;
     s.acc = 0.0;
 }
@@ -289,62 +316,68 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
     // ---- relax ----
     constexpr bool typeR = PAR != 0;  // red cells are the odd-column cells
     const int aA = typeR ? s.aSO : s.aSE, aB = typeR ? s.aSE : s.aSO;
-    const int aPA = typeR ? s.aPO : s.aPE, aPB = typeR ? s.aPE : s.aPO;
     const int qtop = r - s.dq, q = qtop - 1, qb = qtop - 3;
-    // every operand was loaded during the previous step (see the end of this function); with kSkew == 4 the row
-    // above the red row is written by the level below during the previous step and must be read now
-    const dbl2 N = kSkew > 4 ? s.pf_N : lds2(sm, s.o[0] + aA);
-    const dbl2 own = s.pf_own, Pr = s.pf_Pr, Pb = s.pf_Pb;
+    // every operand but (with kSkew == 4) the row above the red row was loaded during the previous step (see the
+    // end of this function); that row is written by the level below during the previous step and is read now
+    const vecP N = kSkew > 4 ? s.pf_N : ldsP(sm, s.o[0] + aA);
+    const vecP own = s.pf_own, Pr = s.pf_Pr, Pb = s.pf_Pb;
     const double x = s.pf_x, xb = s.pf_xb;
-    const dbl2 b = s.h1, S = s.h2;
-    const dbl2 ownb = s.h3, Nb = s.r1, bb = s.r2, Sb = s.r3;
+    const vecP b = s.h1, S = s.h2;
+    const vecP ownb = s.h3, Nb = s.r1, bb = s.r2, Sb = s.r3;
     // even-column cell of pair k: W = odd[k-1], E = odd[k];  odd-column cell: W = even[k], E = even[k+1]
-    double n0 = relax<POW2>(N.x, S.x, typeR ? b.y : b.x, typeR ? b.x : x, own.x, Pr.x, rc);
-    double n1 = relax<POW2>(N.y, S.y, typeR ? x : b.y, typeR ? b.y : b.x, own.y, Pr.y, rc);
-    // black row qb (cells of the other column parity): everything but Pb / xb comes from registers
-    double m0 = relax<POW2>(Nb.x, Sb.x, typeR ? bb.x : bb.y, typeR ? xb : bb.x, ownb.x, Pb.x, rc);
-    double m1 = relax<POW2>(Nb.y, Sb.y, typeR ? bb.y : xb, typeR ? bb.x : bb.y, ownb.y, Pb.y, rc);
+    // red cells (type typeR) have their E/W neighbours in b (+ x at the thread's edge); black cells (the other
+    // type) have theirs in bb (+ xb)
+    vecP n, m;
+#pragma unroll
+    for (int i = 0; i < kPairs; i++) {
+        const double Wr = typeR ? b.v[i] : (i == 0 ? x : b.v[i - 1]);
+        const double Er = typeR ? (i == kPairs - 1 ? x : b.v[i + 1]) : b.v[i];
+        n.v[i] = relax<POW2>(N.v[i], S.v[i], Er, Wr, own.v[i], Pr.v[i], rc);
+        const double Wb = typeR ? (i == 0 ? xb : bb.v[i - 1]) : bb.v[i];
+        const double Eb = typeR ? bb.v[i] : (i == kPairs - 1 ? xb : bb.v[i + 1]);
+        m.v[i] = relax<POW2>(Nb.v[i], Sb.v[i], Eb, Wb, ownb.v[i], Pb.v[i], rc);
+    }
     if (s.allvalid && s.g < nsw && qb >= s.vlo && q <= s.vhi) {
-        // fast path: all four cells updatable (rows q, qb are inside the streamed range by construction)
-        sts2(sm, s.o[1] + aA, n0, n1);
-        sts2(sm, s.o[3] + aB, m0, m1);
+        // fast path: all cells updatable (rows q, qb are inside the streamed range by construction)
+        stsP(sm, s.o[1] + aA, n);
+        stsP(sm, s.o[3] + aB, m);
     } else {
         const bool active = s.g < nsw;
         const bool rowr = active && q >= s.vlo && q <= s.vhi;
         const bool rowb = active && qb >= s.vlo && qb <= s.vhi;
-        n0 = (rowr & (typeR ? s.vO0 : s.vE0)) ? n0 : own.x;
-        n1 = (rowr & (typeR ? s.vO1 : s.vE1)) ? n1 : own.y;
-        m0 = (rowb & (typeR ? s.vE0 : s.vO0)) ? m0 : ownb.x;
-        m1 = (rowb & (typeR ? s.vE1 : s.vO1)) ? m1 : ownb.y;
-        if (q >= s.ylo && q <= s.yhi) sts2(sm, s.o[1] + aA, n0, n1);
-        if (qb >= s.ylo && qb <= s.yhi) sts2(sm, s.o[3] + aB, m0, m1);
+#pragma unroll
+        for (int i = 0; i < kPairs; i++) {
+            const bool vr = (s.vmask >> (2 * i + (typeR ? 1 : 0))) & 1, vb = (s.vmask >> (2 * i + (typeR ? 0 : 1))) & 1;
+            n.v[i] = (rowr & vr) ? n.v[i] : own.v[i];
+            m.v[i] = (rowb & vb) ? m.v[i] : ownb.v[i];
+        }
+        if (q >= s.ylo && q <= s.yhi) stsP(sm, s.o[1] + aA, n);
+        if (qb >= s.ylo && qb <= s.yhi) stsP(sm, s.o[3] + aB, m);
     }
     // L1 update norm of this level (non-updated cells contribute exactly 0)
     if (s.colown) {
         if (q >= s.y0 && q < s.y1) {
-            s.acc = xadd(s.acc, fabs(xsub(n0, own.x)));
-            s.acc = xadd(s.acc, fabs(xsub(n1, own.y)));
+#pragma unroll
+            for (int i = 0; i < kPairs; i++) s.acc = xadd(s.acc, fabs(xsub(n.v[i], own.v[i])));
         }
         if (qb >= s.y0 && qb < s.y1) {
-            s.acc = xadd(s.acc, fabs(xsub(m0, ownb.x)));
-            s.acc = xadd(s.acc, fabs(xsub(m1, ownb.y)));
+#pragma unroll
+            for (int i = 0; i < kPairs; i++) s.acc = xadd(s.acc, fabs(xsub(m.v[i], ownb.v[i])));
         }
     }
     // ---- write back: the black row of the last level is final; its red cells are r2 ----
     if (s.sact && qb >= s.y0 && qb < s.y1) {
         double *dst = out + s.sdst;
-        if (typeR) {  // black cells are the even-column cells
-            stg2(dst, m0, bb.x);
-            stg2(dst + 2, m1, bb.y);
-        } else {
-            stg2(dst, bb.x, m0);
-            stg2(dst + 2, bb.y, m1);
+#pragma unroll
+        for (int i = 0; i < kPairs; i++) {
+            if (typeR) stg2(dst + 2 * i, m.v[i], bb.v[i]);  // black cells are the even-column cells
+            else stg2(dst + 2 * i, bb.v[i], m.v[i]);
         }
     }
     s.sdst += s.ld;
     // rows move up by one: rotate histories and slot offsets
     s.h3 = s.h2; s.h2 = s.h1; s.h1 = N;
-    s.r3 = s.r2; s.r2 = s.r1; s.r1 = dbl2{n0, n1};
+    s.r3 = s.r2; s.r2 = s.r1; s.r1 = n;
     s.o[3] = s.o[2]; s.o[2] = s.o[1]; s.o[1] = s.o[0];
     s.o[0] = wrap_inc_t<T>(s.o[0], s.ss, s.ringend);
     // ---- software pipelining: operands of the NEXT step that nobody writes during this one ----
@@ -355,12 +388,12 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         constexpr bool tN = !typeR;
         const int nA = tN ? s.aSO : s.aSE, nB = tN ? s.aSE : s.aSO;
         const int nPA = tN ? s.aPO : s.aPE, nPB = tN ? s.aPE : s.aPO;
-        if (kSkew > 4) s.pf_N = lds2(sm, s.o[0] + nA);
-        s.pf_own = lds2(sm, s.o[1] + nA);
-        s.pf_Pr = lds2(sm, s.o[1] + nPA);
-        s.pf_x = lds1(sm, s.o[1] + nB + (tN ? 16 : -8));
-        s.pf_Pb = lds2(sm, s.o[3] + nPB);
-        s.pf_xb = lds1(sm, s.o[3] + nA + (tN ? -8 : 16));
+        if (kSkew > 4) s.pf_N = ldsP(sm, s.o[0] + nA);
+        s.pf_own = ldsP(sm, s.o[1] + nA);
+        s.pf_Pr = ldsP(sm, s.o[1] + nPA);
+        s.pf_x = lds1(sm, s.o[1] + nB + (tN ? 8 * kPairs : -8));
+        s.pf_Pb = ldsP(sm, s.o[3] + nPB);
+        s.pf_xb = lds1(sm, s.o[3] + nA + (tN ? -8 : 8 * kPairs));
     }
 }
 

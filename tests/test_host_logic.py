@@ -59,7 +59,7 @@ def test_stream_schedule_bitwise_vs_oracle(emul, port, shape, T):
     n, m = shape
     for mode in (0, 1):                               # 0: pow2 fast path where exact, 1: literal general sequence
         for ws, ch in ((0, 0), (64, 2), (96, 3)):
-            if ws and ws - 2 * max(4, 2 * T) < 4:
+            if ws and ws - 2 * max(8, 2 * T) < 8:
                 continue
             got, want, gn, on = _emul_sweeps(emul, port, n, m, T, 3, mode, ws, ch)
             assert got.tobytes() == want.tobytes(), (shape, T, mode, ws, ch)
