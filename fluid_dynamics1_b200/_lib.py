@@ -74,6 +74,12 @@ CNV_API = {
     "cnv_poisson_set_distributed": (None, [_vp, C.c_int]),
     "cnv_poisson_state": (None, [_vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "cnv_poisson_download": (C.c_int, [_vp, C.c_int, _dp, _vp]),
+    "cnv_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "cnv_comm_create": (_vp, [C.c_int, C.c_int, C.c_char_p]),
+    "cnv_comm_destroy": (None, [_vp]),
+    "cnv_poisson_attach_comm": (None, [_vp, _vp]),
+    "cnv_poisson_enqueue_dist": (None, [_vp, C.c_int, _vp]),
+    "cnv_poisson_exchange_halos": (None, [_vp, _vp, C.c_int, _vp]),
     "cnv_sim_create": (_vp, [C.POINTER(Config), C.c_int]),
     "cnv_sim_create_slab": (_vp, [C.POINTER(Config), C.c_int, C.c_int, C.c_int]),
     "cnv_sim_layout": (None, [_vp, C.POINTER(C.c_int)]),

@@ -7,6 +7,7 @@
 
 #include "../../include/cnavier_b200.h"
 #include "kernels.h"
+#include "nccl_dl.h"
 
 namespace cnv {
 size_t total_launches();
@@ -274,6 +275,46 @@ void cnv_poisson_state(cnv_poisson *p, void *stream, int *state, double *e)
     state[0] = c.state; state[1] = c.cur; state[2] = c.sweeps; state[3] = c.passes; state[4] = c.result_k; state[5] = c.redo;
     if (e) { e[0] = c.result_e; e[1] = c.last_e; }
 }
+// ---- native NCCL communicator for the slab path (one per process; bootstrap id exchanged by the caller) ----
+struct cnv_comm {
+    SlabComm c;
+};
+int cnv_comm_unique_id(unsigned char *out128)
+{
+    const NcclApi &n = nccl_api();
+    if (!n.ok) return 1;
+    ncclUniqueId id;
+    if (n.GetUniqueId(&id) != ncclSuccess) return 2;
+    std::memcpy(out128, &id, 128);
+    return 0;
+}
+cnv_comm *cnv_comm_create(int rank, int world, const unsigned char *id128)
+{
+    const NcclApi &n = nccl_api();
+    if (!n.ok) return nullptr;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclComm_t comm = nullptr;
+    if (n.CommInitRank(&comm, world, id, rank) != ncclSuccess) return nullptr;
+    cnv_comm *c = new cnv_comm;
+    c->c.comm = comm;
+    c->c.rank = rank;
+    c->c.world = world;
+    return c;
+}
+void cnv_comm_destroy(cnv_comm *c)
+{
+    if (!c) return;
+    if (c->c.comm) nccl_api().CommDestroy((ncclComm_t)c->c.comm);
+    delete c;
+}
+void cnv_poisson_attach_comm(cnv_poisson *p, cnv_comm *c) { p->s->attach_comm(c->c); }
+void cnv_poisson_enqueue_dist(cnv_poisson *p, int npasses, void *stream) { p->s->enqueue_passes_dist(npasses, (cudaStream_t)stream); }
+void cnv_poisson_exchange_halos(cnv_poisson *p, double *field_dev, int depth, void *stream)
+{
+    p->s->exchange_halos(field_dev, depth, (cudaStream_t)stream);
+}
+
 int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream)
 {
     const PassGeom &g = p->s->geom();

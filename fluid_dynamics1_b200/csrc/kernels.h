@@ -72,8 +72,11 @@ struct PoissonResult {
     double e;    // L1 update norm of the last sweep
 };
 
-// Slab neighbours for the multi-GPU path (see poisson.cu); all zero/NULL on one GPU.
-struct SlabComm;
+// Slab communicator of the multi-GPU path (poisson.cu): one NCCL communicator over the ranks of the node.
+struct SlabComm {
+    void *comm = nullptr;  // ncclComm_t
+    int rank = 0, world = 1;
+};
 
 class PoissonSolver {
 public:
@@ -109,6 +112,14 @@ public:
     void set_distributed(bool on) { distributed_ = on; }
     double *local_norms() { return norms_; }
     void enqueue_decide(cudaStream_t s);
+    // Native distributed passes: per pass ONE NCCL group on the compute stream (2T halo rows to/from both slab
+    // neighbours + an all-gather of the T norms as 64-byte send/recvs) and a decide kernel that sums the gathered
+    // norms in rank order -- no host synchronisation, no second collective launch.
+    void attach_comm(const SlabComm &c);
+    bool has_comm() const { return comm_.comm != nullptr; }
+    void enqueue_passes_dist(int npasses, cudaStream_t s);
+    void exchange_halos(double *field, int depth, cudaStream_t s);  // any slab-local field with this solver's layout
+    void restart_pass_counter() { dist_passes_ = 0; }
 
 private:
     int T_;
@@ -126,6 +137,9 @@ private:
     size_t smem_ = 0;
     int threads_ = 0;
     size_t smem_optin_ = 0;
+    SlabComm comm_;
+    double *gather_ = nullptr;  // [world][8] norms of every rank
+    int dist_passes_ = 0;       // passes enqueued since the last reset (static exchange pattern)
 };
 
 }  // namespace cnv

@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "kernels.h"
+#include "nccl_dl.h"
 
 namespace cnv {
 
@@ -122,6 +123,22 @@ __global__ void k_decide(PoissonCtl *ctl, const double *norms, int T, double *hi
     *ctl = c;
 }
 
+// multi-GPU, native NCCL path: norms of all ranks were gathered into gather[world][8] (own row included);
+// summing them in rank order gives every rank bit-identical totals, hence the same decision
+__global__ void k_decide_gather(PoissonCtl *ctl, const double *gather, int world, int T, double *hist)
+{
+    if (ctl->state != 0) return;
+    PoissonCtl c = *ctl;
+    double e[8];
+    for (int g = 0; g < 8; g++) {
+        double s = 0.0;
+        for (int r = 0; r < world; r++) s = xadd(s, gather[r * 8 + g]);
+        e[g] = s;
+    }
+    decide(c, e, pass_sweeps(c, T), hist);
+    *ctl = c;
+}
+
 __global__ void k_reset_ctl(PoissonCtl *ctl, int itmax, double tol)
 {
     PoissonCtl c;
@@ -204,6 +221,7 @@ PoissonSolver::~PoissonSolver()
 {
     cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(rhs_); cudaFree(partials_); cudaFree(norms_); cudaFree(ctl_);
     if (hist_) cudaFree(hist_);
+    if (gather_) cudaFree(gather_);
     cudaFreeHost(h_ctl_);
     cudaEventDestroy(ev_);
 }
@@ -212,6 +230,7 @@ void PoissonSolver::set_consts(double dx, double dy, double beta) { rc_ = make_r
 
 void PoissonSolver::reset_ctl(int itmax, double tol, cudaStream_t s)
 {
+    dist_passes_ = 0;
     k_reset_ctl<<<1, 1, 0, s>>>(ctl_, itmax, tol);
     count_launch(1);
 }
@@ -242,6 +261,73 @@ void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
     CNV_CUDA_CHECK(cudaGetLastError());
     launches_ += npasses;
     count_launch(npasses);
+}
+
+#define CNV_NCCL_CHECK(expr)                                                                              \
+    do {                                                                                                  \
+        ncclResult_t r__ = (expr);                                                                        \
+        if (r__ != ncclSuccess) {                                                                         \
+            std::printf("** Error: NCCL failure %s at %s:%d **\n", nccl_api().GetErrorString ? nccl_api().GetErrorString(r__) : "?", \
+                        __FILE__, __LINE__);                                                              \
+            std::fflush(stdout);                                                                          \
+            std::exit(1);                                                                                 \
+        }                                                                                                 \
+    } while (0)
+
+void PoissonSolver::attach_comm(const SlabComm &c)
+{
+    comm_ = c;
+    if (!gather_) {
+        CNV_CUDA_CHECK(cudaMalloc(&gather_, sizeof(double) * 8 * (size_t)c.world));
+        CNV_CUDA_CHECK(cudaMemset(gather_, 0, sizeof(double) * 8 * (size_t)c.world));
+    }
+    distributed_ = true;
+}
+
+// send/recv of `depth` boundary rows with both slab neighbours; must be called inside an NCCL group
+static void halo_ops(const NcclApi &n, const SlabComm &c, const PassGeom &g, double *f, int depth, cudaStream_t s)
+{
+    ncclComm_t comm = (ncclComm_t)c.comm;
+    const size_t cnt = (size_t)depth * g.ld;
+    if (c.rank > 0) {
+        CNV_NCCL_CHECK(n.Send(f + (size_t)g.own_lo * g.ld, cnt, ncclFloat64, c.rank - 1, comm, s));
+        CNV_NCCL_CHECK(n.Recv(f + (size_t)(g.own_lo - depth) * g.ld, cnt, ncclFloat64, c.rank - 1, comm, s));
+    }
+    if (c.rank < c.world - 1) {
+        CNV_NCCL_CHECK(n.Send(f + (size_t)(g.own_hi - depth) * g.ld, cnt, ncclFloat64, c.rank + 1, comm, s));
+        CNV_NCCL_CHECK(n.Recv(f + (size_t)g.own_hi * g.ld, cnt, ncclFloat64, c.rank + 1, comm, s));
+    }
+}
+
+void PoissonSolver::exchange_halos(double *field, int depth, cudaStream_t s)
+{
+    const NcclApi &n = nccl_api();
+    CNV_NCCL_CHECK(n.GroupStart());
+    halo_ops(n, comm_, geom_, field, depth, s);
+    CNV_NCCL_CHECK(n.GroupEnd());
+}
+
+void PoissonSolver::enqueue_passes_dist(int npasses, cudaStream_t s)
+{
+    const NcclApi &n = nccl_api();
+    ncclComm_t comm = (ncclComm_t)comm_.comm;
+    for (int i = 0; i < npasses; i++) {
+        enqueue_passes(1, s);  // local norms -> norms_
+        CNV_NCCL_CHECK(n.GroupStart());
+        // static pattern: pass p writes buffer (p+1)&1 (a "redo" pass only breaks it for the final pass)
+        halo_ops(n, comm_, geom_, buf_[(dist_passes_ + 1) & 1], geom_.HY, s);
+        for (int r = 0; r < comm_.world; r++) {
+            if (r == comm_.rank) continue;
+            CNV_NCCL_CHECK(n.Send(norms_, 8, ncclFloat64, r, comm, s));
+            CNV_NCCL_CHECK(n.Recv(gather_ + 8 * r, 8, ncclFloat64, r, comm, s));
+        }
+        CNV_NCCL_CHECK(n.GroupEnd());
+        CNV_CUDA_CHECK(cudaMemcpyAsync(gather_ + 8 * comm_.rank, norms_, sizeof(double) * 8, cudaMemcpyDeviceToDevice, s));
+        k_decide_gather<<<1, 1, 0, s>>>(ctl_, gather_, comm_.world, T_, use_hist_ ? hist_ : nullptr);
+        count_launch(1);
+        dist_passes_++;
+    }
+    CNV_CUDA_CHECK(cudaGetLastError());
 }
 
 void PoissonSolver::enqueue_decide(cudaStream_t s)

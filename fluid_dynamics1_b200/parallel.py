@@ -16,6 +16,7 @@ Per pass p (device-side state machine, no host synchronisation):
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -47,6 +48,34 @@ class _DevView:
                                          "strides": None}
 
 
+_native_comm = {}  # (rank, world) -> cnv_comm handle (one NCCL communicator per process)
+
+
+def native_comm(L, dist, torch, rank, world):
+    """The library's own NCCL communicator (cnv_comm_*), bootstrapped through torch.distributed: rank 0 creates the
+    NCCL unique id, it is broadcast as a Python object, every rank joins.  Returns None when disabled
+    (CNV_DIST_BACKEND=torch) or unavailable on any rank; the callers then fall back to torch.distributed p2p."""
+    key = (rank, world)
+    if key in _native_comm:
+        return _native_comm[key]
+    handle = None
+    if os.environ.get("CNV_DIST_BACKEND", "nccl") != "torch":
+        ids = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            if L.cnv_comm_unique_id(buf) == 0:
+                ids = [buf.raw]
+        dist.broadcast_object_list(ids, src=0)
+        if ids[0] is not None:
+            handle = L.cnv_comm_create(rank, world, ids[0])
+        ok = torch.tensor([1 if handle else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            handle = None
+    _native_comm[key] = handle
+    return handle
+
+
 class SlabPoisson:
     def __init__(self, total_rows: int, ncols: int, T: int, rank: int, world: int, stream=None, handle=None):
         import torch
@@ -76,6 +105,10 @@ class SlabPoisson:
         self.rhs = torch.as_tensor(_DevView(self.L.cnv_poisson_rhs_ptr(self.h), (self.nrows, self.ld)), device=dev)
         self.norms = torch.as_tensor(_DevView(self.L.cnv_poisson_norms_ptr(self.h), (8,)), device=dev)
         self.passes_enqueued = 0
+        # per-pass exchange: the library's own NCCL group on the compute stream when available, else torch p2p
+        self.comm = native_comm(self.L, dist, torch, rank, world)
+        if self.comm:
+            self.L.cnv_poisson_attach_comm(self.h, self.comm)
 
     # ---- data movement ----------------------------------------------------------------------
     def set_consts(self, dx, dy, beta):
@@ -85,6 +118,9 @@ class SlabPoisson:
         """`depth` (default 2T) boundary rows of tensor `t` (local array, pitch ld) to/from both slab neighbours."""
         dist, H = self.dist, self.H
         d = H if depth is None else depth
+        if self.comm and tuple(t.shape) == (self.nrows, self.ld) and t.is_contiguous():
+            self.L.cnv_poisson_exchange_halos(self.h, C.c_void_p(t.data_ptr()), d, self.stream)
+            return
         ops = []
         if self.rank > 0:  # lower neighbour: my first owned rows -> its high halo; its last owned rows -> my low halo
             ops.append(dist.P2POp(dist.isend, t[self.own_lo:self.own_lo + d], self.rank - 1))
@@ -123,6 +159,10 @@ class SlabPoisson:
         self.passes_enqueued = 0
 
     def enqueue(self, npasses):
+        if self.comm:  # one NCCL group + decide kernel per pass, enqueued by the library (no Python per pass)
+            self.L.cnv_poisson_enqueue_dist(self.h, npasses, self.stream)
+            self.passes_enqueued += npasses
+            return
         for _ in range(npasses):
             self.L.cnv_poisson_enqueue(self.h, 1, self.stream)
             # static host pattern: pass p writes buffer (p+1)&1 (a "redo" pass breaks the alternation only

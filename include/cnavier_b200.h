@@ -91,6 +91,19 @@ void cnv_poisson_set_distributed(cnv_poisson *p, int on);
 void cnv_poisson_state(cnv_poisson *p, void *stream, int *state, double *e);
 int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream);
 
+/* Native multi-GPU plumbing for slab solvers (one process per GPU).  NCCL is loaded at run time (dlopen), so the
+ * library binds to the libnccl the process already holds.  Bootstrap: rank 0 calls cnv_comm_unique_id, the caller
+ * broadcasts the 128 bytes (torch.distributed / MPI / a file), every rank calls cnv_comm_create.
+ * cnv_poisson_enqueue_dist: per pass one NCCL group on `stream` (2T halo rows with both neighbours + an all-gather of
+ * the T per-sweep norms) followed by the device-side stop decision; no host synchronisation. */
+typedef struct cnv_comm cnv_comm;
+int cnv_comm_unique_id(unsigned char *out128);                           /* 0 ok, else NCCL unavailable */
+cnv_comm *cnv_comm_create(int rank, int world, const unsigned char *id128); /* NULL on failure */
+void cnv_comm_destroy(cnv_comm *c);
+void cnv_poisson_attach_comm(cnv_poisson *p, cnv_comm *c);
+void cnv_poisson_enqueue_dist(cnv_poisson *p, int npasses, void *stream);
+void cnv_poisson_exchange_halos(cnv_poisson *p, double *field_dev, int depth, void *stream);
+
 /* ---- device-resident time stepping: the loop body of src/main.c:283-395 ---------------------- */
 typedef struct cnv_sim cnv_sim;
 cnv_sim *cnv_sim_create(const Config *cfg, int T);
