@@ -68,6 +68,8 @@ CNV_API = {
     "cnv_poisson_prepare": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp]),
     "cnv_poisson_solve": (C.c_int, [_vp, C.c_int, C.c_double, _vp, C.POINTER(C.c_int), C.POINTER(C.c_double),
                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cnv_poisson_enable_history": (None, [_vp, C.c_int]),
+    "cnv_poisson_read_history": (C.c_int, [_vp, _dp, C.c_int]),
     "cnv_poisson_reset": (None, [_vp, C.c_int, C.c_double, _vp]),
     "cnv_poisson_enqueue": (None, [_vp, C.c_int, _vp]),
     "cnv_poisson_enqueue_decide": (None, [_vp, _vp]),
@@ -80,6 +82,11 @@ CNV_API = {
     "cnv_poisson_attach_comm": (None, [_vp, _vp]),
     "cnv_poisson_enqueue_dist": (None, [_vp, C.c_int, _vp]),
     "cnv_poisson_exchange_halos": (None, [_vp, _vp, C.c_int, _vp]),
+    "cnv_poisson_peer_export": (None, [_vp, C.c_char_p]),
+    "cnv_poisson_peer_push_counts": (None, [_vp, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "cnv_poisson_peer_import": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int)]),
+    "cnv_poisson_peer_disable": (None, [_vp]),
+    "cnv_poisson_peer_enabled": (C.c_int, [_vp]),
     "cnv_sim_create": (_vp, [C.POINTER(Config), C.c_int]),
     "cnv_sim_create_slab": (_vp, [C.POINTER(Config), C.c_int, C.c_int, C.c_int]),
     "cnv_sim_layout": (None, [_vp, C.POINTER(C.c_int)]),

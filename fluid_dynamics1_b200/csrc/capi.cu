@@ -236,8 +236,10 @@ void cnv_poisson_plan_info(const cnv_poisson *p, long long *out)
 int cnv_poisson_prepare(cnv_poisson *p, const double *f_dev, int ldf, double fsign, void *stream)
 {
     const PassGeom &g = p->s->geom();
+    p->s->peer_quiesce((cudaStream_t)stream);  // multi-GPU peer path: no neighbour push may land after the re-initialisation
     launch_prep_rhs(f_dev, g.nrows, g.ncols, ldf, fsign, p->s->consts().pscale, p->s->rhs(), p->s->buffer(0), p->s->buffer(1),
                     g.ld, (cudaStream_t)stream);
+    p->s->peer_ready((cudaStream_t)stream);
     count_launch(1);
     CNV_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -247,10 +249,12 @@ int cnv_poisson_upload(cnv_poisson *p, const double *f_host, double fsign, void 
     // host f -> the solver's rhs array (pitched) with one 2-D copy, then scaled in place; no staging allocation
     const PassGeom &g = p->s->geom();
     cudaStream_t st = (cudaStream_t)stream;
+    p->s->peer_quiesce(st);
     CNV_CUDA_CHECK(cudaMemcpy2DAsync(p->s->rhs(), sizeof(double) * g.ld, f_host, sizeof(double) * g.ncols,
                                      sizeof(double) * g.ncols, g.nrows, cudaMemcpyHostToDevice, st));
     launch_prep_rhs(p->s->rhs(), g.nrows, g.ncols, g.ld, fsign, p->s->consts().pscale, p->s->rhs(), p->s->buffer(0),
                     p->s->buffer(1), g.ld, st);
+    p->s->peer_ready(st);
     count_launch(1);
     CNV_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -264,6 +268,14 @@ int cnv_poisson_solve(cnv_poisson *p, int itmax, double tol, void *stream, int *
     if (sweeps) *sweeps = r.sweeps;
     if (passes) *passes = r.passes;
     return r.status;
+}
+// residual history of the enqueue()-driven paths: hist[k] = global L1 update norm of sweep k
+void cnv_poisson_enable_history(cnv_poisson *p, int capacity) { p->s->enable_history(capacity); }
+int cnv_poisson_read_history(cnv_poisson *p, double *out, int n)
+{
+    if (!p->s->history()) return 1;
+    CNV_CUDA_CHECK(cudaMemcpy(out, p->s->history(), sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return 0;
 }
 void cnv_poisson_reset(cnv_poisson *p, int itmax, double tol, void *stream) { p->s->reset_ctl(itmax, tol, (cudaStream_t)stream); }
 void cnv_poisson_enqueue(cnv_poisson *p, int npasses, void *stream) { p->s->enqueue_passes(npasses, (cudaStream_t)stream); }
@@ -309,6 +321,18 @@ void cnv_comm_destroy(cnv_comm *c)
     delete c;
 }
 void cnv_poisson_attach_comm(cnv_poisson *p, cnv_comm *c) { p->s->attach_comm(c->c); }
+// ---- peer-memory path (CUDA IPC): see PoissonSolver::peer_* ----
+void cnv_poisson_peer_export(cnv_poisson *p, unsigned char *out192) { p->s->peer_export(out192); }
+void cnv_poisson_peer_push_counts(cnv_poisson *p, int rank, int world, long long *low, long long *high)
+{
+    p->s->peer_push_counts(rank, world, low, high);
+}
+int cnv_poisson_peer_import(cnv_poisson *p, int rank, int world, const unsigned char *handles, const int *layout)
+{
+    return p->s->peer_import(rank, world, handles, layout);
+}
+void cnv_poisson_peer_disable(cnv_poisson *p) { p->s->peer_disable(); }
+int cnv_poisson_peer_enabled(cnv_poisson *p) { return p->s->peer_enabled() ? 1 : 0; }
 void cnv_poisson_enqueue_dist(cnv_poisson *p, int npasses, void *stream) { p->s->enqueue_passes_dist(npasses, (cudaStream_t)stream); }
 void cnv_poisson_exchange_halos(cnv_poisson *p, double *field_dev, int depth, void *stream)
 {

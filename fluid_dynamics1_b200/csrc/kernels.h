@@ -91,6 +91,7 @@ public:
     double *rhs() { return rhs_; }                // device, pitch ld(): pscale * f
     double *buffer(int i) { return buf_[i]; }     // the two iterate buffers
     double *history() { return hist_; }
+    void enable_history(int cap);  // residual history for the enqueue()-driven paths (hist[k] = norm of sweep k)
     size_t launches() const { return launches_; }
     void set_consts(double dx, double dy, double beta);
     const RelaxConsts &consts() const { return rc_; }
@@ -120,6 +121,16 @@ public:
     void enqueue_passes_dist(int npasses, cudaStream_t s);
     void exchange_halos(double *field, int depth, cudaStream_t s);  // any slab-local field with this solver's layout
     void restart_pass_counter() { dist_passes_ = 0; }
+    // Peer-memory path (CUDA IPC over NVLink): boundary rows are stored into the neighbours' halos by the pass
+    // kernel itself, norms are published in every rank's mailbox, each CTA derives the stop decision: one kernel
+    // per pass, no collective launch.  enqueue_passes() takes this path once peer_import() succeeded.
+    void peer_export(unsigned char *out192);
+    void peer_push_counts(int rank, int world, long long *low, long long *high) const;
+    int peer_import(int rank, int world, const unsigned char *handles, const int *layout);
+    void peer_quiesce(cudaStream_t s);  // before re-initialising the iterate: every push launched so far has landed
+    void peer_ready(cudaStream_t s);    // after re-initialising it: the neighbours may push into the new buffers
+    bool peer_enabled() const { return links_.enabled != 0; }
+    void peer_disable() { links_.enabled = 0; }
 
 private:
     int T_;
@@ -140,6 +151,11 @@ private:
     SlabComm comm_;
     double *gather_ = nullptr;  // [world][8] norms of every rank
     int dist_passes_ = 0;       // passes enqueued since the last reset (static exchange pattern)
+    PeerLinks links_ = {};
+    PeerMailbox *mailbox_ = nullptr;
+    PoissonCtl *ctlbuf_ = nullptr;
+    unsigned long long peer_gidx_ = 0;  // passes launched since peer_import (global pass index)
+    unsigned long long peer_epoch_ = 0; // re-initialisations of the iterate since peer_import
 };
 
 }  // namespace cnv

@@ -47,25 +47,113 @@ __device__ __forceinline__ void group_sums(double *sm, double acc, int g, int kk
     __syncthreads();
 }
 
-template <int T, bool POW2>
+// ---- peer-memory helpers (multi-GPU): bounded spin-waits on system-scope flags ----
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;  // a peer that is 4 s late is dead: never hang the GPU
+__device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned long long want)
+{
+    if (ld_acquire_sys(p) >= want) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(p) < want) {
+        if (globaltimer_ns() - t0 > kPeerTimeoutNs) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// State used by pass `pidx` (peer path): S_0 is what k_reset_ctl wrote; S_p = decide(S_{p-1}, norms of pass p-1
+// summed over the ranks in rank order).  Every CTA derives it redundantly (identical inputs -> identical result).
+__device__ PoissonCtl peer_state(const PeerLinks &L, int T, double *hist)
+{
+    if (L.pidx == 0) return L.ctlbuf[0];
+    PoissonCtl c = L.ctlbuf[(L.pidx - 1) & 1];
+    if (c.state != 0) return c;
+    PeerMailbox *mb = L.mail[L.rank];
+    const unsigned long long want = L.gidx;  // pass gidx-1 publishes the value gidx
+    for (int r = 0; r < L.world; r++)
+        if (!wait_ge(&mb->norm_flag[r], want)) {
+            atomicExch(&mb->error, 1ull);
+            c.state = 3;
+            return c;
+        }
+    const int slot = (int)((L.gidx - 1) & 1);
+    double e[8];
+    for (int g = 0; g < 8; g++) {
+        double sum = 0.0;
+        for (int r = 0; r < L.world; r++) sum = xadd(sum, *(volatile double *)&mb->norms[slot][r][g]);
+        e[g] = sum;
+    }
+    decide(c, e, pass_sweeps(c, T), hist);
+    return c;
+}
+
+template <int T, bool POW2, bool PEER>
 __global__ void __launch_bounds__(pass_max_threads(T), pass_min_ctas(T))
 k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0, double *__restrict__ buf1,
                const double *__restrict__ rhs, PoissonCtl *ctl, double *__restrict__ partials, double *hist,
-               double *norms_out, const int fused_decide)
+               double *norms_out, const int fused_decide, const PeerLinks L)
 {
     extern __shared__ double4 sm4[];
     double *sm = reinterpret_cast<double *>(sm4);
     __shared__ double s_e[8];
     __shared__ int s_last;
 
-    if (ctl->state != 0) return;  // solve already finished: later passes of a batch are no-ops
-    const int nsw = pass_sweeps(*ctl, T);
-    const int cur = ctl->cur;
+    const int tid = threadIdx.x;
+    const bool first_cta = blockIdx.x == 0 && blockIdx.y == 0;
+    __shared__ PoissonCtl s_ctl;
+    if (PEER) {
+        // peer path: derive this pass' state from the previous state + every rank's published norms
+        if (tid == 0) {
+            s_ctl = peer_state(L, T, first_cta ? hist : nullptr);
+            if (first_cta && L.pidx > 0) L.ctlbuf[L.pidx & 1] = s_ctl;
+            if (first_cta && s_ctl.state != 0) {
+                // finished solve: a no-op pass still advances the cumulative counters of the protocol
+                if (L.rank > 0) atomicAdd_system(&L.mail[L.rank - 1]->halo_count[1], L.push_low);
+                if (L.rank < L.world - 1) atomicAdd_system(&L.mail[L.rank + 1]->halo_count[0], L.push_high);
+                for (int r = 0; r < L.world; r++) st_release_sys(&L.mail[r]->norm_flag[L.rank], L.gidx + 1);
+            }
+        }
+        __syncthreads();
+    }
+    const PoissonCtl c0 = PEER ? s_ctl : *ctl;
+    if (c0.state != 0) return;  // solve already finished: later passes of a batch are no-ops
+    const int nsw = pass_sweeps(c0, T);
+    const int cur = c0.cur;
     const double *__restrict__ in = cur ? buf1 : buf0;
     double *__restrict__ out = cur ? buf0 : buf1;
 
-    const int tid = threadIdx.x;
     const CtaGeom G = cta_geom(p, blockIdx.x, blockIdx.y);
+    if (PEER) {
+        if (tid == 0) {
+            PeerMailbox *mb = L.mail[L.rank];
+            const bool push_down = L.rank > 0 && G.y0 < p.own_lo + p.HY;
+            const bool push_up = L.rank < L.world - 1 && G.y1 > p.own_hi - p.HY;
+            bool ok = true;
+            // first pass of a solve: the neighbour must have finished zeroing the buffer this CTA pushes into
+            if (L.pidx == 0 && push_down) ok &= wait_ge(&mb->ready[0], L.epoch);
+            if (L.pidx == 0 && push_up) ok &= wait_ge(&mb->ready[1], L.epoch);
+            // this CTA streams halo rows -> the neighbour's pushes of the previous pass must have landed
+            if (L.rank > 0 && G.ylo < p.own_lo) ok &= wait_ge(&mb->halo_count[0], L.gidx * L.need_low);
+            if (L.rank < L.world - 1 && G.yhi >= p.own_hi) ok &= wait_ge(&mb->halo_count[1], L.gidx * L.need_high);
+            if (!ok) atomicExch(&mb->error, 1ull);
+        }
+        __syncthreads();
+    }
     StreamThread<T> st;
     stream_init<T>(st, p, G, sm, in, rhs, tid, blockDim.x);
     const int TPG = p.WS / (2 * kPairs);
@@ -84,6 +172,34 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     const double acc = st.acc;
     struct { int g; } t = {st.g};
 
+    if (PEER) {
+        // Slab boundary rows: copy what this CTA has just written (still L2 resident) into the neighbour GPU's halo
+        // rows with coalesced 16-byte peer stores over NVLink -- outside the streaming loop, which stays identical to
+        // the single-GPU kernel -- then make them visible system-wide and count the push in the neighbour's mailbox.
+        const bool push_down = L.rank > 0 && G.y0 < p.own_lo + p.HY;
+        const bool push_up = L.rank < L.world - 1 && G.y1 > p.own_hi - p.HY;
+        __syncthreads();  // every write-back of this CTA is done and visible to the CTA
+        const int c0 = G.gx0 + p.HX, c1 = (c0 + p.Wout < p.ld ? c0 + p.Wout : p.ld);  // this strip's output columns
+        const int npair = (c1 - c0) >> 1;
+        for (int side = 0; side < 2; side++) {
+            if (side == 0 ? !push_down : !push_up) continue;
+            const int ra = side == 0 ? (G.y0 > p.own_lo ? G.y0 : p.own_lo) : (G.y0 > p.own_hi - p.HY ? G.y0 : p.own_hi - p.HY);
+            const int rb = side == 0 ? (G.y1 < p.own_lo + p.HY ? G.y1 : p.own_lo + p.HY) : (G.y1 < p.own_hi ? G.y1 : p.own_hi);
+            double *peer = (side == 0 ? L.down_buf[cur ^ 1] + L.down_delta : L.up_buf[cur ^ 1] + L.up_delta);
+            for (int idx = tid; idx < (rb - ra) * npair; idx += blockDim.x) {
+                const int rr = ra + idx / npair, cc = c0 + 2 * (idx % npair);
+                const size_t off = (size_t)rr * p.ld + cc;
+                const double2 v = __ldcg(reinterpret_cast<const double2 *>(out + off));
+                *reinterpret_cast<double2 *>(peer + off) = v;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            if (push_down) atomicAdd_system(&L.mail[L.rank - 1]->halo_count[1], 1ull);
+            if (push_up) atomicAdd_system(&L.mail[L.rank + 1]->halo_count[0], 1ull);
+        }
+    }
     // per-CTA L1 update norms, one per sweep of the pass (level g <-> sweep g+1)
     group_sums(sm, acc, t.g, kk, TPG, s_e);
     const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
@@ -92,7 +208,8 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
         __threadfence();
     }
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&ctl->ticket, 1u) == (unsigned)ncta - 1;
+    unsigned *ticket = PEER ? &L.mail[L.rank]->ticket : &ctl->ticket;
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)ncta - 1;
     __syncthreads();
     if (!s_last) return;
 
@@ -101,6 +218,19 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     double part = 0.0;
     for (int c = kk; c < ncta; c += TPG) part = xadd(part, __ldcg(&partials[(size_t)c * T + t.g]));
     group_sums(sm, part, t.g, kk, TPG, s_e);
+    if (PEER) {
+        // publish this rank's norms of the pass in every rank's mailbox, then raise the flag everywhere
+        const int slot = (int)(L.gidx & 1);
+        if (tid < 8)
+            for (int r = 0; r < L.world; r++) L.mail[r]->norms[slot][L.rank][tid] = (tid < T && tid < nsw) ? s_e[tid] : 0.0;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            for (int r = 0; r < L.world; r++) st_release_sys(&L.mail[r]->norm_flag[L.rank], L.gidx + 1);
+            *ticket = 0;
+        }
+        return;
+    }
     if (tid == 0) {
         if (fused_decide) {
             PoissonCtl c = *ctl;
@@ -112,6 +242,31 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
             ctl->ticket = 0;
         }
     }
+}
+
+// peer path: state after `L.pidx` passes -> ctlbuf[pidx & 1] (what the host reads back); also reports timeouts
+__global__ void k_peer_finalize(const PeerLinks L, int T, double *hist)
+{
+    PoissonCtl c = peer_state(L, T, hist);
+    if (*(volatile unsigned long long *)&L.mail[L.rank]->error) c.state = 3;
+    L.ctlbuf[L.pidx & 1] = c;
+}
+// peer path: this rank's iterate buffers are (re-)initialised for solve epoch L.epoch: tell both neighbours
+__global__ void k_peer_ready(const PeerLinks L)
+{
+    __threadfence_system();
+    if (L.rank > 0) st_release_sys(&L.mail[L.rank - 1]->ready[1], L.epoch);          // I am its upper neighbour
+    if (L.rank < L.world - 1) st_release_sys(&L.mail[L.rank + 1]->ready[0], L.epoch);  // I am its lower neighbour
+}
+// peer path: all pushes of the passes launched so far have landed in this rank's halos (called before the
+// iterate is re-initialised for the next solve, so that a late push cannot overwrite the new initial guess)
+__global__ void k_peer_quiesce(const PeerLinks L)
+{
+    PeerMailbox *mb = L.mail[L.rank];
+    bool ok = true;
+    if (L.rank > 0) ok &= wait_ge(&mb->halo_count[0], L.gidx * L.need_low);
+    if (L.rank < L.world - 1) ok &= wait_ge(&mb->halo_count[1], L.gidx * L.need_high);
+    if (!ok) atomicExch(&mb->error, 1ull);
 }
 
 // multi-GPU: stopping decision from all-reduced norms (identical on every rank)
@@ -150,14 +305,20 @@ __global__ void k_reset_ctl(PoissonCtl *ctl, int itmax, double tol)
 
 template <int T, bool POW2>
 static void launch_pass(const PassGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
-                        double *partials, double *hist, double *norms, int fused, int threads, size_t smem, cudaStream_t s)
+                        double *partials, double *hist, double *norms, int fused, int threads, size_t smem, cudaStream_t s,
+                        const PeerLinks &L)
 {
     static size_t configured = 48 * 1024;  // opt in to large dynamic shared memory (static smem counts against the 227 KB)
     if (smem > configured) {
-        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_pass<T, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_pass<T, POW2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_pass<T, POW2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_poisson_pass<T, POW2><<<dim3(g.nstrips, g.nchunks), threads, smem, s>>>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused);
+    const dim3 grid(g.nstrips, g.nchunks);
+    if (L.enabled)
+        k_poisson_pass<T, POW2, true><<<grid, threads, smem, s>>>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, L);
+    else
+        k_poisson_pass<T, POW2, false><<<grid, threads, smem, s>>>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, L);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -222,25 +383,146 @@ PoissonSolver::~PoissonSolver()
     cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(rhs_); cudaFree(partials_); cudaFree(norms_); cudaFree(ctl_);
     if (hist_) cudaFree(hist_);
     if (gather_) cudaFree(gather_);
+    if (mailbox_) cudaFree(mailbox_);
+    if (ctlbuf_) cudaFree(ctlbuf_);
     cudaFreeHost(h_ctl_);
     cudaEventDestroy(ev_);
 }
 
 void PoissonSolver::set_consts(double dx, double dy, double beta) { rc_ = make_relax_consts(dx, dy, beta); }
 
+void PoissonSolver::enable_history(int cap)
+{
+    if (cap <= 0) { use_hist_ = false; return; }
+    if (hist_cap_ < cap) {
+        if (hist_) cudaFree(hist_);
+        CNV_CUDA_CHECK(cudaMalloc(&hist_, sizeof(double) * (size_t)cap));
+        hist_cap_ = cap;
+    }
+    CNV_CUDA_CHECK(cudaMemset(hist_, 0, sizeof(double) * (size_t)hist_cap_));
+    use_hist_ = true;
+}
+
 void PoissonSolver::reset_ctl(int itmax, double tol, cudaStream_t s)
 {
     dist_passes_ = 0;
-    k_reset_ctl<<<1, 1, 0, s>>>(ctl_, itmax, tol);
+    k_reset_ctl<<<1, 1, 0, s>>>(links_.enabled ? links_.ctlbuf : ctl_, itmax, tol);
     count_launch(1);
 }
 
 PoissonCtl PoissonSolver::read_ctl(cudaStream_t s)
 {
-    CNV_CUDA_CHECK(cudaMemcpyAsync(h_ctl_, ctl_, sizeof(PoissonCtl), cudaMemcpyDeviceToHost, s));
+    const PoissonCtl *src = ctl_;
+    if (links_.enabled) {  // the state after the passes enqueued so far is derived by a one-thread kernel
+        PeerLinks L = links_;
+        L.pidx = dist_passes_;
+        L.gidx = peer_gidx_;
+        k_peer_finalize<<<1, 1, 0, s>>>(L, T_, use_hist_ ? hist_ : nullptr);
+        count_launch(1);
+        src = links_.ctlbuf + (dist_passes_ & 1);
+    }
+    CNV_CUDA_CHECK(cudaMemcpyAsync(h_ctl_, src, sizeof(PoissonCtl), cudaMemcpyDeviceToHost, s));
     CNV_CUDA_CHECK(cudaEventRecord(ev_, s));
     CNV_CUDA_CHECK(cudaEventSynchronize(ev_));
+    if (h_ctl_->state == 3) {
+        std::printf("** Error: multi-GPU peer exchange timed out (a neighbour rank stopped responding) **\n");
+        std::fflush(stdout);
+        std::exit(1);
+    }
     return *h_ctl_;
+}
+
+// ---- peer-memory (CUDA IPC) setup ----------------------------------------------------------------
+void PoissonSolver::peer_export(unsigned char *out192)
+{
+    if (!mailbox_) {
+        CNV_CUDA_CHECK(cudaMalloc(&mailbox_, sizeof(PeerMailbox)));
+        CNV_CUDA_CHECK(cudaMemset(mailbox_, 0, sizeof(PeerMailbox)));
+        CNV_CUDA_CHECK(cudaMalloc(&ctlbuf_, 2 * sizeof(PoissonCtl)));
+        CNV_CUDA_CHECK(cudaMemset(ctlbuf_, 0, 2 * sizeof(PoissonCtl)));
+    }
+    cudaIpcMemHandle_t h[3];
+    CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[0], buf_[0]));
+    CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[1], buf_[1]));
+    CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[2], mailbox_));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    std::memcpy(out192, h, 192);
+}
+
+// pushes per pass this slab makes downwards / upwards (CTAs whose output rows reach into the boundary band)
+void PoissonSolver::peer_push_counts(int rank, int world, long long *low, long long *high) const
+{
+    long long lo = 0, hi = 0;
+    for (int by = 0; by < geom_.nchunks; by++) {
+        const CtaGeom G = cta_geom(geom_, 0, by);
+        if (rank > 0 && G.y0 < geom_.own_lo + geom_.HY) lo += geom_.nstrips;
+        if (rank < world - 1 && G.y1 > geom_.own_hi - geom_.HY) hi += geom_.nstrips;
+    }
+    *low = lo; *high = hi;
+}
+
+// handles: world x 192 bytes (peer_export of every rank); layout: world x 4 ints (own_lo, own_hi, push_low, push_high)
+int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles, const int *layout)
+{
+    if (world > kMaxRanks || !mailbox_) return 1;
+    std::memset(&links_, 0, sizeof links_);
+    links_.rank = rank; links_.world = world; links_.ctlbuf = ctlbuf_;
+    auto open = [&](const unsigned char *h64, void **out) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, h64, 64);
+        return cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    };
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { links_.mail[r] = mailbox_; continue; }
+        void *ptr = nullptr;
+        if (!open(handles + 192 * r + 128, &ptr)) { cudaGetLastError(); return 2; }
+        links_.mail[r] = (PeerMailbox *)ptr;
+    }
+    const int *me = layout + 4 * rank;
+    if (rank > 0) {
+        const int *nb = layout + 4 * (rank - 1);
+        for (int b = 0; b < 2; b++) {
+            void *ptr = nullptr;
+            if (!open(handles + 192 * (rank - 1) + 64 * b, &ptr)) { cudaGetLastError(); return 3; }
+            links_.down_buf[b] = (double *)ptr;
+        }
+        links_.down_delta = (long long)(nb[1] - me[0]) * geom_.ld;  // my row own_lo + i -> its row own_hi' + i
+        links_.need_low = (unsigned long long)nb[3];                // its upward pushes land in my low halo
+    }
+    if (rank < world - 1) {
+        const int *nb = layout + 4 * (rank + 1);
+        for (int b = 0; b < 2; b++) {
+            void *ptr = nullptr;
+            if (!open(handles + 192 * (rank + 1) + 64 * b, &ptr)) { cudaGetLastError(); return 4; }
+            links_.up_buf[b] = (double *)ptr;
+        }
+        links_.up_delta = (long long)(nb[0] - me[1]) * geom_.ld;    // my row own_hi - HY + i -> its row own_lo'' - HY + i
+        links_.need_high = (unsigned long long)nb[2];
+    }
+    links_.push_low = (unsigned long long)me[2];
+    links_.push_high = (unsigned long long)me[3];
+    links_.enabled = 1;
+    distributed_ = true;
+    peer_gidx_ = 0;
+    return 0;
+}
+
+void PoissonSolver::peer_quiesce(cudaStream_t s)
+{
+    if (!links_.enabled) return;
+    PeerLinks L = links_;
+    L.gidx = peer_gidx_;
+    k_peer_quiesce<<<1, 1, 0, s>>>(L);
+    count_launch(1);
+}
+
+void PoissonSolver::peer_ready(cudaStream_t s)
+{
+    if (!links_.enabled) return;
+    PeerLinks L = links_;
+    L.epoch = ++peer_epoch_;
+    k_peer_ready<<<1, 1, 0, s>>>(L);
+    count_launch(1);
 }
 
 void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
@@ -248,12 +530,18 @@ void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
     double *hist = use_hist_ ? hist_ : nullptr;
     const int fused = distributed_ ? 0 : 1;
     for (int i = 0; i < npasses; i++) {
+        PeerLinks L = links_;
+        if (L.enabled) {
+            L.pidx = dist_passes_++;
+            L.gidx = peer_gidx_++;
+            L.epoch = peer_epoch_;
+        }
 #define CNV_PASS(TT)                                                                                                     \
     if (T_ == TT) {                                                                                                      \
         if (rc_.pow2)                                                                                                    \
-            launch_pass<TT, true>(geom_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, threads_, smem_, s); \
+            launch_pass<TT, true>(geom_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, threads_, smem_, s, L); \
         else                                                                                                             \
-            launch_pass<TT, false>(geom_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, threads_, smem_, s); \
+            launch_pass<TT, false>(geom_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, threads_, smem_, s, L); \
     }
         CNV_PASS(1) CNV_PASS(2) CNV_PASS(4) CNV_PASS(6) CNV_PASS(8)
 #undef CNV_PASS

@@ -397,6 +397,39 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
     }
 }
 
+// ---- multi-GPU peer-memory path ------------------------------------------------------------------
+// Every rank owns a PeerMailbox in its device memory that the other ranks write over NVLink (CUDA IPC
+// mappings).  All counters are cumulative over the life of the communicator (never reset), indexed by the
+// GLOBAL pass number g (every launched pass, no-ops included, counts on every rank):
+//   halo_count[0|1]  CTAs of the lower|upper neighbour that have finished pushing their boundary rows into my
+//                    low|high halo: after pass g it is (g+1) x (pushing CTAs of that neighbour)
+//   ready[0|1]       the lower|upper neighbour has finished re-initialising its iterate buffers for solve epoch e:
+//                    pass 0 of a solve must not push into a buffer the neighbour is still about to zero
+//   norm_flag[r]     g+1 once rank r has published the per-sweep norms of pass g into norms[g&1][r][*]
+constexpr int kMaxRanks = 8;
+struct PeerMailbox {
+    unsigned long long halo_count[2];
+    unsigned long long ready[2];  // epoch of the lower|upper neighbour's latest (re-)initialised iterate buffers
+    unsigned long long norm_flag[kMaxRanks];
+    double norms[2][kMaxRanks][8];
+    unsigned long long error;  // a spin-wait timed out (a peer died): the host aborts
+    unsigned int ticket;       // local: last-CTA election of the pass kernel
+    unsigned int pad_;
+};
+struct PoissonCtl;
+struct PeerLinks {
+    int enabled, rank, world;
+    int pidx;                  // pass index since the last reset of the state machine
+    unsigned long long gidx;   // global pass index
+    unsigned long long epoch;  // number of (re-)initialisations of the iterate so far (identical on every rank)
+    PeerMailbox *mail[kMaxRanks];
+    double *down_buf[2], *up_buf[2];   // neighbours' iterate buffers (peer mappings), null at the ends
+    long long down_delta, up_delta;    // element offset: my row -> its halo copy in the neighbour's array
+    unsigned long long need_low, need_high;  // pushes per pass arriving in my low / high halo
+    unsigned long long push_low, push_high;  // pushes per pass I make downwards / upwards
+    PoissonCtl *ctlbuf;        // [2]: ctlbuf[p & 1] = state used by pass p
+};
+
 // ---- solver state machine (one instance per solve, device resident) ---------------------------
 // Reference semantics (src/poisson.c:234-284): for k = 0..itmax-1 { sweep; e = sum|u-u0|;
 // if (e < tol) return u (log k) }; exit(1).  A pass applies nsw <= T sweeps and records one norm

@@ -105,10 +105,36 @@ class SlabPoisson:
         self.rhs = torch.as_tensor(_DevView(self.L.cnv_poisson_rhs_ptr(self.h), (self.nrows, self.ld)), device=dev)
         self.norms = torch.as_tensor(_DevView(self.L.cnv_poisson_norms_ptr(self.h), (8,)), device=dev)
         self.passes_enqueued = 0
-        # per-pass exchange: the library's own NCCL group on the compute stream when available, else torch p2p
+        # per-pass exchange, best first (CNV_DIST_BACKEND = peer | nccl | torch):
+        #   peer   boundary rows stored into the neighbours' halos by the pass kernel itself over NVLink (CUDA IPC),
+        #          norms published in every rank's mailbox: one kernel per pass, no collective launch
+        #   nccl   the library's own NCCL group on the compute stream (halos + norm all-gather) + decide kernel
+        #   torch  torch.distributed batch_isend_irecv + all_reduce
+        backend = os.environ.get("CNV_DIST_BACKEND", "peer")
         self.comm = native_comm(self.L, dist, torch, rank, world)
         if self.comm:
             self.L.cnv_poisson_attach_comm(self.h, self.comm)
+        self.peer = backend == "peer" and world <= 8 and self._setup_peer()
+
+    def _setup_peer(self):
+        """Exchange CUDA-IPC handles / push counts and map the neighbours' buffers; all ranks or none."""
+        L, dist, torch = self.L, self.dist, self.torch
+        buf = C.create_string_buffer(192)
+        L.cnv_poisson_peer_export(self.h, buf)
+        lo, hi = C.c_longlong(), C.c_longlong()
+        L.cnv_poisson_peer_push_counts(self.h, self.rank, self.world, C.byref(lo), C.byref(hi))
+        mine = (buf.raw, [self.own_lo, self.own_hi, int(lo.value), int(hi.value)])
+        allr = [None] * self.world
+        dist.all_gather_object(allr, mine)
+        handles = b"".join(a[0] for a in allr)
+        layout = (C.c_int * (4 * self.world))(*[x for a in allr for x in a[1]])
+        rc = L.cnv_poisson_peer_import(self.h, self.rank, self.world, handles, layout)
+        ok = torch.tensor([1 if rc == 0 else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            L.cnv_poisson_peer_disable(self.h)
+            return False
+        return True
 
     # ---- data movement ----------------------------------------------------------------------
     def set_consts(self, dx, dy, beta):
@@ -159,6 +185,10 @@ class SlabPoisson:
         self.passes_enqueued = 0
 
     def enqueue(self, npasses):
+        if self.peer:  # one kernel per pass: the exchange is fused into it (peer stores over NVLink)
+            self.L.cnv_poisson_enqueue(self.h, npasses, self.stream)
+            self.passes_enqueued += npasses
+            return
         if self.comm:  # one NCCL group + decide kernel per pass, enqueued by the library (no Python per pass)
             self.L.cnv_poisson_enqueue_dist(self.h, npasses, self.stream)
             self.passes_enqueued += npasses

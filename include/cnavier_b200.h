@@ -83,6 +83,9 @@ int cnv_poisson_solve(cnv_poisson *p, int itmax, double tol, void *stream, int *
                       int *result_buf);
 /* asynchronous building blocks: reset the device state machine, enqueue passes (each applies up to T
  * sweeps, no-ops once the state machine has stopped), read the state back (synchronises). */
+/* residual history for the asynchronous building blocks: hist[k] = global L1 update norm of sweep k */
+void cnv_poisson_enable_history(cnv_poisson *p, int capacity);
+int cnv_poisson_read_history(cnv_poisson *p, double *out, int n);
 void cnv_poisson_reset(cnv_poisson *p, int itmax, double tol, void *stream);
 void cnv_poisson_enqueue(cnv_poisson *p, int npasses, void *stream);
 void cnv_poisson_enqueue_decide(cnv_poisson *p, void *stream);
@@ -103,6 +106,18 @@ void cnv_comm_destroy(cnv_comm *c);
 void cnv_poisson_attach_comm(cnv_poisson *p, cnv_comm *c);
 void cnv_poisson_enqueue_dist(cnv_poisson *p, int npasses, void *stream);
 void cnv_poisson_exchange_halos(cnv_poisson *p, double *field_dev, int depth, void *stream);
+
+/* Peer-memory path (CUDA IPC over NVLink; one process per GPU on one node).  Once set up, cnv_poisson_enqueue() needs
+ * no collective at all: the pass kernel stores its boundary rows straight into the neighbours' halo rows, counts its
+ * pushes in the neighbours' mailboxes, publishes its per-sweep norms in every rank's mailbox, and every CTA of the next
+ * pass derives the stop decision itself.  Setup: every rank exports 192 bytes (IPC handles of both iterate buffers and
+ * its mailbox) and its push counts; the caller all-gathers them (world x 192 bytes; world x 4 ints: own_lo, own_hi,
+ * push_low, push_high) and every rank imports.  All spin-waits time out after 4 s (message + exit(1)). */
+void cnv_poisson_peer_export(cnv_poisson *p, unsigned char *out192);
+void cnv_poisson_peer_push_counts(cnv_poisson *p, int rank, int world, long long *low, long long *high);
+int cnv_poisson_peer_import(cnv_poisson *p, int rank, int world, const unsigned char *handles, const int *layout);
+void cnv_poisson_peer_disable(cnv_poisson *p);
+int cnv_poisson_peer_enabled(cnv_poisson *p);
 
 /* ---- device-resident time stepping: the loop body of src/main.c:283-395 ---------------------- */
 typedef struct cnv_sim cnv_sim;

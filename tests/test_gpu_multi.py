@@ -19,24 +19,40 @@ def _ngpus():
         return 0
 
 
-def _torchrun(script, args, world, port):
+BACKENDS = ["peer", "nccl", "torch"]  # CNV_DIST_BACKEND: in-kernel NVLink peer stores | library NCCL group | torch p2p
+
+
+def _torchrun(script, args, world, port, backend="peer"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist", script)] + [str(a) for a in args]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, CNV_DIST_BACKEND=backend)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_slab_poisson_bitwise(world):
+def test_slab_poisson_bitwise(world, backend):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    assert "SLAB CHECK PASSED" in _torchrun("slab_gpu_check.py", [world * 40, 96, 4], world, 29700 + world)
-    assert "SLAB CHECK PASSED" in _torchrun("slab_gpu_check.py", [1024, 1024, 8], world, 29710 + world)
+    assert "SLAB CHECK PASSED" in _torchrun("slab_gpu_check.py", [world * 40, 96, 4], world, 29700 + world, backend)
+    assert "SLAB CHECK PASSED" in _torchrun("slab_gpu_check.py", [1024, 1024, 8], world, 29710 + world, backend)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_time_stepping_bitwise(world, backend):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    assert "SLAB SIM CHECK PASSED" in _torchrun("slab_sim_gpu_check.py", [128, 4], world, 29720 + world, backend)
 
 
 @pytest.mark.parametrize("world", [2, 4])
-def test_slab_time_stepping_bitwise(world):
+def test_slab_peer_repeated_solves(world):
+    """Back-to-back solves on the peer-memory path: per-sweep residual history and field identical to the single-GPU
+    solve every time (guards the epoch handshake between re-initialising the iterate and the neighbours' pushes)."""
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    assert "SLAB SIM CHECK PASSED" in _torchrun("slab_sim_gpu_check.py", [128, 4], world, 29720 + world)
+    assert "STRESS PASSED" in _torchrun("slab_stress.py", [world * 100, 96, 4, 12], world, 29730 + world, "peer")
+    assert "STRESS PASSED" in _torchrun("slab_stress.py", [1024, 1024, 8, 4], world, 29740 + world, "peer")
