@@ -232,6 +232,10 @@ void cnv_poisson_plan_info(const cnv_poisson *p, long long *out)
     out[0] = g.WS; out[1] = g.HX; out[2] = g.Wout; out[3] = g.Hout; out[4] = g.nstrips; out[5] = g.nchunks;
     out[6] = pass_threads(p->s->T(), g.WS); out[7] = (long long)pass_smem_bytes(p->s->T(), g.WS);
     out[8] = p->s->T(); out[9] = p->s->consts().pow2;
+    const TileGeom &t = p->s->tile_geom();
+    out[10] = p->s->tiled() ? 1 : 0;
+    out[11] = t.KP; out[12] = t.M; out[13] = t.NSEG; out[14] = t.OW; out[15] = t.OH; out[16] = t.ntx; out[17] = t.nty;
+    if (p->s->tiled()) { out[6] = round_up(t.KP * t.NSEG, 32); out[7] = (long long)tile_smem_bytes(t); }
 }
 int cnv_poisson_prepare(cnv_poisson *p, const double *f_dev, int ldf, double fsign, void *stream)
 {

@@ -8,6 +8,7 @@
 
 #include "fd_coeffs.h"
 #include "poisson_plan.h"
+#include "poisson_tile.h"
 
 // The reference reports failures with a message and exit(1) (src/poisson.c:280-284,
 // src/linearalg.c:58-79); CUDA errors follow the same convention.
@@ -63,6 +64,10 @@ bool resident_plan(int nrows, int ncols, int ld, size_t smem_limit, ResidentGeom
 void launch_resident(const ResidentGeom &g, size_t smem, const RelaxConsts &rc, const double *psi0, const double *rhs, double *out,
                      PoissonCtl *ctl, double *hist, int itmax, double tol, cudaStream_t s);
 
+// ---- poisson_tile.cu: stationary-tile pass kernel for grids that fit shared memory / L2 ----
+void launch_tile_pass(const TileGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
+                      double *partials, double *hist, double *norms, int fused, cudaStream_t s);
+
 // ---- poisson.cu ----
 struct PoissonResult {
     int status;  // 0 converged, 1 itmax reached (the reference exits the process here)
@@ -88,6 +93,8 @@ public:
     int ld() const { return geom_.ld; }
     int T() const { return T_; }
     const PassGeom &geom() const { return geom_; }
+    bool tiled() const { return use_tile_; }  // passes run the stationary-tile kernel (poisson_tile.cu)
+    const TileGeom &tile_geom() const { return tile_; }
     double *rhs() { return rhs_; }                // device, pitch ld(): pscale * f
     double *buffer(int i) { return buf_[i]; }     // the two iterate buffers
     double *history() { return hist_; }
@@ -135,6 +142,8 @@ public:
 private:
     int T_;
     PassGeom geom_;
+    TileGeom tile_ = {};
+    bool use_tile_ = false;
     RelaxConsts rc_;
     double *buf_[2] = {nullptr, nullptr};
     double *rhs_ = nullptr, *partials_ = nullptr, *hist_ = nullptr, *norms_ = nullptr;

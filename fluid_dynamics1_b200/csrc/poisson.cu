@@ -160,13 +160,19 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     const int kk = tid - st.g * TPG;
 
     stream_prologue<T>(st, sm);  // kPrefetch rows in flight
-    for (int r = st.ybase; r <= st.rend; r += 2) {
+    for (int r = st.ybase; r <= st.rend; r += 4) {
         cp_async_wait<kPrefetch - 1 - kLand>();  // row r (+kLand) has landed (this thread's copies) ...
         __syncthreads();                 // ... and everybody's; previous step's updates are visible
         stream_step<T, POW2, 0>(st, rc, sm, out, r, nsw);
         cp_async_wait<kPrefetch - 1 - kLand>();
         __syncthreads();
         stream_step<T, POW2, 1>(st, rc, sm, out, r + 1, nsw);
+        cp_async_wait<kPrefetch - 1 - kLand>();
+        __syncthreads();
+        stream_step<T, POW2, 2>(st, rc, sm, out, r + 2, nsw);
+        cp_async_wait<kPrefetch - 1 - kLand>();
+        __syncthreads();
+        stream_step<T, POW2, 3>(st, rc, sm, out, r + 3, nsw);
     }
     cp_async_wait<0>();
     const double acc = st.acc;
@@ -322,6 +328,8 @@ static void launch_pass(const PassGeom &g, const RelaxConsts &rc, double *b0, do
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int kTileAutoWaves = 0;  // default use of the tile kernel: grids of up to this many waves of tiles (0 = opt-in only)
+
 static int env_int(const char *name, int dflt)
 {
     const char *e = std::getenv(name);
@@ -361,6 +369,17 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
     }
     threads_ = pass_threads(T, geom_.WS);
     smem_ = pass_smem_bytes(T, geom_.WS);
+    // CNV_POISSON_TILE: 1 = stationary-tile kernel whenever a tile plan exists, 0 = never, default = by size
+    // (the tile kernel wins while the grid fits a few waves of tiles, see profiles/)
+    const int tile_mode = env_int("CNV_POISSON_TILE", -1);
+    if (tile_mode != 0 && T >= 2) {
+        double cost = 0;
+        if (tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, lim.num_sms, lim.smem_per_cta - 2560, &tile_, &cost,
+                      env_int("CNV_TILE_KP", 0), env_int("CNV_TILE_M", 0), env_int("CNV_TILE_NSEG", 0))) {
+            const long tiles = (long)tile_.ntx * tile_.nty;
+            use_tile_ = tile_mode == 1 || tiles <= kTileAutoWaves * lim.num_sms;
+        }
+    }
     std::memset(&rc_, 0, sizeof rc_);
     const size_t bytes = (size_t)nrows * ld * sizeof(double);
     for (int i = 0; i < 2; i++) {
@@ -369,7 +388,9 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
     }
     CNV_CUDA_CHECK(cudaMalloc(&rhs_, bytes));
     CNV_CUDA_CHECK(cudaMemset(rhs_, 0, bytes));
-    CNV_CUDA_CHECK(cudaMalloc(&partials_, sizeof(double) * (size_t)geom_.nstrips * geom_.nchunks * T));
+    size_t npart = (size_t)geom_.nstrips * geom_.nchunks * T;
+    if (use_tile_ && npart < (size_t)tile_.ntx * tile_.nty * 8) npart = (size_t)tile_.ntx * tile_.nty * 8;
+    CNV_CUDA_CHECK(cudaMalloc(&partials_, sizeof(double) * npart));
     CNV_CUDA_CHECK(cudaMalloc(&norms_, sizeof(double) * 8));
     CNV_CUDA_CHECK(cudaMemset(norms_, 0, sizeof(double) * 8));
     CNV_CUDA_CHECK(cudaMalloc(&ctl_, sizeof(PoissonCtl)));
@@ -502,6 +523,7 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
     links_.push_low = (unsigned long long)me[2];
     links_.push_high = (unsigned long long)me[3];
     links_.enabled = 1;
+    use_tile_ = false;  // the in-kernel peer exchange is part of the streaming kernel
     distributed_ = true;
     peer_gidx_ = 0;
     return 0;
@@ -530,6 +552,10 @@ void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
     double *hist = use_hist_ ? hist_ : nullptr;
     const int fused = distributed_ ? 0 : 1;
     for (int i = 0; i < npasses; i++) {
+        if (use_tile_) {
+            launch_tile_pass(tile_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, s);
+            continue;
+        }
         PeerLinks L = links_;
         if (L.enabled) {
             L.pidx = dist_passes_++;

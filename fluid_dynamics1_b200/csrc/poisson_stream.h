@@ -130,6 +130,11 @@ __device__ __forceinline__ void sts1(double *, int off, double a)
     asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(off), "d"(a) : "memory");
 }
 __device__ __forceinline__ void stg2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+__device__ __forceinline__ dbl2 ldg2(const double *p)
+{
+    const double2 v = __ldcg(reinterpret_cast<const double2 *>(p));  // L2 only: the other buffer is written every pass
+    return {v.x, v.y};
+}
 #else
 inline int smem_base(const double *) { return 0; }
 inline double *at(const double *sm, int off) { return reinterpret_cast<double *>(reinterpret_cast<char *>(const_cast<double *>(sm)) + off); }
@@ -140,6 +145,7 @@ inline double lds1(const double *sm, int off) { return *at(sm, off); }
 inline void sts2(double *sm, int off, double a, double b) { at(sm, off)[0] = a; at(sm, off)[1] = b; }
 inline void sts1(double *sm, int off, double a) { *at(sm, off) = a; }
 inline void stg2(double *p, double a, double b) { p[0] = a; p[1] = b; }
+inline dbl2 ldg2(const double *p) { return {p[0], p[1]}; }
 #endif
 
 // kPairs doubles of one parity array (pairs k0 .. k0+kPairs-1), moved as 16-byte vectors
@@ -198,12 +204,16 @@ struct StreamThread {
     bool sact;
     // compute
     int g, dq, k0;
-    int o[4];            // byte offsets of the slots of rows qtop, qtop-1, qtop-2, qtop-3 (qtop = r - dq)
+    // byte offsets of the slots of rows qtop, qtop-1, qtop-2, qtop-3 (qtop = r - dq).  Like the histories below the
+    // four entries are a rotating window: the step loop is unrolled by four and in phase PH (= step mod 4) the
+    // offset of row qtop-j lives in o[(j - PH) & 3], so that moving down one row renames instead of copying
+    int o[4];
     int aSE, aSO, aPE, aPO;  // array byte offsets inside a slot, k0 folded in
     int vmask;           // bit 2p / 2p+1: even / odd column of pair k0+p updatable
     bool colown, allvalid;
-    vecP h1, h2, h3;     // N loaded 1, 2, 3 steps ago
-    vecP r1, r2, r3;     // red results of 1, 2, 3 steps ago
+    // h[(PH - a) & 3] = N loaded a steps ago, rr[(PH - a) & 3] = red results of a steps ago (a = 0: this step);
+    // compile-time indices, so both stay in registers and no register moves are needed to age them
+    vecP h[4], rr[4];
     vecP pf_N, pf_own, pf_Pr, pf_Pb;  // operands of THIS step, loaded during the previous step (software pipelining)
     double pf_x, pf_xb;
     double acc;
@@ -228,7 +238,7 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     // are loaded one step before they are used)
     s.ybase = G.ylo - kLand - ((p.grow0 + G.ylo - kLand - 1) & 1);
     s.rend = G.y1 + 2 + kSkew * (T - 1);  // the last level's black stage reaches row y1-1
-    if (((s.rend - s.ybase) & 1) == 0) s.rend++;  // whole pairs of steps
+    s.rend += (4 - ((s.rend - s.ybase + 1) & 3)) & 3;  // whole quads of steps (the extra ones find nothing to do)
     s.ylo = G.ylo; s.yhi = G.yhi; s.y0 = G.y0; s.y1 = G.y1;
     s.vlo = G.ylo + 1 > 1 - p.grow0 ? G.ylo + 1 : 1 - p.grow0;
     s.vhi = G.yhi - 1 < p.gnrows - 2 - p.grow0 ? G.yhi - 1 : p.gnrows - 2 - p.grow0;
@@ -260,7 +270,7 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     const int gc4 = G.gx0 + 2 * t.k0;  // first of this thread's columns
     s.sact = t.g == T - 1 && t.colown && gc4 >= 0 && gc4 < p.ld;
     s.sdst = (long long)(s.ybase - 3 - s.dq) * p.ld + gc4;
-    s.h1 = s.h2 = s.h3 = s.r1 = s.r2 = s.r3 = zeroP();
+    for (int j = 0; j < 4; j++) s.h[j] = s.rr[j] = zeroP();
     s.pf_N = s.pf_own = s.pf_Pr = s.pf_Pb = zeroP();
     s.pf_x = s.pf_xb = 0.0;
     s.acc = 0.0;
@@ -299,11 +309,14 @@ CNV_HD void stream_prologue(const StreamThread<T> &s, double *sm)
 // One step of the stream (the caller has waited for row r and passed the CTA barrier):
 // issue the copy of row r+kPrefetch, then update this thread's red row r-1-dq and black row r-3-dq;
 // threads of the last level write the finished black row back to global memory.
-// PAR = parity of (global red row): 0 -> the red cells of this step are the even-column cells.
+// PH = step number mod 4 (selects the rotating register windows); PAR = PH & 1 = parity of (global red row):
+// 0 -> the red cells of this step are the even-column cells.
 // Loads and arithmetic are unconditional so that the four cell updates of a step interleave; validity
 // (Dirichlet ring, halo edges, pipeline fill/drain) is applied by selects only on the slow path -- threads
 // whose four columns are all updatable take the select-free path whenever both rows are updatable.
-template <int T, bool POW2, int PAR>
+constexpr int rot4(int j, int ph) { return (j - ph) & 3; }
+
+template <int T, bool POW2, int PH>
 CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, double *__restrict__ out, int r, int nsw)
 {
     // ---- load ----
@@ -314,20 +327,24 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
     s.lslot = wrap_inc_t<T>(s.lslot, s.ss, s.ringend);
 
     // ---- relax ----
-    constexpr bool typeR = PAR != 0;  // red cells are the odd-column cells
+    constexpr bool typeR = (PH & 1) != 0;  // red cells are the odd-column cells
+    constexpr int O0 = rot4(0, PH), O1 = rot4(1, PH), O3 = rot4(3, PH);  // slots of rows qtop, qtop-1, qtop-3
+    constexpr int A0 = PH, A1 = (PH + 3) & 3, A2 = (PH + 2) & 3, A3 = (PH + 1) & 3;  // history of 0..3 steps ago
     const int aA = typeR ? s.aSO : s.aSE, aB = typeR ? s.aSE : s.aSO;
     const int qtop = r - s.dq, q = qtop - 1, qb = qtop - 3;
     // every operand but (with kSkew == 4) the row above the red row was loaded during the previous step (see the
     // end of this function); that row is written by the level below during the previous step and is read now
-    const vecP N = kSkew > 4 ? s.pf_N : ldsP(sm, s.o[0] + aA);
+    s.h[A0] = kSkew > 4 ? s.pf_N : ldsP(sm, s.o[O0] + aA);
+    const vecP &N = s.h[A0];
     const vecP own = s.pf_own, Pr = s.pf_Pr, Pb = s.pf_Pb;
     const double x = s.pf_x, xb = s.pf_xb;
-    const vecP b = s.h1, S = s.h2;
-    const vecP ownb = s.h3, Nb = s.r1, bb = s.r2, Sb = s.r3;
+    const vecP &b = s.h[A1], &S = s.h[A2];
+    const vecP &ownb = s.h[A3], &Nb = s.rr[A1], &bb = s.rr[A2], &Sb = s.rr[A3];
     // even-column cell of pair k: W = odd[k-1], E = odd[k];  odd-column cell: W = even[k], E = even[k+1]
     // red cells (type typeR) have their E/W neighbours in b (+ x at the thread's edge); black cells (the other
     // type) have theirs in bb (+ xb)
-    vecP n, m;
+    vecP &n = s.rr[A0];  // (overwrites the red results of four steps ago, which nobody needs any more)
+    vecP m;
 #pragma unroll
     for (int i = 0; i < kPairs; i++) {
         const double Wr = typeR ? b.v[i] : (i == 0 ? x : b.v[i - 1]);
@@ -339,8 +356,8 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
     }
     if (s.allvalid && s.g < nsw && qb >= s.vlo && q <= s.vhi) {
         // fast path: all cells updatable (rows q, qb are inside the streamed range by construction)
-        stsP(sm, s.o[1] + aA, n);
-        stsP(sm, s.o[3] + aB, m);
+        stsP(sm, s.o[O1] + aA, n);
+        stsP(sm, s.o[O3] + aB, m);
     } else {
         const bool active = s.g < nsw;
         const bool rowr = active && q >= s.vlo && q <= s.vhi;
@@ -351,8 +368,8 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
             n.v[i] = (rowr & vr) ? n.v[i] : own.v[i];
             m.v[i] = (rowb & vb) ? m.v[i] : ownb.v[i];
         }
-        if (q >= s.ylo && q <= s.yhi) stsP(sm, s.o[1] + aA, n);
-        if (qb >= s.ylo && qb <= s.yhi) stsP(sm, s.o[3] + aB, m);
+        if (q >= s.ylo && q <= s.yhi) stsP(sm, s.o[O1] + aA, n);
+        if (qb >= s.ylo && qb <= s.yhi) stsP(sm, s.o[O3] + aB, m);
     }
     // L1 update norm of this level (non-updated cells contribute exactly 0)
     if (s.colown) {
@@ -375,11 +392,10 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         }
     }
     s.sdst += s.ld;
-    // rows move up by one: rotate histories and slot offsets
-    s.h3 = s.h2; s.h2 = s.h1; s.h1 = N;
-    s.r3 = s.r2; s.r2 = s.r1; s.r1 = n;
-    s.o[3] = s.o[2]; s.o[2] = s.o[1]; s.o[1] = s.o[0];
-    s.o[0] = wrap_inc_t<T>(s.o[0], s.ss, s.ringend);
+    // rows move up by one: the windows rotate by renaming (PH -> PH+1); only the new top slot is computed
+    constexpr int PN = (PH + 1) & 3;
+    constexpr int N0 = rot4(0, PN), N1 = rot4(1, PN), N3 = rot4(3, PN);
+    s.o[N0] = wrap_inc_t<T>(s.o[O0], s.ss, s.ringend);
     // ---- software pipelining: operands of the NEXT step that nobody writes during this one ----
     // next red row = this step's row qtop (its red cells carry the level below since >= 3 steps, its black
     // cells since the previous step; rhs is static); next black row = this step's row q-1 (its red cells were
@@ -388,12 +404,12 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         constexpr bool tN = !typeR;
         const int nA = tN ? s.aSO : s.aSE, nB = tN ? s.aSE : s.aSO;
         const int nPA = tN ? s.aPO : s.aPE, nPB = tN ? s.aPE : s.aPO;
-        if (kSkew > 4) s.pf_N = ldsP(sm, s.o[0] + nA);
-        s.pf_own = ldsP(sm, s.o[1] + nA);
-        s.pf_Pr = ldsP(sm, s.o[1] + nPA);
-        s.pf_x = lds1(sm, s.o[1] + nB + (tN ? 8 * kPairs : -8));
-        s.pf_Pb = ldsP(sm, s.o[3] + nPB);
-        s.pf_xb = lds1(sm, s.o[3] + nA + (tN ? -8 : 8 * kPairs));
+        if (kSkew > 4) s.pf_N = ldsP(sm, s.o[N0] + nA);
+        s.pf_own = ldsP(sm, s.o[N1] + nA);
+        s.pf_Pr = ldsP(sm, s.o[N1] + nPA);
+        s.pf_x = lds1(sm, s.o[N1] + nB + (tN ? 8 * kPairs : -8));
+        s.pf_Pb = ldsP(sm, s.o[N3] + nPB);
+        s.pf_xb = lds1(sm, s.o[N3] + nA + (tN ? -8 : 8 * kPairs));
     }
 }
 

@@ -1,0 +1,120 @@
+// poisson_tile.cu -- the stationary-tile pass kernel of the Poisson solve (see poisson_tile.h) and its planner.
+//
+// Replaces the same reference code as the streaming kernel (src/poisson.c:224-285: T red-black SOR sweeps and the
+// sum |u - u0| of each of them per launch) for grids small enough that the streaming kernel's pipeline fill and
+// y-halo dominate.  Control flow (PoissonCtl, decide(): first sweep with e < tol, "redo" pass, itmax) is shared.
+#include <cstring>
+
+#include "kernels.h"
+
+namespace cnv {
+
+
+template <int M, bool POW2>
+__global__ void __launch_bounds__(tile_max_threads(M), 1)
+k_poisson_tile(const TileGeom g, const RelaxConsts rc, double *__restrict__ buf0, double *__restrict__ buf1,
+               const double *__restrict__ rhs, PoissonCtl *ctl, double *__restrict__ partials, double *hist, double *norms_out,
+               const int fused_decide)
+{
+    extern __shared__ double4 sm4[];
+    double *sm = reinterpret_cast<double *>(sm4);
+    __shared__ double s_part[8][32];  // [sweep of the pass][warp]
+    __shared__ double s_e[8];
+    __shared__ int s_last;
+
+    const PoissonCtl c0 = *ctl;
+    if (c0.state != 0) return;  // solve already finished: later passes of a batch are no-ops
+    const int nsw = pass_sweeps(c0, g.T);
+    const double *__restrict__ in = c0.cur ? buf1 : buf0;
+    double *__restrict__ out = c0.cur ? buf0 : buf1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+
+    // the block is rounded up to whole warps (shuffles, barriers); the surplus threads own no cells
+    const bool active = tid < g.KP * g.NSEG;
+    TileThread<M> t;
+    t.acc = 0.0;
+    if (active) tile_load<M>(t, g, blockIdx.x, blockIdx.y, tid, sm, in, rhs);
+    // colour 0 (red) = (global row + column) even; tile column 0 is even, so in tile row 0 the red cell of a pair is
+    // its even column iff the global row of tile row 0 is even
+    const int par0 = (g.grow0 + g.own_lo + (int)blockIdx.y * g.OH - g.HT) & 1;
+    __syncthreads();
+    for (int s = 0; s < nsw; s++) {
+        if (active) {
+            if (par0 == 0) tile_half_sweep<M, POW2, 0>(t, rc, sm); else tile_half_sweep<M, POW2, 1>(t, rc, sm);
+        }
+        __syncthreads();
+        if (active) {
+            if (par0 == 0) tile_half_sweep<M, POW2, 1>(t, rc, sm); else tile_half_sweep<M, POW2, 0>(t, rc, sm);
+        }
+        // this sweep's norm: fixed-order warp sum -> one slot per warp
+        double a = t.acc;
+        t.acc = 0.0;
+        for (int o = 16; o > 0; o >>= 1) a = xadd(a, __shfl_xor_sync(0xffffffffu, a, o));
+        if (lane == 0) s_part[s][warp] = a;
+        __syncthreads();
+    }
+    if (active) tile_store<M>(t, out);
+
+    if (tid < nsw) {
+        double e = 0.0;
+        for (int w = 0; w < nwarps; w++) e = xadd(e, s_part[tid][w]);
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+        partials[(size_t)cta * 8 + tid] = e;
+        __threadfence();
+    }
+    __syncthreads();
+    const int ncta = gridDim.x * gridDim.y;
+    if (tid == 0) s_last = atomicAdd(&ctl->ticket, 1u) == (unsigned)ncta - 1;
+    __syncthreads();
+    if (!s_last) return;
+
+    // last CTA: grid-wide sums in a fixed order (warp w <-> sweep w), then the stopping decision (src/poisson.c:272-279)
+    __threadfence();
+    for (int w = warp; w < 8; w += nwarps) {
+        double e = 0.0;
+        if (w < nsw) {
+            for (int c = lane; c < ncta; c += 32) e = xadd(e, __ldcg(&partials[(size_t)c * 8 + w]));
+            for (int o = 16; o > 0; o >>= 1) e = xadd(e, __shfl_xor_sync(0xffffffffu, e, o));
+        }
+        if (lane == 0) s_e[w] = e;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (fused_decide) {
+            PoissonCtl c = *ctl;
+            decide(c, s_e, nsw, hist);
+            c.ticket = 0;
+            *ctl = c;
+        } else {
+            for (int i = 0; i < 8; i++) norms_out[i] = i < nsw ? s_e[i] : 0.0;
+            ctl->ticket = 0;
+        }
+    }
+}
+
+template <int M, bool POW2>
+static void launch_tile_t(const TileGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
+                          double *partials, double *hist, double *norms, int fused, cudaStream_t s)
+{
+    const size_t smem = tile_smem_bytes(g);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_tile<M, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_poisson_tile<M, POW2><<<dim3(g.ntx, g.nty), round_up(g.KP * g.NSEG, 32), smem, s>>>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused);
+}
+
+void launch_tile_pass(const TileGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
+                      double *partials, double *hist, double *norms, int fused, cudaStream_t s)
+{
+#define CNV_TILE(MM)                                                                                  \
+    if (g.M == MM) {                                                                                  \
+        if (rc.pow2) launch_tile_t<MM, true>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, s); \
+        else launch_tile_t<MM, false>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, s);       \
+    }
+    CNV_TILE(6) CNV_TILE(8) CNV_TILE(10) CNV_TILE(12) CNV_TILE(14) CNV_TILE(16)
+#undef CNV_TILE
+}
+
+}  // namespace cnv

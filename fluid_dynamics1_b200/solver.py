@@ -114,9 +114,10 @@ class PoissonSolver:
             grow0, gnrows, own_lo, own_hi = slab
             self.h = self.L.cnv_poisson_create_slab(nrows, ncols, T, grow0, gnrows, own_lo, own_hi)
         self.nrows, self.ncols = nrows, ncols
-        info = (C.c_longlong * 10)()
+        info = (C.c_longlong * 18)()
         self.L.cnv_poisson_plan_info(self.h, info)
-        keys = ("WS", "HX", "Wout", "Hout", "nstrips", "nchunks", "threads", "smem", "T", "pow2")
+        keys = ("WS", "HX", "Wout", "Hout", "nstrips", "nchunks", "threads", "smem", "T", "pow2",
+                "tiled", "KP", "M", "NSEG", "OW", "OH", "ntx", "nty")
         self.plan = dict(zip(keys, list(info)))
         self.T = self.plan["T"]
         self.ld = self.L.cnv_poisson_ld(self.h)
@@ -130,7 +131,7 @@ class PoissonSolver:
 
     def set_consts(self, dx, dy, beta):
         self.L.cnv_poisson_set_consts(self.h, dx, dy, beta)
-        info = (C.c_longlong * 10)()
+        info = (C.c_longlong * 18)()
         self.L.cnv_poisson_plan_info(self.h, info)
         self.plan["pow2"] = info[9]
 

@@ -72,7 +72,8 @@ int cnv_poisson_ld(const cnv_poisson *p);                 /* pitch (doubles) of 
 double *cnv_poisson_rhs_ptr(cnv_poisson *p);              /* device: prepared right-hand side */
 double *cnv_poisson_buf_ptr(cnv_poisson *p, int which);   /* device: iterate buffers 0/1 */
 double *cnv_poisson_norms_ptr(cnv_poisson *p);            /* device: T per-sweep norms of the last pass */
-/* out[0..9] = WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, T, pow2-path flag */
+/* out[0..17] = WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, T, pow2-path flag (streaming kernel);
+   tiled (1: passes run the stationary-tile kernel), KP, M, NSEG, OW, OH, ntx, nty (its tile shape) */
 void cnv_poisson_plan_info(const cnv_poisson *p, long long *out);
 /* stage a host right-hand side f (nrows x ncols, dense) and zero the iterate; fsign = -1 solves with -f */
 int cnv_poisson_upload(cnv_poisson *p, const double *f_host, double fsign, void *stream);

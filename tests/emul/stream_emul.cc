@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../fluid_dynamics1_b200/csrc/poisson_plan.h"
+#include "../../fluid_dynamics1_b200/csrc/poisson_tile.h"
 
 using namespace cnv;
 
@@ -31,17 +32,78 @@ static void run_pass(const PassGeom &p, const RelaxConsts &rc, const double *in,
             const CtaGeom G = cta_geom(p, bx, by);
             for (int t = 0; t < NT; t++) stream_init<T>(st[t], p, G, sm.data(), in, rhs, t, NT);
             for (int t = 0; t < NT; t++) stream_prologue<T>(st[t], sm.data());
-            for (int r = st[0].ybase; r <= st[0].rend; r += 2) {
-                // --- barrier ---
+            for (int r = st[0].ybase; r <= st[0].rend; r += 4) {
+                // --- barrier before every step ---
                 for (int t = 0; t < NT; t++) stream_step<T, POW2, 0>(st[t], rc, sm.data(), out, r, nsw);
-                // --- barrier ---
                 for (int t = 0; t < NT; t++) stream_step<T, POW2, 1>(st[t], rc, sm.data(), out, r + 1, nsw);
+                for (int t = 0; t < NT; t++) stream_step<T, POW2, 2>(st[t], rc, sm.data(), out, r + 2, nsw);
+                for (int t = 0; t < NT; t++) stream_step<T, POW2, 3>(st[t], rc, sm.data(), out, r + 3, nsw);
             }
             for (int t = 0; t < NT; t++) norms[st[t].g] += st[t].acc;
         }
 }
 
+// stationary-tile kernel (poisson_tile.h): the same phases as k_poisson_tile, a barrier between them
+template <int M, bool POW2>
+static void run_tile_pass(const TileGeom &g, const RelaxConsts &rc, const double *in, const double *rhs, double *out, int nsw,
+                          double *norms)
+{
+    const int NT = g.KP * g.NSEG;
+    std::vector<double> sm(tile_smem_bytes(g) / sizeof(double));
+    std::vector<TileThread<M>> th(NT);
+    for (int s = 0; s < 8; s++) norms[s] = 0.0;
+    for (int by = 0; by < g.nty; by++)
+        for (int bx = 0; bx < g.ntx; bx++) {
+            for (auto &x : sm) x = std::nan("");
+            for (int t = 0; t < NT; t++) tile_load<M>(th[t], g, bx, by, t, sm.data(), in, rhs);
+            const int par0 = (g.grow0 + g.own_lo + by * g.OH - g.HT) & 1;
+            for (int s = 0; s < nsw; s++) {
+                for (int t = 0; t < NT; t++) {
+                    if (par0 == 0) tile_half_sweep<M, POW2, 0>(th[t], rc, sm.data()); else tile_half_sweep<M, POW2, 1>(th[t], rc, sm.data());
+                }
+                for (int t = 0; t < NT; t++) {
+                    if (par0 == 0) tile_half_sweep<M, POW2, 1>(th[t], rc, sm.data()); else tile_half_sweep<M, POW2, 0>(th[t], rc, sm.data());
+                }
+                for (int t = 0; t < NT; t++) { norms[s] += th[t].acc; th[t].acc = 0.0; }
+            }
+            for (int t = 0; t < NT; t++) tile_store<M>(th[t], out);
+        }
+}
+
 extern "C" {
+
+// tile plan only: KP, M, NSEG, OW, OH, ntx, nty, smem bytes in out[8]; returns 0 if a plan exists
+int emul_tile_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T, int fkp, int fm, int fnseg,
+                   long *out)
+{
+    TileGeom g;
+    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, nullptr, fkp, fm, fnseg)) return -1;
+    out[0] = g.KP; out[1] = g.M; out[2] = g.NSEG; out[3] = g.OW; out[4] = g.OH; out[5] = g.ntx; out[6] = g.nty;
+    out[7] = (long)tile_smem_bytes(g);
+    return 0;
+}
+
+// one pass of the tile kernel's schedule (see emul_pass for the arguments); fkp/fm/fnseg pin the tile shape
+int emul_tile_pass(int T, int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int fkp, int fm, int fnseg,
+                   double dx, double dy, double beta, int mode, const double *in, const double *f, double *out, int nsw,
+                   double *norms)
+{
+    TileGeom g;
+    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, nullptr, fkp, fm, fnseg)) return -1;
+    RelaxConsts rc = make_relax_consts(dx, dy, beta);
+    if (mode == 1) { rc.pow2 = 0; rc.pscale = rc.cf; }
+    std::vector<double> rhs((size_t)nrows * ld);
+    for (size_t i = 0; i < rhs.size(); i++) rhs[i] = rc.pscale * f[i];
+#define RUNT(MM)                                                                          \
+    if (g.M == MM) {                                                                      \
+        if (rc.pow2) run_tile_pass<MM, true>(g, rc, in, rhs.data(), out, nsw, norms);     \
+        else run_tile_pass<MM, false>(g, rc, in, rhs.data(), out, nsw, norms);            \
+        return 0;                                                                         \
+    }
+    RUNT(6) RUNT(8) RUNT(10) RUNT(12) RUNT(14) RUNT(16)
+#undef RUNT
+    return -2;
+}
 
 // plan only: returns WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes in out[8]
 void emul_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T, int force_ws,

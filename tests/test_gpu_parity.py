@@ -25,11 +25,12 @@ def _gpu():
     fd.require_gpu()
 
 
-@pytest.fixture(params=["resident", "stream"])
+@pytest.fixture(params=["resident", "stream", "tile"])
 def small_grid_path(request, monkeypatch):
-    """Small grids (<= ~360^2) are solved by the shared-memory-resident cluster kernel by default; the same
-    tests also run with it disabled so the streaming kernel stays covered at small sizes."""
+    """The three Poisson kernels: the whole-solve cluster kernel (single-CTA grids by default, forced here for every
+    grid it can hold), the streaming pass kernel, and the stationary-tile pass kernel (forced here for every grid)."""
     monkeypatch.setenv("CNV_POISSON_RESIDENT", "2" if request.param == "resident" else "0")  # 2 = force (clusters too)
+    monkeypatch.setenv("CNV_POISSON_TILE", "1" if request.param == "tile" else "0")
     return request.param
 
 
@@ -168,14 +169,19 @@ def test_poisson_full_size_fixed_sweeps(port, n, sweeps):
     f = rng.standard_normal((n, n))
     beta = port.beta(n, n)
     want, norms = port.poisson_sweeps(f, 1 / n, 1 / n, sweeps, beta)
-    for T in (1, 4):
-        s = fd.PoissonSolver(n, n, T)
+    for T, tile in ((1, 0), (4, 0), (8, 1), (6, 1)):
+        os.environ["CNV_POISSON_TILE"] = str(tile)
+        try:
+            s = fd.PoissonSolver(n, n, T)
+        finally:
+            del os.environ["CNV_POISSON_TILE"]
+        assert s.plan["tiled"] == tile
         s.set_consts(1 / n, 1 / n, beta)
         s.upload(f)
         r = s.solve(sweeps, 0.0)
         assert r["status"] == 1 and r["sweeps"] == sweeps
         got = s.download(r["buf"])
-        assert got.tobytes() == want.tobytes(), T
+        assert got.tobytes() == want.tobytes(), (T, tile)
         assert abs(r["e"] - norms[-1]) <= 1e-11 * norms[-1]
         s.close()
 

@@ -26,6 +26,8 @@ def emul():
     E.emul_plan.argtypes = [C.c_int] * 10 + [np.ctypeslib.ndpointer(dtype=np.int64)]
     E.emul_decide.argtypes = [ip, dp, dp, C.c_int, C.c_void_p]
     E.emul_pass_sweeps.argtypes = [C.c_int] * 4
+    E.emul_tile_pass.argtypes = [C.c_int] * 11 + [C.c_double] * 3 + [C.c_int, dp, dp, dp, C.c_int, dp]
+    E.emul_tile_plan.argtypes = [C.c_int] * 11 + [np.ctypeslib.ndpointer(dtype=np.int64)]
     E.emul_check_div.restype = C.c_long
     E.emul_check_div.argtypes = [C.c_double, dp, C.c_long]
     return E
@@ -64,6 +66,60 @@ def test_stream_schedule_bitwise_vs_oracle(emul, port, shape, T):
             got, want, gn, on = _emul_sweeps(emul, port, n, m, T, 3, mode, ws, ch)
             assert got.tobytes() == want.tobytes(), (shape, T, mode, ws, ch)
             np.testing.assert_allclose(gn, on, rtol=1e-13)
+
+
+def _emul_tile_sweeps(E, port, n, m, T, npass, mode, shape=(0, 0, 0), dx=None, dy=None, seed=0, last_nsw=None):
+    rng = np.random.default_rng(seed)
+    dx = dx or 1.0 / n
+    dy = dy or 1.0 / m
+    beta = port.beta(n, m)
+    f = rng.standard_normal((n, m))
+    ld = (m + 15) // 16 * 16
+    fp = np.zeros((n, ld))
+    fp[:, :m] = f
+    a, b = np.zeros((n, ld)), np.zeros((n, ld))
+    got_norms, total = [], 0
+    for ip in range(npass):
+        nsw = last_nsw if (last_nsw and ip == npass - 1) else T
+        norms = np.zeros(8)
+        assert E.emul_tile_pass(T, n, m, ld, 0, n, 0, n, *shape, dx, dy, beta, mode, a, fp, b, nsw, norms) == 0
+        a, b = b, a
+        got_norms += list(norms[:nsw])
+        total += nsw
+    u, onorms = port.poisson_sweeps(f, dx, dy, total, beta)
+    return a[:, :m], u, np.array(got_norms), onorms
+
+
+@pytest.mark.parametrize("T", [2, 4, 6, 8])
+@pytest.mark.parametrize("shape", [(64, 64), (40, 72), (100, 100), (33, 47), (131, 90)])
+def test_tile_schedule_bitwise_vs_oracle(emul, port, shape, T):
+    """The stationary-tile kernel's schedule (register-resident thread columns, 2T-cell halo on all four sides,
+    one barrier per half-sweep) == T plain red-black sweeps of the oracle, bit for bit; automatic and pinned tile
+    shapes (several tiles in x and y, odd and even tile origins), both arithmetic paths, short last pass."""
+    n, m = shape
+    for mode in (0, 1):
+        for tshape in ((0, 0, 0), (2 * T + 6, 6, 0), (2 * T + 9, 8, 0), (2 * T + 5, 10, 0), (2 * T + 8, 12, 0), (2 * T + 4, 14, 0), (2 * T + 4, 16, 0)):
+            got, want, gn, on = _emul_tile_sweeps(emul, port, n, m, T, 3, mode, tshape, last_nsw=max(1, T - 1))
+            assert got.tobytes() == want.tobytes(), (shape, T, mode, tshape)
+            np.testing.assert_allclose(gn, on, rtol=1e-13)
+
+
+def test_tile_schedule_nonuniform_spacing(emul, port):
+    got, want, gn, on = _emul_tile_sweeps(emul, port, 50, 38, 4, 2, 0, dx=0.013, dy=0.02)
+    assert got.tobytes() == want.tobytes()
+    np.testing.assert_allclose(gn, on, rtol=1e-13)
+
+
+def test_tile_planner_properties(emul):
+    for nrows, ncols in [(64, 64), (128, 128), (256, 256), (1024, 1024), (544, 4096), (2048, 2048), (33, 47)]:
+        for T in (2, 4, 6, 8):
+            o = np.zeros(8, dtype=np.int64)
+            assert emul.emul_tile_plan(nrows, ncols, (ncols + 15) // 16 * 16, 0, nrows, 0, nrows, T, 0, 0, 0, o) == 0
+            KP, M, NSEG, OW, OH, ntx, nty, smem = (int(x) for x in o)
+            assert M % 2 == 0 and OW == 2 * KP - 4 * T and OH == NSEG * M - 4 * T and OW > 0 and OH > 0
+            assert (KP * NSEG + 31) // 32 * 32 <= (640 if M <= 10 else 448)
+            assert smem <= 224 * 1024
+            assert ntx * OW >= ncols and nty * OH >= nrows
 
 
 def test_stream_schedule_nonuniform_spacing(emul, port):

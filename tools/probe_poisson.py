@@ -1,6 +1,7 @@
-"""Device-time probe of the streaming Poisson kernel: fixed sweeps on an nrows x ncols grid for several
-temporal block depths / strip widths / chunk counts.  Prints cell-updates/s and the fraction of the 24 B/cell
-HBM roofline.   python tools/probe_poisson.py NROWS NCOLS "T:WS:CHUNKS,T:WS:CHUNKS,..." [sweeps]"""
+"""Device-time probe of the Poisson pass kernels: fixed sweeps on an nrows x ncols grid for several temporal block
+depths and plans.  Prints cell-updates/s and the fraction of the 24 B/cell HBM roofline.
+python tools/probe_poisson.py NROWS NCOLS "SPEC,SPEC,..." [sweeps]
+SPEC = T:WS:CHUNKS (streaming kernel; 0 = planner's choice) or tT:KP:M:NSEG (stationary-tile kernel)"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -14,8 +15,11 @@ except Exception:
     pass
 
 
-def run(nr, nc, T, ws=0, chunks=0, sweeps=256, reps=3):
+def run(nr, nc, T, ws=0, chunks=0, sweeps=256, reps=3, tile=None):
     os.environ["CNV_POISSON_WS"] = str(ws); os.environ["CNV_POISSON_CHUNKS"] = str(chunks)
+    os.environ["CNV_POISSON_TILE"] = "1" if tile else "0"
+    for k, v in zip(("KP", "M", "NSEG"), tile or (0, 0, 0)):
+        os.environ["CNV_TILE_" + k] = str(v)
     s = fd.PoissonSolver(nr, nc, T)
     s.set_consts(1.0 / nc, 1.0 / nc, fd.sor_beta(nc, nc))
     rng = np.random.default_rng(0)
@@ -32,6 +36,11 @@ def run(nr, nc, T, ws=0, chunks=0, sweeps=256, reps=3):
     assert st["sweeps"] == sweeps, st
     cu = (nr - 2) * (nc - 2) * sweeps / best
     p = s.plan
+    if p["tiled"]:
+        print(f"{nr}x{nc} T={T} tile KP={p['KP']} M={p['M']} NSEG={p['NSEG']} out={p['OH']}x{p['OW']} ctas={p['ntx']}x{p['nty']} "
+              f"thr={p['threads']} smem={p['smem']//1024}K {best/sweeps*1e6:8.2f} us/sweep {cu:.3e} cu/s frac={cu*24/peak:.3f}", flush=True)
+        s.close()
+        return
     print(f"{nr}x{nc} T={T} WS={p['WS']} Hout={p['Hout']} ctas={p['nstrips']}x{p['nchunks']} thr={p['threads']} smem={p['smem']//1024}K "
           f"{best/sweeps*1e6:8.2f} us/sweep {cu:.3e} cu/s frac={cu*24/peak:.3f}", flush=True)
     s.close()
@@ -42,8 +51,12 @@ if __name__ == "__main__":
     specs = sys.argv[3] if len(sys.argv) > 3 else "1:0:0,2:0:0,4:0:0,8:0:0"
     sweeps = int(sys.argv[4]) if len(sys.argv) > 4 else 256
     for spec in specs.split(","):
-        T, ws, ch = (int(x) for x in spec.split(":"))
         try:
+            if spec.startswith("t"):
+                T, kp, m, nseg = (int(x) for x in spec[1:].split(":"))
+                run(nr, nc, T, sweeps=sweeps, tile=(kp, m, nseg))
+                continue
+            T, ws, ch = (int(x) for x in spec.split(":"))
             run(nr, nc, T, ws, ch, sweeps)
         except Exception as e:
             print("skip", spec, e)
