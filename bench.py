@@ -110,6 +110,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def _config_name(n):
+    return {1024: "BASELINE config 3", 4096: "BASELINE config 4", 16384: "BASELINE config 5"}.get(n, "custom")
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -263,12 +267,14 @@ def run_gpu(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{total_rows}x{ncols} Re=1000 lid-driven cavity, red-black SOR Poisson solve "
-                                   f"(BASELINE config 4 grid{' per GPU' if args.scaling == 'weak' and world > 1 else ''})",
+                                   f"({_config_name(args.n)} grid{' per GPU' if args.scaling == 'weak' and world > 1 else ''})",
                        "grid": [total_rows, ncols], "slab_rows_per_gpu": rows_per, "sweeps_per_step": S,
                        "temporal_block_T": T, "strip_width": plan["WS"], "rows_per_chunk": plan["Hout"],
                        "ctas": plan["nstrips"] * plan["nchunks"], "arith_path": "pow2-exact" if plan["pow2"] else "general",
                        "parallelism": f"slab{world}" if world > 1 else "single",
-                       "l2": "inputs larger than L2 (3 x %.0f MB resident arrays per GPU vs 126 MB L2), no flush" %
+                       "l2": ("inputs larger than L2 (3 x %.0f MB resident arrays per GPU vs 126 MB L2), no flush" if
+                              3 * rows_per * ncols * 8 > 126e6 else
+                              "arrays fit L2 at this slab size (3 x %.0f MB per GPU vs 126 MB L2): L2-resident run, no flush") %
                              (rows_per * ncols * 8 / 1e6)},
             "sweeps_per_s": S * args.steps / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -417,7 +423,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "poisson_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{total_rows}x{args.n} Re=1000 lid-driven cavity, red-black SOR Poisson solve (BASELINE config 4 grid)",
+           "config": {"workload": f"{total_rows}x{args.n} Re=1000 lid-driven cavity, red-black SOR Poisson solve ({_config_name(args.n)} grid)",
                       "note": "CPU arm: each step is a bounded sample of sweeps on the 4096x4096 grid; rate is size-independent per cell"},
            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": threads, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -430,7 +436,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=4096, help="grid columns (and rows per GPU under weak scaling)")
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=4096,
+                    help="grid columns (and rows per GPU under weak scaling); use --grid under torchrun, whose own parser trips over --n")
     ap.add_argument("--sweeps", type=int, default=1024, help="red-black SOR sweeps per step")
     ap.add_argument("--T", type=int, default=0, help="temporal block depth (0 = library default)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
