@@ -53,6 +53,7 @@ CNV_API = {
     "cnv_continuity_host": (C.c_int, [_dp, _dp, C.c_int, C.c_int, _dp]),
     "cnv_vorticity_host": (C.c_int, [_dp, _dp, C.c_int, C.c_int, _dp]),
     "cnv_error_host": (C.c_double, [_dp, _dp, C.c_int, C.c_int]),
+    "cnv_pressure_rhs_host": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
     "cnv_poisson_host": (C.c_int, [_dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
                                    _dp, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp]),
     "cnv_poisson_create": (_vp, [C.c_int, C.c_int, C.c_int]),
@@ -101,6 +102,7 @@ CNV_API = {
     "cnv_sim_set_diagnostics": (None, [_vp, C.c_int]),
     "cnv_sim_stencil_phase": (None, [_vp, C.c_int, _vp]),
     "cnv_sim_counters": (None, [_vp, C.POINTER(C.c_longlong)]),
+    "cnv_sim_pressure": (C.c_int, [_vp, C.c_int, C.c_double, _vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "cnv_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "cnv_config_default": (None, [C.POINTER(Config)]),
     "cnv_config_from_file": (None, [C.c_char_p, C.POINTER(Config)]),

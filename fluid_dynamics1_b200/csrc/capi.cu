@@ -81,6 +81,7 @@ struct cnv_sim {
     FdTable d1x, d1y, d2x, d2y;
     double *u = nullptr, *v = nullptr, *w = nullptr, *w2 = nullptr;
     PoissonSolver *ps = nullptr;
+    PoissonSolver *pp = nullptr;  // pressure solves (created on first use; psi stays intact in `ps`)
     int psi_buf = 0;
     double *cont_partial = nullptr, *cont_result = nullptr, *h_cont = nullptr;
     unsigned *cont_ticket = nullptr;
@@ -184,6 +185,22 @@ int cnv_continuity_host(const double *dudx, const double *dvdy, int nrows, int n
 int cnv_vorticity_host(const double *a, const double *b, int nrows, int ncols, double *out)
 {
     return addsub_host(a, b, nrows, ncols, out, 1);
+}
+
+// f = dudx^2 + dvdy^2 + 2*dudy*dvdx from host u, v (the commented pressure recipe, src/main.c:421-427)
+int cnv_pressure_rhs_host(const double *u, const double *v, int nrows, int ncols, int order, double dx, double dy, double *f_out)
+{
+    FdTable tx, ty;
+    if (ncols < order || nrows < order || !fd_make_table(ncols, order, 1, dx, &tx) || !fd_make_table(nrows, order, 1, dy, &ty)) return 1;
+    require_device();
+    DevArray du(nrows, ncols), dv(nrows, ncols), df(nrows, ncols);
+    du.upload(u); dv.upload(v);
+    const RowMap m = {nrows, 0, nrows, 0, nrows};
+    launch_pressure_rhs(du.p, dv.p, m, ncols, du.ld, tx, ty, 1.0, df.p, nullptr, df.ld, 0);
+    count_launch(1);
+    CNV_CUDA_CHECK(cudaGetLastError());
+    df.download(f_out);
+    return 0;
 }
 
 double cnv_error_host(const double *a, const double *b, int nrows, int ncols)
@@ -498,6 +515,7 @@ void cnv_sim_destroy(cnv_sim *s)
 {
     if (!s) return;
     delete s->ps;
+    delete s->pp;
     cudaFree(s->u); cudaFree(s->v); cudaFree(s->w); cudaFree(s->w2);
     cudaFree(s->cont_partial); cudaFree(s->cont_result); cudaFree(s->cont_ticket);
     cudaFreeHost(s->h_cont);
@@ -587,6 +605,38 @@ int cnv_sim_set_fields(cnv_sim *s, const double *psi, const double *w, const dou
             CNV_CUDA_CHECK(cudaMemcpy2D(dst[i], sizeof(double) * s->ld, src[i], sizeof(double) * s->ncols,
                                         sizeof(double) * s->ncols, s->nrows, cudaMemcpyHostToDevice));
     return 0;
+}
+
+// Pressure from the current velocity field: p = poisson(-(dudx^2 + dvdy^2 + 2 dudy dvdx)) with the configured
+// Poisson variant (src/main.c:421-427 uses an FFT solver that the reference never shipped; here it is the same
+// SOR / Gauss-Seidel solve as for psi: zero Dirichlet ring, zero initial guess, first sweep with e < tol).
+// itmax <= 0 / tol <= 0 take the configuration's values.  Returns 0, 1 (itmax reached) or -1 (slab simulations).
+int cnv_sim_pressure(cnv_sim *s, int itmax, double tol, double *p_host, int *k, double *e)
+{
+    if (s->map.nloc != s->map.gnrows) {
+        std::printf("** Error: pressure is available on single-GPU simulations only **\n");
+        return -1;
+    }
+    const Config &c = s->cfg;
+    cudaStream_t st = s->stream;
+    if (!s->pp) {
+        s->pp = new PoissonSolver(s->nrows, s->ncols, s->ps->T());
+        s->pp->set_consts(s->dx, s->dy, c.poisson_type == 2 ? s->beta : 1.0);
+    }
+    launch_pressure_rhs(s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->pp->consts().pscale, nullptr, s->pp->rhs(), s->ld, st);
+    count_launch(1);
+    const size_t bytes = sizeof(double) * (size_t)s->nrows * s->ld;
+    CNV_CUDA_CHECK(cudaMemsetAsync(s->pp->buffer(0), 0, bytes, st));
+    int buf = 0;
+    PoissonResult r = s->pp->solve(itmax > 0 ? itmax : c.poisson_max_it, tol > 0 ? tol : c.poisson_tol, st, &buf, false);
+    if (k) *k = r.k;
+    if (e) *e = r.e;
+    if (p_host) {
+        CNV_CUDA_CHECK(cudaStreamSynchronize(st));
+        CNV_CUDA_CHECK(cudaMemcpy2D(p_host, sizeof(double) * s->ncols, s->pp->buffer(buf), sizeof(double) * s->ld,
+                                    sizeof(double) * s->ncols, s->nrows, cudaMemcpyDeviceToHost));
+    }
+    return r.status;
 }
 
 void cnv_sim_counters(cnv_sim *s, long long *out)

@@ -44,6 +44,8 @@ void launch_euler_pointwise(double *w, const double *dwdx, const double *dwdy, c
 void launch_pointwise_addsub(const double *a, const double *b, double *out, size_t n, int sub, cudaStream_t s);
 void launch_velocity(const double *psi, const RowMap &m, int ncols, int ldp, const FdTable &d1x, const FdTable &d1y, double *u,
                      double *v, int ld, cudaStream_t s);
+void launch_pressure_rhs(const double *u, const double *v, const RowMap &m, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
+                         double pscale, double *f_out, double *rhs, int ldo, cudaStream_t s);
 int continuity_blocks(int nrows, int ncols);
 void launch_continuity(const double *u, const double *v, const RowMap &m, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
                        double *partial, unsigned *ticket, double *result, cudaStream_t s);

@@ -373,6 +373,52 @@ k_continuity(const double *__restrict__ u, const double *__restrict__ v, RowMap 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pressure-Poisson right-hand side, the recipe the reference leaves commented out (src/main.c:421-427, declared
+// as pressure() in include/fluiddyn.h:11 but never defined):
+//     f = dudx**2 + dvdy**2 + 2*dudy*dvdx          p = poisson(-f)
+// evaluated left to right with separately rounded operations: ((dudx*dudx) + (dvdy*dvdy)) + ((2*dudy)*dvdx).
+// One 64 x 32 tile of u and v per CTA; the four first derivatives use the same closures as everywhere else.
+// Writes f (optional) and the solver's pre-scaled right-hand side pscale * (-f) (optional).
+template <int HALF>
+__global__ void __launch_bounds__(256)
+k_pressure_rhs(const double *__restrict__ u, const double *__restrict__ v, RowMap m, int ncols, int ld, const FdTable d1x,
+               const FdTable d1y, double pscale, double *__restrict__ f_out, double *__restrict__ rhs, int ldo)
+{
+    __shared__ Tile tu, tv;
+    const int j0 = blockIdx.x * TW, i0 = m.own_lo + blockIdx.y * TH, gi0 = m.grow0 + i0;
+    tile_load(tu, u, i0, j0, m.nloc, ncols, ld);
+    tile_load(tv, v, i0, j0, m.nloc, ncols, ld);
+    double c1x[7], c1y[7];
+    load_coefs(d1x, c1x); load_coefs(d1y, c1y);
+    __syncthreads();
+    const int j = j0 + threadIdx.x, lj = threadIdx.x + THALO;
+    if (j >= ncols) return;
+    auto body = [&](auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
+        double uy[7], vy[7], wx[7];
+        win_y_init(tu, threadIdx.y * TROWS + THALO, lj, uy);
+        win_y_init(tv, threadIdx.y * TROWS + THALO, lj, vy);
+#pragma unroll
+        for (int rr = 0; rr < TROWS; rr++) {
+            const int i = i0 + threadIdx.y * TROWS + rr, li = threadIdx.y * TROWS + rr + THALO;
+            if (!INTERIOR && i >= m.own_hi) break;
+            if (rr > 0) { win_y_slide(tu, li, lj, uy); win_y_slide(tv, li, lj, vy); }
+            win_x(tu, li, lj, wx);
+            const double dudx = tile_dx<HALF, INTERIOR>(tu, d1x, c1x, wx, li, j, j0);
+            win_x(tv, li, lj, wx);
+            const double dvdx = tile_dx<HALF, INTERIOR>(tv, d1x, c1x, wx, li, j, j0);
+            const double dudy = tile_dy<HALF, INTERIOR>(tu, d1y, c1y, uy, lj, m.grow0 + i, gi0);
+            const double dvdy = tile_dy<HALF, INTERIOR>(tv, d1y, c1y, vy, lj, m.grow0 + i, gi0);
+            const double f = xadd(xadd(xmul(dudx, dudx), xmul(dvdy, dvdy)), xmul(xmul(2.0, dudy), dvdx));
+            if (f_out) f_out[(size_t)i * ldo + j] = f;
+            if (rhs) rhs[(size_t)i * ld + j] = xmul(pscale, -f);
+        }
+    };
+    if (tile_is_interior(i0, j0, m, ncols)) body(std::true_type{});
+    else body(std::false_type{});
+}
+
 // rhs = pscale * (sign * f), psi0 = 0: prologue of a stand-alone Poisson solve
 // (f may alias rhs with ldf == ld: the host-buffer upload copies straight into rhs and scales in place)
 __global__ void k_prep_rhs(const double *f, int nrows, int ncols, int ldf, double sign, double pscale,
@@ -438,6 +484,15 @@ void launch_velocity(const double *psi, const RowMap &m, int ncols, int ldp, con
     CNV_BY_HALF(d1x.half, CALL);
 #undef CALL
 }
+void launch_pressure_rhs(const double *u, const double *v, const RowMap &m, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
+                         double pscale, double *f_out, double *rhs, int ldo, cudaStream_t s)
+{
+    const dim3 b(TW, 4), g = tile_grid(m, ncols);
+#define CALL(H) k_pressure_rhs<H><<<g, b, 0, s>>>(u, v, m, ncols, ld, d1x, d1y, pscale, f_out, rhs, ldo)
+    CNV_BY_HALF(d1x.half, CALL);
+#undef CALL
+}
+
 int continuity_blocks(int nrows, int ncols) { return ((ncols + TW - 1) / TW) * ((nrows + TH - 1) / TH); }
 void launch_continuity(const double *u, const double *v, const RowMap &m, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
                        double *partial, unsigned *ticket, double *result, cudaStream_t s)

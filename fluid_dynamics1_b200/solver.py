@@ -68,6 +68,17 @@ def vorticity(first, second) -> np.ndarray:
     return out
 
 
+def pressure_rhs(u, v, order: int, dx: float, dy: float) -> np.ndarray:
+    """f = dudx**2 + dvdy**2 + 2*dudy*dvdx, the right-hand side of the pressure recipe the reference leaves commented
+    out (src/main.c:421-427); p = poisson(-f)."""
+    _lib.require_gpu()
+    a = _c(u)
+    out = np.empty_like(a)
+    if _lib.lib().cnv_pressure_rhs_host(a, _c(v), a.shape[0], a.shape[1], order, dx, dy, out):
+        raise ValueError("valid orders are 2, 4 or 6 (and the grid must be at least that large)")
+    return out
+
+
 def error(a, b) -> float:
     """sum |a - b| (src/poisson.c:34-60)."""
     _lib.require_gpu()
@@ -188,6 +199,16 @@ class Simulation:
         failed = self.L.cnv_sim_step(self.h, nsteps, k.ctypes.data, e.ctypes.data,
                                      cmax.ctypes.data if diagnostics else None, cmin.ctypes.data if diagnostics else None)
         return dict(failed_step=failed, k=k, e=e, cont_max=cmax, cont_min=cmin)
+
+    def pressure(self, itmax: int = 0, tol: float = 0.0):
+        """Pressure of the current velocity field: p = poisson(-f) with the configured Poisson variant
+        (itmax / tol default to the configuration's)."""
+        p = np.empty(self.shape)
+        k, e = C.c_int(), C.c_double()
+        st = self.L.cnv_sim_pressure(self.h, itmax, tol, p.ctypes.data, C.byref(k), C.byref(e))
+        if st < 0:
+            raise RuntimeError("pressure is available on single-GPU simulations only")
+        return dict(status=st, p=p, k=k.value, e=e.value)
 
     def fields(self):
         out = {n: np.empty(self.shape) for n in ("psi", "w", "u", "v")}

@@ -49,6 +49,10 @@ int cnv_continuity_host(const double *dudx, const double *dvdy, int nrows, int n
 int cnv_vorticity_host(const double *a, const double *b, int nrows, int ncols, double *out); /* out = b - a */
 /* L1 distance sum|a-b| over the grid: error(), src/poisson.c:34-60 */
 double cnv_error_host(const double *a, const double *b, int nrows, int ncols);
+/* Pressure-Poisson right-hand side f = dudx^2 + dvdy^2 + 2*dudy*dvdx of the recipe the reference leaves commented
+ * out (src/main.c:421-427; `pressure()` is declared in include/fluiddyn.h:11 and defined nowhere): the four first
+ * derivatives with the Diff1 closures, evaluated left to right with separately rounded operations. */
+int cnv_pressure_rhs_host(const double *u, const double *v, int nrows, int ncols, int order, double dx, double dy, double *f_out);
 
 /* ---- Poisson solve: src/poisson.c:62-285 -------------------------------------------------------
  * Solves lap(u) = f, zero Dirichlet ring, zero initial guess, red-black ordering ((i+j) even first,
@@ -145,6 +149,10 @@ void cnv_sim_set_diagnostics(cnv_sim *s, int continuity_on);
 void cnv_sim_stencil_phase(cnv_sim *s, int reps, void *stream);
 /* cumulative counters: [0] Poisson sweeps, [1] Poisson passes, [2] steps */
 void cnv_sim_counters(cnv_sim *s, long long *out);
+/* p = poisson(-f), f as in cnv_pressure_rhs_host from the simulation's current u, v; the configured Poisson variant
+ * (src/main.c:351/355), zero ring, zero guess.  itmax <= 0 / tol <= 0: the configuration's values.  p_host (nx*ny,
+ * may be NULL), *k, *e as logged by poisson_SOR_log.  Returns 0, 1 = itmax reached, -1 = slab simulation. */
+int cnv_sim_pressure(cnv_sim *s, int itmax, double tol, double *p_host, int *k, double *e);
 
 /* ---- whole driver: restates src/main.c:27-481 on top of the device-resident path ---------------
  * (same config file, same stdout/log lines, same step order; VTK through printvtk-compatible writer

@@ -55,6 +55,7 @@ class Port:
         L.orc_euler.argtypes = [_dp] * 7 + [C.c_double, C.c_double, C.c_size_t]
         L.orc_continuity.argtypes = [_dp, _dp, _dp, C.c_size_t]
         L.orc_vorticity.argtypes = [_dp, _dp, _dp, C.c_size_t]
+        L.orc_pressure_rhs.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp]
         L.orc_beta.restype = C.c_double
         L.orc_beta.argtypes = [C.c_int, C.c_int]
         L.orc_num_steps.argtypes = [C.c_double, C.c_double]
@@ -110,6 +111,14 @@ class Port:
         self.L.orc_euler(w, *[np.ascontiguousarray(a, dtype=np.float64) for a in (dwdx, dwdy, d2wdx2, d2wdy2, u, v)],
                          Re, dt, w.size)
         return w
+
+    def pressure_rhs(self, u, v, order, dx, dy):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.empty_like(u)
+        if self.L.orc_pressure_rhs(u, v, u.shape[0], u.shape[1], order, dx, dy, out):
+            raise ValueError("orc_pressure_rhs failed")
+        return out
 
     def beta(self, nx, ny):
         return float(self.L.orc_beta(nx, ny))

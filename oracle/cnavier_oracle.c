@@ -261,6 +261,24 @@ void orc_vorticity(const double *a, const double *b, double *out, size_t ncell)
 }
 
 /* SOR relaxation factor, src/main.c:134 (truncated PI). */
+/* Pressure-Poisson right-hand side of the commented recipe, src/main.c:421-427:
+ *     dudx = DX u, dudy = DY u, dvdx = DX v, dvdy = DY v;   f = dudx**2 + dvdy**2 + 2*dudy*dvdx
+ * (DX acts along j with dx, DY along i with dy, src/main.c:146-152).  Left-to-right evaluation, every operation
+ * rounded separately; x**2 == x*x.  The pressure itself is p = poisson(-f) with the ordinary solver above. */
+int orc_pressure_rhs(const double *u, const double *v, int nx, int ny, int order, double dx, double dy, double *f)
+{
+    size_t n = (size_t)nx * ny;
+    double *d = (double *)malloc(sizeof(double) * 4 * n);
+    if (!d) return -2;
+    double *dudx = d, *dudy = d + n, *dvdx = d + 2 * n, *dvdy = d + 3 * n;
+    int rc = orc_apply(u, nx, ny, 1, 1, order, dx, dudx) | orc_apply(u, nx, ny, 0, 1, order, dy, dudy) |
+             orc_apply(v, nx, ny, 1, 1, order, dx, dvdx) | orc_apply(v, nx, ny, 0, 1, order, dy, dvdy);
+    if (!rc)
+        for (size_t p = 0; p < n; p++) f[p] = dudx[p] * dudx[p] + dvdy[p] * dvdy[p] + 2 * dudy[p] * dvdx[p];
+    free(d);
+    return rc ? -1 : 0;
+}
+
 double orc_beta(int nx, int ny)
 {
     return 0.5 * (2 / (1 + sin(ORC_PI / (nx + 1))) + 2 / (1 + sin(ORC_PI / (ny + 1))));

@@ -68,6 +68,37 @@ def test_pointwise_bitwise(port):
     assert abs(e - np.abs(a[0] - a[1]).sum()) <= 1e-12 * e
 
 
+@pytest.mark.parametrize("order", [2, 4, 6])
+@pytest.mark.parametrize("shape", [(16, 16), (33, 50), (64, 64), (200, 131)])
+def test_pressure_rhs_bitwise(port, order, shape):
+    """f = dudx**2 + dvdy**2 + 2*dudy*dvdx (the commented recipe of src/main.c:421-427), bitwise vs the oracle."""
+    rng = np.random.default_rng(order * 100 + shape[0])
+    u, v = rng.standard_normal(shape), rng.standard_normal(shape)
+    dx, dy = 1.0 / shape[1], 1.0 / shape[0]
+    assert fd.pressure_rhs(u, v, order, dx, dy).tobytes() == port.pressure_rhs(u, v, order, dx, dy).tobytes()
+
+
+def test_simulation_pressure_vs_oracle(port):
+    """Pressure of the cavity flow after 20 steps of config_default: p = poisson(-f) with the configured SOR solve,
+    sweep count and field bitwise vs the oracle; psi and the other fields are left untouched."""
+    sim = fd.Simulation(dict(api.CONFIG_DEFAULT))
+    sim.step(20)
+    before = sim.fields()
+    r = sim.pressure()
+    after = sim.fields()
+    n = 64
+    f = port.pressure_rhs(before["u"], before["v"], 6, 1.0 / n, 1.0 / n)
+    want = port.poisson(-f, 1.0 / n, 1.0 / n, 10000, 1e-3, port.beta(n, n), redblack=True, sor=True)
+    assert r["status"] == 0 and r["k"] == want["k"]
+    assert r["p"].tobytes() == want["u"].tobytes()
+    assert "%E" % r["e"] == "%E" % want["e"]
+    for name in before:
+        assert before[name].tobytes() == after[name].tobytes(), name
+    r2 = sim.pressure(itmax=5, tol=1e-30)
+    assert r2["status"] == 1
+    sim.close()
+
+
 # ---- Poisson ------------------------------------------------------------------------------------
 @pytest.mark.parametrize("T", [1, 2, 4, 8])
 @pytest.mark.parametrize("n", [16, 64, 100, 257])
