@@ -165,6 +165,8 @@ extern "C" int cnv_main(int argc, char **argv)
 
     const double sim_start = now_s();
     std::vector<double> psi, w, u, v;
+    std::vector<int> k_hist;       // metrics file: logged k and residual of every step
+    std::vector<double> e_hist;
     int rc = 0;
     for (int t = 0; t <= it_max; t++) {
         const double t0 = now_s();
@@ -177,6 +179,8 @@ extern "C" int cnv_main(int argc, char **argv)
             break;
         }
         log_line(log, "Poisson equation solved with %d iterations - root-sum-of-squares error: %E\n", k, e);
+        k_hist.push_back(k);
+        e_hist.push_back(e);
         const double t1 = now_s();
         const double elapsed = t1 - sim_start;
         log_line(log, "Iteration: %d | ", t);
@@ -214,6 +218,24 @@ extern "C" int cnv_main(int argc, char **argv)
     if (log) {
         std::fclose(log);
         std::printf("Log saved to: %s\n", log_filename.c_str());
+    }
+    // CNV_METRICS_JSON=<path>: machine-readable run metrics next to the reference-format log (throughput against the
+    // algorithmic traffic of SURVEY.md section 8d: 24 B per interior cell per sweep + 72 B per cell per step)
+    if (const char *mj = std::getenv("CNV_METRICS_JSON")) {
+        if (FILE *f = std::fopen(mj, "w")) {
+            const double secs = end - sim_start, cells = (double)cfg.nx * cfg.ny, icells = (double)(cfg.nx - 2) * (cfg.ny - 2);
+            const double steps = (double)counters[2], sweeps = (double)counters[0];
+            std::fprintf(f, "{\"grid\": [%d, %d], \"steps\": %lld, \"poisson_sweeps\": %lld, \"poisson_passes\": %lld, "
+                            "\"simulation_seconds\": %.6f, \"timestep_cell_updates_per_s\": %.6e, \"poisson_cell_updates_per_s\": %.6e, "
+                            "\"poisson_sweeps_per_s\": %.6e, \"algorithmic_gb_per_s\": %.3f, \"status\": %d,\n \"poisson_k\": [",
+                         cfg.nx, cfg.ny, counters[2], counters[0], counters[1], secs, cells * steps / secs, icells * sweeps / secs,
+                         sweeps / secs, (24.0 * icells * sweeps + 72.0 * cells * steps) / secs / 1e9, rc);
+            for (size_t i = 0; i < k_hist.size(); i++) std::fprintf(f, "%s%d", i ? ", " : "", k_hist[i]);
+            std::fprintf(f, "],\n \"poisson_residual\": [");
+            for (size_t i = 0; i < e_hist.size(); i++) std::fprintf(f, "%s%.6E", i ? ", " : "", e_hist[i]);
+            std::fprintf(f, "]}\n");
+            std::fclose(f);
+        }
     }
     return rc;
 }

@@ -39,10 +39,11 @@ struct TileGeom {
 constexpr int tile_max_threads(int M) { return M <= 10 ? 640 : 448; }
 
 CNV_HD int tile_rows(const TileGeom &g) { return g.NSEG * g.M; }
-// four arrays (SE, SO: psi even/odd columns; PE, PO: right-hand side) of TH*PK + 2 doubles each, behind a lead pad
-// of one row: "row -1" of SE and "row TH" of every array are addressable (their values only reach discarded cells)
-CNV_HD int tile_arr_doubles(const TileGeom &g) { return tile_rows(g) * g.PK + 2; }
-CNV_HD size_t tile_smem_bytes(const TileGeom &g) { return ((size_t)4 * tile_arr_doubles(g) + 2 * g.PK) * sizeof(double); }
+// four arrays (SE, SO: psi even/odd columns; PE, PO: right-hand side), each with a pad row below row 0 and above
+// row TH-1 plus one pad element at either end: "row -1" and "row TH" are addressable and belong to nobody (the
+// first / last segment read them for tile rows that are never updated; no aliasing with another array's cells)
+CNV_HD int tile_arr_doubles(const TileGeom &g) { return (tile_rows(g) + 2) * g.PK + 2; }
+CNV_HD size_t tile_smem_bytes(const TileGeom &g) { return (size_t)4 * tile_arr_doubles(g) * sizeof(double); }
 
 template <int M>
 struct TileThread {
@@ -73,7 +74,7 @@ CNV_HD void tile_load(TileThread<M> &t, const TileGeom &g, int bx, int by, int t
     const int gc = gx0 + 2 * kp;
     const int arr = tile_arr_doubles(g) * 8;
     t.pitch = g.PK * 8;
-    t.base = smem_base(sm) + (g.PK + 1) * 8 + (tr0 * g.PK + kp) * 8;
+    t.base = smem_base(sm) + (g.PK + 1) * 8 + (tr0 * g.PK + kp) * 8;  // (pad element + pad row) in front of row 0
     t.aSO = arr; t.aPE = 2 * arr; t.aPO = 3 * arr;
     t.ld = g.ld;
     t.colin = gc >= 0 && gc < g.ld;
