@@ -77,6 +77,7 @@ CNV_API = {
     "cnv_poisson_set_distributed": (None, [_vp, C.c_int]),
     "cnv_poisson_state": (None, [_vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "cnv_poisson_download": (C.c_int, [_vp, C.c_int, _dp, _vp]),
+    "cnv_poisson_download_async": (C.c_int, [_vp, C.c_int, _dp, _vp]),
     "cnv_comm_unique_id": (C.c_int, [C.c_char_p]),
     "cnv_comm_create": (_vp, [C.c_int, C.c_int, C.c_char_p]),
     "cnv_comm_destroy": (None, [_vp]),

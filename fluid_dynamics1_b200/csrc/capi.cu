@@ -369,6 +369,16 @@ int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream
     return 0;
 }
 
+// same copy without the synchronisation: u_host (pinned) is valid once `stream` has drained; lets a caller keep several
+// solves in flight on different streams (copy of one overlapping the sweeps of another)
+int cnv_poisson_download_async(cnv_poisson *p, int which, double *u_host, void *stream)
+{
+    const PassGeom &g = p->s->geom();
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(u_host, sizeof(double) * g.ncols, p->s->buffer(which & 1), sizeof(double) * g.ld,
+                                     sizeof(double) * g.ncols, g.nrows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+
 int cnv_poisson_host(const double *f, int nrows, int ncols, double dx, double dy, int itmax, double tol, double beta, int T,
                      double *u, int *k, double *e, double *history)
 {

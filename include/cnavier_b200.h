@@ -97,7 +97,10 @@ void cnv_poisson_enqueue_decide(cnv_poisson *p, void *stream);
 void cnv_poisson_set_distributed(cnv_poisson *p, int on);
 /* state[0..5] = state (0 running, 1 converged, 2 itmax), cur buffer, sweeps, passes, k, redo */
 void cnv_poisson_state(cnv_poisson *p, void *stream, int *state, double *e);
-int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream);
+int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream);       /* synchronises `stream` */
+/* the same copy without the synchronisation (u_host pinned; valid once `stream` has drained): several solver objects
+ * on different streams overlap the host copies of one solve with the sweeps of another */
+int cnv_poisson_download_async(cnv_poisson *p, int which, double *u_host, void *stream);
 
 /* Native multi-GPU plumbing for slab solvers (one process per GPU).  NCCL is loaded at run time (dlopen), so the
  * library binds to the libnccl the process already holds.  Bootstrap: rank 0 calls cnv_comm_unique_id, the caller

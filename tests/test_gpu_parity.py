@@ -367,9 +367,15 @@ def test_driver_log_and_vtk_match_reference_executable(tmp_path, golden_logs):
     mine = tmp_path / "mine"
     mine.mkdir()
     api.write_config(cfg, str(mine / "cfg.txt"))
-    r = subprocess.run([exe, "cfg.txt", "run"], cwd=mine, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, "cfg.txt", "run"], cwd=mine, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, CNV_METRICS_JSON=str(mine / "metrics.json")))
     assert r.returncode == 0, r.stdout[-2000:]
     assert "Poisson SOR parameter: 1.907826" in r.stdout and "Simulation complete!" in r.stdout
+    import json
+    met = json.loads((mine / "metrics.json").read_text())     # opt-in machine-readable run summary
+    assert met["grid"] == [64, 64] and met["steps"] == 12 and met["status"] == 0
+    assert met["poisson_k"] == golden_logs["testRunOMP"]["k"][:12]
+    assert met["poisson_sweeps"] == sum(k + 1 for k in met["poisson_k"]) and met["poisson_cell_updates_per_s"] > 0
     log = (mine / "output" / "logs" / "run.txt").read_text()
     pl = api.parse_poisson_log(log)
     assert [k for k, _ in pl] == golden_logs["testRunOMP"]["k"][:12]
