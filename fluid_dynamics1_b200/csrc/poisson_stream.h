@@ -6,30 +6,31 @@
 // Algorithm (restates src/poisson.c:238-262, the OpenMP red-black sweep, T sweeps per HBM pass)
 // ---------------------------------------------------------------------------------------------
 // One CTA owns a strip of Wout output columns x Hout output rows and streams rows bottom-up
-// through a ring buffer of R = kSkew*T+PF-1 rows in shared memory.  Each row lives in column-parity
+// through a ring buffer of R = kSkew*T + kPrefetch rows in shared memory.  Each row lives in column-parity
 // split form (SE = even columns, SO = odd columns) so that every access of a half-row update is
 // unit stride: for an even-column cell (pair k) N/S are SE[q+-1][k], E/W are SO[q][k], SO[q][k-1].
-// The 2T half-sweeps (red L1, black L1, red L2, ..., black LT) are skewed: at step r level g updates its
-// red row r-1-kSkew*g and its black row two rows below (kSkew = 4 would be 2 rows per half-sweep).  All inputs of every
-// stage were produced in EARLIER steps, so the 2T stages of one step are independent and one
-// __syncthreads per step suffices; the update is in place (same dependency structure as the
-// reference's in-place sweeps, only the order of independent cell updates changes, so every
-// cell sees bit-identical operands).  A row is final once the last level's black stage has
-// processed it, and is written back from registers in that same step.  Dependencies reach 2 cells per sweep, so strips/chunks overlap by 2T halo cells whose
-// (stale-neighbour) results are discarded: the first/last loaded row is never updated and the
-// first/last loaded column sees a pad value; the region of influence of either stays inside the halo.
-// Thread (g, kk) of the CTA owns level g+1 (its red and black stage) and four adjacent columns
-// (pairs 2kk, 2kk+1), so its |u - u0| contributions all belong to sweep g+1: one accumulator.
+// The 2T half-sweeps (red L1, black L1, red L2, ..., black LT) are skewed: at step r level g updates
+// its red row r-1-kSkew*g and its black row two rows below.  All inputs of every stage were produced in
+// EARLIER steps, so the 2T stages of one step are independent and one __syncthreads per step suffices;
+// the update is in place (same dependency structure as the reference's in-place sweeps, only the order
+// of independent cell updates changes, so every cell sees bit-identical operands).  A row is final once
+// the last level's black stage has processed it, and is written back from registers in that same step.
+// Dependencies reach 2 cells per sweep, so strips/chunks overlap by 2T halo cells whose (stale-neighbour)
+// results are discarded: the first/last loaded row is never updated and the first/last loaded column
+// sees a pad value; the region of influence of either stays inside the halo.
+// Thread (g, kk) of the CTA owns level g+1 (its red and black stage) and 2*kPairs adjacent columns,
+// so its |u - u0| contributions all belong to sweep g+1: one accumulator.
 #pragma once
 #include "exact.h"
 
 namespace cnv {
 
 constexpr int kPrefetch = 3;  // rows in flight ahead of the compute front (cp.async groups)
-// Rows between consecutive levels.  4 is the minimum (red + black stage, 2 rows each); with 5 every shared
-// (even) every shared-memory operand of step r+1 -- including the row above the red row -- is already final during step r, so
-// all operand loads are issued one step ahead (software pipelining) and none waits behind the barrier.
-constexpr int kSkew = 4;  // even (compile-time colour parity).  6 = full operand prefetch: measured slower (larger ring, fewer threads)
+// Rows between consecutive levels; must be even (compile-time colour parity).  4 is the minimum (red + black stage,
+// 2 rows each): every operand of step r+1 except the row above the red row is final during step r and is loaded one
+// step ahead (software pipelining).  With 6 that row could be prefetched too: measured slower on B200 (larger ring,
+// fewer threads).
+constexpr int kSkew = 4;
 constexpr int kLand = kSkew > 4 ? 1 : 0;  // input rows must have landed this many steps early
 // Column pairs per thread (a thread owns 2*kPairs adjacent columns).  More pairs = more independent
 // cell updates in flight per thread (fp64 latency) and less per-cell overhead, at the price of registers.
