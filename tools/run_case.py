@@ -1,8 +1,9 @@
 """Whole time-stepping runs of the BASELINE configurations on the device-resident stepper (timed on the host around
-cnv_sim_step, fields stay in HBM, no VTK):  python tools/run_case.py default|high_re|c3 [steps]
+cnv_sim_step, fields stay in HBM, no VTK):  python tools/run_case.py default|high_re|c3|c4 [steps]
   default  config_default.txt   64^2   Re 1000  dt .005  4000 steps  tol 1e-3
   high_re  config_high_re.txt   128^2  Re 5000  dt .001  10000 steps tol 5e-4
-  c3       1024^2 Re 1000 dt 1e-4 tol 1e-3 (BASELINE config 3; default 100 steps here, the config asks for 10000)"""
+  c3       1024^2 Re 1000 dt 1e-4 tol 1e-3 (BASELINE config 3; default 100 steps here, the config asks for 10000)
+  c4       4096^2 Re 1000 dt 5e-6 tol 1e-3 (BASELINE config 4 as a whole time step; ~13k sweeps per step)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -12,6 +13,7 @@ CASES = {
     "default": (dict(), 4000),
     "high_re": (dict(Re=5000.0, nx=128, ny=128, dt=0.001, tf=10.0, poisson_max_it=15000, poisson_tol=5e-4), 10000),
     "c3": (dict(nx=1024, ny=1024, Re=1000.0, dt=1e-4, poisson_max_it=20000, poisson_tol=1e-3), 100),
+    "c4": (dict(nx=4096, ny=4096, Re=1000.0, dt=5e-6, poisson_max_it=100000, poisson_tol=1e-3), 3),
 }
 name = sys.argv[1]
 cfg, steps = CASES[name]
