@@ -304,7 +304,7 @@ def run_gpu(args):
             "metric": "poisson_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{total_rows}x{ncols} Re=1000 lid-driven cavity, red-black SOR Poisson solve "
+            "config": {"workload": f"{total_rows}x{ncols} Re={5000 if ncols == 16384 else 1000} lid-driven cavity, red-black SOR Poisson solve "
                                    f"({_config_name(args.n)} grid{' per GPU' if args.scaling == 'weak' and world > 1 else ''})",
                        "grid": [total_rows, ncols], "slab_rows_per_gpu": rows_per, "sweeps_per_step": S,
                        "temporal_block_T": T, "strip_width": plan["WS"], "rows_per_chunk": plan["Hout"],
@@ -464,7 +464,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "poisson_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{total_rows}x{args.n} Re=1000 lid-driven cavity, red-black SOR Poisson solve ({_config_name(args.n)} grid)",
+           "config": {"workload": f"{total_rows}x{args.n} Re={5000 if args.n == 16384 else 1000} lid-driven cavity, red-black SOR Poisson solve ({_config_name(args.n)} grid)",
                       "note": "CPU arm: each step is a bounded sample of sweeps on the 4096x4096 grid; rate is size-independent per cell"},
            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": threads, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
