@@ -89,6 +89,8 @@ CNV_API = {
     "cnv_poisson_peer_import": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int)]),
     "cnv_poisson_peer_disable": (None, [_vp]),
     "cnv_poisson_peer_enabled": (C.c_int, [_vp]),
+    "cnv_poisson_peer_trace": (C.c_int, [_vp, C.c_int]),
+    "cnv_poisson_peer_trace_read": (None, [_vp, _vp, C.c_longlong]),
     "cnv_sim_create": (_vp, [C.POINTER(Config), C.c_int]),
     "cnv_sim_create_slab": (_vp, [C.POINTER(Config), C.c_int, C.c_int, C.c_int]),
     "cnv_sim_layout": (None, [_vp, C.POINTER(C.c_int)]),

@@ -354,6 +354,8 @@ int cnv_poisson_peer_import(cnv_poisson *p, int rank, int world, const unsigned 
     return p->s->peer_import(rank, world, handles, layout);
 }
 void cnv_poisson_peer_disable(cnv_poisson *p) { p->s->peer_disable(); }
+int cnv_poisson_peer_trace(cnv_poisson *p, int passes) { return p->s->peer_trace_enable(passes); }
+void cnv_poisson_peer_trace_read(cnv_poisson *p, unsigned long long *out, long long n) { p->s->peer_trace_read(out, (size_t)n); }
 int cnv_poisson_peer_enabled(cnv_poisson *p) { return p->s->peer_enabled() ? 1 : 0; }
 void cnv_poisson_enqueue_dist(cnv_poisson *p, int npasses, void *stream) { p->s->enqueue_passes_dist(npasses, (cudaStream_t)stream); }
 void cnv_poisson_exchange_halos(cnv_poisson *p, double *field_dev, int depth, void *stream)

@@ -142,6 +142,9 @@ public:
     void peer_ready(cudaStream_t s);    // after re-initialising it: the neighbours may push into the new buffers
     bool peer_enabled() const { return links_.enabled != 0; }
     void peer_disable() { links_.enabled = 0; }
+    // diagnostics: record per-CTA timestamps of the first `passes` passes after every reset (tools/peer_trace.py)
+    int peer_trace_enable(int passes);                       // returns CTAs per pass
+    void peer_trace_read(unsigned long long *out, size_t n);  // n = passes * ctas * 6
 
 private:
     int T_;
@@ -169,6 +172,8 @@ private:
     PoissonCtl *ctlbuf_ = nullptr;
     unsigned long long peer_gidx_ = 0;  // passes launched since peer_import (global pass index)
     unsigned long long peer_epoch_ = 0; // re-initialisations of the iterate since peer_import
+    unsigned long long *trace_ = nullptr;
+    int trace_pass_ = 0;
 };
 
 }  // namespace cnv

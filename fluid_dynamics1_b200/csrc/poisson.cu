@@ -113,13 +113,54 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     __shared__ double s_e[8];
     __shared__ int s_last;
 
+    // Programmatic dependent launch: passes are launched back to back with programmatic stream serialisation, so the
+    // next pass may become resident while this one drains (its CTAs then sit in griddepcontrol.wait until this grid
+    // has completed and its writes are visible) -- hides the launch latency between dependent passes.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const bool first_cta = blockIdx.x == 0 && blockIdx.y == 0;
     __shared__ PoissonCtl s_ctl;
+    unsigned long long *trace = nullptr;
+    if (L.trace && L.pidx < L.trace_passes && tid == 0) {
+        trace = L.trace + ((size_t)L.pidx * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x) * 6;
+        trace[0] = globaltimer_ns();
+    }
     if (PEER) {
-        // peer path: derive this pass' state from the previous state + every rank's published norms
+        // peer path: derive this pass' state from the previous state + every rank's published norms.  The whole CTA
+        // cooperates -- one thread per rank waits for that rank's flag, 8 x world threads fetch the norms -- so the
+        // start-up cost does not grow with the number of GPUs (64 dependent loads by one thread were ~10 us at 8 GPUs).
+        __shared__ double s_nrm[kMaxRanks][8];
+        __shared__ int s_bad;
+        const bool need = L.pidx > 0 && L.ctlbuf[(L.pidx - 1) & 1].state == 0;  // uniform
+        if (tid == 0) s_bad = 0;
+        __syncthreads();
+        if (need) {
+            PeerMailbox *mb = L.mail[L.rank];
+            for (int r = tid; r < L.world; r += blockDim.x)
+                if (!wait_ge(&mb->norm_flag[r], L.gidx)) s_bad = 1;  // pass gidx-1 publishes the value gidx
+            __syncthreads();
+            const int slot = (int)((L.gidx - 1) & 1);
+            for (int i = tid; i < 8 * L.world; i += blockDim.x) s_nrm[i >> 3][i & 7] = *(volatile double *)&mb->norms[slot][i >> 3][i & 7];
+            __syncthreads();
+        }
         if (tid == 0) {
-            s_ctl = peer_state(L, T, first_cta ? hist : nullptr);
+            PoissonCtl c = L.ctlbuf[L.pidx == 0 ? 0 : (L.pidx - 1) & 1];
+            if (need) {
+                if (s_bad) {
+                    atomicExch(&L.mail[L.rank]->error, 1ull);
+                    c.state = 3;
+                } else {
+                    double e[8];
+                    for (int g = 0; g < 8; g++) {
+                        double sum = 0.0;
+                        for (int r = 0; r < L.world; r++) sum = xadd(sum, s_nrm[r][g]);  // rank order: identical on every rank
+                        e[g] = sum;
+                    }
+                    decide(c, e, pass_sweeps(c, T), first_cta ? hist : nullptr);
+                }
+            }
+            s_ctl = c;
             if (first_cta && L.pidx > 0) L.ctlbuf[L.pidx & 1] = s_ctl;
             if (first_cta && s_ctl.state != 0) {
                 // finished solve: a no-op pass still advances the cumulative counters of the protocol
@@ -131,6 +172,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
         __syncthreads();
     }
     const PoissonCtl c0 = PEER ? s_ctl : *ctl;
+    if (trace) trace[1] = globaltimer_ns();
     if (c0.state != 0) return;  // solve already finished: later passes of a batch are no-ops
     const int nsw = pass_sweeps(c0, T);
     const int cur = c0.cur;
@@ -151,6 +193,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
             if (L.rank > 0 && G.ylo < p.own_lo) ok &= wait_ge(&mb->halo_count[0], L.gidx * L.need_low);
             if (L.rank < L.world - 1 && G.yhi >= p.own_hi) ok &= wait_ge(&mb->halo_count[1], L.gidx * L.need_high);
             if (!ok) atomicExch(&mb->error, 1ull);
+            if (trace) trace[2] = globaltimer_ns();
         }
         __syncthreads();
     }
@@ -177,6 +220,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     cp_async_wait<0>();
     const double acc = st.acc;
     struct { int g; } t = {st.g};
+    if (trace) trace[3] = globaltimer_ns();
 
     if (PEER) {
         // Slab boundary rows: copy what this CTA has just written (still L2 resident) into the neighbour GPU's halo
@@ -204,6 +248,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
         if (tid == 0) {
             if (push_down) atomicAdd_system(&L.mail[L.rank - 1]->halo_count[1], 1ull);
             if (push_up) atomicAdd_system(&L.mail[L.rank + 1]->halo_count[0], 1ull);
+            if (trace) trace[4] = globaltimer_ns();
         }
     }
     // per-CTA L1 update norms, one per sweep of the pass (level g <-> sweep g+1)
@@ -217,6 +262,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     unsigned *ticket = PEER ? &L.mail[L.rank]->ticket : &ctl->ticket;
     if (tid == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)ncta - 1;
     __syncthreads();
+    if (trace && !s_last) trace[5] = globaltimer_ns();
     if (!s_last) return;
 
     // last CTA: grid-wide sums in a fixed order, then the stopping decision (src/poisson.c:272-279)
@@ -225,15 +271,19 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     for (int c = kk; c < ncta; c += TPG) part = xadd(part, __ldcg(&partials[(size_t)c * T + t.g]));
     group_sums(sm, part, t.g, kk, TPG, s_e);
     if (PEER) {
-        // publish this rank's norms of the pass in every rank's mailbox, then raise the flag everywhere
+        // publish this rank's norms of the pass in every rank's mailbox, then raise the flag everywhere: thread
+        // (r, g) stores one norm into rank r's mailbox, then one thread per destination rank releases its flag
         const int slot = (int)(L.gidx & 1);
-        if (tid < 8)
-            for (int r = 0; r < L.world; r++) L.mail[r]->norms[slot][L.rank][tid] = (tid < T && tid < nsw) ? s_e[tid] : 0.0;
+        for (int i = tid; i < 8 * L.world; i += blockDim.x) {
+            const int r = i >> 3, g = i & 7;
+            L.mail[r]->norms[slot][L.rank][g] = (g < T && g < nsw) ? s_e[g] : 0.0;
+        }
         __threadfence_system();
         __syncthreads();
+        for (int r = tid; r < L.world; r += blockDim.x) st_release_sys(&L.mail[r]->norm_flag[L.rank], L.gidx + 1);
         if (tid == 0) {
-            for (int r = 0; r < L.world; r++) st_release_sys(&L.mail[r]->norm_flag[L.rank], L.gidx + 1);
             *ticket = 0;
+            if (trace) trace[5] = globaltimer_ns();
         }
         return;
     }
@@ -320,11 +370,22 @@ static void launch_pass(const PassGeom &g, const RelaxConsts &rc, double *b0, do
         CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_pass<T, POW2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const dim3 grid(g.nstrips, g.nchunks);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.nstrips, g.nchunks);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = !(std::getenv("CNV_POISSON_PDL") && std::atoi(std::getenv("CNV_POISSON_PDL")) == 0);
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const double *crhs = rhs;
     if (L.enabled)
-        k_poisson_pass<T, POW2, true><<<grid, threads, smem, s>>>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, L);
+        CNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_poisson_pass<T, POW2, true>, g, rc, b0, b1, crhs, ctl, partials, hist, norms, fused, L));
     else
-        k_poisson_pass<T, POW2, false><<<grid, threads, smem, s>>>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, L);
+        CNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_poisson_pass<T, POW2, false>, g, rc, b0, b1, crhs, ctl, partials, hist, norms, fused, L));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -405,6 +466,7 @@ PoissonSolver::~PoissonSolver()
     if (hist_) cudaFree(hist_);
     if (gather_) cudaFree(gather_);
     if (mailbox_) cudaFree(mailbox_);
+    if (trace_) cudaFree(trace_);
     if (ctlbuf_) cudaFree(ctlbuf_);
     cudaFreeHost(h_ctl_);
     cudaEventDestroy(ev_);
@@ -529,6 +591,25 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
     return 0;
 }
 
+int PoissonSolver::peer_trace_enable(int passes)
+{
+    const int ctas = geom_.nstrips * geom_.nchunks;
+    if (trace_) cudaFree(trace_);
+    const size_t bytes = sizeof(unsigned long long) * 6 * (size_t)ctas * passes;
+    CNV_CUDA_CHECK(cudaMalloc(&trace_, bytes));
+    CNV_CUDA_CHECK(cudaMemset(trace_, 0, bytes));
+    links_.trace = trace_;
+    links_.trace_passes = passes;
+    trace_pass_ = 0;
+    return ctas;
+}
+
+void PoissonSolver::peer_trace_read(unsigned long long *out, size_t n)
+{
+    CNV_CUDA_CHECK(cudaDeviceSynchronize());
+    CNV_CUDA_CHECK(cudaMemcpy(out, trace_, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+}
+
 void PoissonSolver::peer_quiesce(cudaStream_t s)
 {
     if (!links_.enabled) return;
@@ -561,6 +642,8 @@ void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
             L.pidx = dist_passes_++;
             L.gidx = peer_gidx_++;
             L.epoch = peer_epoch_;
+        } else if (L.trace) {
+            L.pidx = trace_pass_++;  // diagnostics only (tools/peer_trace.py --single)
         }
 #define CNV_PASS(TT)                                                                                                     \
     if (T_ == TT) {                                                                                                      \

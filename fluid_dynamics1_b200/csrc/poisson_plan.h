@@ -66,8 +66,11 @@ struct PlanLimits {
 // halo and pipeline fill/drain; CTAs resident on one SM share it; the pass ends with the last wave, so the
 // CTA count should fill the SM slots (148 x occupancy) as exactly as possible.
 inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T,
-                          const PlanLimits &lim, int force_ws = 0, int force_chunks = 0)
+                          const PlanLimits &lim, int force_ws = 0, int force_chunks = 0, int trim = -1)
 {
+    // rows taken off a boundary chunk whose CTAs exchange with a neighbour slab (see PassGeom::trim_lo)
+    if (trim < 0) trim = std::getenv("CNV_POISSON_TRIM") ? std::atoi(std::getenv("CNV_POISSON_TRIM")) : 32;
+    const int want_lo = own_lo > 0 ? trim : 0, want_hi = own_hi < nrows ? trim : 0;
     PassGeom best;
     std::memset(&best, 0, sizeof best);
     double best_cost = 1e300;
@@ -100,8 +103,13 @@ inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, i
                     const int max_chunks = own / (4 * T) > 1 ? own / (4 * T) : 1;
                     if (nchunks > max_chunks) nchunks = max_chunks;
                 }
-                const int Hout = (own + nchunks - 1) / nchunks;
-                nchunks = (own + Hout - 1) / Hout;
+                int tl = want_lo, th = want_hi;
+                int Hout = (own + tl + th + nchunks - 1) / nchunks;
+                if (nchunks < 3 || Hout - (tl > th ? tl : th) < 4 * T) {  // too few / too small chunks to skew them
+                    tl = th = 0;
+                    Hout = (own + nchunks - 1) / nchunks;
+                }
+                nchunks = (own + tl + Hout - 1) / Hout;
                 const long ctas = (long)nstrips * nchunks;
                 const long nwaves = (ctas + slots - 1) / slots;
                 const int steps = Hout + 2 * HY + kSkew * T + 6;  // halo + pipeline fill + fixed per-CTA start-up cost
@@ -117,7 +125,7 @@ inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, i
                 if (cost < best_cost) {
                     best_cost = cost;
                     best.WS = WS; best.HX = HX; best.Wout = Wout; best.Hout = Hout; best.HY = HY;
-                    best.nstrips = nstrips; best.nchunks = nchunks;
+                    best.nstrips = nstrips; best.nchunks = nchunks; best.trim_lo = tl; best.trim_hi = th;
                 }
             }
             if (force_chunks) break;

@@ -47,6 +47,10 @@ struct PassGeom {
     int HX;    // x halo (multiple of 4, >= 2T)
     int Wout;  // WS - 2*HX
     int Hout;  // output rows per chunk
+    // Slabs with a neighbour: the first / last chunk is trim_lo / trim_hi rows shorter than the others.  Its CTAs wait
+    // for the neighbour's halo rows at the start and push their boundary rows at the end; a little less streaming
+    // work keeps them off the critical path of the pass.
+    int trim_lo, trim_hi;
     int HY;    // y halo = 2T
     int nstrips, nchunks;
 };
@@ -61,8 +65,9 @@ CNV_HD CtaGeom cta_geom(const PassGeom &p, int bx, int by)
 {
     CtaGeom G;
     G.gx0 = bx * p.Wout - p.HX;
-    G.y0 = p.own_lo + by * p.Hout;
-    G.y1 = G.y0 + p.Hout < p.own_hi ? G.y0 + p.Hout : p.own_hi;
+    G.y0 = p.own_lo + by * p.Hout - (by > 0 ? p.trim_lo : 0);
+    G.y1 = p.own_lo + (by + 1) * p.Hout - p.trim_lo;
+    if (G.y1 > p.own_hi || by == p.nchunks - 1) G.y1 = p.own_hi;
     G.ylo = G.y0 - p.HY > 0 ? G.y0 - p.HY : 0;
     G.yhi = G.y1 - 1 + p.HY < p.nrows - 1 ? G.y1 - 1 + p.HY : p.nrows - 1;
     return G;
@@ -149,6 +154,13 @@ inline void stg2(double *p, double a, double b) { p[0] = a; p[1] = b; }
 inline dbl2 ldg2(const double *p) { return {p[0], p[1]}; }
 #endif
 
+// true if the predicate holds for any lane of the calling warp (host schedule checker: the thread itself)
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ bool warp_any(bool x) { return __any_sync(__activemask(), x) != 0; }
+#else
+inline bool warp_any(bool x) { return x; }
+#endif
+
 // kPairs doubles of one parity array (pairs k0 .. k0+kPairs-1), moved as 16-byte vectors
 struct vecP { double v[kPairs]; };
 CNV_HD vecP ldsP(const double *sm, int off)
@@ -212,6 +224,7 @@ struct StreamThread {
     int aSE, aSO, aPE, aPO;  // array byte offsets inside a slot, k0 folded in
     int vmask;           // bit 2p / 2p+1: even / odd column of pair k0+p updatable
     bool colown, allvalid;
+    bool mask_path;      // warp-uniform: some lane of this warp owns a column that must not be updated (see stream_step)
     // h[(PH - a) & 3] = N loaded a steps ago, rr[(PH - a) & 3] = red results of a steps ago (a = 0: this step);
     // compile-time indices, so both stay in registers and no register moves are needed to age them
     vecP h[4], rr[4];
@@ -267,6 +280,7 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.aPE = (arr_off(p.WS, 2) + t.k0) * 8; s.aPO = (arr_off(p.WS, 3) + t.k0) * 8;
     s.vmask = t.vmask;
     s.allvalid = t.vmask == (1 << (2 * kPairs)) - 1;
+    s.mask_path = warp_any(!s.allvalid);
     s.colown = t.colown;
     const int gc4 = G.gx0 + 2 * t.k0;  // first of this thread's columns
     s.sact = t.g == T - 1 && t.colown && gc4 >= 0 && gc4 < p.ld;
@@ -355,8 +369,19 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         const double Eb = typeR ? bb.v[i] : (i == kPairs - 1 ? xb : bb.v[i + 1]);
         m.v[i] = relax<POW2>(Nb.v[i], Sb.v[i], Eb, Wb, ownb.v[i], Pb.v[i], rc);
     }
-    if (s.allvalid && s.g < nsw && qb >= s.vlo && q <= s.vhi) {
-        // fast path: all cells updatable (rows q, qb are inside the streamed range by construction)
+    if (s.g < nsw && qb >= s.vlo && q <= s.vhi) {
+        // steady state: both rows updatable (and inside the streamed range by construction).  Warps none of whose
+        // lanes owns a protected column (Dirichlet ring, outside the domain) store unconditionally; a warp that has
+        // such a lane applies the column mask in ALL its lanes, so it does not diverge into the general path below
+        // (the first and last strip would otherwise run ~9 % longer than the others and set the pass time).
+        if (s.mask_path) {
+#pragma unroll
+            for (int i = 0; i < kPairs; i++) {
+                const bool vr = (s.vmask >> (2 * i + (typeR ? 1 : 0))) & 1, vb = (s.vmask >> (2 * i + (typeR ? 0 : 1))) & 1;
+                n.v[i] = vr ? n.v[i] : own.v[i];
+                m.v[i] = vb ? m.v[i] : ownb.v[i];
+            }
+        }
         stsP(sm, s.o[O1] + aA, n);
         stsP(sm, s.o[O3] + aB, m);
     } else {
@@ -445,6 +470,10 @@ struct PeerLinks {
     unsigned long long need_low, need_high;  // pushes per pass arriving in my low / high halo
     unsigned long long push_low, push_high;  // pushes per pass I make downwards / upwards
     PoissonCtl *ctlbuf;        // [2]: ctlbuf[p & 1] = state used by pass p
+    // optional trace (tools/peer_trace.py): [pass][cta][6] globaltimer stamps of thread 0 -- start, state known,
+    // halos landed, stream done, push done, exit; null in production
+    unsigned long long *trace;
+    int trace_passes;
 };
 
 // ---- solver state machine (one instance per solve, device resident) ---------------------------

@@ -126,6 +126,10 @@ void cnv_poisson_peer_push_counts(cnv_poisson *p, int rank, int world, long long
 int cnv_poisson_peer_import(cnv_poisson *p, int rank, int world, const unsigned char *handles, const int *layout);
 void cnv_poisson_peer_disable(cnv_poisson *p);
 int cnv_poisson_peer_enabled(cnv_poisson *p);
+/* diagnostics of the peer path: per-CTA globaltimer stamps (start, state known, halos landed, stream done, push done,
+ * exit) of the first `passes` passes after a reset; returns the CTAs per pass.  Read passes*ctas*6 values back. */
+int cnv_poisson_peer_trace(cnv_poisson *p, int passes);
+void cnv_poisson_peer_trace_read(cnv_poisson *p, unsigned long long *out, long long n);
 
 /* ---- device-resident time stepping: the loop body of src/main.c:283-395 ---------------------- */
 typedef struct cnv_sim cnv_sim;

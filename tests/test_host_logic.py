@@ -122,6 +122,31 @@ def test_tile_planner_properties(emul):
             assert ntx * OW >= ncols and nty * OH >= nrows
 
 
+@pytest.mark.parametrize("trim", [0, 8, 11])
+def test_stream_schedule_slab_with_trimmed_boundary_chunks(emul, port, trim, monkeypatch):
+    """A middle slab (neighbours on both sides): its first / last chunk is `trim` rows shorter than the others
+    (PassGeom::trim_lo/hi).  One pass from the exact global state must reproduce the oracle's T sweeps on the owned
+    rows, bit for bit, whatever the chunk heights."""
+    monkeypatch.setenv("CNV_POISSON_TRIM", str(trim))
+    T, gn, m = 4, 160, 72
+    r0, r1, h = 32, 128, 2 * T
+    rng = np.random.default_rng(trim)
+    f = rng.standard_normal((gn, m))
+    dx, dy, beta = 1.0 / m, 1.0 / gn, port.beta(gn, m)
+    u0, _ = port.poisson_sweeps(f, dx, dy, 3, beta)              # a non-trivial global state
+    want, _ = port.poisson_sweeps(f, dx, dy, T, beta, u=u0.copy())
+    ld = (m + 15) // 16 * 16
+    lo, hi = r0 - h, r1 + h
+    a, b, fp = np.zeros((hi - lo, ld)), np.zeros((hi - lo, ld)), np.zeros((hi - lo, ld))
+    a[:, :m] = u0[lo:hi]
+    fp[:, :m] = f[lo:hi]
+    norms = np.zeros(T)
+    for chunks in (3, 4):
+        b[:] = 0
+        assert emul.emul_pass(T, hi - lo, m, ld, lo, gn, h, h + (r1 - r0), 0, chunks, dx, dy, beta, 0, a, fp, b, T, norms) == 0
+        assert b[h:h + (r1 - r0), :m].tobytes() == want[r0:r1].tobytes(), (trim, chunks)
+
+
 def test_stream_schedule_nonuniform_spacing(emul, port):
     got, want, gn, on = _emul_sweeps(emul, port, 50, 38, 4, 2, 0, dx=0.013, dy=0.02)
     assert got.tobytes() == want.tobytes()
