@@ -65,8 +65,8 @@ def main():
         nsw = E.emul_pass_sweeps(int(ints[2]), int(ints[3]), itmax, T)
         cur = int(ints[1])
         norms = np.zeros(8)
-        rc = E.emul_pass(T, nloc, cols, ld, grow0, rows, own_lo, own_hi, 0, 0, dx, dy, beta, 0, bufs[cur], floc, bufs[cur ^ 1],
-                         nsw, norms)
+        rc = E.emul_pass(T, nloc, cols, ld, grow0, rows, own_lo, own_hi, 0, int(os.environ.get("CNV_TEST_CHUNKS", "0")), dx, dy, beta, 0,
+                         bufs[cur], floc, bufs[cur ^ 1], nsw, norms)
         assert rc == 0
         # same static pattern as the GPU host loop: exchange the buffer pass p is assumed to have written
         exchange(bufs[(p + 1) & 1])

@@ -10,11 +10,11 @@ from conftest import ROOT
 from fluid_dynamics1_b200.parallel import slab_bounds, slab_layout
 
 
-def _run(world, rows, cols, T, tol, itmax, port):
+def _run(world, rows, cols, T, tol, itmax, port, extra_env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist", "slab_cpu_worker.py"), str(rows), str(cols), str(T),
            str(tol), str(itmax)]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env = dict(os.environ, OMP_NUM_THREADS="1", **(extra_env or {}))
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok=True" in r.stdout
@@ -31,6 +31,12 @@ def test_slab_bounds_partition():
     assert (g0, n, lo, hi, hlo, hhi) == (1536 - 8, 512 + 16, 8, 520, 8, 8)
     assert slab_layout(4096, 8, 0, 4)[:4] == (0, 512 + 8, 0, 512)
     assert slab_layout(4096, 8, 7, 4)[:4] == (3584 - 8, 512 + 8, 8, 520)
+
+
+def test_slab_protocol_gloo_trimmed_boundary_chunks():
+    """Three slabs whose boundary chunks are shorter than the interior ones (PassGeom::trim_lo/hi; the middle rank is
+    trimmed at both ends): same field and sweep count as the single-domain oracle."""
+    _run(3, 180, 40, 2, 1e-3, 5000, 29690, dict(CNV_POISSON_TRIM="4", CNV_TEST_CHUNKS="4"))
 
 
 @pytest.mark.parametrize("world,T,tol,itmax", [(2, 4, 1e-3, 5000), (2, 2, 0.0, 9), (3, 1, 1e-2, 5000)])
