@@ -147,6 +147,33 @@ def test_stream_schedule_slab_with_trimmed_boundary_chunks(emul, port, trim, mon
         assert b[h:h + (r1 - r0), :m].tobytes() == want[r0:r1].tobytes(), (trim, chunks)
 
 
+@pytest.mark.parametrize("own,cols,lower,upper", [(512, 4096, True, True), (512, 4096, False, True), (4096, 4096, True, True),
+                                                  (4096, 4096, True, False), (2048, 16384, True, True)])
+def test_production_slab_plans_bitwise(emul, port, own, cols, lower, upper):
+    """The slab shapes of the multi-GPU benchmark runs (4096^2 over 8 GPUs, 4096 x 4096 per GPU, 16384^2 over 8 GPUs)
+    with the planner's own choice of strips / chunks / trimmed boundary chunks at T = 8: one pass from the exact global
+    state reproduces 8 oracle sweeps on the owned rows, bit for bit."""
+    T = 8
+    h, pad = 2 * T, 6 * T
+    hlo, hhi = (h if lower else 0), (h if upper else 0)
+    nloc = own + hlo + hhi
+    gn = nloc + (pad if lower else 0) + (pad if upper else 0)     # a "global" grid that extends beyond the halos
+    g0 = pad if lower else 0
+    rng = np.random.default_rng(own + cols)
+    f = rng.standard_normal((gn, cols))
+    dx = dy = 1.0 / cols
+    beta = port.beta(cols, cols)
+    u0, _ = port.poisson_sweeps(f, dx, dy, 2, beta)
+    want, _ = port.poisson_sweeps(f, dx, dy, T, beta, u=u0.copy())
+    ld = (cols + 15) // 16 * 16
+    a, b, fp = np.zeros((nloc, ld)), np.zeros((nloc, ld)), np.zeros((nloc, ld))
+    a[:, :cols] = u0[g0:g0 + nloc]
+    fp[:, :cols] = f[g0:g0 + nloc]
+    norms = np.zeros(T)
+    assert emul.emul_pass(T, nloc, cols, ld, g0, gn, hlo, hlo + own, 0, 0, dx, dy, beta, 0, a, fp, b, T, norms) == 0
+    assert b[hlo:hlo + own, :cols].tobytes() == want[g0 + hlo:g0 + hlo + own].tobytes()
+
+
 def test_stream_schedule_nonuniform_spacing(emul, port):
     got, want, gn, on = _emul_sweeps(emul, port, 50, 38, 4, 2, 0, dx=0.013, dy=0.02)
     assert got.tobytes() == want.tobytes()
