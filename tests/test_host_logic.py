@@ -148,10 +148,11 @@ def test_stream_schedule_slab_with_trimmed_boundary_chunks(emul, port, trim, mon
 
 
 @pytest.mark.parametrize("own,cols,lower,upper", [(512, 4096, True, True), (512, 4096, False, True), (4096, 4096, True, True),
-                                                  (4096, 4096, True, False), (2048, 16384, True, True)])
+                                                  (4096, 4096, True, False), (2048, 16384, True, True),
+                                                  (4096, 4096, False, False), (1024, 1024, False, False)])
 def test_production_slab_plans_bitwise(emul, port, own, cols, lower, upper):
-    """The slab shapes of the multi-GPU benchmark runs (4096^2 over 8 GPUs, 4096 x 4096 per GPU, 16384^2 over 8 GPUs)
-    with the planner's own choice of strips / chunks / trimmed boundary chunks at T = 8: one pass from the exact global
+    """The shapes of the benchmark runs (single-GPU 4096^2 and 1024^2; slabs: 4096^2 over 8 GPUs, 4096 x 4096 per GPU,
+    16384^2 over 8 GPUs) with the planner's own choice of strips / chunks / trimmed boundary chunks at T = 8: one pass from the exact global
     state reproduces 8 oracle sweeps on the owned rows, bit for bit."""
     T = 8
     h, pad = 2 * T, 6 * T
