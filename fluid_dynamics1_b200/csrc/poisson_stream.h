@@ -47,9 +47,10 @@ struct PassGeom {
     int HX;    // x halo (multiple of 4, >= 2T)
     int Wout;  // WS - 2*HX
     int Hout;  // output rows per chunk
-    // Slabs with a neighbour: the first / last chunk is trim_lo / trim_hi rows shorter than the others.  Its CTAs wait
-    // for the neighbour's halo rows at the start and push their boundary rows at the end; a little less streaming
-    // work keeps them off the critical path of the pass.
+    // The first / last chunk is trim_lo / trim_hi rows shorter than the others (negative: taller).  Next to a neighbour
+    // slab its CTAs wait for halo rows at the start and push their boundary rows at the end, so a little less streaming
+    // work keeps them off the critical path of the pass; at the domain boundary there are no halo rows to stream on
+    // that side, so the chunk takes 2T rows more.
     int trim_lo, trim_hi;
     int HY;    // y halo = 2T
     int nstrips, nchunks;

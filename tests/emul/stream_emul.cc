@@ -105,7 +105,7 @@ int emul_tile_pass(int T, int nrows, int ncols, int ld, int grow0, int gnrows, i
     return -2;
 }
 
-// plan only: returns WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes in out[8]
+// plan only: returns WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, trim_lo, trim_hi in out[10]
 void emul_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T, int force_ws,
                int force_chunks, long *out)
 {
@@ -113,6 +113,7 @@ void emul_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, 
     PassGeom p = make_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, lim, force_ws, force_chunks);
     out[0] = p.WS; out[1] = p.HX; out[2] = p.Wout; out[3] = p.Hout; out[4] = p.nstrips; out[5] = p.nchunks;
     out[6] = pass_threads(T, p.WS); out[7] = (long)pass_smem_bytes(T, p.WS);
+    out[8] = p.trim_lo; out[9] = p.trim_hi;
 }
 
 // One pass of nsw <= T sweeps.  in/out: nrows x ld; rhs = pscale * f (prepared like the product's

@@ -234,12 +234,16 @@ def test_stream_schedule_nonuniform_spacing(emul, port):
 def test_planner_properties(emul):
     for (nrows, ncols) in [(64, 64), (128, 128), (1024, 1024), (4096, 4096), (2064, 16384), (512, 4096), (3, 3), (7, 1000)]:
         for T in (1, 2, 4, 6, 8):
-            o = np.zeros(8, dtype=np.int64)
+            o = np.zeros(10, dtype=np.int64)
             emul.emul_plan(nrows, ncols, (ncols + 15) // 16 * 16, 0, nrows, 0, nrows, T, 0, 0, o)
-            WS, HX, Wout, Hout, nstrips, nchunks, threads, smem = o
+            WS, HX, Wout, Hout, nstrips, nchunks, threads, smem, tlo, thi = (int(x) for x in o)
             assert WS > 0, (nrows, ncols, T)
             assert WS % 4 == 0 and HX % 4 == 0 and HX >= 2 * T and Wout == WS - 2 * HX
-            assert nstrips * Wout >= ncols and nchunks * Hout >= nrows
+            assert nstrips * Wout >= ncols
+            # chunks tile the rows: first = Hout - trim_lo, interior = Hout, the last one takes the remainder
+            last = nrows - ((nchunks - 1) * Hout - tlo) if nchunks > 1 else nrows
+            assert Hout - tlo >= 1 and 1 <= last <= Hout - thi + nchunks, (nrows, ncols, T, Hout, nchunks, tlo, thi)
+            assert tlo in (0, -2 * T) and thi in (0, -2 * T)   # whole domain: boundary chunks are 2T rows taller or untouched
             assert threads == T * WS // 4 and threads <= (640 if T >= 6 else 320)
             assert smem <= 227 * 1024 - 1024
 
