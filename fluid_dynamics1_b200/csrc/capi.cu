@@ -242,7 +242,9 @@ void cnv_poisson_destroy(cnv_poisson *p)
 void cnv_poisson_set_consts(cnv_poisson *p, double dx, double dy, double beta) { p->s->set_consts(dx, dy, beta); }
 int cnv_poisson_ld(const cnv_poisson *p) { return p->s->ld(); }
 double *cnv_poisson_rhs_ptr(cnv_poisson *p) { return p->s->rhs(); }
-double *cnv_poisson_buf_ptr(cnv_poisson *p, int which) { return p->s->buffer(which & 1); }
+static int buf_index(cnv_poisson *p, int which) { return which >= 0 && which < p->s->num_buffers() ? which : which & 1; }
+double *cnv_poisson_buf_ptr(cnv_poisson *p, int which) { return p->s->buffer(buf_index(p, which)); }
+int cnv_poisson_num_buffers(cnv_poisson *p) { return p->s->num_buffers(); }
 double *cnv_poisson_norms_ptr(cnv_poisson *p) { return p->s->local_norms(); }
 void cnv_poisson_plan_info(const cnv_poisson *p, long long *out)
 {
@@ -261,6 +263,7 @@ int cnv_poisson_prepare(cnv_poisson *p, const double *f_dev, int ldf, double fsi
     p->s->peer_quiesce((cudaStream_t)stream);  // multi-GPU peer path: no neighbour push may land after the re-initialisation
     launch_prep_rhs(f_dev, g.nrows, g.ncols, ldf, fsign, p->s->consts().pscale, p->s->rhs(), p->s->buffer(0), p->s->buffer(1),
                     g.ld, (cudaStream_t)stream);
+    p->s->zero_extra_buffer((cudaStream_t)stream);
     p->s->peer_ready((cudaStream_t)stream);
     count_launch(1);
     CNV_CUDA_CHECK(cudaGetLastError());
@@ -276,6 +279,7 @@ int cnv_poisson_upload(cnv_poisson *p, const double *f_host, double fsign, void 
                                      sizeof(double) * g.ncols, g.nrows, cudaMemcpyHostToDevice, st));
     launch_prep_rhs(p->s->rhs(), g.nrows, g.ncols, g.ld, fsign, p->s->consts().pscale, p->s->rhs(), p->s->buffer(0),
                     p->s->buffer(1), g.ld, st);
+    p->s->zero_extra_buffer(st);
     p->s->peer_ready(st);
     count_launch(1);
     CNV_CUDA_CHECK(cudaGetLastError());
@@ -344,7 +348,7 @@ void cnv_comm_destroy(cnv_comm *c)
 }
 void cnv_poisson_attach_comm(cnv_poisson *p, cnv_comm *c) { p->s->attach_comm(c->c); }
 // ---- peer-memory path (CUDA IPC): see PoissonSolver::peer_* ----
-void cnv_poisson_peer_export(cnv_poisson *p, unsigned char *out192) { p->s->peer_export(out192); }
+void cnv_poisson_peer_export(cnv_poisson *p, unsigned char *out256) { p->s->peer_export(out256); }
 void cnv_poisson_peer_push_counts(cnv_poisson *p, int rank, int world, long long *low, long long *high)
 {
     p->s->peer_push_counts(rank, world, low, high);
@@ -366,7 +370,7 @@ void cnv_poisson_exchange_halos(cnv_poisson *p, double *field_dev, int depth, vo
 int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream)
 {
     const PassGeom &g = p->s->geom();
-    CNV_CUDA_CHECK(cudaMemcpy2DAsync(u_host, sizeof(double) * g.ncols, p->s->buffer(which & 1), sizeof(double) * g.ld,
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(u_host, sizeof(double) * g.ncols, p->s->buffer(buf_index(p, which)), sizeof(double) * g.ld,
                                      sizeof(double) * g.ncols, g.nrows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CNV_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
@@ -377,7 +381,7 @@ int cnv_poisson_download(cnv_poisson *p, int which, double *u_host, void *stream
 int cnv_poisson_download_async(cnv_poisson *p, int which, double *u_host, void *stream)
 {
     const PassGeom &g = p->s->geom();
-    CNV_CUDA_CHECK(cudaMemcpy2DAsync(u_host, sizeof(double) * g.ncols, p->s->buffer(which & 1), sizeof(double) * g.ld,
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(u_host, sizeof(double) * g.ncols, p->s->buffer(buf_index(p, which)), sizeof(double) * g.ld,
                                      sizeof(double) * g.ncols, g.nrows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return 0;
 }
@@ -490,7 +494,7 @@ double *cnv_sim_field_ptr(cnv_sim *s, int which)
     default: return nullptr;
     }
 }
-void cnv_sim_set_psi_buf(cnv_sim *s, int which) { s->psi_buf = which & 1; }
+void cnv_sim_set_psi_buf(cnv_sim *s, int which) { s->psi_buf = which >= 0 && which < s->ps->num_buffers() ? which : which & 1; }
 
 // One phase of a time step, asynchronously on `stream` (multi-GPU orchestration interleaves halo exchanges):
 //   0  BCs + wall vorticity on owned ring cells        (needs u, v halos)

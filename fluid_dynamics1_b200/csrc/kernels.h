@@ -100,7 +100,12 @@ public:
     bool tiled() const { return use_tile_; }  // passes run the stationary-tile kernel (poisson_tile.cu)
     const TileGeom &tile_geom() const { return tile_; }
     double *rhs() { return rhs_; }                // device, pitch ld(): pscale * f
-    double *buffer(int i) { return buf_[i]; }     // the two iterate buffers
+    double *buffer(int i) { return buf_[i]; }     // the iterate buffers: 0, 1 (and 2 with the lagged peer decision)
+    int num_buffers() const { return links_.enabled && links_.lag && buf_[2] ? 3 : 2; }
+    void zero_extra_buffer(cudaStream_t s)  // third buffer of the lagged peer decision: same initial state as 0 and 1
+    {
+        if (buf_[2]) CNV_CUDA_CHECK(cudaMemsetAsync(buf_[2], 0, (size_t)geom_.nrows * geom_.ld * sizeof(double), s));
+    }
     double *history() { return hist_; }
     void enable_history(int cap);  // residual history for the enqueue()-driven paths (hist[k] = norm of sweep k)
     size_t launches() const { return launches_; }
@@ -135,7 +140,7 @@ public:
     // Peer-memory path (CUDA IPC over NVLink): boundary rows are stored into the neighbours' halos by the pass
     // kernel itself, norms are published in every rank's mailbox, each CTA derives the stop decision: one kernel
     // per pass, no collective launch.  enqueue_passes() takes this path once peer_import() succeeded.
-    void peer_export(unsigned char *out192);
+    void peer_export(unsigned char *out256);
     void peer_push_counts(int rank, int world, long long *low, long long *high) const;
     int peer_import(int rank, int world, const unsigned char *handles, const int *layout);
     void peer_quiesce(cudaStream_t s);  // before re-initialising the iterate: every push launched so far has landed
@@ -152,7 +157,8 @@ private:
     TileGeom tile_ = {};
     bool use_tile_ = false;
     RelaxConsts rc_;
-    double *buf_[2] = {nullptr, nullptr};
+    double *buf_[3] = {nullptr, nullptr, nullptr};
+    bool lag_ = false;  // CNV_PEER_LAG=1: lagged stop decision on the peer path (three iterate buffers)
     double *rhs_ = nullptr, *partials_ = nullptr, *hist_ = nullptr, *norms_ = nullptr;
     int hist_cap_ = 0;
     PoissonCtl *ctl_ = nullptr, *h_ctl_ = nullptr;

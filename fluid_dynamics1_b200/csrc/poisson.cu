@@ -76,29 +76,55 @@ __device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned lo
     return true;
 }
 
-// State used by pass `pidx` (peer path): S_0 is what k_reset_ctl wrote; S_p = decide(S_{p-1}, norms of pass p-1
-// summed over the ranks in rank order).  Every CTA derives it redundantly (identical inputs -> identical result).
+// Sum over the ranks (rank order: identical on every rank) of the norms pass `g` published in this rank's mailbox.
+// Returns false if a rank's flag did not arrive in time.
+__device__ bool gather_norms(const PeerLinks &L, unsigned long long g, double *e)
+{
+    PeerMailbox *mb = L.mail[L.rank];
+    for (int r = 0; r < L.world; r++)
+        if (!wait_ge(&mb->norm_flag[r], g + 1)) return false;  // pass g publishes the value g+1
+    const int slot = (int)(g & (kNormSlots - 1));
+    for (int i = 0; i < 8; i++) {
+        double sum = 0.0;
+        for (int r = 0; r < L.world; r++) sum = xadd(sum, *(volatile double *)&mb->norms[slot][r][i]);
+        e[i] = sum;
+    }
+    return true;
+}
+
+// Host-visible state after `L.pidx` passes (peer path), derived by one thread.
+// Plain machine: S_0 is what k_reset_ctl wrote; S_p = decide(S_{p-1}, norms of pass p-1); ctlbuf[p & 1] = S_p.
+// Lagged machine (L.lag): ctlbuf[p & 1] = X_p = lag_fold(X_{p-1}, norms of pass p-2); the host sees
+// lag_final(X_P, norms of pass P-1), see poisson_stream.h.
 __device__ PoissonCtl peer_state(const PeerLinks &L, int T, double *hist)
 {
     if (L.pidx == 0) return L.ctlbuf[0];
     PoissonCtl c = L.ctlbuf[(L.pidx - 1) & 1];
-    if (c.state != 0) return c;
-    PeerMailbox *mb = L.mail[L.rank];
-    const unsigned long long want = L.gidx;  // pass gidx-1 publishes the value gidx
-    for (int r = 0; r < L.world; r++)
-        if (!wait_ge(&mb->norm_flag[r], want)) {
-            atomicExch(&mb->error, 1ull);
+    double e[8];
+    if (!L.lag) {
+        if (c.state != 0) return c;
+        if (!gather_norms(L, L.gidx - 1, e)) {
+            atomicExch(&L.mail[L.rank]->error, 1ull);
             c.state = 3;
             return c;
         }
-    const int slot = (int)((L.gidx - 1) & 1);
-    double e[8];
-    for (int g = 0; g < 8; g++) {
-        double sum = 0.0;
-        for (int r = 0; r < L.world; r++) sum = xadd(sum, *(volatile double *)&mb->norms[slot][r][g]);
-        e[g] = sum;
+        decide(c, e, pass_sweeps(c, T), hist);
+        return c;
     }
-    decide(c, e, pass_sweeps(c, T), hist);
+    bool ok = true;
+    if (L.pidx >= 2) {  // X_{P-1} -> X_P
+        for (int i = 0; i < 8; i++) e[i] = 0.0;
+        if (c.state == 0 && c.redo == 0) ok = gather_norms(L, L.gidx - 2, e);
+        if (ok) lag_fold(c, e, T, hist);
+    }
+    if (ok && lag_final_needs_last(c, L.pidx)) {
+        ok = gather_norms(L, L.gidx - 1, e);
+        if (ok) lag_final(c, L.pidx, e, T, hist);
+    }
+    if (!ok) {
+        atomicExch(&L.mail[L.rank]->error, 1ull);
+        c.state = 3;
+    }
     return c;
 }
 
@@ -126,44 +152,58 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
         trace = L.trace + ((size_t)L.pidx * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x) * 6;
         trace[0] = globaltimer_ns();
     }
+    __shared__ LagAction s_act;  // (peer path only)
     if (PEER) {
         // peer path: derive this pass' state from the previous state + every rank's published norms.  The whole CTA
         // cooperates -- one thread per rank waits for that rank's flag, 8 x world threads fetch the norms -- so the
         // start-up cost does not grow with the number of GPUs (64 dependent loads by one thread were ~10 us at 8 GPUs).
+        // Plain machine: the norms of pass gidx-1 (a rendezvous of all ranks per pass).  Lagged machine (L.lag): the
+        // norms of pass gidx-2, which have normally long arrived; the pass runs speculatively (poisson_stream.h).
         __shared__ double s_nrm[kMaxRanks][8];
         __shared__ int s_bad;
-        const bool need = L.pidx > 0 && L.ctlbuf[(L.pidx - 1) & 1].state == 0;  // uniform
+        const int lagd = L.lag ? 2 : 1;  // this pass folds the norms of pass gidx - lagd
+        const PoissonCtl prev = L.ctlbuf[L.pidx == 0 ? 0 : (L.pidx - 1) & 1];
+        const bool need = L.pidx >= lagd && prev.state == 0 && (!L.lag || prev.redo == 0);  // uniform
         if (tid == 0) s_bad = 0;
         __syncthreads();
         if (need) {
             PeerMailbox *mb = L.mail[L.rank];
             for (int r = tid; r < L.world; r += blockDim.x)
-                if (!wait_ge(&mb->norm_flag[r], L.gidx)) s_bad = 1;  // pass gidx-1 publishes the value gidx
+                if (!wait_ge(&mb->norm_flag[r], L.gidx - lagd + 1)) s_bad = 1;  // pass g publishes the value g+1
             __syncthreads();
-            const int slot = (int)((L.gidx - 1) & 1);
+            const int slot = (int)((L.gidx - lagd) & (kNormSlots - 1));
             for (int i = tid; i < 8 * L.world; i += blockDim.x) s_nrm[i >> 3][i & 7] = *(volatile double *)&mb->norms[slot][i >> 3][i & 7];
             __syncthreads();
         }
         if (tid == 0) {
-            PoissonCtl c = L.ctlbuf[L.pidx == 0 ? 0 : (L.pidx - 1) & 1];
-            if (need) {
-                if (s_bad) {
-                    atomicExch(&L.mail[L.rank]->error, 1ull);
-                    c.state = 3;
-                } else {
-                    double e[8];
-                    for (int g = 0; g < 8; g++) {
-                        double sum = 0.0;
-                        for (int r = 0; r < L.world; r++) sum = xadd(sum, s_nrm[r][g]);  // rank order: identical on every rank
-                        e[g] = sum;
-                    }
-                    decide(c, e, pass_sweeps(c, T), first_cta ? hist : nullptr);
-                }
+            PoissonCtl c = prev;
+            double e[8];
+            for (int g = 0; g < 8; g++) {
+                double sum = 0.0;
+                if (need)
+                    for (int r = 0; r < L.world; r++) sum = xadd(sum, s_nrm[r][g]);  // rank order: identical on every rank
+                e[g] = sum;
+            }
+            if (need && s_bad) {
+                atomicExch(&L.mail[L.rank]->error, 1ull);
+                c.state = 3;
+            } else if (L.lag) {
+                if (L.pidx >= 2) lag_fold(c, e, T, first_cta ? hist : nullptr);
+            } else if (need) {
+                decide(c, e, pass_sweeps(c, T), first_cta ? hist : nullptr);
+            }
+            LagAction a;
+            if (L.lag) {
+                a = lag_action(c, L.pidx, T);
+            } else {
+                a.kind = c.state == 0 ? 1 : 0; a.in = c.cur; a.out = c.cur ^ 1; a.nsw = pass_sweeps(c, T);
             }
             s_ctl = c;
-            if (first_cta && L.pidx > 0) L.ctlbuf[L.pidx & 1] = s_ctl;
-            if (first_cta && s_ctl.state != 0) {
-                // finished solve: a no-op pass still advances the cumulative counters of the protocol
+            s_act = a;
+            if (first_cta && L.pidx > 0) L.ctlbuf[L.pidx & 1] = c;
+            if (first_cta && a.kind == 0) {
+                // nothing to do (solve finished, or the pass in flight reaches itmax): a no-op pass still advances
+                // the cumulative counters of the protocol
                 if (L.rank > 0) atomicAdd_system(&L.mail[L.rank - 1]->halo_count[1], L.push_low);
                 if (L.rank < L.world - 1) atomicAdd_system(&L.mail[L.rank + 1]->halo_count[0], L.push_high);
                 for (int r = 0; r < L.world; r++) st_release_sys(&L.mail[r]->norm_flag[L.rank], L.gidx + 1);
@@ -173,11 +213,12 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     }
     const PoissonCtl c0 = PEER ? s_ctl : *ctl;
     if (trace) trace[1] = globaltimer_ns();
-    if (c0.state != 0) return;  // solve already finished: later passes of a batch are no-ops
-    const int nsw = pass_sweeps(c0, T);
-    const int cur = c0.cur;
-    const double *__restrict__ in = cur ? buf1 : buf0;
-    double *__restrict__ out = cur ? buf0 : buf1;
+    if (PEER ? s_act.kind == 0 : c0.state != 0) return;  // solve already finished: later passes of a batch are no-ops
+    const int nsw = PEER ? s_act.nsw : pass_sweeps(c0, T);
+    const int cur = PEER ? s_act.in : c0.cur;
+    const int nxt = PEER ? s_act.out : cur ^ 1;
+    const double *__restrict__ in = cur ? (PEER && cur == 2 ? L.buf2 : buf1) : buf0;
+    double *__restrict__ out = PEER ? (nxt == 0 ? buf0 : nxt == 1 ? buf1 : L.buf2) : (cur ? buf0 : buf1);
 
     const CtaGeom G = cta_geom(p, blockIdx.x, blockIdx.y);
     if (PEER) {
@@ -189,9 +230,12 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
             // first pass of a solve: the neighbour must have finished zeroing the buffer this CTA pushes into
             if (L.pidx == 0 && push_down) ok &= wait_ge(&mb->ready[0], L.epoch);
             if (L.pidx == 0 && push_up) ok &= wait_ge(&mb->ready[1], L.epoch);
-            // this CTA streams halo rows -> the neighbour's pushes of the previous pass must have landed
-            if (L.rank > 0 && G.ylo < p.own_lo) ok &= wait_ge(&mb->halo_count[0], L.gidx * L.need_low);
-            if (L.rank < L.world - 1 && G.yhi >= p.own_hi) ok &= wait_ge(&mb->halo_count[1], L.gidx * L.need_high);
+            // this CTA streams halo rows -> the neighbour's pushes of the previous pass must have landed (a redo
+            // pass of the lagged machine re-reads an older buffer whose halos landed passes ago)
+            if (s_act.kind == 1) {
+                if (L.rank > 0 && G.ylo < p.own_lo) ok &= wait_ge(&mb->halo_count[0], L.gidx * L.need_low);
+                if (L.rank < L.world - 1 && G.yhi >= p.own_hi) ok &= wait_ge(&mb->halo_count[1], L.gidx * L.need_high);
+            }
             if (!ok) atomicExch(&mb->error, 1ull);
             if (trace) trace[2] = globaltimer_ns();
         }
@@ -235,7 +279,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
             if (side == 0 ? !push_down : !push_up) continue;
             const int ra = side == 0 ? (G.y0 > p.own_lo ? G.y0 : p.own_lo) : (G.y0 > p.own_hi - p.HY ? G.y0 : p.own_hi - p.HY);
             const int rb = side == 0 ? (G.y1 < p.own_lo + p.HY ? G.y1 : p.own_lo + p.HY) : (G.y1 < p.own_hi ? G.y1 : p.own_hi);
-            double *peer = (side == 0 ? L.down_buf[cur ^ 1] + L.down_delta : L.up_buf[cur ^ 1] + L.up_delta);
+            double *peer = (side == 0 ? L.down_buf[nxt] + L.down_delta : L.up_buf[nxt] + L.up_delta);
             for (int idx = tid; idx < (rb - ra) * npair; idx += blockDim.x) {
                 const int rr = ra + idx / npair, cc = c0 + 2 * (idx % npair);
                 const size_t off = (size_t)rr * p.ld + cc;
@@ -273,7 +317,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     if (PEER) {
         // publish this rank's norms of the pass in every rank's mailbox, then raise the flag everywhere: thread
         // (r, g) stores one norm into rank r's mailbox, then one thread per destination rank releases its flag
-        const int slot = (int)(L.gidx & 1);
+        const int slot = (int)(L.gidx & (kNormSlots - 1));
         for (int i = tid; i < 8 * L.world; i += blockDim.x) {
             const int r = i >> 3, g = i & 7;
             L.mail[r]->norms[slot][L.rank][g] = (g < T && g < nsw) ? s_e[g] : 0.0;
@@ -305,7 +349,7 @@ __global__ void k_peer_finalize(const PeerLinks L, int T, double *hist)
 {
     PoissonCtl c = peer_state(L, T, hist);
     if (*(volatile unsigned long long *)&L.mail[L.rank]->error) c.state = 3;
-    L.ctlbuf[L.pidx & 1] = c;
+    L.ctlbuf[L.lag ? 2 : L.pidx & 1] = c;  // (lagged machine: slots 0/1 carry the chain X_p the passes read)
 }
 // peer path: this rank's iterate buffers are (re-)initialised for solve epoch L.epoch: tell both neighbours
 __global__ void k_peer_ready(const PeerLinks L)
@@ -350,12 +394,12 @@ __global__ void k_decide_gather(PoissonCtl *ctl, const double *gather, int world
     *ctl = c;
 }
 
-__global__ void k_reset_ctl(PoissonCtl *ctl, int itmax, double tol)
+__global__ void k_reset_ctl(PoissonCtl *ctl, int itmax, double tol, int nbuf)
 {
     PoissonCtl c;
     c.state = itmax > 0 ? 0 : 2;
     c.cur = 0; c.sweeps = 0; c.redo = 0; c.itmax = itmax; c.result_k = -1; c.ticket = 0; c.passes = 0;
-    c.tol = tol; c.result_e = 0.0; c.last_e = 0.0;
+    c.tol = tol; c.result_e = 0.0; c.last_e = 0.0; c.hit_e = 0.0; c.nbuf = nbuf; c.pad_ = 0;
     *ctl = c;
 }
 
@@ -462,7 +506,7 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
 
 PoissonSolver::~PoissonSolver()
 {
-    cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(rhs_); cudaFree(partials_); cudaFree(norms_); cudaFree(ctl_);
+    cudaFree(buf_[0]); cudaFree(buf_[1]); if (buf_[2]) cudaFree(buf_[2]); cudaFree(rhs_); cudaFree(partials_); cudaFree(norms_); cudaFree(ctl_);
     if (hist_) cudaFree(hist_);
     if (gather_) cudaFree(gather_);
     if (mailbox_) cudaFree(mailbox_);
@@ -489,7 +533,7 @@ void PoissonSolver::enable_history(int cap)
 void PoissonSolver::reset_ctl(int itmax, double tol, cudaStream_t s)
 {
     dist_passes_ = 0;
-    k_reset_ctl<<<1, 1, 0, s>>>(links_.enabled ? links_.ctlbuf : ctl_, itmax, tol);
+    k_reset_ctl<<<1, 1, 0, s>>>(links_.enabled ? links_.ctlbuf : ctl_, itmax, tol, links_.enabled && links_.lag ? 3 : 2);
     count_launch(1);
 }
 
@@ -502,7 +546,7 @@ PoissonCtl PoissonSolver::read_ctl(cudaStream_t s)
         L.gidx = peer_gidx_;
         k_peer_finalize<<<1, 1, 0, s>>>(L, T_, use_hist_ ? hist_ : nullptr);
         count_launch(1);
-        src = links_.ctlbuf + (dist_passes_ & 1);
+        src = links_.ctlbuf + (links_.lag ? 2 : dist_passes_ & 1);
     }
     CNV_CUDA_CHECK(cudaMemcpyAsync(h_ctl_, src, sizeof(PoissonCtl), cudaMemcpyDeviceToHost, s));
     CNV_CUDA_CHECK(cudaEventRecord(ev_, s));
@@ -516,20 +560,29 @@ PoissonCtl PoissonSolver::read_ctl(cudaStream_t s)
 }
 
 // ---- peer-memory (CUDA IPC) setup ----------------------------------------------------------------
-void PoissonSolver::peer_export(unsigned char *out192)
+void PoissonSolver::peer_export(unsigned char *out256)
 {
     if (!mailbox_) {
         CNV_CUDA_CHECK(cudaMalloc(&mailbox_, sizeof(PeerMailbox)));
         CNV_CUDA_CHECK(cudaMemset(mailbox_, 0, sizeof(PeerMailbox)));
-        CNV_CUDA_CHECK(cudaMalloc(&ctlbuf_, 2 * sizeof(PoissonCtl)));
-        CNV_CUDA_CHECK(cudaMemset(ctlbuf_, 0, 2 * sizeof(PoissonCtl)));
+        CNV_CUDA_CHECK(cudaMalloc(&ctlbuf_, 3 * sizeof(PoissonCtl)));
+        CNV_CUDA_CHECK(cudaMemset(ctlbuf_, 0, 3 * sizeof(PoissonCtl)));
     }
-    cudaIpcMemHandle_t h[3];
+    // CNV_PEER_LAG=1: lagged stop decision (poisson_stream.h) -- a third iterate buffer joins the rotation
+    lag_ = env_int("CNV_PEER_LAG", 0) != 0;
+    if (lag_ && !buf_[2]) {
+        const size_t bytes = (size_t)geom_.nrows * geom_.ld * sizeof(double);
+        CNV_CUDA_CHECK(cudaMalloc(&buf_[2], bytes));
+        CNV_CUDA_CHECK(cudaMemset(buf_[2], 0, bytes));
+    }
+    cudaIpcMemHandle_t h[4];
+    std::memset(h, 0, sizeof h);
     CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[0], buf_[0]));
     CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[1], buf_[1]));
     CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[2], mailbox_));
+    if (lag_) CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[3], buf_[2]));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
-    std::memcpy(out192, h, 192);
+    std::memcpy(out256, h, 256);
 }
 
 // pushes per pass this slab makes downwards / upwards (CTAs whose output rows reach into the boundary band)
@@ -544,12 +597,15 @@ void PoissonSolver::peer_push_counts(int rank, int world, long long *low, long l
     *low = lo; *high = hi;
 }
 
-// handles: world x 192 bytes (peer_export of every rank); layout: world x 4 ints (own_lo, own_hi, push_low, push_high)
+// handles: world x 256 bytes (peer_export of every rank: buffer 0, buffer 1, mailbox, buffer 2 or zeros); layout: world x 4 ints (own_lo, own_hi, push_low, push_high)
 int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles, const int *layout)
 {
     if (world > kMaxRanks || !mailbox_) return 1;
     std::memset(&links_, 0, sizeof links_);
     links_.rank = rank; links_.world = world; links_.ctlbuf = ctlbuf_;
+    links_.lag = lag_ ? 1 : 0;
+    links_.buf2 = buf_[2];
+    const int nbuf = lag_ ? 3 : 2;
     auto open = [&](const unsigned char *h64, void **out) {
         cudaIpcMemHandle_t h;
         std::memcpy(&h, h64, 64);
@@ -558,15 +614,15 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
     for (int r = 0; r < world; r++) {
         if (r == rank) { links_.mail[r] = mailbox_; continue; }
         void *ptr = nullptr;
-        if (!open(handles + 192 * r + 128, &ptr)) { cudaGetLastError(); return 2; }
+        if (!open(handles + 256 * r + 128, &ptr)) { cudaGetLastError(); return 2; }
         links_.mail[r] = (PeerMailbox *)ptr;
     }
     const int *me = layout + 4 * rank;
     if (rank > 0) {
         const int *nb = layout + 4 * (rank - 1);
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < nbuf; b++) {
             void *ptr = nullptr;
-            if (!open(handles + 192 * (rank - 1) + 64 * b, &ptr)) { cudaGetLastError(); return 3; }
+            if (!open(handles + 256 * (rank - 1) + 64 * (b == 2 ? 3 : b), &ptr)) { cudaGetLastError(); return 3; }
             links_.down_buf[b] = (double *)ptr;
         }
         links_.down_delta = (long long)(nb[1] - me[0]) * geom_.ld;  // my row own_lo + i -> its row own_hi' + i
@@ -574,9 +630,9 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
     }
     if (rank < world - 1) {
         const int *nb = layout + 4 * (rank + 1);
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < nbuf; b++) {
             void *ptr = nullptr;
-            if (!open(handles + 192 * (rank + 1) + 64 * b, &ptr)) { cudaGetLastError(); return 4; }
+            if (!open(handles + 256 * (rank + 1) + 64 * (b == 2 ? 3 : b), &ptr)) { cudaGetLastError(); return 4; }
             links_.up_buf[b] = (double *)ptr;
         }
         links_.up_delta = (long long)(nb[0] - me[1]) * geom_.ld;    // my row own_hi - HY + i -> its row own_lo'' - HY + i
@@ -765,7 +821,9 @@ PoissonResult PoissonSolver::solve(int itmax, double tol, cudaStream_t s, int *r
     // sweeps per step), so the first batch covers the previous solve's pass count plus one and is
     // followed by small batches.  Passes enqueued after convergence exit immediately.
     int batch = predicted_passes_ > 0 ? predicted_passes_ + 1 : 16;
-    const int max_passes = (itmax + T_ - 1) / T_ + 2;
+    // (+2: the redo pass and the slack of the batching; the lagged peer decision adds a speculative pass and may
+    // waste one more at a batch boundary)
+    const int max_passes = (itmax + T_ - 1) / T_ + 2 + (links_.enabled && links_.lag ? 3 : 0);
     int enq = 0;
     PoissonCtl c;
     for (;;) {

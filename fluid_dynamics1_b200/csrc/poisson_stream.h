@@ -448,13 +448,20 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
 //                    low|high halo: after pass g it is (g+1) x (pushing CTAs of that neighbour)
 //   ready[0|1]       the lower|upper neighbour has finished re-initialising its iterate buffers for solve epoch e:
 //                    pass 0 of a solve must not push into a buffer the neighbour is still about to zero
-//   norm_flag[r]     g+1 once rank r has published the per-sweep norms of pass g into norms[g&1][r][*]
+//   norm_flag[r]     g+1 once rank r has published the per-sweep norms of pass g into norms[g % kNormSlots][r][*]
+//                    (a no-op pass raises the flag without touching the norms)
+// Norm slots.  Within a solve a rank that reads the norms of pass g-2 (lagged decision) can see remote publications of
+// passes g-1, g and g+1 at most (a working pass g+2 needs this rank's flag of pass g): four slots.  Across solves a
+// rank that is two hops away from a finished rank may still be reading slot g-2 of the old solve while the finished
+// rank's first pass of the NEXT solve (global index g+2) publishes; its later passes need the neighbours'
+// re-initialisation, which in turn waits for everybody's old passes.  Eight slots keep those apart as well.
 constexpr int kMaxRanks = 8;
+constexpr int kNormSlots = 8;
 struct PeerMailbox {
     unsigned long long halo_count[2];
     unsigned long long ready[2];  // epoch of the lower|upper neighbour's latest (re-)initialised iterate buffers
     unsigned long long norm_flag[kMaxRanks];
-    double norms[2][kMaxRanks][8];
+    double norms[kNormSlots][kMaxRanks][8];
     unsigned long long error;  // a spin-wait timed out (a peer died): the host aborts
     unsigned int ticket;       // local: last-CTA election of the pass kernel
     unsigned int pad_;
@@ -466,11 +473,13 @@ struct PeerLinks {
     unsigned long long gidx;   // global pass index
     unsigned long long epoch;  // number of (re-)initialisations of the iterate so far (identical on every rank)
     PeerMailbox *mail[kMaxRanks];
-    double *down_buf[2], *up_buf[2];   // neighbours' iterate buffers (peer mappings), null at the ends
+    int lag;                   // 1: lagged stop decision (three iterate buffers, see lag_fold / lag_action)
+    double *buf2;              // this rank's third iterate buffer (lagged decision only)
+    double *down_buf[3], *up_buf[3];   // neighbours' iterate buffers (peer mappings), null at the ends
     long long down_delta, up_delta;    // element offset: my row -> its halo copy in the neighbour's array
     unsigned long long need_low, need_high;  // pushes per pass arriving in my low / high halo
     unsigned long long push_low, push_high;  // pushes per pass I make downwards / upwards
-    PoissonCtl *ctlbuf;        // [2]: ctlbuf[p & 1] = state used by pass p
+    PoissonCtl *ctlbuf;        // [3]: ctlbuf[p & 1] = state used by pass p; [2] = host-visible state of the lagged machine
     // optional trace (tools/peer_trace.py): [pass][cta][6] globaltimer stamps of thread 0 -- start, state known,
     // halos landed, stream done, push done, exit; null in production
     unsigned long long *trace;
@@ -495,7 +504,17 @@ struct PoissonCtl {
     double tol;
     double result_e;
     double last_e;
+    double hit_e;  // lagged decision: norm of the converged sweep while its "redo" pass is pending
+    int nbuf;      // iterate buffers in rotation: 2 (ping-pong; 0 reads as 2) or 3 (lagged decision)
+    int pad_;
 };
+
+CNV_HD int next_buf(const PoissonCtl &c, int b, int by = 1)
+{
+    if (c.nbuf != 3) return (b + by) & 1;
+    b += by;
+    return b >= 3 ? b - 3 : b;
+}
 
 CNV_HD int pass_sweeps(const PoissonCtl &c, int T)
 {
@@ -509,7 +528,7 @@ CNV_HD void decide(PoissonCtl &c, const double *e, int nsw, double *hist)
 {
     c.passes++;
     if (c.redo > 0) {  // recomputation up to the converged sweep: done
-        c.cur ^= 1;
+        c.cur = next_buf(c, c.cur);
         c.sweeps += nsw;
         c.result_k = c.sweeps - 1;
         c.result_e = e[nsw - 1];
@@ -524,7 +543,7 @@ CNV_HD void decide(PoissonCtl &c, const double *e, int nsw, double *hist)
         if (e[s] < c.tol) { hit = s; break; }
     }
     if (hit == nsw - 1) {
-        c.cur ^= 1;
+        c.cur = next_buf(c, c.cur);
         c.sweeps += nsw;
         c.result_k = c.sweeps - 1;
         c.result_e = e[hit];
@@ -532,14 +551,79 @@ CNV_HD void decide(PoissonCtl &c, const double *e, int nsw, double *hist)
         c.state = 1;
     } else if (hit >= 0) {
         c.redo = hit + 1;  // `cur` untouched: the pass input is recomputed with hit+1 sweeps
+        c.hit_e = e[hit];
     } else {
-        c.cur ^= 1;
+        c.cur = next_buf(c, c.cur);
         c.sweeps += nsw;
         c.last_e = e[nsw - 1];
         c.result_k = c.sweeps - 1;
         c.result_e = e[nsw - 1];
         if (c.sweeps >= c.itmax) c.state = 2;
     }
+}
+
+// ---- lagged stop decision (multi-GPU peer path, opt-in) ---------------------------------------------
+// With the plain machine pass p needs every rank's norms of pass p-1 before it can start: each pass is a
+// rendezvous of all ranks.  The lagged machine lets pass p start knowing only the norms of passes <= p-2 and run
+// SPECULATIVELY as if pass p-1 did not converge.  Three iterate buffers rotate (pass p reads B[p%3], writes
+// B[(p+1)%3]) so that whatever the late decision turns out to be, the data it needs is still intact:
+//   * pass h holds the first sweep with e < tol, at its LAST sweep: the answer is its output B[(h+1)%3]; the
+//     speculative pass h+1 only read it.  Passes >= h+2 are no-ops.
+//   * ... at an EARLIER sweep s: pass h+2 recomputes s+1 sweeps from the input of pass h, B[h%3] (the speculative
+//     pass h+1 wrote B[(h+2)%3]), into B[(h+2)%3], and is final -- its norms need not be awaited: they equal those
+//     pass h reported (same input, same arithmetic, same summation order), so result_e = e_h[s].
+// X_p below is the chain state a pass derives at its start: X_0 = X_1 = reset state, X_p = lag_fold(X_{p-1}, e_{p-2}).
+// Write-after-read safety of the peer pushes: pass p pushes into the neighbours' B[(p+1)%3], which they last read
+// in pass p-2; every CTA of pass p has seen every rank's norm flag of pass p-2, published after that rank's last read.
+
+// X_{p-1}, norms of pass p-2 (ignored when the solve is finished or pass p-1 was the redo pass) -> X_p
+CNV_HD void lag_fold(PoissonCtl &c, const double *e, int T, double *hist)
+{
+    if (c.state != 0) return;
+    if (c.redo > 0) {  // pass p-1 was the redo pass: final (e = norms of the discarded speculative pass)
+        c.passes++;
+        c.cur = next_buf(c, c.cur, 2);
+        c.sweeps += c.redo;
+        c.result_k = c.sweeps - 1;
+        c.result_e = c.hit_e;
+        c.last_e = c.hit_e;
+        c.redo = 0;
+        c.state = 1;
+        return;
+    }
+    decide(c, e, pass_sweeps(c, T), hist);
+}
+
+struct LagAction {
+    int kind;  // 0 no-op, 1 run (speculative), 2 redo
+    int in, out, nsw;
+};
+
+// what pass number `pidx` (since the reset) does, given X_pidx
+CNV_HD LagAction lag_action(const PoissonCtl &c, int pidx, int T)
+{
+    LagAction a = {0, 0, 0, 0};
+    if (c.state != 0) return a;
+    if (c.redo > 0) {
+        a.kind = 2; a.in = c.cur; a.out = next_buf(c, c.cur, 2); a.nsw = c.redo;
+        return a;
+    }
+    // pass pidx-1 (if any) is in flight: it reads B[cur] and applies pass_sweeps(c) sweeps
+    const int pending = pidx > 0 ? 1 : 0;
+    const int base = c.sweeps + (pending ? pass_sweeps(c, T) : 0);
+    int left = c.itmax - base;
+    if (left > T) left = T;
+    if (left <= 0) return a;  // the pass in flight reaches itmax
+    a.kind = 1; a.in = next_buf(c, c.cur, pending); a.out = next_buf(c, c.cur, pending + 1); a.nsw = left;
+    return a;
+}
+
+// Host-visible state after P passes were launched: X_P (chain) + the norms of pass P-1 where they count.
+// Returns true if e_last (norms of pass P-1) is needed, i.e. the caller must wait for them first.
+CNV_HD bool lag_final_needs_last(const PoissonCtl &xP, int P) { return P > 0 && xP.state == 0 && xP.redo == 0; }
+CNV_HD void lag_final(PoissonCtl &xP, int P, const double *e_last, int T, double *hist)
+{
+    if (lag_final_needs_last(xP, P)) decide(xP, e_last, pass_sweeps(xP, T), hist);
 }
 
 }  // namespace cnv

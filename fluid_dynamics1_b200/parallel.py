@@ -100,8 +100,8 @@ class SlabPoisson:
         self.stream = stream
         self.L.cnv_poisson_set_distributed(self.h, 1)
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.bufs = [torch.as_tensor(_DevView(self.L.cnv_poisson_buf_ptr(self.h, i), (self.nrows, self.ld)), device=dev)
-                     for i in range(2)]
+        self._dev = dev
+        self._map_bufs()
         self.rhs = torch.as_tensor(_DevView(self.L.cnv_poisson_rhs_ptr(self.h), (self.nrows, self.ld)), device=dev)
         self.norms = torch.as_tensor(_DevView(self.L.cnv_poisson_norms_ptr(self.h), (8,)), device=dev)
         self.passes_enqueued = 0
@@ -115,11 +115,17 @@ class SlabPoisson:
         if self.comm:
             self.L.cnv_poisson_attach_comm(self.h, self.comm)
         self.peer = backend == "peer" and world <= 8 and self._setup_peer()
+        self._map_bufs()  # (the lagged peer decision, CNV_PEER_LAG=1, adds a third iterate buffer)
+
+    def _map_bufs(self):
+        n = self.L.cnv_poisson_num_buffers(self.h)
+        self.bufs = [self.torch.as_tensor(_DevView(self.L.cnv_poisson_buf_ptr(self.h, i), (self.nrows, self.ld)), device=self._dev)
+                     for i in range(n)]
 
     def _setup_peer(self):
         """Exchange CUDA-IPC handles / push counts and map the neighbours' buffers; all ranks or none."""
         L, dist, torch = self.L, self.dist, self.torch
-        buf = C.create_string_buffer(192)
+        buf = C.create_string_buffer(256)
         L.cnv_poisson_peer_export(self.h, buf)
         lo, hi = C.c_longlong(), C.c_longlong()
         L.cnv_poisson_peer_push_counts(self.h, self.rank, self.world, C.byref(lo), C.byref(hi))
@@ -174,8 +180,12 @@ class SlabPoisson:
     def zero_iterate(self):
         self.L.cnv_poisson_prepare(self.h, None, 0, 1.0, self.stream)
 
+    def buf_after(self, npasses):
+        """Index of the buffer holding the iterate after `npasses` full passes of a solve that did not stop early."""
+        return npasses % len(self.bufs)
+
     def download_owned(self, which, out):
-        t = self.bufs[which & 1][self.own_lo:self.own_hi, :self.ncols]
+        t = self.bufs[which % len(self.bufs)][self.own_lo:self.own_hi, :self.ncols]
         self.torch.from_numpy(out).copy_(t)  # synchronising D2H
         return out
 
@@ -209,7 +219,7 @@ class SlabPoisson:
         """Run to convergence / itmax with the reference's stopping rule; every rank returns the same dict."""
         self.zero_iterate()
         self.reset(itmax, tol)
-        max_passes = (itmax + self.T - 1) // self.T + 2
+        max_passes = (itmax + self.T - 1) // self.T + 2 + (3 if len(self.bufs) == 3 else 0)  # lagged decision: speculative passes
         batch = first_batch
         while True:
             self.enqueue(min(batch, max_passes + 1 - self.passes_enqueued))
@@ -225,7 +235,7 @@ class SlabPoisson:
     def gather_result(self, which):
         """Full field on rank 0 (tests / small grids)."""
         torch, dist = self.torch, self.dist
-        mine = self.bufs[which & 1][self.own_lo:self.own_hi, :self.ncols].contiguous()
+        mine = self.bufs[which % len(self.bufs)][self.own_lo:self.own_hi, :self.ncols].contiguous()
         sizes = [slab_bounds(self.total_rows, self.world, r) for r in range(self.world)]
         if self.rank == 0:
             parts = [torch.empty((b - a, self.ncols), dtype=torch.float64, device=mine.device) for a, b in sizes]

@@ -146,11 +146,46 @@ void emul_decide(int *ctl_ints, double *ctl_dbls, const double *e, int nsw, doub
     PoissonCtl c;
     c.state = ctl_ints[0]; c.cur = ctl_ints[1]; c.sweeps = ctl_ints[2]; c.redo = ctl_ints[3]; c.itmax = ctl_ints[4];
     c.result_k = ctl_ints[5]; c.passes = ctl_ints[6]; c.ticket = 0;
-    c.tol = ctl_dbls[0]; c.result_e = ctl_dbls[1]; c.last_e = ctl_dbls[2];
+    c.tol = ctl_dbls[0]; c.result_e = ctl_dbls[1]; c.last_e = ctl_dbls[2]; c.hit_e = 0.0; c.nbuf = 2; c.pad_ = 0;
     decide(c, e, nsw, hist);
     ctl_ints[0] = c.state; ctl_ints[1] = c.cur; ctl_ints[2] = c.sweeps; ctl_ints[3] = c.redo; ctl_ints[5] = c.result_k;
     ctl_ints[6] = c.passes;
     ctl_dbls[1] = c.result_e; ctl_dbls[2] = c.last_e;
+}
+// ---- lagged stop decision (poisson_stream.h lag_fold / lag_action / lag_final) ----
+// ints: state, cur, sweeps, redo, itmax, result_k, passes, nbuf;  dbls: tol, result_e, last_e, hit_e
+static PoissonCtl ctl_from(const int *i, const double *d)
+{
+    PoissonCtl c; std::memset(&c, 0, sizeof c);
+    c.state = i[0]; c.cur = i[1]; c.sweeps = i[2]; c.redo = i[3]; c.itmax = i[4]; c.result_k = i[5]; c.passes = i[6]; c.nbuf = i[7];
+    c.tol = d[0]; c.result_e = d[1]; c.last_e = d[2]; c.hit_e = d[3];
+    return c;
+}
+static void ctl_to(const PoissonCtl &c, int *i, double *d)
+{
+    i[0] = c.state; i[1] = c.cur; i[2] = c.sweeps; i[3] = c.redo; i[4] = c.itmax; i[5] = c.result_k; i[6] = c.passes; i[7] = c.nbuf;
+    d[0] = c.tol; d[1] = c.result_e; d[2] = c.last_e; d[3] = c.hit_e;
+}
+void emul_lag_fold(int *ints, double *dbls, const double *e, int T, double *hist)
+{
+    PoissonCtl c = ctl_from(ints, dbls);
+    lag_fold(c, e, T, hist);
+    ctl_to(c, ints, dbls);
+}
+// out: kind (0 no-op, 1 run, 2 redo), in, out, nsw
+void emul_lag_action(const int *ints, const double *dbls, int pidx, int T, int *out)
+{
+    const LagAction a = lag_action(ctl_from(ints, dbls), pidx, T);
+    out[0] = a.kind; out[1] = a.in; out[2] = a.out; out[3] = a.nsw;
+}
+// host-visible state after P launched passes; returns 1 if e_last (norms of pass P-1) was consumed
+int emul_lag_final(int *ints, double *dbls, int P, const double *e_last, int T, double *hist)
+{
+    PoissonCtl c = ctl_from(ints, dbls);
+    const bool need = lag_final_needs_last(c, P);
+    lag_final(c, P, e_last, T, hist);
+    ctl_to(c, ints, dbls);
+    return need ? 1 : 0;
 }
 int emul_pass_sweeps(int sweeps, int redo, int itmax, int T)
 {

@@ -1,0 +1,235 @@
+"""Lagged stop decision of the multi-GPU peer path (CNV_PEER_LAG=1; csrc/poisson_stream.h lag_fold / lag_action /
+lag_final), checked on the CPU: the ranks of a slab decomposition are simulated in ONE process, each pass executed
+by the schedule emulator (tests/emul, the kernel's own per-thread code), with exactly the waits the kernel performs
+-- norm flags of pass p-2 from every rank, halo pushes of pass p-1 from the neighbours -- and a RANDOM interleaving
+of the ranks within those constraints (a rank runs as far ahead as the protocol lets it).  Three iterate buffers
+rotate, norms travel through the mailbox slots (indexed by the GLOBAL pass number, which keeps counting across solves), pushes land in the neighbours' halo rows.  The result must be the
+single-domain oracle's field, iteration count and residual, bit for bit, for every position of the converged sweep
+inside a pass and every position of the host's batch boundary."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from fluid_dynamics1_b200.parallel import slab_layout
+from oracle import api
+
+NSLOTS = 8  # csrc/poisson_stream.h kNormSlots
+dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def E():
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emul", "libstream_emul.so"))
+    lib.emul_pass.argtypes = [C.c_int] * 10 + [C.c_double] * 3 + [C.c_int, dp, dp, dp, C.c_int, dp]
+    lib.emul_lag_fold.argtypes = [ip, dp, dp, C.c_int, C.c_void_p]
+    lib.emul_lag_action.argtypes = [ip, dp, C.c_int, C.c_int, ip]
+    lib.emul_lag_final.argtypes = [ip, dp, C.c_int, dp, C.c_int, C.c_void_p]
+    return lib
+
+
+class Rank:
+    def __init__(self, E, r, world, rows, cols, T, f, itmax, tol):
+        self.E, self.r, self.world, self.T = E, r, world, T
+        self.rows, self.cols = rows, cols
+        self.grow0, self.nloc, self.own_lo, self.own_hi, _, _ = slab_layout(rows, world, r, T)
+        self.ld = (cols + 15) // 16 * 16
+        self.floc = np.zeros((self.nloc, self.ld))
+        self.floc[:, :cols] = f[self.grow0:self.grow0 + self.nloc]
+        self.bufs = [np.zeros((self.nloc, self.ld)) for _ in range(3)]
+        # chain X_p: two slots like ctlbuf[p & 1]; slot 0 = reset state
+        ints = np.array([0 if itmax > 0 else 2, 0, 0, 0, itmax, -1, 0, 3], dtype=np.int32)
+        dbls = np.array([tol, 0.0, 0.0, 0.0])
+        self.chain = [(ints.copy(), dbls.copy()), (ints.copy(), dbls.copy())]
+        self.norms = np.zeros((NSLOTS, world, 8))  # my mailbox: [slot][rank][sweep]
+        self.norm_flag = np.zeros(world, dtype=np.int64)
+        self.halo_passes = [0, 0]                  # pushes landed in my low / high halo, in passes (cumulative)
+        self.p = 0                                 # next pass of the current solve
+        self.g0 = 0                                # global index of pass 0 of the current solve
+
+    def new_solve(self, f, itmax, tol):
+        """Re-initialise for the next solve (the kernel path: quiesce, zero the iterate, ready); the mailbox counters
+        keep counting."""
+        self.g0 += self.p
+        self.p = 0
+        self.floc[:, :self.cols] = f[self.grow0:self.grow0 + self.nloc]
+        for b in self.bufs:
+            b[:] = 0.0
+        ints = np.array([0 if itmax > 0 else 2, 0, 0, 0, itmax, -1, 0, 3], dtype=np.int32)
+        dbls = np.array([tol, 0.0, 0.0, 0.0])
+        self.chain = [(ints.copy(), dbls.copy()), (ints.copy(), dbls.copy())]
+
+    def gather(self, p):
+        g = self.g0 + p
+        assert all(self.norm_flag >= g + 1)
+        e = np.zeros(8)
+        for i in range(8):
+            s = 0.0
+            for r in range(self.world):
+                s = s + self.norms[g % NSLOTS, r, i]
+            e[i] = s
+        return e
+
+    def state_for(self, p):
+        """X_p and whether deriving it needs the norms of pass p-2."""
+        ints, dbls = (a.copy() for a in self.chain[0 if p == 0 else (p - 1) & 1])
+        need = p >= 2 and ints[0] == 0 and ints[3] == 0
+        return ints, dbls, need
+
+    def runnable(self, ranks):
+        p = self.p
+        ints, dbls, need = self.state_for(p)
+        if need and not all(self.norm_flag >= self.g0 + p - 1):
+            return False
+        if p >= 2:
+            e = self.gather(p - 2) if need else np.zeros(8)
+            self.E.emul_lag_fold(ints, dbls, e, self.T, None)
+        act = np.zeros(4, dtype=np.int32)
+        self.E.emul_lag_action(ints, dbls, p, self.T, act)
+        if act[0] == 1:  # a speculative run streams halo rows: the neighbours' pushes of pass p-1 must have landed
+            if self.r > 0 and self.halo_passes[0] < self.g0 + p:
+                return False
+            if self.r < self.world - 1 and self.halo_passes[1] < self.g0 + p:
+                return False
+        return True
+
+    def run_pass(self, ranks, dx, dy, beta):
+        p, T, H = self.p, self.T, 2 * self.T
+        ints, dbls, need = self.state_for(p)
+        if p >= 2:
+            e = self.gather(p - 2) if need else np.zeros(8)
+            self.E.emul_lag_fold(ints, dbls, e, T, None)
+        act = np.zeros(4, dtype=np.int32)
+        self.E.emul_lag_action(ints, dbls, p, T, act)
+        if p > 0:
+            self.chain[p & 1] = (ints.copy(), dbls.copy())
+        kind, bi, bo, nsw = (int(x) for x in act)
+        norms = np.zeros(8)
+        if kind != 0:
+            # write-after-read check of the protocol: nobody may still have to READ the buffer this pass pushes into
+            for nb in (self.r - 1, self.r + 1):
+                if 0 <= nb < self.world and kind == 1:
+                    assert ranks[nb].p >= p - 1, "push into a buffer the neighbour has not finished reading"
+            rc = self.E.emul_pass(T, self.nloc, self.cols, self.ld, self.grow0, self.rows, self.own_lo, self.own_hi, 0,
+                                  int(os.environ.get("CNV_TEST_CHUNKS", "0")), dx, dy, beta, 0, self.bufs[bi], self.floc,
+                                  self.bufs[bo], nsw, norms)
+            assert rc == 0
+            if self.r > 0:                     # my first owned rows -> the lower neighbour's high halo
+                nb = ranks[self.r - 1]
+                nb.bufs[bo][nb.own_hi:nb.own_hi + H] = self.bufs[bo][self.own_lo:self.own_lo + H]
+            if self.r < self.world - 1:        # my last owned rows -> the upper neighbour's low halo
+                nb = ranks[self.r + 1]
+                nb.bufs[bo][nb.own_lo - H:nb.own_lo] = self.bufs[bo][self.own_hi - H:self.own_hi]
+        if self.r > 0:
+            ranks[self.r - 1].halo_passes[1] += 1
+        if self.r < self.world - 1:
+            ranks[self.r + 1].halo_passes[0] += 1
+        for other in ranks:                    # publish; a no-op pass only raises the flag (like the kernel): a finished
+            if kind != 0:                      # rank runs ahead through its no-ops and must not touch the norm slots
+                other.norms[(self.g0 + p) % NSLOTS, self.r, :] = norms
+            other.norm_flag[self.r] = self.g0 + p + 1
+        self.p += 1
+
+    def finalize(self, P):
+        ints, dbls, need = self.state_for(P)
+        if P >= 2:
+            e = self.gather(P - 2) if need else np.zeros(8)
+            self.E.emul_lag_fold(ints, dbls, e, self.T, None)
+        e_last = self.gather(P - 1) if P >= 1 else np.zeros(8)
+        self.E.emul_lag_final(ints, dbls, P, e_last, self.T, None)
+        return ints, dbls
+
+
+def lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed, ranks=None, fseed=11):
+    rng = np.random.default_rng(seed)
+    f = np.random.default_rng(fseed).standard_normal((rows, cols))
+    dx, dy = 1.0 / cols, 1.0 / rows
+    port = api.port()
+    beta = port.beta(rows, cols)
+    if ranks is None:
+        ranks = [Rank(E, r, world, rows, cols, T, f, itmax, tol) for r in range(world)]
+    else:
+        for k in ranks:
+            k.new_solve(f, itmax, tol)
+    P, nb = 0, 0
+    while True:
+        P += batches[min(nb, len(batches) - 1)]
+        nb += 1
+        while any(k.p < P for k in ranks):
+            ready = [k for k in ranks if k.p < P and k.runnable(ranks)]
+            assert ready, "protocol deadlock"
+            ready[rng.integers(len(ready))].run_pass(ranks, dx, dy, beta)
+        finals = [k.finalize(P) for k in ranks]
+        assert all(np.array_equal(finals[0][0], x[0]) and np.array_equal(finals[0][1], x[1]) for x in finals)
+        ints, dbls = finals[0]
+        if ints[0] != 0:
+            break
+        assert P < itmax + 8
+    full = np.concatenate([k.bufs[int(ints[1])][k.own_lo:k.own_hi, :cols] for k in ranks])
+    want = port.poisson(f, dx, dy, itmax, tol, beta, redblack=True)
+    lagged_solve.last_ranks = ranks
+    return ints, dbls, full, want, P
+
+
+@pytest.mark.parametrize("world,T", [(2, 2), (3, 2), (2, 4)])
+def test_lagged_machine_every_stop_position(E, world, T):
+    """tol chosen so that the converged sweep falls on every position inside a pass; batch sizes 1..4 move the host's
+    read-back (finalize) over every phase of the speculative pass / redo pass sequence."""
+    rows, cols = 24 * world, 40
+    f = np.random.default_rng(11).standard_normal((rows, cols))
+    port = api.port()
+    # residual history of a run that never converges (tol = 0 -> itmax sweeps): hist[k] = norm of sweep k
+    hist = np.zeros(8 * T)
+    for ks in range(3 * T, 5 * T + 1):
+        hist[ks] = port.poisson(f, 1.0 / cols, 1.0 / rows, ks + 1, 0.0, port.beta(rows, cols), redblack=True)["e"]
+    seen = set()
+    for ksweep in range(3 * T, 5 * T + 1):
+        # a tolerance just above the norm of sweep `ksweep`: first sweep with e < tol
+        tol = hist[ksweep] * (1 + 1e-9)
+        for batch in ([1], [2], [3], [4], [ksweep // T + 1, 1], [ksweep // T + 2, 2]):
+            ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, 5000, tol, batch, seed=ksweep * 7 + batch[0])
+            assert ints[0] == 1 and want["status"] == 0
+            assert int(ints[5]) == want["k"], (ksweep, batch, int(ints[5]), want["k"])
+            assert full.tobytes() == want["u"].tobytes(), (ksweep, batch)
+            assert abs(dbls[1] - want["e"]) <= 1e-12 * want["e"]
+            seen.add(want["k"] % T)
+    assert seen == set(range(T))
+
+
+@pytest.mark.parametrize("itmax", [1, 2, 3, 4, 5, 7, 8, 9])
+def test_lagged_machine_itmax(E, itmax):
+    """No convergence (tol = 0): exactly itmax sweeps, state 2, whatever the batch size; the speculative pass past
+    itmax is a no-op."""
+    for batch in ([1], [2], [5]):
+        ints, dbls, full, want, P = lagged_solve(E, 48, 40, 2, 2, itmax, 0.0, batch, seed=itmax)
+        assert ints[0] == 2 and want["status"] == 1 and int(ints[2]) == itmax
+        assert full.tobytes() == want["u"].tobytes()
+
+
+def test_lagged_machine_first_sweep_converges(E):
+    """Huge tolerance: the very first sweep is below it (hit inside pass 0, redo pass with 1 sweep)."""
+    ints, dbls, full, want, P = lagged_solve(E, 48, 40, 4, 2, 100, 1e30, [1], seed=3)
+    assert ints[0] == 1 and int(ints[5]) == want["k"] == 0
+    assert full.tobytes() == want["u"].tobytes()
+
+
+def test_lagged_machine_consecutive_solves(E):
+    """Several solves on the same ranks: the global pass index (norm slots, flags, halo counters) keeps counting while
+    the per-solve pass number restarts, as in a time-stepping run."""
+    rows, cols, T, world = 72, 40, 2, 3
+    ranks = None
+    for i, (tol, batch) in enumerate([(0.05, [3]), (0.2, [1]), (0.01, [7, 2]), (1e30, [2]), (0.1, [4])]):
+        ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, 5000, tol, batch, seed=i, ranks=ranks, fseed=20 + i)
+        assert ints[0] == 1 and int(ints[5]) == want["k"]
+        assert full.tobytes() == want["u"].tobytes()
+        ranks = lagged_solve.last_ranks
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_lagged_machine_random_schedules_world4(E, seed):
+    ints, dbls, full, want, P = lagged_solve(E, 96, 40, 4, 4, 5000, 0.02 * (1 + seed), [2 + seed % 3], seed=100 + seed)
+    assert ints[0] == 1 and int(ints[5]) == want["k"]
+    assert full.tobytes() == want["u"].tobytes()
