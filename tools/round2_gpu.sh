@@ -1,0 +1,50 @@
+#!/bin/bash
+# First GPU calls of the next round: verify on hardware what was written after round 1's GPU budget was spent
+# (planner change 97f5c9d: taller chunks at the domain boundary; the lagged stop decision of the peer path,
+# CNV_PEER_LAG=1), then measure it.  Everything writes into gpurun_out/.
+#
+#   1 GPU :  gpurun --timeout 1500 -- 'bash tools/round2_gpu.sh single'
+#   2 GPUs:  gpurun --gpus 2 --timeout 1200 -- 'bash tools/round2_gpu.sh lag 2'
+#   8 GPUs:  gpurun --gpus 8 --timeout 1200 -- 'bash tools/round2_gpu.sh lag 8'
+set -u
+mkdir -p gpurun_out
+mode=${1:-single}
+case "$mode" in
+single)
+    # parity first (the planner change is covered by the emulator on the CPU; this is the hardware confirmation)
+    timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1
+    echo "pytest exit $?" >> gpurun_out/r2_pytest_gpu.log
+    tail -3 gpurun_out/r2_pytest_gpu.log
+    # headline, with and without the boundary-chunk change (CNV_POISSON_TRIM only affects slab neighbours; the
+    # domain-boundary extension is unconditional, so compare against a forced plan of the old shape: 9 equal chunks)
+    python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
+    CNV_POISSON_WS=288 CNV_POISSON_CHUNKS=9 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/r2_bench_n1_forced9.json 2>&1
+    # launch list + one full capture of the pass kernel
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv \
+        python bench.py --steps 2 --warmup 3 --sweeps 128 --no-cpu > gpurun_out/r2_launches.log 2>&1
+    ncu --set full --clock-control none --import-source on -k regex:k_poisson_pass -s 20 -c 2 -o gpurun_out/r2_pass \
+        python tools/prof_one.py 4096 8 > gpurun_out/r2_ncu_pass.log 2>&1
+    ;;
+lag)
+    n=${2:-2}
+    run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port "$1" "${@:2}"; }
+    # correctness of the lagged decision on hardware (opt-in tests), then the plain suite
+    CNV_TEST_LAG=1 timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "lagged" > gpurun_out/r2_lag_tests_$n.log 2>&1
+    echo "pytest exit $?" >> gpurun_out/r2_lag_tests_$n.log
+    tail -3 gpurun_out/r2_lag_tests_$n.log
+    # weak scaling: plain peer path vs lagged decision, same box, back to back
+    run 29801 bench.py --gpus "$n" --steps 10 --warmup 3 > gpurun_out/r2_scale_peer_$n.json 2> gpurun_out/r2_scale_peer_$n.err
+    CNV_PEER_LAG=1 run 29802 bench.py --gpus "$n" --steps 10 --warmup 3 > gpurun_out/r2_scale_lag_$n.json 2> gpurun_out/r2_scale_lag_$n.err
+    # strong scaling of one 4096^2 grid
+    run 29803 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_peer_$n.json 2>&1
+    CNV_PEER_LAG=1 run 29804 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_lag_$n.json 2>&1
+    # where the pass time goes (per-CTA stamps), both variants
+    run 29805 tools/peer_trace.py 4096 4096 24 > gpurun_out/r2_trace_peer_$n.log 2>&1
+    CNV_PEER_LAG=1 run 29806 tools/peer_trace.py 4096 4096 24 > gpurun_out/r2_trace_lag_$n.log 2>&1
+    tail -n 2 gpurun_out/r2_scale_peer_$n.json gpurun_out/r2_scale_lag_$n.json
+    ;;
+*)
+    echo "usage: $0 single | lag N" >&2
+    exit 2
+    ;;
+esac
