@@ -461,7 +461,7 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
     CNV_CUDA_CHECK(cudaGetDevice(&dev));
     CNV_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     lim.num_sms = prop.multiProcessorCount;
-    lim.smem_per_cta = prop.sharedMemPerBlockOptin - 1024;  // room for the kernel's static shared memory
+    lim.smem_per_cta = prop.sharedMemPerBlockOptin - 2048;  // room for the kernel's static shared memory (<= 1.7 KB, ptxas -v)
     smem_optin_ = lim.smem_per_cta;
     lim.smem_per_sm = prop.sharedMemPerMultiprocessor;
     lim.max_threads_per_sm = prop.maxThreadsPerMultiProcessor;

@@ -233,3 +233,66 @@ def test_lagged_machine_random_schedules_world4(E, seed):
     ints, dbls, full, want, P = lagged_solve(E, 96, 40, 4, 4, 5000, 0.02 * (1 + seed), [2 + seed % 3], seed=100 + seed)
     assert ints[0] == 1 and int(ints[5]) == want["k"]
     assert full.tobytes() == want["u"].tobytes()
+
+
+def test_lagged_machine_abstract_model_fuzz(E):
+    """State machine alone, no arithmetic: a buffer is modelled by the number of sweeps applied to it, a pass by
+    content[out] = content[in] + nsw and the norms h[content[in] : content[in] + nsw] of a synthetic residual history.
+    For thousands of random (T, itmax, history, batch pattern) the lagged machine must end with the buffer that holds
+    exactly k+1 sweeps, k = first index with h[k] < tol (or itmax sweeps, state 2) -- the plain machine's answer."""
+    rng = np.random.default_rng(2024)
+    for case in range(3000):
+        T = int(rng.choice([1, 2, 4, 6, 8]))
+        itmax = int(rng.integers(1, 60))
+        n = itmax + 4 * T
+        h = np.sort(rng.random(n))[::-1].copy() + 0.5          # decreasing, > 0.5
+        if rng.random() < 0.8:
+            kstop = int(rng.integers(0, itmax + 6))             # first sweep below tol (possibly beyond itmax)
+            tol = 0.25
+            h[kstop:] = rng.random(n - kstop) * 0.2 if kstop < n else h[kstop:]
+        else:
+            kstop, tol = n + 1, 0.0
+        want_sweeps = min(kstop + 1, itmax) if kstop < itmax else itmax
+        want_state = 1 if kstop < itmax else 2
+        chain = [None, None]
+        ints0 = np.array([0, 0, 0, 0, itmax, -1, 0, 3], dtype=np.int32)
+        dbls0 = np.array([tol, 0.0, 0.0, 0.0])
+        chain[0] = (ints0.copy(), dbls0.copy())
+        content = [0, -1, -1]                                   # sweeps applied to each buffer (-1: garbage)
+        norms = {}                                              # pass -> e[8]
+        P = 0
+        while True:
+            P_next = P + int(rng.integers(1, 6))
+            for p in range(P, P_next):
+                ints, dbls = (a.copy() for a in chain[0 if p == 0 else (p - 1) & 1])
+                if p >= 2:
+                    need = ints[0] == 0 and ints[3] == 0
+                    E.emul_lag_fold(ints, dbls, norms[p - 2] if need else np.zeros(8), T, None)
+                if p > 0:
+                    chain[p & 1] = (ints.copy(), dbls.copy())
+                act = np.zeros(4, dtype=np.int32)
+                E.emul_lag_action(ints, dbls, p, T, act)
+                kind, bi, bo, nsw = (int(x) for x in act)
+                e = np.zeros(8)
+                if kind:
+                    assert content[bi] >= 0 and bi != bo and 1 <= nsw <= T
+                    if kind == 1:
+                        assert bi == p % 3 and bo == (p + 1) % 3   # the rotation the write-after-read argument relies on
+                    else:
+                        assert bi == (p - 2) % 3 and bo == p % 3   # redo: input of pass p-2, into the speculative pass' output
+                    e[:nsw] = h[content[bi]:content[bi] + nsw]
+                    content[bo] = content[bi] + nsw
+                norms[p] = e
+            P = P_next
+            ints, dbls = (a.copy() for a in chain[0 if P == 0 else (P - 1) & 1])
+            if P >= 2:
+                need = ints[0] == 0 and ints[3] == 0
+                E.emul_lag_fold(ints, dbls, norms[P - 2] if need else np.zeros(8), T, None)
+            E.emul_lag_final(ints, dbls, P, norms[P - 1], T, None)
+            if ints[0] != 0:
+                break
+            assert P <= itmax + 12
+        assert int(ints[0]) == want_state, (case, T, itmax, kstop, ints)
+        assert int(ints[2]) == want_sweeps and content[int(ints[1])] == want_sweeps, (case, T, itmax, kstop, ints, content)
+        if want_state == 1:
+            assert int(ints[5]) == kstop and dbls[1] == h[kstop]
