@@ -332,6 +332,8 @@ def run_gpu(args):
         if world == 1:
             out["stencil_phase"] = stencil_phase(fd, torch, args.n, sp, stream, peak)
             out["timestep_1024"] = timestep_1024(fd, peak, cpu=not args.no_cpu)
+            if args.n == 4096:
+                out["timestep_4096"] = timestep_4096(fd, peak)
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.n, args.cpu_seconds)
         print(json.dumps(out), flush=True)
@@ -386,6 +388,25 @@ def timestep_1024(fd, peak, steps=4, cpu=True):
         out["cpu_port"] = {"ms_per_step": tc * 1e3, "cell_steps_per_s": n * n / tc, "threads": port.max_threads(),
                            "sweeps": int(ref["k"][0]) + 1, "kind": "port (the reference executable cannot run beyond 128^2)"}
     return out
+
+
+def timestep_4096(fd, peak, steps=2):
+    """BASELINE config 4 (4096^2, Re 1000) as WHOLE time steps on one GPU: every step solves the streamfunction
+    Poisson equation to the reference's tolerance (about 6 k sweeps per step at the start of the run) between the
+    stencil phases.  cell-steps/s = N^2 x steps / t; bytes per cell-step = 72 + 24 x sweeps."""
+    n = 4096
+    cfg = dict(nx=n, ny=n, Re=1000.0, dt=5e-6, poisson_max_it=100000, poisson_tol=1e-3)
+    sim = fd.Simulation(cfg)
+    sim.step(1)                                   # warm-up (fills the pass-count predictor)
+    t0 = time.perf_counter()
+    r = sim.step(steps)
+    dt = (time.perf_counter() - t0) / steps       # cnv_sim_step synchronises once per step
+    sweeps = float(np.mean(r["k"])) + 1
+    sim.close()
+    gbs = (72 + 24 * sweeps) * n * n / dt / 1e9
+    return {"grid": [n, n], "steps": steps, "ms_per_step": dt * 1e3, "cell_steps_per_s": n * n / dt,
+            "poisson_sweeps_per_step": sweeps, "poisson_cell_updates_per_s": (n - 2) ** 2 * sweeps / dt,
+            "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
 
 
 # ------------------------------------------------------------------------------------------------
