@@ -13,6 +13,10 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libcnavier_b200.so")
+# CNV_LIB=lean: the same library with the experimental leaner streaming-step body (csrc/poisson_stream.h kLean,
+# `make -C csrc lean`); for A/B measurements only -- the default is the measured kernel
+if os.environ.get("CNV_LIB", "") == "lean":
+    LIB_PATH = os.path.join(PKG, "libcnavier_b200_lean.so")
 DROPIN_PATH = os.path.join(PKG, "libcnavier_dropin.so")
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")

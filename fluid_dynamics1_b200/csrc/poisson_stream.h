@@ -37,6 +37,16 @@ constexpr int kLand = kSkew > 4 ? 1 : 0;  // input rows must have landed this ma
 constexpr int kPairs = 2;  // 4 measured slower on B200 (128 registers + spills, 12 warps/SM: 47 vs 36 us/sweep at 4096^2)
 static_assert(kPairs % 2 == 0, "pairs are moved as 16-byte vectors");
 constexpr int ring_rows(int T) { return kSkew * T + kPrefetch - (kSkew > 4 ? 1 : 0); }
+// Experimental leaner step body (build with -DCNV_STREAM_LEAN; `make lean` -> libcnavier_b200_lean.so, selected at run time
+// by CNV_LIB=lean): one range test selects an "interior" body without per-row range checks for the norm and the
+// write-back, and the L1 norm is accumulated as acc += (|d0| + |d1|) per colour (a 2-long dependent chain instead of
+// 4 adds + 2 selects at the end of every step).  The iterate is bit-identical; only the association of the norm sum
+// differs (1e-16 relative).  Not measured yet (profiles/analysis_r1.md, items 2 and 3).
+#ifdef CNV_STREAM_LEAN
+constexpr bool kLean = true;
+#else
+constexpr bool kLean = false;
+#endif
 
 struct PassGeom {
     // local array: nrows x ncols doubles with pitch ld; row 0 is global row grow0 of gnrows
@@ -226,6 +236,7 @@ struct StreamThread {
     int vmask;           // bit 2p / 2p+1: even / odd column of pair k0+p updatable
     bool colown, allvalid;
     bool mask_path;      // warp-uniform: some lane of this warp owns a column that must not be updated (see stream_step)
+    int int_lo; unsigned int_span;  // kLean: steps r in [int_lo, int_lo + int_span] have both rows updatable AND inside [y0, y1)
     // h[(PH - a) & 3] = N loaded a steps ago, rr[(PH - a) & 3] = red results of a steps ago (a = 0: this step);
     // compile-time indices, so both stay in registers and no register moves are needed to age them
     vecP h[4], rr[4];
@@ -283,6 +294,7 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.allvalid = t.vmask == (1 << (2 * kPairs)) - 1;
     s.mask_path = warp_any(!s.allvalid);
     s.colown = t.colown;
+    s.int_lo = 0x7fffffff; s.int_span = 0;
     const int gc4 = G.gx0 + 2 * t.k0;  // first of this thread's columns
     s.sact = t.g == T - 1 && t.colown && gc4 >= 0 && gc4 < p.ld;
     s.sdst = (long long)(s.ybase - 3 - s.dq) * p.ld + gc4;
@@ -290,6 +302,18 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.pf_N = s.pf_own = s.pf_Pr = s.pf_Pb = zeroP();
     s.pf_x = s.pf_xb = 0.0;
     s.acc = 0.0;
+}
+
+// kLean: the steps in which this thread's red row q = r-1-dq and black row q-2 are both updatable and both inside the
+// CTA's output rows [y0, y1) -- there the norm and the write-back need no range checks (nsw = sweeps of this pass)
+template <int T>
+CNV_HD void stream_set_sweeps(StreamThread<T> &s, int nsw)
+{
+    const int lo = s.vlo > s.y0 ? s.vlo : s.y0;               // black row q-2 >= lo
+    const int hi = s.vhi < s.y1 - 1 ? s.vhi : s.y1 - 1;       // red row q <= hi
+    const int r_lo = lo + 3 + s.dq, r_hi = hi + 1 + s.dq;
+    if (s.g < nsw && r_hi >= r_lo) { s.int_lo = r_lo; s.int_span = (unsigned)(r_hi - r_lo); }
+    else { s.int_lo = 0x7fffffff; s.int_span = 0; }
 }
 
 // copy this thread's chunks of one row into the ring slot at byte offset `slot`; `back` = how many rows
@@ -370,11 +394,8 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         const double Eb = typeR ? bb.v[i] : (i == kPairs - 1 ? xb : bb.v[i + 1]);
         m.v[i] = relax<POW2>(Nb.v[i], Sb.v[i], Eb, Wb, ownb.v[i], Pb.v[i], rc);
     }
-    if (s.g < nsw && qb >= s.vlo && q <= s.vhi) {
-        // steady state: both rows updatable (and inside the streamed range by construction).  Warps none of whose
-        // lanes owns a protected column (Dirichlet ring, outside the domain) store unconditionally; a warp that has
-        // such a lane applies the column mask in ALL its lanes, so it does not diverge into the general path below
-        // (the first and last strip would otherwise run ~9 % longer than the others and set the pass time).
+    if (kLean && (unsigned)(r - s.int_lo) <= s.int_span) {
+        // interior: both rows updatable and inside the output rows -- no per-row range checks at all
         if (s.mask_path) {
 #pragma unroll
             for (int i = 0; i < kPairs; i++) {
@@ -385,37 +406,82 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         }
         stsP(sm, s.o[O1] + aA, n);
         stsP(sm, s.o[O3] + aB, m);
+        if (s.colown) {
+            double dr = 0.0, db = 0.0;
+#pragma unroll
+            for (int i = 0; i < kPairs; i++) {
+                dr = i == 0 ? fabs(xsub(n.v[i], own.v[i])) : xadd(dr, fabs(xsub(n.v[i], own.v[i])));
+                db = i == 0 ? fabs(xsub(m.v[i], ownb.v[i])) : xadd(db, fabs(xsub(m.v[i], ownb.v[i])));
+            }
+            s.acc = xadd(xadd(s.acc, dr), db);
+        }
+        if (s.sact) {
+            double *dst = out + s.sdst;
+#pragma unroll
+            for (int i = 0; i < kPairs; i++) {
+                if (typeR) stg2(dst + 2 * i, m.v[i], bb.v[i]);
+                else stg2(dst + 2 * i, bb.v[i], m.v[i]);
+            }
+        }
     } else {
-        const bool active = s.g < nsw;
-        const bool rowr = active && q >= s.vlo && q <= s.vhi;
-        const bool rowb = active && qb >= s.vlo && qb <= s.vhi;
+        if (s.g < nsw && qb >= s.vlo && q <= s.vhi) {
+            // steady state: both rows updatable (and inside the streamed range by construction).  Warps none of whose
+            // lanes owns a protected column (Dirichlet ring, outside the domain) store unconditionally; a warp that has
+            // such a lane applies the column mask in ALL its lanes, so it does not diverge into the general path below
+            // (the first and last strip would otherwise run ~9 % longer than the others and set the pass time).
+            if (s.mask_path) {
 #pragma unroll
-        for (int i = 0; i < kPairs; i++) {
-            const bool vr = (s.vmask >> (2 * i + (typeR ? 1 : 0))) & 1, vb = (s.vmask >> (2 * i + (typeR ? 0 : 1))) & 1;
-            n.v[i] = (rowr & vr) ? n.v[i] : own.v[i];
-            m.v[i] = (rowb & vb) ? m.v[i] : ownb.v[i];
+                for (int i = 0; i < kPairs; i++) {
+                    const bool vr = (s.vmask >> (2 * i + (typeR ? 1 : 0))) & 1, vb = (s.vmask >> (2 * i + (typeR ? 0 : 1))) & 1;
+                    n.v[i] = vr ? n.v[i] : own.v[i];
+                    m.v[i] = vb ? m.v[i] : ownb.v[i];
+                }
+            }
+            stsP(sm, s.o[O1] + aA, n);
+            stsP(sm, s.o[O3] + aB, m);
+        } else {
+            const bool active = s.g < nsw;
+            const bool rowr = active && q >= s.vlo && q <= s.vhi;
+            const bool rowb = active && qb >= s.vlo && qb <= s.vhi;
+#pragma unroll
+            for (int i = 0; i < kPairs; i++) {
+                const bool vr = (s.vmask >> (2 * i + (typeR ? 1 : 0))) & 1, vb = (s.vmask >> (2 * i + (typeR ? 0 : 1))) & 1;
+                n.v[i] = (rowr & vr) ? n.v[i] : own.v[i];
+                m.v[i] = (rowb & vb) ? m.v[i] : ownb.v[i];
+            }
+            if (q >= s.ylo && q <= s.yhi) stsP(sm, s.o[O1] + aA, n);
+            if (qb >= s.ylo && qb <= s.yhi) stsP(sm, s.o[O3] + aB, m);
         }
-        if (q >= s.ylo && q <= s.yhi) stsP(sm, s.o[O1] + aA, n);
-        if (qb >= s.ylo && qb <= s.yhi) stsP(sm, s.o[O3] + aB, m);
-    }
-    // L1 update norm of this level (non-updated cells contribute exactly 0)
-    if (s.colown) {
-        if (q >= s.y0 && q < s.y1) {
+        // L1 update norm of this level (non-updated cells contribute exactly 0)
+        if (s.colown) {
+            if (kLean) {  // same association as the interior body: acc + (|d0| + |d1|) per colour; acc + 0.0 is exact
+                double dr = 0.0, db = 0.0;
 #pragma unroll
-            for (int i = 0; i < kPairs; i++) s.acc = xadd(s.acc, fabs(xsub(n.v[i], own.v[i])));
+                for (int i = 0; i < kPairs; i++) {
+                    dr = i == 0 ? fabs(xsub(n.v[i], own.v[i])) : xadd(dr, fabs(xsub(n.v[i], own.v[i])));
+                    db = i == 0 ? fabs(xsub(m.v[i], ownb.v[i])) : xadd(db, fabs(xsub(m.v[i], ownb.v[i])));
+                }
+                s.acc = xadd(s.acc, (q >= s.y0 && q < s.y1) ? dr : 0.0);
+                s.acc = xadd(s.acc, (qb >= s.y0 && qb < s.y1) ? db : 0.0);
+            } else {
+                if (q >= s.y0 && q < s.y1) {
+#pragma unroll
+                    for (int i = 0; i < kPairs; i++) s.acc = xadd(s.acc, fabs(xsub(n.v[i], own.v[i])));
+                }
+                if (qb >= s.y0 && qb < s.y1) {
+#pragma unroll
+                    for (int i = 0; i < kPairs; i++) s.acc = xadd(s.acc, fabs(xsub(m.v[i], ownb.v[i])));
+                }
+            }
         }
-        if (qb >= s.y0 && qb < s.y1) {
+        // ---- write back: the black row of the last level is final; its red cells are r2 ----
+        if (s.sact && qb >= s.y0 && qb < s.y1) {
+            double *dst = out + s.sdst;
 #pragma unroll
-            for (int i = 0; i < kPairs; i++) s.acc = xadd(s.acc, fabs(xsub(m.v[i], ownb.v[i])));
-        }
-    }
-    // ---- write back: the black row of the last level is final; its red cells are r2 ----
-    if (s.sact && qb >= s.y0 && qb < s.y1) {
-        double *dst = out + s.sdst;
-#pragma unroll
-        for (int i = 0; i < kPairs; i++) {
-            if (typeR) stg2(dst + 2 * i, m.v[i], bb.v[i]);  // black cells are the even-column cells
-            else stg2(dst + 2 * i, bb.v[i], m.v[i]);
+            for (int i = 0; i < kPairs; i++) {
+                if (typeR) stg2(dst + 2 * i, m.v[i], bb.v[i]);  // black cells are the even-column cells
+                else stg2(dst + 2 * i, bb.v[i], m.v[i]);
+            }
         }
     }
     s.sdst += s.ld;

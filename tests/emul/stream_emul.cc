@@ -31,6 +31,7 @@ static void run_pass(const PassGeom &p, const RelaxConsts &rc, const double *in,
             for (auto &x : sm) x = std::nan("");
             const CtaGeom G = cta_geom(p, bx, by);
             for (int t = 0; t < NT; t++) stream_init<T>(st[t], p, G, sm.data(), in, rhs, t, NT);
+            if (kLean) for (int t = 0; t < NT; t++) stream_set_sweeps<T>(st[t], nsw);
             for (int t = 0; t < NT; t++) stream_prologue<T>(st[t], sm.data());
             for (int r = st[0].ybase; r <= st[0].rend; r += 4) {
                 // --- barrier before every step ---
@@ -193,6 +194,8 @@ int emul_pass_sweeps(int sweeps, int redo, int itmax, int T)
     c.sweeps = sweeps; c.redo = redo; c.itmax = itmax;
     return pass_sweeps(c, T);
 }
+
+int emul_is_lean() { return kLean ? 1 : 0; }
 
 // Markstein division vs hardware division: returns the number of mismatches
 long emul_check_div(double d, const double *a, long n)

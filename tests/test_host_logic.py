@@ -14,14 +14,29 @@ dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
-@pytest.fixture(scope="module")
-def emul():
-    so = os.path.join(ROOT, "tests", "emul", "libstream_emul.so")
+_EMUL = {}
+
+
+def _load_emul(variant):
+    """The schedule emulator, compiled from the kernel's own header; "lean" = the experimental step body
+    (-DCNV_STREAM_LEAN, csrc/poisson_stream.h kLean; libcnavier_b200_lean.so on the GPU side)."""
+    if variant in _EMUL:
+        return _EMUL[variant]
+    so = os.path.join(ROOT, "tests", "emul", "libstream_emul.so" if variant == "default" else "libstream_emul_lean.so")
     src = os.path.join(ROOT, "tests", "emul", "stream_emul.cc")
     hdrs = [os.path.join(ROOT, "fluid_dynamics1_b200", "csrc", h) for h in ("poisson_stream.h", "poisson_plan.h", "exact.h")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(x) for x in [src] + hdrs):
-        subprocess.run(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", src, "-o", so], check=True)
+        subprocess.run(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17"] +
+                       (["-DCNV_STREAM_LEAN"] if variant == "lean" else []) + [src, "-o", so], check=True)
     E = C.CDLL(so)
+    assert E.emul_is_lean() == (1 if variant == "lean" else 0)
+    _EMUL[variant] = E
+    return E
+
+
+@pytest.fixture(scope="module", params=["default", "lean"])
+def emul(request):
+    E = _load_emul(request.param)
     E.emul_pass.argtypes = [C.c_int] * 10 + [C.c_double] * 3 + [C.c_int, dp, dp, dp, C.c_int, dp]
     E.emul_plan.argtypes = [C.c_int] * 10 + [np.ctypeslib.ndpointer(dtype=np.int64)]
     E.emul_decide.argtypes = [ip, dp, dp, C.c_int, C.c_void_p]

@@ -19,6 +19,12 @@ single)
     # domain-boundary extension is unconditional, so compare against a forced plan of the old shape: 9 equal chunks)
     python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
     CNV_POISSON_WS=288 CNV_POISSON_CHUNKS=9 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/r2_bench_n1_forced9.json 2>&1
+    # A/B: the leaner step body (libcnavier_b200_lean.so: 87 instead of 111 instructions per thread and row-step on the
+    # steady-state path, 2-long norm chain; bit-exact on the emulator) -- parity on hardware first, then the same bench
+    CNV_LIB=lean timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "poisson or steps or golden" > gpurun_out/r2_pytest_lean.log 2>&1
+    echo "pytest exit $?" >> gpurun_out/r2_pytest_lean.log
+    CNV_LIB=lean python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_bench_n1_lean.json 2> gpurun_out/r2_bench_n1_lean.err
+    python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_bench_n1_again.json 2>&1   # same box, same moment: the A of the A/B
     # launch list + one full capture of the pass kernel
     ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv \
         python bench.py --steps 2 --warmup 3 --sweeps 128 --no-cpu > gpurun_out/r2_launches.log 2>&1
