@@ -73,7 +73,9 @@ inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, i
     // ... and rows ADDED to a chunk at the domain boundary: it has no halo rows on that side, i.e. 2T fewer rows to stream
     // than an interior chunk of the same height (per-CTA trace: 3 % shorter at 4096^2); equalising the streamed rows
     // shortens the longest CTA
-    const int want_lo = own_lo > 0 ? trim : -2 * T, want_hi = own_hi < nrows ? trim : -2 * T;
+    // (CNV_POISSON_EDGE=<rows> overrides the 2T, 0 switches it off: A/B switch)
+    const int edge = std::getenv("CNV_POISSON_EDGE") ? std::atoi(std::getenv("CNV_POISSON_EDGE")) : 2 * T;
+    const int want_lo = own_lo > 0 ? trim : -edge, want_hi = own_hi < nrows ? trim : -edge;
     PassGeom best;
     std::memset(&best, 0, sizeof best);
     double best_cost = 1e300;
