@@ -161,9 +161,9 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
         // norms of pass gidx-2, which have normally long arrived; the pass runs speculatively (poisson_stream.h).
         __shared__ double s_nrm[kMaxRanks][8];
         __shared__ int s_bad;
-        const int lagd = L.lag ? 2 : 1;  // this pass folds the norms of pass gidx - lagd
+        const int lagd = peer_lag_distance(L.lag);  // this pass folds the norms of pass gidx - lagd
         const PoissonCtl prev = L.ctlbuf[L.pidx == 0 ? 0 : (L.pidx - 1) & 1];
-        const bool need = L.pidx >= lagd && prev.state == 0 && (!L.lag || prev.redo == 0);  // uniform
+        const bool need = peer_needs_norms(prev, L.pidx, L.lag);  // uniform
         if (tid == 0) s_bad = 0;
         __syncthreads();
         if (need) {
@@ -184,20 +184,8 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
                     for (int r = 0; r < L.world; r++) sum = xadd(sum, s_nrm[r][g]);  // rank order: identical on every rank
                 e[g] = sum;
             }
-            if (need && s_bad) {
-                atomicExch(&L.mail[L.rank]->error, 1ull);
-                c.state = 3;
-            } else if (L.lag) {
-                if (L.pidx >= 2) lag_fold(c, e, T, first_cta ? hist : nullptr);
-            } else if (need) {
-                decide(c, e, pass_sweeps(c, T), first_cta ? hist : nullptr);
-            }
-            LagAction a;
-            if (L.lag) {
-                a = lag_action(c, L.pidx, T);
-            } else {
-                a.kind = c.state == 0 ? 1 : 0; a.in = c.cur; a.out = c.cur ^ 1; a.nsw = pass_sweeps(c, T);
-            }
+            if (need && s_bad) atomicExch(&L.mail[L.rank]->error, 1ull);
+            const LagAction a = peer_advance(c, e, need, s_bad != 0, L.pidx, L.lag, T, first_cta ? hist : nullptr);
             s_ctl = c;
             s_act = a;
             if (first_cta && L.pidx > 0) L.ctlbuf[L.pidx & 1] = c;

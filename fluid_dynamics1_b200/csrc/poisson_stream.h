@@ -684,6 +684,32 @@ CNV_HD LagAction lag_action(const PoissonCtl &c, int pidx, int T)
     return a;
 }
 
+// ---- what a pass of the peer path does at its start (shared by the kernel and the CPU protocol simulation) ----
+// `prev` = chain state the previous pass stored (ctlbuf[(pidx-1) & 1]; the reset state for pidx == 0).
+// lag == 0: plain machine, the pass folds the norms of pass pidx-1; lag == 1: lagged machine, those of pass pidx-2.
+CNV_HD int peer_lag_distance(int lag) { return lag ? 2 : 1; }
+CNV_HD bool peer_needs_norms(const PoissonCtl &prev, int pidx, int lag)
+{
+    return pidx >= peer_lag_distance(lag) && prev.state == 0 && (!lag || prev.redo == 0);
+}
+// c (in: prev, out: the state of this pass, stored for the next one) and the pass' action.  e = the needed norms summed
+// over the ranks in rank order (ignored unless `need`); bad = a rank's norm flag timed out.
+CNV_HD LagAction peer_advance(PoissonCtl &c, const double *e, bool need, bool bad, int pidx, int lag, int T, double *hist)
+{
+    if (need && bad) {
+        c.state = 3;
+    } else if (lag) {
+        if (pidx >= 2) lag_fold(c, e, T, hist);
+    } else if (need) {
+        decide(c, e, pass_sweeps(c, T), hist);
+    }
+    if (lag) return lag_action(c, pidx, T);
+    LagAction a;
+    a.kind = c.state == 0 ? 1 : 0;
+    a.in = c.cur; a.out = next_buf(c, c.cur); a.nsw = pass_sweeps(c, T);
+    return a;
+}
+
 // Host-visible state after P passes were launched: X_P (chain) + the norms of pass P-1 where they count.
 // Returns true if e_last (norms of pass P-1) is needed, i.e. the caller must wait for them first.
 CNV_HD bool lag_final_needs_last(const PoissonCtl &xP, int P) { return P > 0 && xP.state == 0 && xP.redo == 0; }

@@ -179,6 +179,18 @@ void emul_lag_action(const int *ints, const double *dbls, int pidx, int T, int *
     const LagAction a = lag_action(ctl_from(ints, dbls), pidx, T);
     out[0] = a.kind; out[1] = a.in; out[2] = a.out; out[3] = a.nsw;
 }
+// start of a pass of the peer path (the kernel's own decision code): does it need norms, and what does it do
+int emul_peer_needs_norms(const int *ints, const double *dbls, int pidx, int lag)
+{
+    return peer_needs_norms(ctl_from(ints, dbls), pidx, lag) ? 1 : 0;
+}
+void emul_peer_advance(int *ints, double *dbls, const double *e, int need, int bad, int pidx, int lag, int T, int *out)
+{
+    PoissonCtl c = ctl_from(ints, dbls);
+    const LagAction a = peer_advance(c, e, need != 0, bad != 0, pidx, lag, T, nullptr);
+    ctl_to(c, ints, dbls);
+    out[0] = a.kind; out[1] = a.in; out[2] = a.out; out[3] = a.nsw;
+}
 // host-visible state after P launched passes; returns 1 if e_last (norms of pass P-1) was consumed
 int emul_lag_final(int *ints, double *dbls, int P, const double *e_last, int T, double *hist)
 {

@@ -28,20 +28,23 @@ def E():
     lib.emul_lag_fold.argtypes = [ip, dp, dp, C.c_int, C.c_void_p]
     lib.emul_lag_action.argtypes = [ip, dp, C.c_int, C.c_int, ip]
     lib.emul_lag_final.argtypes = [ip, dp, C.c_int, dp, C.c_int, C.c_void_p]
+    lib.emul_peer_needs_norms.argtypes = [ip, dp, C.c_int, C.c_int]
+    lib.emul_peer_advance.argtypes = [ip, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip]
     return lib
 
 
 class Rank:
-    def __init__(self, E, r, world, rows, cols, T, f, itmax, tol):
+    def __init__(self, E, r, world, rows, cols, T, f, itmax, tol, lag=1):
         self.E, self.r, self.world, self.T = E, r, world, T
+        self.lag, self.lagd, self.nbuf = lag, (2 if lag else 1), (3 if lag else 2)
         self.rows, self.cols = rows, cols
         self.grow0, self.nloc, self.own_lo, self.own_hi, _, _ = slab_layout(rows, world, r, T)
         self.ld = (cols + 15) // 16 * 16
         self.floc = np.zeros((self.nloc, self.ld))
         self.floc[:, :cols] = f[self.grow0:self.grow0 + self.nloc]
-        self.bufs = [np.zeros((self.nloc, self.ld)) for _ in range(3)]
+        self.bufs = [np.zeros((self.nloc, self.ld)) for _ in range(self.nbuf)]
         # chain X_p: two slots like ctlbuf[p & 1]; slot 0 = reset state
-        ints = np.array([0 if itmax > 0 else 2, 0, 0, 0, itmax, -1, 0, 3], dtype=np.int32)
+        ints = np.array([0 if itmax > 0 else 2, 0, 0, 0, itmax, -1, 0, self.nbuf], dtype=np.int32)
         dbls = np.array([tol, 0.0, 0.0, 0.0])
         self.chain = [(ints.copy(), dbls.copy()), (ints.copy(), dbls.copy())]
         self.norms = np.zeros((NSLOTS, world, 8))  # my mailbox: [slot][rank][sweep]
@@ -58,7 +61,7 @@ class Rank:
         self.floc[:, :self.cols] = f[self.grow0:self.grow0 + self.nloc]
         for b in self.bufs:
             b[:] = 0.0
-        ints = np.array([0 if itmax > 0 else 2, 0, 0, 0, itmax, -1, 0, 3], dtype=np.int32)
+        ints = np.array([0 if itmax > 0 else 2, 0, 0, 0, itmax, -1, 0, self.nbuf], dtype=np.int32)
         dbls = np.array([tol, 0.0, 0.0, 0.0])
         self.chain = [(ints.copy(), dbls.copy()), (ints.copy(), dbls.copy())]
 
@@ -73,23 +76,27 @@ class Rank:
             e[i] = s
         return e
 
-    def state_for(self, p):
-        """X_p and whether deriving it needs the norms of pass p-2."""
+    def start_of_pass(self, p):
+        """What the kernel's preamble does (csrc/poisson_stream.h peer_needs_norms / peer_advance): returns
+        (state of this pass, action, norms available?)."""
         ints, dbls = (a.copy() for a in self.chain[0 if p == 0 else (p - 1) & 1])
-        need = p >= 2 and ints[0] == 0 and ints[3] == 0
-        return ints, dbls, need
+        need = bool(self.E.emul_peer_needs_norms(ints, dbls, p, self.lag))
+        if need and not all(self.norm_flag >= self.g0 + p - self.lagd + 1):
+            return None
+        e = self.gather(p - self.lagd) if need else np.zeros(8)
+        act = np.zeros(4, dtype=np.int32)
+        self.E.emul_peer_advance(ints, dbls, e, int(need), 0, p, self.lag, self.T, act)
+        return ints, dbls, [int(x) for x in act]
 
     def runnable(self, ranks):
         p = self.p
-        ints, dbls, need = self.state_for(p)
-        if need and not all(self.norm_flag >= self.g0 + p - 1):
+        st = self.start_of_pass(p)
+        if st is None:
             return False
-        if p >= 2:
-            e = self.gather(p - 2) if need else np.zeros(8)
-            self.E.emul_lag_fold(ints, dbls, e, self.T, None)
-        act = np.zeros(4, dtype=np.int32)
-        self.E.emul_lag_action(ints, dbls, p, self.T, act)
-        if act[0] == 1:  # a speculative run streams halo rows: the neighbours' pushes of pass p-1 must have landed
+        kind = st[2][0]
+        # a working pass of the plain machine, or a speculative run of the lagged one, streams halo rows: the
+        # neighbours' pushes of pass p-1 must have landed (the lagged redo pass re-reads an older buffer)
+        if kind == 1:
             if self.r > 0 and self.halo_passes[0] < self.g0 + p:
                 return False
             if self.r < self.world - 1 and self.halo_passes[1] < self.g0 + p:
@@ -98,21 +105,16 @@ class Rank:
 
     def run_pass(self, ranks, dx, dy, beta):
         p, T, H = self.p, self.T, 2 * self.T
-        ints, dbls, need = self.state_for(p)
-        if p >= 2:
-            e = self.gather(p - 2) if need else np.zeros(8)
-            self.E.emul_lag_fold(ints, dbls, e, T, None)
-        act = np.zeros(4, dtype=np.int32)
-        self.E.emul_lag_action(ints, dbls, p, T, act)
+        ints, dbls, (kind, bi, bo, nsw) = self.start_of_pass(p)
         if p > 0:
             self.chain[p & 1] = (ints.copy(), dbls.copy())
-        kind, bi, bo, nsw = (int(x) for x in act)
         norms = np.zeros(8)
         if kind != 0:
             # write-after-read check of the protocol: nobody may still have to READ the buffer this pass pushes into
+            # (lagged: the neighbours read it in pass p-2; plain: in pass p-1)
             for nb in (self.r - 1, self.r + 1):
                 if 0 <= nb < self.world and kind == 1:
-                    assert ranks[nb].p >= p - 1, "push into a buffer the neighbour has not finished reading"
+                    assert ranks[nb].p >= p - self.lagd + 1, "push into a buffer the neighbour has not finished reading"
             rc = self.E.emul_pass(T, self.nloc, self.cols, self.ld, self.grow0, self.rows, self.own_lo, self.own_hi, 0,
                                   int(os.environ.get("CNV_TEST_CHUNKS", "0")), dx, dy, beta, 0, self.bufs[bi], self.floc,
                                   self.bufs[bo], nsw, norms)
@@ -134,23 +136,28 @@ class Rank:
         self.p += 1
 
     def finalize(self, P):
-        ints, dbls, need = self.state_for(P)
-        if P >= 2:
-            e = self.gather(P - 2) if need else np.zeros(8)
-            self.E.emul_lag_fold(ints, dbls, e, self.T, None)
-        e_last = self.gather(P - 1) if P >= 1 else np.zeros(8)
-        self.E.emul_lag_final(ints, dbls, P, e_last, self.T, None)
-        return ints, dbls
+        """k_peer_finalize: the state the host reads after P launched passes."""
+        if self.lag:
+            ints, dbls = (a.copy() for a in self.chain[0 if P == 0 else (P - 1) & 1])
+            if P >= 2:
+                need = ints[0] == 0 and ints[3] == 0
+                self.E.emul_lag_fold(ints, dbls, self.gather(P - 2) if need else np.zeros(8), self.T, None)
+            e_last = self.gather(P - 1) if P >= 1 else np.zeros(8)
+            self.E.emul_lag_final(ints, dbls, P, e_last, self.T, None)
+            return ints, dbls
+        st = self.start_of_pass(P)             # plain machine: S_P = what pass P itself would derive
+        assert st is not None
+        return st[0], st[1]
 
 
-def lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed, ranks=None, fseed=11):
+def lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed, ranks=None, fseed=11, lag=1):
     rng = np.random.default_rng(seed)
     f = np.random.default_rng(fseed).standard_normal((rows, cols))
     dx, dy = 1.0 / cols, 1.0 / rows
     port = api.port()
     beta = port.beta(rows, cols)
     if ranks is None:
-        ranks = [Rank(E, r, world, rows, cols, T, f, itmax, tol) for r in range(world)]
+        ranks = [Rank(E, r, world, rows, cols, T, f, itmax, tol, lag) for r in range(world)]
     else:
         for k in ranks:
             k.new_solve(f, itmax, tol)
@@ -296,3 +303,21 @@ def test_lagged_machine_abstract_model_fuzz(E):
         assert int(ints[2]) == want_sweeps and content[int(ints[1])] == want_sweeps, (case, T, itmax, kstop, ints, content)
         if want_state == 1:
             assert int(ints[5]) == kstop and dbls[1] == h[kstop]
+
+
+@pytest.mark.parametrize("world,T", [(2, 2), (3, 4)])
+def test_plain_peer_machine_same_simulation(E, world, T):
+    """The same simulation with the PLAIN peer machine (lag = 0: two buffers, a pass folds the norms of the previous
+    pass): the kernel's start-of-pass code is shared with this test (peer_needs_norms / peer_advance), so this covers
+    the default multi-GPU path's decision logic, buffer alternation, redo pass and no-op passes."""
+    rows, cols = 24 * world, 40
+    f = np.random.default_rng(11).standard_normal((rows, cols))
+    port = api.port()
+    for ksweep in range(2 * T, 3 * T + 1):
+        tol = port.poisson(f, 1.0 / cols, 1.0 / rows, ksweep + 1, 0.0, port.beta(rows, cols), redblack=True)["e"] * (1 + 1e-9)
+        for batch in ([1], [3], [ksweep // T + 1, 2]):
+            ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, 5000, tol, batch, seed=ksweep + batch[0], lag=0)
+            assert ints[0] == 1 and int(ints[5]) == want["k"]
+            assert full.tobytes() == want["u"].tobytes()
+    ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, 7, 0.0, [2], seed=1, lag=0)
+    assert ints[0] == 2 and int(ints[2]) == 7 and full.tobytes() == want["u"].tobytes()
