@@ -3,6 +3,7 @@
 // Replaces the same reference code as the streaming kernel (src/poisson.c:224-285: T red-black SOR sweeps and the
 // sum |u - u0| of each of them per launch) for grids small enough that the streaming kernel's pipeline fill and
 // y-halo dominate.  Control flow (PoissonCtl, decide(): first sweep with e < tol, "redo" pass, itmax) is shared.
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -22,6 +23,10 @@ k_poisson_tile(const TileGeom g, const RelaxConsts rc, double *__restrict__ buf0
     __shared__ double s_e[8];
     __shared__ int s_last;
 
+    // programmatic dependent launch (only when launched with the attribute, CNV_TILE_PDL=1; otherwise both are no-ops):
+    // the next pass may become resident while this one drains and waits here for its completion
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const PoissonCtl c0 = *ctl;
     if (c0.state != 0) return;  // solve already finished: later passes of a batch are no-ops
     const int nsw = pass_sweeps(c0, g.T);
@@ -102,7 +107,21 @@ static void launch_tile_t(const TileGeom &g, const RelaxConsts &rc, double *b0, 
         CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_tile<M, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_poisson_tile<M, POW2><<<dim3(g.ntx, g.nty), round_up(g.KP * g.NSEG, 32), smem, s>>>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused);
+    // CNV_TILE_PDL=1: programmatic stream serialisation between consecutive passes (hides the launch latency, which is a
+    // large share of a pass on the small grids this kernel is for); off by default until measured
+    static const bool pdl = std::getenv("CNV_TILE_PDL") && std::atoi(std::getenv("CNV_TILE_PDL")) != 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.ntx, g.nty);
+    cfg.blockDim = dim3(round_up(g.KP * g.NSEG, 32));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const double *crhs = rhs;
+    CNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_poisson_tile<M, POW2>, g, rc, b0, b1, crhs, ctl, partials, hist, norms, fused));
 }
 
 void launch_tile_pass(const TileGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,

@@ -109,46 +109,94 @@ CNV_HD void tile_load(TileThread<M> &t, const TileGeom &g, int bx, int by, int t
     }
 }
 
+// The M updates of a half-sweep are independent of each other: their shared-memory operands are cells of the OTHER
+// colour and right-hand sides (nobody writes those during this half-sweep), and the vertical neighbours of row i are
+// cells of the column that rows i-1 / i+1 do NOT update now (the updated column alternates from row to row).  So they
+// run in batches of CH rows -- all loads of a batch, then its updates, then its stores -- instead of M
+// load -> relax -> store round trips behind ordered shared-memory accesses.
+// SEL: apply the per-row / per-column validity selects (threads next to the Dirichlet ring, the array edge or the tile
+// edge).  NORM: 0 = the thread owns no output cell, 1 = all its cells are output cells, 2 = per-row test.
+template <int M, bool POW2, int PH, bool SEL, int NORM>
+CNV_HD void tile_half_sweep_body(TileThread<M> &t, const RelaxConsts &rc, double *sm)
+{
+    constexpr int p0 = PH & 1, pl = (PH + M - 1) & 1;
+    constexpr int CH = 4;  // rows per batch: 4 independent updates in flight (like the streaming kernel's 4 cells per step)
+    // vertical neighbours outside the thread's rows: same parity array as the cell that needs them
+    const double below = lds1(sm, t.base + (p0 ? t.aSO : 0) - t.pitch);
+    const double above = lds1(sm, t.base + (pl ? t.aSO : 0) + M * t.pitch);
+#pragma unroll
+    for (int c = 0; c < M; c += CH) {
+        double X[CH], P[CH], nv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const int i = c + j;
+            if (i < M) {
+                const int a = t.base + i * t.pitch;
+                const bool odd = ((PH + i) & 1) != 0;
+                // even-column cell of pair k: W = odd[k-1] (neighbour thread);  odd-column cell: E = even[k+1] (neighbour thread)
+                X[j] = lds1(sm, odd ? a + 8 : a + t.aSO - 8);
+                P[j] = lds1(sm, a + (odd ? t.aPO : t.aPE));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const int i = c + j;
+            if (i < M) {
+                const bool odd = ((PH + i) & 1) != 0;
+                if (!odd) {  // even-column cell: W = odd[k-1] (neighbour thread), E = odd[k] (own)
+                    const double S = i == 0 ? below : t.E[i > 0 ? i - 1 : 0], N = i == M - 1 ? above : t.E[i < M - 1 ? i + 1 : M - 1];
+                    nv[j] = relax<POW2>(N, S, t.O[i], X[j], t.E[i], P[j], rc);
+                } else {     // odd-column cell: W = even[k] (own), E = even[k+1] (neighbour thread)
+                    const double S = i == 0 ? below : t.O[i > 0 ? i - 1 : 0], N = i == M - 1 ? above : t.O[i < M - 1 ? i + 1 : M - 1];
+                    nv[j] = relax<POW2>(N, S, X[j], t.E[i], t.O[i], P[j], rc);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const int i = c + j;
+            if (i < M) {
+                const int a = t.base + i * t.pitch;
+                const bool odd = ((PH + i) & 1) != 0;
+                const double old = odd ? t.O[i] : t.E[i];
+                double v = nv[j];
+                if (SEL) {
+                    const bool ok = ((t.rvalid >> i) & 1u) && (odd ? t.co : t.ce);
+                    v = ok ? v : old;
+                }
+                if (odd) { t.O[i] = v; sts1(sm, a + t.aSO, v); }
+                else { t.E[i] = v; sts1(sm, a, v); }
+                // L1 update norm over the output cells (cells that were not updated contribute exactly 0)
+                if (NORM == 1) t.acc = xadd(t.acc, fabs(xsub(v, old)));
+                else if (NORM == 2 && ((t.rown >> i) & 1u)) t.acc = xadd(t.acc, fabs(xsub(v, old)));
+            }
+        }
+    }
+}
+
 // ---- one half-sweep.  PH = column parity (0 even, 1 odd) of the cell this thread updates in its row 0; the
 // parity alternates from row to row.  M is even and so is every segment start, hence PH is the same for all
 // threads of the CTA: PH = (global row of tile row 0 + colour) & 1, colour 0 = red = (i + j) even (src/poisson.c:247).
 template <int M, bool POW2, int PH>
 CNV_HD void tile_half_sweep(TileThread<M> &t, const RelaxConsts &rc, double *sm)
 {
-    constexpr int p0 = PH & 1, pl = (PH + M - 1) & 1;
-    // vertical neighbours outside the thread's rows: same parity array as the cell that needs them
-    const double below = lds1(sm, t.base + (p0 ? t.aSO : 0) - t.pitch);
-    const double above = lds1(sm, t.base + (pl ? t.aSO : 0) + M * t.pitch);
+#if defined(__CUDA_ARCH__)
+    // Row addresses are base + i * pitch with a run-time pitch.  Left alone, the compiler hoists all of them (4 arrays x M
+    // rows) out of the sweep loop, which costs ~3M registers, spills, and leaves one temporary for all loads of a batch
+    // (i.e. serialises them).  An opaque base makes them cheap per-use arithmetic instead.
+    asm volatile("" : "+r"(t.base));
+    // likewise the row masks: evaluated where the (rare) general bodies use them, not packed into predicates at the top of
+    // every sweep for all threads
+    asm volatile("" : "+r"(t.rvalid), "+r"(t.rown));
+#endif
+    // interior threads (everything updatable) either own output cells in all their rows or none (tile halo): two
+    // select-free bodies; everything else (ring, array edge, tile edge, partial output rows) takes the general one
     const bool allown = t.colown && t.rown == (1u << M) - 1;
-#pragma unroll
-    for (int i = 0; i < M; i++) {
-        const int a = t.base + i * t.pitch;
-        const bool odd = ((PH + i) & 1) != 0;
-        double old, nv;
-        if (!odd) {
-            // even-column cell of pair k: W = odd[k-1] (neighbour thread), E = odd[k] (own)
-            const double W = lds1(sm, a + t.aSO - 8), P = lds1(sm, a + t.aPE);
-            const double S = i == 0 ? below : t.E[i > 0 ? i - 1 : 0], N = i == M - 1 ? above : t.E[i < M - 1 ? i + 1 : M - 1];
-            old = t.E[i];
-            nv = relax<POW2>(N, S, t.O[i], W, old, P, rc);
-        } else {
-            // odd-column cell: W = even[k] (own), E = even[k+1] (neighbour thread)
-            const double Ea = lds1(sm, a + 8), P = lds1(sm, a + t.aPO);
-            const double S = i == 0 ? below : t.O[i > 0 ? i - 1 : 0], N = i == M - 1 ? above : t.O[i < M - 1 ? i + 1 : M - 1];
-            old = t.O[i];
-            nv = relax<POW2>(N, S, Ea, t.E[i], old, P, rc);
-        }
-        if (!t.fast) {
-            const bool v = ((t.rvalid >> i) & 1u) && (odd ? t.co : t.ce);
-            nv = v ? nv : old;
-        }
-        // (the vertical neighbours of the rows still to come are cells of the OTHER colour: E/O[i] may be replaced now)
-        if (odd) { t.O[i] = nv; sts1(sm, a + t.aSO, nv); }
-        else { t.E[i] = nv; sts1(sm, a, nv); }
-        // L1 update norm over the output cells (cells that were not updated contribute exactly 0)
-        if (allown) t.acc = xadd(t.acc, fabs(xsub(nv, old)));
-        else if (t.colown && ((t.rown >> i) & 1u)) t.acc = xadd(t.acc, fabs(xsub(nv, old)));
-    }
+    const bool noown = !t.colown || t.rown == 0;
+    if (t.fast && allown) tile_half_sweep_body<M, POW2, PH, false, 1>(t, rc, sm);
+    else if (t.fast && noown) tile_half_sweep_body<M, POW2, PH, false, 0>(t, rc, sm);
+    else if (noown) tile_half_sweep_body<M, POW2, PH, true, 0>(t, rc, sm);
+    else tile_half_sweep_body<M, POW2, PH, true, 2>(t, rc, sm);
 }
 
 // ---- write back the output cells of this thread ----

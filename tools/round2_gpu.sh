@@ -24,6 +24,13 @@ single)
     echo "pytest exit $?" >> gpurun_out/r2_pytest_lean.log
     CNV_LIB=lean python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_bench_n1_lean.json 2> gpurun_out/r2_bench_n1_lean.err
     python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_bench_n1_again.json 2>&1   # same box, same moment: the A of the A/B
+    # stationary-tile kernel after the batching rework (loads of a batch of 4 rows issued together, select-free bodies, no
+    # spills): vs the streaming kernel on the L2-resident shapes (planner's tile plans for T = 2, 4, 6, 8; with and without
+    # programmatic dependent launch)
+    for shape in "1024 1024" "2048 2048" "528 4096" "256 256"; do
+        python tools/probe_poisson.py $shape "8:0:0,t2:0:0:0,t4:0:0:0,t6:0:0:0,t8:0:0:0" 512 >> gpurun_out/r2_probe_tile.log 2>&1
+        CNV_TILE_PDL=1 python tools/probe_poisson.py $shape "t2:0:0:0,t4:0:0:0,t6:0:0:0,t8:0:0:0" 512 >> gpurun_out/r2_probe_tile_pdl.log 2>&1
+    done
     # launch list + one full capture of the pass kernel
     ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv \
         python bench.py --steps 2 --warmup 3 --sweeps 128 --no-cpu > gpurun_out/r2_launches.log 2>&1
