@@ -336,6 +336,12 @@ def test_cabi_exports_every_declared_symbol():
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert dropin_decl <= exported, dropin_decl - exported
     assert L.cnv_device_count() >= 0 and b"sm_100a" in L.cnv_version()
+    # the experimental build variant (CNV_LIB=lean) exports the same ABI
+    lean = os.path.join(os.path.dirname(_lib.LIB_PATH), "libcnavier_b200_lean.so")
+    if os.path.exists(lean):
+        out = subprocess.run(["nm", "-D", "--defined-only", lean], capture_output=True, text=True).stdout
+        exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+        assert declared <= exported, declared - exported
 
 
 def test_cabi_scalars_and_coefficients_on_cpu(port):
