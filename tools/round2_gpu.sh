@@ -27,7 +27,7 @@ single)
     # stationary-tile kernel after the batching rework (loads of a batch of 4 rows issued together, select-free bodies, no
     # spills): vs the streaming kernel on the L2-resident shapes (planner's tile plans for T = 2, 4, 6, 8; with and without
     # programmatic dependent launch)
-    for shape in "1024 1024" "2048 2048" "528 4096" "256 256"; do
+    for shape in "1024 1024" "2048 2048" "4096 4096" "528 4096" "256 256"; do
         python tools/probe_poisson.py $shape "8:0:0,t2:0:0:0,t4:0:0:0,t6:0:0:0,t8:0:0:0" 512 >> gpurun_out/r2_probe_tile.log 2>&1
         CNV_TILE_PDL=1 python tools/probe_poisson.py $shape "t2:0:0:0,t4:0:0:0,t6:0:0:0,t8:0:0:0" 512 >> gpurun_out/r2_probe_tile_pdl.log 2>&1
     done
