@@ -50,6 +50,13 @@ lag)
     # strong scaling of one 4096^2 grid
     run 29803 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_peer_$n.json 2>&1
     CNV_PEER_LAG=1 run 29804 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_lag_$n.json 2>&1
+    # strong scaling with the stationary-tile kernel on the (L2-resident) slabs, NCCL exchange (the peer exchange lives in the
+    # streaming kernel only): T = 4 and 8
+    for T in 4 8; do
+        CNV_DIST_BACKEND=nccl CNV_POISSON_TILE=1 run 29807 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong --T $T \
+            > gpurun_out/r2_strong_tile_T${T}_$n.json 2>&1
+    done
+    CNV_DIST_BACKEND=nccl run 29808 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_nccl_$n.json 2>&1
     # where the pass time goes (per-CTA stamps), both variants
     run 29805 tools/peer_trace.py 4096 4096 24 > gpurun_out/r2_trace_peer_$n.log 2>&1
     CNV_PEER_LAG=1 run 29806 tools/peer_trace.py 4096 4096 24 > gpurun_out/r2_trace_lag_$n.log 2>&1
