@@ -52,6 +52,7 @@ lag)
     CNV_PEER_LAG=1 run 29804 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_lag_$n.json 2>&1
     # strong scaling with the stationary-tile kernel on the (L2-resident) slabs, NCCL exchange (the peer exchange lives in the
     # streaming kernel only): T = 4 and 8
+    CNV_DIST_BACKEND=nccl CNV_POISSON_TILE=1 run 29809 tests/dist/slab_gpu_check.py 1024 1024 4 > gpurun_out/r2_tile_slab_check_$n.log 2>&1   # parity first
     for T in 4 8; do
         CNV_DIST_BACKEND=nccl CNV_POISSON_TILE=1 run 29807 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong --T $T \
             > gpurun_out/r2_strong_tile_T${T}_$n.json 2>&1
