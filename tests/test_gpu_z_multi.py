@@ -1,5 +1,6 @@
 """Multi-GPU parity (needs >= 2 visible GPUs; skipped on a 1-GPU box): the slab-decomposed Poisson solve and the
-slab-decomposed time stepping must be bit-identical to the single-GPU path and the oracle."""
+slab-decomposed time stepping must be bit-identical to the single-GPU path and the oracle.
+(The file name sorts after test_gpu_parity.py on purpose: under `pytest -x` the single-GPU parity suite runs first.)"""
 import os
 import subprocess
 import sys

@@ -42,7 +42,7 @@ lag)
     n=${2:-2}
     run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port "$1" "${@:2}"; }
     # correctness of the lagged decision on hardware (opt-in tests), then the plain suite
-    CNV_TEST_LAG=1 timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "lagged" > gpurun_out/r2_lag_tests_$n.log 2>&1
+    CNV_TEST_LAG=1 timeout 1500 python -m pytest tests/test_gpu_z_multi.py -m gpu -x -q -k "lagged" > gpurun_out/r2_lag_tests_$n.log 2>&1
     echo "pytest exit $?" >> gpurun_out/r2_lag_tests_$n.log
     tail -3 gpurun_out/r2_lag_tests_$n.log
     # weak scaling: plain peer path vs lagged decision, same box, back to back
