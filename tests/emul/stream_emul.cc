@@ -78,10 +78,20 @@ int emul_tile_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_
                    long *out)
 {
     TileGeom g;
-    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, nullptr, fkp, fm, fnseg)) return -1;
+    double cost = 0;
+    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, &cost, fkp, fm, fnseg)) return -1;
     out[0] = g.KP; out[1] = g.M; out[2] = g.NSEG; out[3] = g.OW; out[4] = g.OH; out[5] = g.ntx; out[6] = g.nty;
     out[7] = (long)tile_smem_bytes(g);
     return 0;
+}
+
+// the tile planner's cost estimate per sweep (arbitrary units), < 0 if no plan exists
+double emul_tile_cost(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T)
+{
+    TileGeom g;
+    double cost = 0;
+    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, &cost)) return -1.0;
+    return cost;
 }
 
 // one pass of the tile kernel's schedule (see emul_pass for the arguments); fkp/fm/fnseg pin the tile shape
