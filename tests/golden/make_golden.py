@@ -12,6 +12,12 @@ Outputs (all small, committed):
   fields_highre_rb.npz     psi,w,u,v after step 5 of config_high_re.txt (128^2), same build, + k/e log
   fields_default_lex_tight.npz  psi,w,u,v after step 2 of config_default.txt with poisson_tol=1e-11 from the
                            serial (lexicographic) reference build: ordering-independent comparison point
+  fields_order2_rb.npz, fields_order4_rb.npz   psi,w,u,v after every one of 4 steps of a 32^2 cavity with moving side
+                           walls, finite-difference order 2 / 4, red-black SOR (OpenMP build) -- the `order` config key
+  fields_gs_lex_tight.npz  the same cavity, order 4, poisson_type = 1 (Gauss-Seidel), poisson_tol = 1e-11, 3 steps, serial
+                           build.  The reference's Gauss-Seidel variants sweep LEXICOGRAPHICALLY in both builds
+                           (src/poisson.c:80-86, 193-200; the OpenMP pragma merely runs that loop in parallel above 64^2),
+                           so the red-black GPU path is compared with it at a tolerance where the ordering is immaterial
   poisson_sine.json        sweep counts of the reference's poisson_SOR_log on f=-2pi^2 sin(pi x) sin(pi y)
 """
 import json, os, sys, tempfile
@@ -72,3 +78,7 @@ if __name__ == "__main__":
     fields(dict(api.CONFIG_DEFAULT, poisson_tol=1e-11, poisson_max_it=100000, output_interval=2), 3,
            "fields_default_lex_tight.npz", serial=True)
     fields(dict(api.CONFIG_HIGH_RE), 6, "fields_highre_rb.npz")
+    small = dict(api.CONFIG_DEFAULT, nx=32, ny=32, dt=0.004, u1=0.05, u2=-0.03, v3=0.02, v4=0.01, output_interval=1)
+    fields(dict(small, order=2), 4, "fields_order2_rb.npz")
+    fields(dict(small, order=4), 4, "fields_order4_rb.npz")
+    fields(dict(small, order=4, poisson_type=1, poisson_tol=1e-11, poisson_max_it=200000), 3, "fields_gs_lex_tight.npz", serial=True)

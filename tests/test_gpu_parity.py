@@ -304,6 +304,38 @@ def test_fused_velocity_continuity_equals_split_kernels(order, nx, ny, monkeypat
         assert fa[name].tobytes() == fb[name].tobytes(), name
 
 
+SMALL = dict(api.CONFIG_DEFAULT, nx=32, ny=32, dt=0.004, u1=0.05, u2=-0.03, v3=0.02, v4=0.01, output_interval=1)
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_other_orders_vs_reference_executable(order, small_grid_path):
+    """Finite-difference order 2 / 4: fields after each of 4 steps and the Poisson iteration counts equal the raw dumps of
+    the reference executable (tests/golden/fields_order{2,4}_rb.npz, OpenMP build), bit for bit."""
+    g = load_golden(f"fields_order{order}_rb.npz")
+    sim = fd.Simulation(dict(SMALL, order=order))
+    ks = []
+    for idx in range(4):
+        r = sim.step(1)
+        ks.append(int(r["k"][0]))
+        f = sim.fields()
+        for name in ("psi", "w", "u", "v"):
+            assert np.array_equal(f[name], g[name][idx]), (name, idx, rel_l2(f[name], g[name][idx]))
+    assert ks == list(g["k"])
+
+
+def test_gauss_seidel_vs_lexicographic_reference(small_grid_path):
+    """poisson_type = 1.  The reference's Gauss-Seidel sweeps lexicographically in both of its builds; the GPU path
+    sweeps red-black.  Compared the way the north_star prescribes for differing orderings: both converged to the same
+    tight tolerance (1e-11), fields within 1e-8 relative L2 of the serial reference executable's dumps."""
+    g = load_golden("fields_gs_lex_tight.npz")
+    sim = fd.Simulation(dict(SMALL, order=4, poisson_type=1, poisson_tol=1e-11, poisson_max_it=200000))
+    r = sim.step(3)
+    assert r["failed_step"] == 0
+    f = sim.fields()
+    for name in ("psi", "w", "u", "v"):
+        assert rel_l2(f[name], g[name][-1]) <= 1e-8, (name, rel_l2(f[name], g[name][-1]))
+
+
 def test_tight_tolerance_vs_lexicographic_reference():
     """Ordering-independent check: at poisson_tol = 1e-11 the red-black GPU fields agree with the
     SERIAL (lexicographic) reference executable within the north_star tolerance."""
