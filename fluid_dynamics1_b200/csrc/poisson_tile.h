@@ -93,18 +93,25 @@ CNV_HD void tile_load(TileThread<M> &t, const TileGeom &g, int bx, int by, int t
     t.fast = t.ce && t.co && t.rvalid == (1u << M) - 1;
     t.gofs = (long long)(ty0 + tr0) * g.ld + gc;
     t.acc = 0.0;
+    // all 2M global loads first (they are independent; the shared-memory stores below are ordered asm statements with a
+    // memory clobber, so loads issued between them would wait for one L2 round trip per row), then the stores
+    dbl2 f[M];
 #pragma unroll
     for (int i = 0; i < M; i++) {
-        double e = 0.0, o = 0.0, pe = 0.0, po = 0.0;
+        dbl2 u = {0.0, 0.0};
+        f[i] = u;
         if (t.colin && ((t.rin >> i) & 1u)) {
             const long long off = t.gofs + (long long)i * g.ld;
-            const dbl2 u = ldg2(in + off), f = ldg2(rhs + off);
-            e = u.x; o = u.y; pe = f.x; po = f.y;
+            u = ldg2(in + off);
+            f[i] = ldg2(rhs + off);
         }
-        t.E[i] = e; t.O[i] = o;
+        t.E[i] = u.x; t.O[i] = u.y;
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++) {
         const int a = t.base + i * t.pitch;
-        sts1(sm, a, e); sts1(sm, a + t.aSO, o);
-        sts1(sm, a + t.aPE, pe); sts1(sm, a + t.aPO, po);
+        sts1(sm, a, t.E[i]); sts1(sm, a + t.aSO, t.O[i]);
+        sts1(sm, a + t.aPE, f[i].x); sts1(sm, a + t.aPO, f[i].y);
         if (kp == 0) { sts1(sm, a - 8, 0.0); sts1(sm, a + t.aSO - 8, 0.0); }  // the row pads (deterministic halo garbage)
     }
 }
