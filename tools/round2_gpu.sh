@@ -3,9 +3,9 @@
 # (planner change 97f5c9d: taller chunks at the domain boundary; the lagged stop decision of the peer path,
 # CNV_PEER_LAG=1), then measure it.  Everything writes into gpurun_out/.
 #
-#   1 GPU :  gpurun --timeout 1500 -- 'bash tools/round2_gpu.sh single'
-#   2 GPUs:  gpurun --gpus 2 --timeout 1200 -- 'bash tools/round2_gpu.sh lag 2'
-#   8 GPUs:  gpurun --gpus 8 --timeout 1200 -- 'bash tools/round2_gpu.sh lag 8'
+#   1 GPU :  gpurun --timeout 2400 -- 'bash tools/round2_gpu.sh single'
+#   2 GPUs:  gpurun --gpus 2 --timeout 1800 -- 'bash tools/round2_gpu.sh lag 2'
+#   8 GPUs:  gpurun --gpus 8 --timeout 1800 -- 'bash tools/round2_gpu.sh lag 8'
 # Afterwards, here:  python tools/collect_round2.py gpurun_out > profiles/ab_r2.md   (one report of all A/B results)
 set -u
 mkdir -p gpurun_out
