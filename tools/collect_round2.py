@@ -88,7 +88,7 @@ def section_probes():
 
 
 def section_multi():
-    out = ["## Multi-GPU (`round2_gpu.sh lag N`)", ""]
+    out = ["## Multi-GPU (`round2_gpu.sh lagtest|scale|extra N`)", ""]
     ns = sorted({int(m.group(1)) for f in glob.glob(os.path.join(D, "r2_scale_peer_*.json")) for m in [re.search(r"_(\d+)\.json$", f)] if m})
     if not ns:
         return out + ["(not run)", ""]
@@ -110,6 +110,7 @@ def section_multi():
             rel = f"{j['value'] / ref['value']:.3f}" if ref else ""
             out.append(f"| {n} | {label} | {j['value']:.4e} | {j['ms_per_step']:.2f} | {j.get('roofline', {}).get('launch_us', float('nan')):.1f} | {eff} | {rel} |")
         out.append(f"| {n} | lagged GPU tests | `{' / '.join(tail(os.path.join(D, f'r2_lag_tests_{n}.log'), 2))}` | | | | |")
+        out.append(f"| {n} | plain multi-GPU suite | `{' / '.join(tail(os.path.join(D, f'r2_multi_tests_{n}.log'), 2))}` | | | | |")
         out.append(f"| {n} | tile-kernel slab parity | `{' / '.join(tail(os.path.join(D, f'r2_tile_slab_check_{n}.log'), 1))}` | | | | |")
     for n in ns:
         for tag in ("peer", "lag"):

@@ -3,9 +3,12 @@
 # (planner change 97f5c9d: taller chunks at the domain boundary; the lagged stop decision of the peer path,
 # CNV_PEER_LAG=1), then measure it.  Everything writes into gpurun_out/.
 #
-#   1 GPU :  gpurun --timeout 2400 -- 'bash tools/round2_gpu.sh single'
-#   2 GPUs:  gpurun --gpus 2 --timeout 1800 -- 'bash tools/round2_gpu.sh lag 2'
-#   8 GPUs:  gpurun --gpus 8 --timeout 1800 -- 'bash tools/round2_gpu.sh lag 8'
+# An N-GPU call is charged N x its wall time against the round's 180 GPU-minutes, so the multi-GPU modes are short:
+#   1 GPU  (~25 min):  gpurun --timeout 2400 -- 'bash tools/round2_gpu.sh single'
+#   2 GPUs (~8 min) :  gpurun --gpus 2 --timeout 900 -- 'bash tools/round2_gpu.sh lagtest 2'
+#   2 GPUs (~4 min) :  gpurun --gpus 2 --timeout 600 -- 'bash tools/round2_gpu.sh scale 2'
+#   8 GPUs (~4 min) :  gpurun --gpus 8 --timeout 600 -- 'bash tools/round2_gpu.sh scale 8'     (only after lagtest passed)
+#   optional        :  gpurun --gpus N --timeout 600 -- 'bash tools/round2_gpu.sh extra N'
 # Afterwards, here:  python tools/collect_round2.py gpurun_out > profiles/ab_r2.md   (one report of all A/B results)
 set -u
 mkdir -p gpurun_out
@@ -38,34 +41,43 @@ single)
     ncu --set full --clock-control none --import-source on -k regex:k_poisson_pass -s 20 -c 2 -o gpurun_out/r2_pass \
         python tools/prof_one.py 4096 8 > gpurun_out/r2_ncu_pass.log 2>&1
     ;;
-lag)
+lagtest)
+    # correctness of the lagged decision on hardware (opt-in tests; each pytest case skips itself if it needs more GPUs than
+    # the box has), then the plain multi-GPU suite.  Run this on 2 GPUs: an N-GPU call is charged N x its wall time.
     n=${2:-2}
-    run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port "$1" "${@:2}"; }
-    # correctness of the lagged decision on hardware (opt-in tests), then the plain suite
-    CNV_TEST_LAG=1 timeout 1500 python -m pytest tests/test_gpu_z_multi.py -m gpu -x -q -k "lagged" > gpurun_out/r2_lag_tests_$n.log 2>&1
+    CNV_TEST_LAG=1 timeout 1200 python -m pytest tests/test_gpu_z_multi.py -m gpu -x -q -k "lagged" > gpurun_out/r2_lag_tests_$n.log 2>&1
     echo "pytest exit $?" >> gpurun_out/r2_lag_tests_$n.log
     tail -3 gpurun_out/r2_lag_tests_$n.log
-    # weak scaling: plain peer path vs lagged decision, same box, back to back
+    timeout 1200 python -m pytest tests/test_gpu_z_multi.py -m gpu -x -q > gpurun_out/r2_multi_tests_$n.log 2>&1
+    echo "pytest exit $?" >> gpurun_out/r2_multi_tests_$n.log
+    tail -3 gpurun_out/r2_multi_tests_$n.log
+    ;;
+scale)
+    # plain peer path vs lagged decision, same box, back to back: weak and strong scaling (about 4 minutes of wall time)
+    n=${2:-2}
+    run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port "$1" "${@:2}"; }
     run 29801 bench.py --gpus "$n" --steps 10 --warmup 3 > gpurun_out/r2_scale_peer_$n.json 2> gpurun_out/r2_scale_peer_$n.err
     CNV_PEER_LAG=1 run 29802 bench.py --gpus "$n" --steps 10 --warmup 3 > gpurun_out/r2_scale_lag_$n.json 2> gpurun_out/r2_scale_lag_$n.err
-    # strong scaling of one 4096^2 grid
     run 29803 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_peer_$n.json 2>&1
     CNV_PEER_LAG=1 run 29804 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_lag_$n.json 2>&1
-    # strong scaling with the stationary-tile kernel on the (L2-resident) slabs, NCCL exchange (the peer exchange lives in the
-    # streaming kernel only): T = 4 and 8
+    tail -n 2 gpurun_out/r2_scale_peer_$n.json gpurun_out/r2_scale_lag_$n.json
+    ;;
+extra)
+    # optional: strong scaling with the stationary-tile kernel on the (L2-resident) slabs over the NCCL exchange (the peer
+    # exchange lives in the streaming kernel only), and where the pass time goes (per-CTA stamps) for both peer variants
+    n=${2:-2}
+    run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port "$1" "${@:2}"; }
     CNV_DIST_BACKEND=nccl CNV_POISSON_TILE=1 run 29809 tests/dist/slab_gpu_check.py 1024 1024 4 > gpurun_out/r2_tile_slab_check_$n.log 2>&1   # parity first
     for T in 4 8; do
         CNV_DIST_BACKEND=nccl CNV_POISSON_TILE=1 run 29807 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong --T $T \
             > gpurun_out/r2_strong_tile_T${T}_$n.json 2>&1
     done
     CNV_DIST_BACKEND=nccl run 29808 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_nccl_$n.json 2>&1
-    # where the pass time goes (per-CTA stamps), both variants
     run 29805 tools/peer_trace.py 4096 4096 24 > gpurun_out/r2_trace_peer_$n.log 2>&1
     CNV_PEER_LAG=1 run 29806 tools/peer_trace.py 4096 4096 24 > gpurun_out/r2_trace_lag_$n.log 2>&1
-    tail -n 2 gpurun_out/r2_scale_peer_$n.json gpurun_out/r2_scale_lag_$n.json
     ;;
 *)
-    echo "usage: $0 single | lag N" >&2
+    echo "usage: $0 single | lagtest N | scale N | extra N" >&2
     exit 2
     ;;
 esac
