@@ -400,3 +400,66 @@ def test_no_oracle_or_cpu_fallback_in_product():
             fd.poisson_sor(np.zeros((8, 8)), 0.1, 0.1, 10, 1e-3)
         with pytest.raises(RuntimeError):
             fd.Simulation(fd.load_default_config())
+
+
+def test_dropin_host_linear_algebra_vs_reference(ref):
+    """The host-side part of the drop-in library (no GPU involved): the reference's `mtrx` container and dense helpers that
+    an unmodified main.c still calls (src/linearalg.c: initm/eye/reshape/kronecker/mtrxmul/mtrxcpy/invsig/maxel/minel/freem)
+    and Diff1/Diff2 (src/finitediff.c:51, :178), called through the reference's own by-value `mtrx` ABI in BOTH libraries
+    (libcnavier_dropin.so vs the compiled reference oracle/_ref/libcnavier_ref_ser.so) and compared bit for bit."""
+    import fluid_dynamics1_b200 as fd
+    from fluid_dynamics1_b200 import _lib
+    D = fd.dropin()
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libcnavier_ref_ser.so"), mode=C.RTLD_LOCAL)
+    names = ("initm", "eye", "reshape", "kronecker", "mtrxmul", "mtrxcpy", "invsig", "maxel", "minel", "freem", "Diff1", "Diff2")
+    for name in names:
+        res, args = _lib.DROPIN_API[name]
+        fn = getattr(R, name)
+        fn.restype, fn.argtypes = res, args
+
+    def fill(L, a):
+        m = L.initm(a.shape[0], a.shape[1])
+        for i in range(a.shape[0]):
+            for j in range(a.shape[1]):
+                m.M[i][j] = a[i, j]
+        return m
+
+    def read(m):
+        return np.array([[m.M[i][j] for j in range(m.n)] for i in range(m.m)])
+
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal((5, 4)), rng.standard_normal((4, 6))
+    for L in (D, R):
+        assert read(L.initm(3, 2)).tobytes() == np.zeros((3, 2)).tobytes()
+    got, want = [], []
+    for L, out in ((D, got), (R, want)):
+        A, B = fill(L, a), fill(L, b)
+        out.append(read(L.eye(4)))
+        out.append(read(L.mtrxmul(A, B)))                  # ascending-k accumulation (src/linearalg.c:254-265)
+        S1, S2 = fill(L, a[:4, :4]), fill(L, b[:4, :4])
+        out.append(read(L.kronecker(S1, S2)))              # (the reference's index arithmetic only holds for equal square sizes, Q17)
+        out.append(read(L.reshape(A, 4, 5)))
+        out.append(read(L.reshape(A, 10, 2)))
+        out.append(np.array([L.maxel(A), L.minel(A)]))
+        Cc = L.initm(5, 4)
+        L.mtrxcpy(Cc, A)
+        L.invsig(Cc)
+        out.append(read(Cc))
+        for order in (2, 4, 6):
+            for n in (7, 12):
+                out.append(read(L.Diff1(n, order, 0.125)))
+                out.append(read(L.Diff2(n, order, 0.3)))
+        for m in (A, B, Cc):
+            L.freem(m)                                     # same ownership convention: one malloc per row + the row table
+    assert len(got) == len(want)
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == w.shape and g.tobytes() == w.tobytes(), k
+    # the dense operator route an unmodified main.c takes: DX = kron(I, Diff1), DX * vec(A) -- identical in both libraries
+    n = 6
+    x = rng.standard_normal((n, n))
+    res = []
+    for L in (D, R):
+        DX = L.kronecker(L.eye(n), L.Diff1(n, 4, 1.0 / n))
+        v = L.reshape(fill(L, x), n * n, 1)
+        res.append(read(L.reshape(L.mtrxmul(DX, v), n, n)))
+    assert res[0].tobytes() == res[1].tobytes()
