@@ -98,6 +98,20 @@ double now_s()
 
 }  // namespace
 
+// The driver's VTK writer on its own (printvtk semantics, src/utils.c:38-100): row-major m x n values, appended to
+// <dir>/<title>-1-<count>.vtk, one counter across all calls of the process.  Returns the counter value the file was written
+// with.  Host code only (no GPU involved).
+extern "C" int cnv_vtk_write(const double *values, int m, int n, const char *title, const char *output_dir)
+{
+    if (!values || m < 1 || n < 1) {
+        std::printf("\n** Error: Invalid parameter **\n");  // src/utils.c:46-55
+        std::exit(1);
+    }
+    const int used = g_vtk_count;
+    write_vtk(std::vector<double>(values, values + (size_t)m * n), m, n, title, output_dir);
+    return used;
+}
+
 extern "C" int cnv_main(int argc, char **argv)
 {
     Config cfg;

@@ -171,6 +171,10 @@ int cnv_sim_pressure(cnv_sim *s, int itmax, double tol, double *p_host, int *k, 
  * (same config file, same stdout/log lines, same step order; VTK through printvtk-compatible writer
  * unless CNV_NO_VTK=1).  Returns the process exit code. */
 int cnv_main(int argc, char **argv);
+/* The driver's VTK writer on its own: replaces printvtk (src/utils.c:38-100) -- ASCII STRUCTURED_POINTS, "%.6lf", file
+ * <output_dir>/<title>-1-<count>.vtk opened in append mode, ONE counter across all fields and calls of the process.
+ * `values` is row-major m x n (the reference's A.M[i][j]).  Returns the counter value used.  Host only. */
+int cnv_vtk_write(const double *values, int m, int n, const char *title, const char *output_dir);
 
 /* configuration system (src/config.c) under cnv_ names for callers that do not want the
  * reference-named symbols of the drop-in library */

@@ -463,3 +463,36 @@ def test_dropin_host_linear_algebra_vs_reference(ref):
         v = L.reshape(fill(L, x), n * n, 1)
         res.append(read(L.reshape(L.mtrxmul(DX, v), n, n)))
     assert res[0].tobytes() == res[1].tobytes()
+
+
+def test_vtk_writer_vs_reference_printvtk(tmp_path):
+    """cnv_vtk_write (the driver's writer) against the reference's own printvtk (src/utils.c:38-100, compiled
+    into oracle/_ref): same file names (one counter across all fields: stream-function-1-0, vorticity-1-1, ...), same
+    bytes, append mode.  Host code only."""
+    import fluid_dynamics1_b200 as fd
+    from fluid_dynamics1_b200 import _lib
+    L = fd.lib()
+    so = os.path.join(ROOT, "oracle", "_ref", "libcnavier_ref_ser.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built")
+    R = C.CDLL(so, mode=C.RTLD_LOCAL)
+    R.initm.restype, R.initm.argtypes = _lib.Mtrx, [C.c_int, C.c_int]
+    R.printvtk.restype, R.printvtk.argtypes = None, [_lib.Mtrx, C.c_char_p, C.c_char_p]
+    rng = np.random.default_rng(8)
+    mine, theirs = tmp_path / "mine", tmp_path / "theirs"
+    fields = [("stream-function", rng.standard_normal((5, 7)) * 1e-3), ("vorticity", rng.standard_normal((5, 7)) * 40),
+              ("x-velocity", np.array([[0.0, -0.0, 1.0, 0.9999995, -1e-7, 123456.789, 5e-7]] * 5)), ("y-velocity", np.zeros((5, 7)))]
+    for rep in range(2):                                     # two output steps: the counter keeps counting (0..7)
+        for title, a in fields:
+            a = np.ascontiguousarray(a + rep)
+            used = L.cnv_vtk_write(a, a.shape[0], a.shape[1], title.encode(), str(mine).encode())
+            m = R.initm(a.shape[0], a.shape[1])
+            for i in range(a.shape[0]):
+                for j in range(a.shape[1]):
+                    m.M[i][j] = a[i, j]
+            R.printvtk(m, title.encode(), str(theirs).encode())
+            assert used == rep * 4 + [t for t, _ in fields].index(title)
+    a_files, b_files = sorted(os.listdir(mine)), sorted(os.listdir(theirs))
+    assert a_files == b_files and len(a_files) == 8
+    for name in a_files:
+        assert (mine / name).read_bytes() == (theirs / name).read_bytes(), name
