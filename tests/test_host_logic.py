@@ -496,3 +496,46 @@ def test_vtk_writer_vs_reference_printvtk(tmp_path):
     assert a_files == b_files and len(a_files) == 8
     for name in a_files:
         assert (mine / name).read_bytes() == (theirs / name).read_bytes(), name
+
+
+def test_config_printing_matches_reference(tmp_path, ref):
+    """print_config (src/config.c:230): the drop-in library prints what the reference prints, character for character, for the
+    default configuration and for a parsed file -- except the two OpenMP lines, which describe the build (both libraries run
+    in a child process so that their C stdio output can be captured).  print_usage: same synopsis line; the help text below
+    it is this repo's own wording."""
+    import sys
+    cfgfile = tmp_path / "c.txt"
+    cfgfile.write_text("Re = 400.5\nnx = 33\nny = 35\npoisson_tol = 5E-4\nu4 = 2.5\norder = 4\nv1 = -0.25\ntf = 0.58\noutput_interval = 7\n")
+    code = r"""
+import ctypes as C, sys
+sys.path.insert(0, {root!r})
+from fluid_dynamics1_b200._lib import Config
+which, path = sys.argv[1], sys.argv[2]
+if which == "mine":
+    import fluid_dynamics1_b200 as fd
+    L = fd.dropin()
+else:
+    L = C.CDLL({ref!r}, mode=C.RTLD_LOCAL)
+    L.load_default_config.restype = Config
+    L.load_config_from_file.restype, L.load_config_from_file.argtypes = Config, [C.c_char_p]
+    L.print_config.argtypes = [C.POINTER(Config)]
+    L.print_usage.argtypes = [C.c_char_p]
+for cfg in (L.load_default_config(), L.load_config_from_file(path.encode())):
+    L.print_config(C.byref(cfg))
+L.print_usage(b"./cnavier")
+C.CDLL(None).fflush(None)
+""".format(root=ROOT, ref=os.path.join(ROOT, "oracle", "_ref", "libcnavier_ref_ser.so"))
+    outs = {}
+    for which in ("mine", "ref"):
+        r = subprocess.run([sys.executable, "-c", code, which, str(cfgfile)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[which] = r.stdout
+    assert "Re" in outs["ref"] and len(outs["ref"]) > 200
+
+    def config_part(text):
+        lines = text.splitlines()
+        cut = next(i for i, ln in enumerate(lines) if ln.startswith("Usage:"))
+        return [ln for ln in lines[:cut] if "OpenMP" not in ln], lines[cut]
+    mine, ref_ = config_part(outs["mine"]), config_part(outs["ref"])
+    assert mine[0] == ref_[0] and len(mine[0]) > 30
+    assert mine[1] == ref_[1] == "Usage: ./cnavier [config_file] [output_folder]"
