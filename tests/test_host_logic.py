@@ -539,3 +539,54 @@ C.CDLL(None).fflush(None)
     mine, ref_ = config_part(outs["mine"]), config_part(outs["ref"])
     assert mine[0] == ref_[0] and len(mine[0]) > 30
     assert mine[1] == ref_[1] == "Usage: ./cnavier [config_file] [output_folder]"
+
+
+def test_driver_courant_check_matches_reference_executable(tmp_path):
+    """The driver's stability check (src/main.c:165-174: Courant numbers from u1, message + exit status 1) happens before
+    any GPU work, so the executable can be compared with the reference executable on the CPU: same three lines, same
+    exit status; a stable configuration passes the check in both."""
+    exe = os.path.join(ROOT, "fluid_dynamics1_b200", "cnavier_b200")
+    refexe = os.path.join(ROOT, "oracle", "_ref", "cnavier_ser")
+    if not (os.path.exists(exe) and os.path.exists(refexe)):
+        pytest.skip("executables not built")
+    cfg = tmp_path / "unstable.txt"
+    cfg.write_text("nx = 8\nny = 8\ndt = 0.1\ntf = 0.35\nu1 = 100.0\nmax_co = 1.0\n")
+    outs = []
+    for binary in (exe, refexe):
+        r = subprocess.run([binary, str(cfg), "t"], capture_output=True, text=True, cwd=tmp_path, timeout=120)
+        lines = r.stdout.splitlines()
+        assert "Unstable Solution!" in lines, r.stdout[-1500:]
+        i = lines.index("Unstable Solution!")
+        outs.append((r.returncode, lines[i:i + 3]))
+    assert outs[0] == outs[1] and outs[0][0] == 1
+    assert outs[0][1][1].startswith("r1: 80.0") and outs[0][1][2].startswith("r2: 80.0")
+
+
+def test_dropin_bad_order_exits_like_reference():
+    """Diff1 / Diff2 with an order other than 2, 4, 6: message and exit(1) (src/finitediff.c:150-151, 289-290) -- the drop-in
+    library and the compiled reference behave the same (each in a child process, since both end the process)."""
+    import sys
+    code = r"""
+import ctypes as C, sys
+sys.path.insert(0, {root!r})
+from fluid_dynamics1_b200 import _lib
+which, fn = sys.argv[1], sys.argv[2]
+if which == "mine":
+    import fluid_dynamics1_b200 as fd
+    L = fd.dropin()
+else:
+    L = C.CDLL({ref!r}, mode=C.RTLD_LOCAL)
+    for name in ("Diff1", "Diff2"):
+        getattr(L, name).restype, getattr(L, name).argtypes = _lib.DROPIN_API[name]
+getattr(L, fn)(8, 3, 0.125)
+print("returned")
+""".format(root=ROOT, ref=os.path.join(ROOT, "oracle", "_ref", "libcnavier_ref_ser.so"))
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcnavier_ref_ser.so")):
+        pytest.skip("oracle/_ref not built")
+    for fn in ("Diff1", "Diff2"):
+        res = []
+        for which in ("mine", "ref"):
+            r = subprocess.run([sys.executable, "-c", code, which, fn], capture_output=True, text=True, timeout=120)
+            res.append((r.returncode, r.stdout.strip()))
+        assert res[0] == res[1], res
+        assert res[0][0] == 1 and "returned" not in res[0][1] and "rror" in res[0][1]
