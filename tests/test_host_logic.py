@@ -563,8 +563,9 @@ def test_driver_courant_check_matches_reference_executable(tmp_path):
 
 
 def test_dropin_bad_order_exits_like_reference():
-    """Diff1 / Diff2 with an order other than 2, 4, 6: message and exit(1) (src/finitediff.c:150-151, 289-290) -- the drop-in
-    library and the compiled reference behave the same (each in a child process, since both end the process)."""
+    """Diff1 / Diff2 with an order other than 2, 4, 6 (src/finitediff.c:150-151, 289-290), mtrxmul / reshape with
+    mismatching shapes (src/linearalg.c:241-247, 378-384): message and exit(1) -- the drop-in library and the compiled
+    reference print the same text and end with the same status (each in a child process, since both end the process)."""
     import sys
     code = r"""
 import ctypes as C, sys
@@ -578,12 +579,19 @@ else:
     L = C.CDLL({ref!r}, mode=C.RTLD_LOCAL)
     for name in ("Diff1", "Diff2"):
         getattr(L, name).restype, getattr(L, name).argtypes = _lib.DROPIN_API[name]
-getattr(L, fn)(8, 3, 0.125)
+for name in ("initm", "mtrxmul", "reshape"):
+    getattr(L, name).restype, getattr(L, name).argtypes = _lib.DROPIN_API[name]
+if fn in ("Diff1", "Diff2"):
+    getattr(L, fn)(8, 3, 0.125)
+elif fn == "mtrxmul":
+    L.mtrxmul(L.initm(2, 3), L.initm(2, 3))      # inner dimensions differ (src/linearalg.c:241-247)
+else:
+    L.reshape(L.initm(2, 3), 4, 2)               # element counts differ (src/linearalg.c:378-384)
 print("returned")
 """.format(root=ROOT, ref=os.path.join(ROOT, "oracle", "_ref", "libcnavier_ref_ser.so"))
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcnavier_ref_ser.so")):
         pytest.skip("oracle/_ref not built")
-    for fn in ("Diff1", "Diff2"):
+    for fn in ("Diff1", "Diff2", "mtrxmul", "reshape"):
         res = []
         for which in ("mine", "ref"):
             r = subprocess.run([sys.executable, "-c", code, which, fn], capture_output=True, text=True, timeout=120)
