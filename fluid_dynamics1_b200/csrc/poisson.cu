@@ -231,7 +231,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     }
     StreamThread<T> st;
     stream_init<T>(st, p, G, sm, in, rhs, tid, blockDim.x);
-    if (kLean) stream_set_sweeps<T>(st, nsw);
+    if (kLean) { stream_set_sweeps<T>(st, nsw); stream_prezero<T>(st, sm); }
     const int TPG = p.WS / (2 * kPairs);
     const int kk = tid - st.g * TPG;
 

@@ -327,9 +327,28 @@ CNV_HD void stream_load_row(const StreamThread<T> &s, double *sm, int slot, long
             const double *g = s.lptr[j] - back_elems;
             cp_async8(sm, slot + s.ldE[j], g);
             cp_async8(sm, slot + s.ldO[j], g + 1);
-        } else if (s.lzero[j]) {
+        } else if (!kLean && s.lzero[j]) {  // (kLean: zero-filled once for all ring slots, stream_prezero)
             sts1(sm, slot + s.ldE[j], 0.0);
             sts1(sm, slot + s.ldO[j], 0.0);
+        }
+    }
+}
+
+// kLean: columns outside the local array (strips hanging over the domain edge) hold zeros in every ring slot for the
+// whole pass -- nobody ever stores anything else there (their update mask is 0, so a store writes back the loaded 0) --
+// so they are filled once here instead of once per streamed row.  Call before stream_prologue; the first CTA barrier of
+// the step loop orders these stores before any read.
+template <int T>
+CNV_HD void stream_prezero(const StreamThread<T> &s, double *sm)
+{
+    const int base = s.lslot - (kPrefetch % StreamThread<T>::R) * s.ss;
+#pragma unroll
+    for (int j = 0; j < StreamThread<T>::NCH; j++) {
+        if (s.lzero[j]) {
+            for (int q = 0; q < StreamThread<T>::R; q++) {
+                sts1(sm, base + q * s.ss + s.ldE[j], 0.0);
+                sts1(sm, base + q * s.ss + s.ldO[j], 0.0);
+            }
         }
     }
 }

@@ -31,7 +31,7 @@ static void run_pass(const PassGeom &p, const RelaxConsts &rc, const double *in,
             for (auto &x : sm) x = std::nan("");
             const CtaGeom G = cta_geom(p, bx, by);
             for (int t = 0; t < NT; t++) stream_init<T>(st[t], p, G, sm.data(), in, rhs, t, NT);
-            if (kLean) for (int t = 0; t < NT; t++) stream_set_sweeps<T>(st[t], nsw);
+            if (kLean) for (int t = 0; t < NT; t++) { stream_set_sweeps<T>(st[t], nsw); stream_prezero<T>(st[t], sm.data()); }
             for (int t = 0; t < NT; t++) stream_prologue<T>(st[t], sm.data());
             for (int r = st[0].ybase; r <= st[0].rend; r += 4) {
                 // --- barrier before every step ---
