@@ -48,7 +48,7 @@ def section_single():
     out.append(bench_row("default (first run, with cpu_baseline)", base))
     out.append(bench_row("default (again, right after the lean run)", again, base))
     out.append(bench_row("CNV_POISSON_EDGE=0 (equal chunks, the plan measured in round 1)", last_json(os.path.join(D, "r2_bench_n1_edge0.json")), again or base))
-    out.append(bench_row("CNV_LIB=lean (87-instruction step body)", last_json(os.path.join(D, "r2_bench_n1_lean.json")), again or base))
+    out.append(bench_row("CNV_LIB=lean (leaner step body)", last_json(os.path.join(D, "r2_bench_n1_lean.json")), again or base))
     if base:
         for key in ("e2e", "stencil_phase", "timestep_1024", "timestep_4096", "cpu_baseline"):
             if key in base:

@@ -22,7 +22,7 @@ single)
     # headline, with and without the taller chunks at the domain boundary (planner change 97f5c9d; CNV_POISSON_EDGE=0 = old plan)
     python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
     CNV_POISSON_EDGE=0 python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_bench_n1_edge0.json 2>&1
-    # A/B: the leaner step body (libcnavier_b200_lean.so: 87 instead of 111 instructions per thread and row-step on the
+    # A/B: the leaner step body (libcnavier_b200_lean.so: about 82 instead of 111 instructions per thread and row-step on the
     # steady-state path, 2-long norm chain; bit-exact on the emulator) -- parity on hardware first, then the same bench
     CNV_LIB=lean timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "poisson or steps or golden" > gpurun_out/r2_pytest_lean.log 2>&1
     echo "pytest exit $?" >> gpurun_out/r2_pytest_lean.log
