@@ -311,7 +311,8 @@ def run_gpu(args):
                        "ctas": plan["nstrips"] * plan["nchunks"], "arith_path": "pow2-exact" if plan["pow2"] else "general",
                        "parallelism": f"slab{world}" if world > 1 else "single",
                        **({"exchange": ("peer" if slab.peer else "nccl" if slab.comm else "torch") +
-                                       ("+lagged-decision" if slab.peer and len(slab.bufs) == 3 else "")} if slab is not None else {}),
+                                       ("+lagged-decision" if slab.peer and len(slab.bufs) == 3 else "") +
+                                       ("+tile-kernel" if plan.get("tiled") else "")} if slab is not None else {}),
                        "l2": ("inputs larger than L2 (3 x %.0f MB resident arrays per GPU vs 126 MB L2), no flush" if
                               3 * rows_per * ncols * 8 > 126e6 else
                               "arrays fit L2 at this slab size (3 x %.0f MB per GPU vs 126 MB L2): L2-resident run, no flush") %

@@ -70,7 +70,7 @@ void launch_resident(const ResidentGeom &g, size_t smem, const RelaxConsts &rc, 
 
 // ---- poisson_tile.cu: stationary-tile pass kernel for grids that fit shared memory / L2 ----
 void launch_tile_pass(const TileGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
-                      double *partials, double *hist, double *norms, int fused, cudaStream_t s);
+                      double *partials, double *hist, double *norms, int fused, cudaStream_t s, const PeerLinks &L);
 
 // ---- poisson.cu ----
 struct PoissonResult {

@@ -578,6 +578,15 @@ void PoissonSolver::peer_export(unsigned char *out256)
 void PoissonSolver::peer_push_counts(int rank, int world, long long *low, long long *high) const
 {
     long long lo = 0, hi = 0;
+    if (use_tile_ && env_int("CNV_TILE_PEER", 0) != 0 && !lag_) {  // tiles whose output rows reach into the boundary band
+        for (int by = 0; by < tile_.nty; by++) {
+            const TileRows r = tile_rows_of(tile_, by);
+            if (rank > 0 && r.pa[0] < r.pb[0]) lo += tile_.ntx;
+            if (rank < world - 1 && r.pa[1] < r.pb[1]) hi += tile_.ntx;
+        }
+        *low = lo; *high = hi;
+        return;
+    }
     for (int by = 0; by < geom_.nchunks; by++) {
         const CtaGeom G = cta_geom(geom_, 0, by);
         if (rank > 0 && G.y0 < geom_.own_lo + geom_.HY) lo += geom_.nstrips;
@@ -630,7 +639,9 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
     links_.push_low = (unsigned long long)me[2];
     links_.push_high = (unsigned long long)me[3];
     links_.enabled = 1;
-    use_tile_ = false;  // the in-kernel peer exchange is part of the streaming kernel
+    // the in-kernel peer exchange is part of the streaming kernel; the stationary-tile kernel has it as well (plain stop
+    // machine only), opt-in until it has run on hardware: CNV_TILE_PEER=1 together with CNV_POISSON_TILE=1
+    if (!(use_tile_ && env_int("CNV_TILE_PEER", 0) != 0 && !lag_)) use_tile_ = false;
     distributed_ = true;
     peer_gidx_ = 0;
     return 0;
@@ -678,10 +689,6 @@ void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
     double *hist = use_hist_ ? hist_ : nullptr;
     const int fused = distributed_ ? 0 : 1;
     for (int i = 0; i < npasses; i++) {
-        if (use_tile_) {
-            launch_tile_pass(tile_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, s);
-            continue;
-        }
         PeerLinks L = links_;
         if (L.enabled) {
             L.pidx = dist_passes_++;
@@ -689,6 +696,10 @@ void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
             L.epoch = peer_epoch_;
         } else if (L.trace) {
             L.pidx = trace_pass_++;  // diagnostics only (tools/peer_trace.py --single)
+        }
+        if (use_tile_) {
+            launch_tile_pass(tile_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, s, L);
+            continue;
         }
 #define CNV_PASS(TT)                                                                                                     \
     if (T_ == TT) {                                                                                                      \

@@ -7,15 +7,20 @@
 #include <cstring>
 
 #include "kernels.h"
+#include "peer_device.cuh"
 
 namespace cnv {
 
 
-template <int M, bool POW2>
+// PEER: slab of a multi-GPU run with the in-kernel peer-memory exchange (CNV_TILE_PEER=1; the protocol of the streaming
+// kernel, poisson_stream.h PeerMailbox / PeerLinks, plain stop machine): the pass derives its state from every rank's
+// published norms, tiles that read halo rows wait for the neighbours' pushes of the previous pass, tiles whose output rows
+// lie in the 2T boundary band store them into the neighbour's halo rows over NVLink, the last CTA publishes the norms.
+template <int M, bool POW2, bool PEER>
 __global__ void __launch_bounds__(tile_max_threads(M), 1)
 k_poisson_tile(const TileGeom g, const RelaxConsts rc, double *__restrict__ buf0, double *__restrict__ buf1,
                const double *__restrict__ rhs, PoissonCtl *ctl, double *__restrict__ partials, double *hist, double *norms_out,
-               const int fused_decide)
+               const int fused_decide, const PeerLinks L)
 {
     extern __shared__ double4 sm4[];
     double *sm = reinterpret_cast<double *>(sm4);
@@ -27,12 +32,32 @@ k_poisson_tile(const TileGeom g, const RelaxConsts rc, double *__restrict__ buf0
     // the next pass may become resident while this one drains and waits here for its completion
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const PoissonCtl c0 = *ctl;
-    if (c0.state != 0) return;  // solve already finished: later passes of a batch are no-ops
-    const int nsw = pass_sweeps(c0, g.T);
-    const double *__restrict__ in = c0.cur ? buf1 : buf0;
-    double *__restrict__ out = c0.cur ? buf0 : buf1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+    __shared__ PoissonCtl s_ctl;
+    __shared__ LagAction s_act;
+    int cur, nxt, nsw;
+    if (PEER) {
+        __shared__ double s_nrm[kMaxRanks][8];
+        __shared__ int s_flag;
+        const LagAction a = peerdev::begin_pass(L, g.T, hist, blockIdx.x == 0 && blockIdx.y == 0, s_nrm, &s_flag, &s_ctl, &s_act);
+        if (a.kind == 0) return;  // solve already finished: later passes of a batch are no-ops
+        cur = a.in; nxt = a.out; nsw = a.nsw;
+    } else {
+        const PoissonCtl c0 = *ctl;
+        if (c0.state != 0) return;  // solve already finished: later passes of a batch are no-ops
+        nsw = pass_sweeps(c0, g.T);
+        cur = c0.cur; nxt = cur ^ 1;
+    }
+    const double *__restrict__ in = cur ? buf1 : buf0;
+    double *__restrict__ out = nxt ? buf1 : buf0;
+    const TileRows rows = tile_rows_of(g, blockIdx.y);
+    const bool push_down = PEER && L.rank > 0 && rows.pa[0] < rows.pb[0];
+    const bool push_up = PEER && L.rank < L.world - 1 && rows.pa[1] < rows.pb[1];
+    if (PEER) {
+        if (tid == 0)
+            peerdev::wait_inputs(L, push_down, push_up, L.rank > 0 && rows.rlo < g.own_lo, L.rank < L.world - 1 && rows.rhi > g.own_hi);
+        __syncthreads();
+    }
 
     // the block is rounded up to whole warps (shuffles, barriers); the surplus threads own no cells
     const bool active = tid < g.KP * g.NSEG;
@@ -60,6 +85,20 @@ k_poisson_tile(const TileGeom g, const RelaxConsts rc, double *__restrict__ buf0
     }
     if (active) tile_store<M>(t, out);
 
+    if (PEER && (push_down || push_up)) {
+        // boundary rows this tile has just written (still L2 resident) -> the neighbour's halo rows, then count the push
+        __syncthreads();  // every write-back of this CTA is done and visible to the CTA
+        const int c0 = (int)blockIdx.x * g.OW, c1 = c0 + g.OW < g.ld ? c0 + g.OW : g.ld;
+        if (push_down) peerdev::push_rows(out, L.down_buf[nxt] + L.down_delta, g.ld, rows.pa[0], rows.pb[0], c0, c1);
+        if (push_up) peerdev::push_rows(out, L.up_buf[nxt] + L.up_delta, g.ld, rows.pa[1], rows.pb[1], c0, c1);
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            if (push_down) atomicAdd_system(&L.mail[L.rank - 1]->halo_count[1], 1ull);
+            if (push_up) atomicAdd_system(&L.mail[L.rank + 1]->halo_count[0], 1ull);
+        }
+    }
+
     if (tid < nsw) {
         double e = 0.0;
         for (int w = 0; w < nwarps; w++) e = xadd(e, s_part[tid][w]);
@@ -69,7 +108,8 @@ k_poisson_tile(const TileGeom g, const RelaxConsts rc, double *__restrict__ buf0
     }
     __syncthreads();
     const int ncta = gridDim.x * gridDim.y;
-    if (tid == 0) s_last = atomicAdd(&ctl->ticket, 1u) == (unsigned)ncta - 1;
+    unsigned *ticket = PEER ? &L.mail[L.rank]->ticket : &ctl->ticket;
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)ncta - 1;
     __syncthreads();
     if (!s_last) return;
 
@@ -84,6 +124,11 @@ k_poisson_tile(const TileGeom g, const RelaxConsts rc, double *__restrict__ buf0
         if (lane == 0) s_e[w] = e;
     }
     __syncthreads();
+    if (PEER) {
+        peerdev::publish_norms(L, s_e, nsw);
+        if (tid == 0) *ticket = 0;
+        return;
+    }
     if (tid == 0) {
         if (fused_decide) {
             PoissonCtl c = *ctl;
@@ -97,14 +142,14 @@ k_poisson_tile(const TileGeom g, const RelaxConsts rc, double *__restrict__ buf0
     }
 }
 
-template <int M, bool POW2>
+template <int M, bool POW2, bool PEER>
 static void launch_tile_t(const TileGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
-                          double *partials, double *hist, double *norms, int fused, cudaStream_t s)
+                          double *partials, double *hist, double *norms, int fused, cudaStream_t s, const PeerLinks &L)
 {
     const size_t smem = tile_smem_bytes(g);
     static size_t configured = 48 * 1024;
     if (smem > configured) {
-        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_tile<M, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_tile<M, POW2, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     // CNV_TILE_PDL=1: programmatic stream serialisation between consecutive passes (hides the launch latency, which is a
@@ -121,16 +166,21 @@ static void launch_tile_t(const TileGeom &g, const RelaxConsts &rc, double *b0, 
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const double *crhs = rhs;
-    CNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_poisson_tile<M, POW2>, g, rc, b0, b1, crhs, ctl, partials, hist, norms, fused));
+    CNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_poisson_tile<M, POW2, PEER>, g, rc, b0, b1, crhs, ctl, partials, hist, norms, fused, L));
 }
 
 void launch_tile_pass(const TileGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
-                      double *partials, double *hist, double *norms, int fused, cudaStream_t s)
+                      double *partials, double *hist, double *norms, int fused, cudaStream_t s, const PeerLinks &L)
 {
-#define CNV_TILE(MM)                                                                                  \
-    if (g.M == MM) {                                                                                  \
-        if (rc.pow2) launch_tile_t<MM, true>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, s); \
-        else launch_tile_t<MM, false>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, s);       \
+#define CNV_TILE(MM)                                                                                                       \
+    if (g.M == MM) {                                                                                                       \
+        if (L.enabled) {                                                                                                   \
+            if (rc.pow2) launch_tile_t<MM, true, true>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, s, L);       \
+            else launch_tile_t<MM, false, true>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, s, L);              \
+        } else {                                                                                                           \
+            if (rc.pow2) launch_tile_t<MM, true, false>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, s, L);      \
+            else launch_tile_t<MM, false, false>(g, rc, b0, b1, rhs, ctl, partials, hist, norms, fused, s, L);             \
+        }                                                                                                                  \
     }
     CNV_TILE(6) CNV_TILE(8) CNV_TILE(10) CNV_TILE(12) CNV_TILE(14) CNV_TILE(16)
 #undef CNV_TILE

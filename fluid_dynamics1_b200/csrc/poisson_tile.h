@@ -216,6 +216,29 @@ CNV_HD void tile_store(const TileThread<M> &t, double *out)
         if ((t.rown >> i) & 1u) stg2(out + t.gofs + (long long)i * t.ld, t.E[i], t.O[i]);
 }
 
+// ---- slab geometry of a tile row `by` (multi-GPU peer exchange; shared with the CPU tests) ------------------------
+// Output rows [y0, y1) of the tiles in tile row `by`, the local rows the tile reads, and the boundary rows it has to push
+// into the lower (side 0) / upper (side 1) neighbour's halo: the 2T owned rows next to that slab edge.
+struct TileRows {
+    int y0, y1;        // output rows
+    int rlo, rhi;      // rows read: [rlo, rhi)
+    int pa[2], pb[2];  // rows to push towards side s: [pa[s], pb[s]) (empty if pa >= pb)
+};
+CNV_HD TileRows tile_rows_of(const TileGeom &g, int by)
+{
+    TileRows r;
+    r.y0 = g.own_lo + by * g.OH;
+    r.y1 = r.y0 + g.OH < g.own_hi ? r.y0 + g.OH : g.own_hi;
+    const int ty0 = r.y0 - g.HT, TH = tile_rows(g);
+    r.rlo = ty0 > 0 ? ty0 : 0;
+    r.rhi = ty0 + TH < g.nrows ? ty0 + TH : g.nrows;
+    r.pa[0] = r.y0 > g.own_lo ? r.y0 : g.own_lo;
+    r.pb[0] = r.y1 < g.own_lo + g.HT ? r.y1 : g.own_lo + g.HT;
+    r.pa[1] = r.y0 > g.own_hi - g.HT ? r.y0 : g.own_hi - g.HT;
+    r.pb[1] = r.y1 < g.own_hi ? r.y1 : g.own_hi;
+    return r;
+}
+
 // ---- planner -----------------------------------------------------------------------------------
 // Picks the tile shape (KP, M, NSEG) with the lowest estimated time per sweep: waves x (fixed cost + 2T half-sweeps x
 // M rows x the warps sharing a scheduler) / T.  Feasible: whole warps <= tile_max_threads(M), shared memory within the

@@ -116,6 +116,7 @@ class SlabPoisson:
             self.L.cnv_poisson_attach_comm(self.h, self.comm)
         self.peer = backend == "peer" and world <= 8 and self._setup_peer()
         self._map_bufs()  # (the lagged peer decision, CNV_PEER_LAG=1, adds a third iterate buffer)
+        self.solver.refresh_plan()
 
     def _map_bufs(self):
         n = self.L.cnv_poisson_num_buffers(self.h)

@@ -125,13 +125,17 @@ class PoissonSolver:
             grow0, gnrows, own_lo, own_hi = slab
             self.h = self.L.cnv_poisson_create_slab(nrows, ncols, T, grow0, gnrows, own_lo, own_hi)
         self.nrows, self.ncols = nrows, ncols
+        self.refresh_plan()
+        self.T = self.plan["T"]
+        self.ld = self.L.cnv_poisson_ld(self.h)
+
+    def refresh_plan(self):
+        """(Re-)read the launch plan: which pass kernel runs can change when the multi-GPU exchange is set up."""
         info = (C.c_longlong * 18)()
         self.L.cnv_poisson_plan_info(self.h, info)
         keys = ("WS", "HX", "Wout", "Hout", "nstrips", "nchunks", "threads", "smem", "T", "pow2",
                 "tiled", "KP", "M", "NSEG", "OW", "OH", "ntx", "nty")
         self.plan = dict(zip(keys, list(info)))
-        self.T = self.plan["T"]
-        self.ld = self.L.cnv_poisson_ld(self.h)
 
     def close(self):
         if self.h and self.owned:

@@ -85,6 +85,16 @@ int emul_tile_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_
     return 0;
 }
 
+// slab geometry of tile row `by` (poisson_tile.h tile_rows_of, the kernel's own code): y0, y1, rlo, rhi, pa0, pb0, pa1, pb1
+int emul_tile_rows(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T, int by, int *out)
+{
+    TileGeom g;
+    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, nullptr)) return -1;
+    const TileRows r = tile_rows_of(g, by);
+    out[0] = r.y0; out[1] = r.y1; out[2] = r.rlo; out[3] = r.rhi; out[4] = r.pa[0]; out[5] = r.pb[0]; out[6] = r.pa[1]; out[7] = r.pb[1];
+    return 0;
+}
+
 // the tile planner's cost estimate per sweep (arbitrary units), < 0 if no plan exists
 double emul_tile_cost(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T)
 {

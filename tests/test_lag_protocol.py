@@ -30,13 +30,17 @@ def E():
     lib.emul_lag_final.argtypes = [ip, dp, C.c_int, dp, C.c_int, C.c_void_p]
     lib.emul_peer_needs_norms.argtypes = [ip, dp, C.c_int, C.c_int]
     lib.emul_peer_advance.argtypes = [ip, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip]
+    lib.emul_tile_pass.argtypes = [C.c_int] * 11 + [C.c_double] * 3 + [C.c_int, dp, dp, dp, C.c_int, dp]
+    lib.emul_tile_plan.argtypes = [C.c_int] * 11 + [np.ctypeslib.ndpointer(dtype=np.int64)]
+    lib.emul_tile_rows.argtypes = [C.c_int] * 9 + [ip]
     return lib
 
 
 class Rank:
-    def __init__(self, E, r, world, rows, cols, T, f, itmax, tol, lag=1):
+    def __init__(self, E, r, world, rows, cols, T, f, itmax, tol, lag=1, tile=False):
         self.E, self.r, self.world, self.T = E, r, world, T
         self.lag, self.lagd, self.nbuf = lag, (2 if lag else 1), (3 if lag else 2)
+        self.tile = tile  # passes by the stationary-tile kernel, pushes with ITS per-tile-row geometry (tile_rows_of)
         self.rows, self.cols = rows, cols
         self.grow0, self.nloc, self.own_lo, self.own_hi, _, _ = slab_layout(rows, world, r, T)
         self.ld = (cols + 15) // 16 * 16
@@ -115,16 +119,42 @@ class Rank:
             for nb in (self.r - 1, self.r + 1):
                 if 0 <= nb < self.world and kind == 1:
                     assert ranks[nb].p >= p - self.lagd + 1, "push into a buffer the neighbour has not finished reading"
-            rc = self.E.emul_pass(T, self.nloc, self.cols, self.ld, self.grow0, self.rows, self.own_lo, self.own_hi, 0,
-                                  int(os.environ.get("CNV_TEST_CHUNKS", "0")), dx, dy, beta, 0, self.bufs[bi], self.floc,
-                                  self.bufs[bo], nsw, norms)
+            geo = (self.nloc, self.cols, self.ld, self.grow0, self.rows, self.own_lo, self.own_hi)
+            if self.tile:
+                rc = self.E.emul_tile_pass(T, *geo, 0, 0, 0, dx, dy, beta, 0, self.bufs[bi], self.floc, self.bufs[bo], nsw, norms)
+            else:
+                rc = self.E.emul_pass(T, *geo, 0, int(os.environ.get("CNV_TEST_CHUNKS", "0")), dx, dy, beta, 0, self.bufs[bi],
+                                      self.floc, self.bufs[bo], nsw, norms)
             assert rc == 0
-            if self.r > 0:                     # my first owned rows -> the lower neighbour's high halo
-                nb = ranks[self.r - 1]
-                nb.bufs[bo][nb.own_hi:nb.own_hi + H] = self.bufs[bo][self.own_lo:self.own_lo + H]
-            if self.r < self.world - 1:        # my last owned rows -> the upper neighbour's low halo
-                nb = ranks[self.r + 1]
-                nb.bufs[bo][nb.own_lo - H:nb.own_lo] = self.bufs[bo][self.own_hi - H:self.own_hi]
+            if self.tile:
+                # the kernel's pushes, tile row by tile row: rows [pa, pb) of side 0 go to the lower neighbour's high halo
+                # (my row own_lo + i -> its row own_hi' + i), of side 1 to the upper neighbour's low halo
+                plan = np.zeros(8, dtype=np.int64)
+                assert self.E.emul_tile_plan(*geo, T, 0, 0, 0, plan) == 0
+                ntx, nty, ow = int(plan[5]), int(plan[6]), int(plan[3])
+                c1 = min(ntx * ow, self.ld)
+                pushed = [0, 0]
+                for by in range(nty):
+                    tr = np.zeros(8, dtype=np.int32)
+                    assert self.E.emul_tile_rows(*geo, T, by, tr) == 0
+                    if self.r > 0 and tr[4] < tr[5]:
+                        nb = ranks[self.r - 1]
+                        d = nb.own_hi - self.own_lo
+                        nb.bufs[bo][tr[4] + d:tr[5] + d, :c1] = self.bufs[bo][tr[4]:tr[5], :c1]
+                        pushed[0] += int(tr[5] - tr[4])
+                    if self.r < self.world - 1 and tr[6] < tr[7]:
+                        nb = ranks[self.r + 1]
+                        d = (nb.own_lo - H) - (self.own_hi - H)
+                        nb.bufs[bo][tr[6] + d:tr[7] + d, :c1] = self.bufs[bo][tr[6]:tr[7], :c1]
+                        pushed[1] += int(tr[7] - tr[6])
+                assert pushed[0] == (H if self.r > 0 else 0) and pushed[1] == (H if self.r < self.world - 1 else 0)
+            else:
+                if self.r > 0:                     # my first owned rows -> the lower neighbour's high halo
+                    nb = ranks[self.r - 1]
+                    nb.bufs[bo][nb.own_hi:nb.own_hi + H] = self.bufs[bo][self.own_lo:self.own_lo + H]
+                if self.r < self.world - 1:        # my last owned rows -> the upper neighbour's low halo
+                    nb = ranks[self.r + 1]
+                    nb.bufs[bo][nb.own_lo - H:nb.own_lo] = self.bufs[bo][self.own_hi - H:self.own_hi]
         if self.r > 0:
             ranks[self.r - 1].halo_passes[1] += 1
         if self.r < self.world - 1:
@@ -150,14 +180,14 @@ class Rank:
         return st[0], st[1]
 
 
-def lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed, ranks=None, fseed=11, lag=1):
+def lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed, ranks=None, fseed=11, lag=1, tile=False):
     rng = np.random.default_rng(seed)
     f = np.random.default_rng(fseed).standard_normal((rows, cols))
     dx, dy = 1.0 / cols, 1.0 / rows
     port = api.port()
     beta = port.beta(rows, cols)
     if ranks is None:
-        ranks = [Rank(E, r, world, rows, cols, T, f, itmax, tol, lag) for r in range(world)]
+        ranks = [Rank(E, r, world, rows, cols, T, f, itmax, tol, lag, tile) for r in range(world)]
     else:
         for k in ranks:
             k.new_solve(f, itmax, tol)
@@ -321,3 +351,18 @@ def test_plain_peer_machine_same_simulation(E, world, T):
             assert full.tobytes() == want["u"].tobytes()
     ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, 7, 0.0, [2], seed=1, lag=0)
     assert ints[0] == 2 and int(ints[2]) == 7 and full.tobytes() == want["u"].tobytes()
+
+
+@pytest.mark.parametrize("world,T", [(2, 2), (3, 2), (2, 4)])
+def test_plain_peer_machine_with_tile_kernel(E, world, T):
+    """The stationary-tile kernel inside the peer protocol (CNV_POISSON_TILE=1 + CNV_TILE_PEER=1): passes by the tile kernel's
+    own per-thread code, boundary rows pushed tile row by tile row with the kernel's own geometry (tile_rows_of): exactly the
+    2T boundary rows reach each neighbour, and field, iteration count and residual equal the single-domain oracle."""
+    rows, cols = 56 * world, 72
+    f = np.random.default_rng(11).standard_normal((rows, cols))
+    port = api.port()
+    for ksweep in range(2 * T, 3 * T + 1):
+        tol = port.poisson(f, 1.0 / cols, 1.0 / rows, ksweep + 1, 0.0, port.beta(rows, cols), redblack=True)["e"] * (1 + 1e-9)
+        ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, 5000, tol, [2], seed=ksweep, lag=0, tile=True)
+        assert ints[0] == 1 and int(ints[5]) == want["k"]
+        assert full.tobytes() == want["u"].tobytes()

@@ -100,7 +100,9 @@ def section_multi():
                           ("strong 4096², peer", f"r2_strong_peer_{n}.json"), ("strong 4096², peer + lagged", f"r2_strong_lag_{n}.json"),
                           ("strong 4096², nccl, streaming kernel", f"r2_strong_nccl_{n}.json"),
                           ("strong 4096², nccl, tile kernel T=4", f"r2_strong_tile_T4_{n}.json"),
-                          ("strong 4096², nccl, tile kernel T=8", f"r2_strong_tile_T8_{n}.json")):
+                          ("strong 4096², nccl, tile kernel T=8", f"r2_strong_tile_T8_{n}.json"),
+                          ("strong 4096², peer, tile kernel T=4", f"r2_strong_tilepeer_T4_{n}.json"),
+                          ("strong 4096², peer, tile kernel T=8", f"r2_strong_tilepeer_T8_{n}.json")):
             j = last_json(os.path.join(D, fn))
             if j is None:
                 out.append(f"| {n} | {label} | not run | | | | |")
@@ -110,6 +112,7 @@ def section_multi():
             rel = f"{j['value'] / ref['value']:.3f}" if ref else ""
             out.append(f"| {n} | {label} | {j['value']:.4e} | {j['ms_per_step']:.2f} | {j.get('roofline', {}).get('launch_us', float('nan')):.1f} | {eff} | {rel} |")
         out.append(f"| {n} | lagged GPU tests | `{' / '.join(tail(os.path.join(D, f'r2_lag_tests_{n}.log'), 2))}` | | | | |")
+        out.append(f"| {n} | tile-kernel peer tests | `{' / '.join(tail(os.path.join(D, f'r2_tile_peer_tests_{n}.log'), 2))}` | | | | |")
         out.append(f"| {n} | plain multi-GPU suite | `{' / '.join(tail(os.path.join(D, f'r2_multi_tests_{n}.log'), 2))}` | | | | |")
         out.append(f"| {n} | tile-kernel slab parity | `{' / '.join(tail(os.path.join(D, f'r2_tile_slab_check_{n}.log'), 1))}` | | | | |")
     for n in ns:

@@ -48,6 +48,9 @@ lagtest)
     CNV_TEST_LAG=1 timeout 1200 python -m pytest tests/test_gpu_z_multi.py -m gpu -x -q -k "lagged" > gpurun_out/r2_lag_tests_$n.log 2>&1
     echo "pytest exit $?" >> gpurun_out/r2_lag_tests_$n.log
     tail -3 gpurun_out/r2_lag_tests_$n.log
+    CNV_TEST_TILE_PEER=1 timeout 900 python -m pytest tests/test_gpu_z_multi.py -m gpu -x -q -k "tile_peer" > gpurun_out/r2_tile_peer_tests_$n.log 2>&1
+    echo "pytest exit $?" >> gpurun_out/r2_tile_peer_tests_$n.log
+    tail -3 gpurun_out/r2_tile_peer_tests_$n.log
     timeout 1200 python -m pytest tests/test_gpu_z_multi.py -m gpu -x -q > gpurun_out/r2_multi_tests_$n.log 2>&1
     echo "pytest exit $?" >> gpurun_out/r2_multi_tests_$n.log
     tail -3 gpurun_out/r2_multi_tests_$n.log
@@ -73,6 +76,11 @@ extra)
             > gpurun_out/r2_strong_tile_T${T}_$n.json 2>&1
     done
     CNV_DIST_BACKEND=nccl run 29808 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong > gpurun_out/r2_strong_nccl_$n.json 2>&1
+    # ... and with the peer exchange inside the tile kernel (only after `lagtest` showed its tests green)
+    for T in 4 8; do
+        CNV_POISSON_TILE=1 CNV_TILE_PEER=1 run 29810 bench.py --gpus "$n" --steps 10 --warmup 3 --scaling strong --T $T \
+            > gpurun_out/r2_strong_tilepeer_T${T}_$n.json 2>&1
+    done
     run 29805 tools/peer_trace.py 4096 4096 24 > gpurun_out/r2_trace_peer_$n.log 2>&1
     CNV_PEER_LAG=1 run 29806 tools/peer_trace.py 4096 4096 24 > gpurun_out/r2_trace_lag_$n.log 2>&1
     ;;
