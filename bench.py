@@ -319,7 +319,8 @@ def run_gpu(args):
                              (rows_per * ncols * 8 / 1e6)},
             "sweeps_per_s": S * args.steps / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": f"k_poisson_pass<T={T}>",
+                         "traffic": traffic if not plan.get("tiled") else None, "peak_source": peak_src,
+                         "kernel": (f"k_poisson_tile<M={plan['M']}> (T={T})" if plan.get("tiled") else f"k_poisson_pass<T={T}>"),
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_SWEEP * per_gpu_cells * T,
                          "launch_us": launch_s * 1e6,
                          "note": "temporal blocking: T sweeps per HBM pass, so algorithmic GB/s may exceed the HBM peak"},
