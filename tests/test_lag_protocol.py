@@ -366,3 +366,27 @@ def test_plain_peer_machine_with_tile_kernel(E, world, T):
         ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, 5000, tol, [2], seed=ksweep, lag=0, tile=True)
         assert ints[0] == 1 and int(ints[5]) == want["k"]
         assert full.tobytes() == want["u"].tobytes()
+
+
+def test_peer_protocol_random_configurations(E):
+    """Seeded sweep over the whole protocol simulation: 2-4 ranks, T = 2/4/8, plain and lagged machine, streaming and tile
+    kernel passes, random tolerance (converging anywhere or hitting itmax) and random host batch sizes."""
+    rng = np.random.default_rng(77)
+    for case in range(24):
+        world = int(rng.integers(2, 5))
+        T = int(rng.choice([2, 4, 8]))
+        lag = int(rng.integers(0, 2))
+        tile = bool(lag == 0 and T <= 4 and rng.integers(0, 3) == 0)
+        rows = int(rng.integers(max(4 * T + 2, 24), 70)) * world
+        cols = int(rng.integers(40, 90))
+        if tile:
+            rows, cols = max(rows, 56 * world), max(cols, 64)
+        tol = float(10 ** rng.uniform(-3, 0.5))
+        itmax = int(rng.choice([5000, 5000, 17, 40]))
+        batches = [int(x) for x in rng.integers(1, 7, size=3)]
+        ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed=case, lag=lag, tile=tile, fseed=case)
+        where = dict(case=case, world=world, T=T, lag=lag, tile=tile, rows=rows, cols=cols, tol=tol, itmax=itmax, batches=batches)
+        assert int(ints[0]) == (1 if want["status"] == 0 else 2), where
+        assert full.tobytes() == want["u"].tobytes(), where
+        if want["status"] == 0:
+            assert int(ints[5]) == want["k"], where
