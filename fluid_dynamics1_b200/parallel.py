@@ -221,7 +221,11 @@ class SlabPoisson:
         self.zero_iterate()
         self.reset(itmax, tol)
         max_passes = (itmax + self.T - 1) // self.T + 2 + (3 if len(self.bufs) == 3 else 0)  # lagged decision: speculative passes
-        batch = first_batch
+        # like PoissonSolver::solve: sweep counts drift slowly from one time step to the next, so the first batch covers the
+        # previous solve's pass count (+ the speculative / redo passes of the lagged machine) and is followed by small ones
+        # -- every read-back of the state is a host synchronisation and, on the peer path, a rendezvous of all ranks
+        predicted = getattr(self, "_predicted_passes", 0)
+        batch = predicted + (3 if len(self.bufs) == 3 else 1) if predicted > 0 else first_batch
         while True:
             self.enqueue(min(batch, max_passes + 1 - self.passes_enqueued))
             st = self.state()
@@ -230,6 +234,7 @@ class SlabPoisson:
             if self.passes_enqueued > max_passes:
                 raise RuntimeError("Poisson state machine did not terminate")
             batch = 4
+        self._predicted_passes = st["passes"]
         return dict(status=0 if st["state"] == 1 else 1, k=st["k"], e=st["e"] if st["state"] == 1 else st["last_e"],
                     sweeps=st["sweeps"], passes=st["passes"], buf=st["cur"])
 
