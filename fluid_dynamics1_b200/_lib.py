@@ -13,10 +13,6 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libcnavier_b200.so")
-# CNV_LIB=lean: the same library with the experimental leaner streaming-step body (csrc/poisson_stream.h kLean,
-# `make -C csrc lean`); for A/B measurements only -- the default is the measured kernel
-if os.environ.get("CNV_LIB", "") == "lean":
-    LIB_PATH = os.path.join(PKG, "libcnavier_b200_lean.so")
 DROPIN_PATH = os.path.join(PKG, "libcnavier_dropin.so")
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -49,6 +45,9 @@ CNV_API = {
     "cnv_set_device": (C.c_int, [C.c_int]),
     "cnv_get_device": (C.c_int, []),
     "cnv_device_synchronize": (None, []),
+    "cnv_host_alloc": (_vp, [C.c_size_t]),
+    "cnv_host_free": (None, [_vp]),
+    "cnv_host_is_pinned": (C.c_int, [_vp]),
     "cnv_sor_beta": (C.c_double, [C.c_int, C.c_int]),
     "cnv_num_steps": (C.c_int, [C.c_double, C.c_double]),
     "cnv_diff_dense": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
@@ -60,6 +59,7 @@ CNV_API = {
     "cnv_pressure_rhs_host": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
     "cnv_poisson_host": (C.c_int, [_dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
                                    _dp, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp]),
+    "cnv_poisson_host_cache_clear": (None, []),
     "cnv_poisson_create": (_vp, [C.c_int, C.c_int, C.c_int]),
     "cnv_poisson_create_slab": (_vp, [C.c_int] * 7),
     "cnv_poisson_destroy": (None, [_vp]),
@@ -71,6 +71,8 @@ CNV_API = {
     "cnv_poisson_norms_ptr": (_vp, [_vp]),
     "cnv_poisson_plan_info": (None, [_vp, C.POINTER(C.c_longlong)]),
     "cnv_poisson_upload": (C.c_int, [_vp, _dp, C.c_double, _vp]),
+    "cnv_poisson_upload_owned": (C.c_int, [_vp, _dp, C.c_double, _vp]),
+    "cnv_poisson_download_owned_async": (C.c_int, [_vp, C.c_int, _dp, _vp]),
     "cnv_poisson_prepare": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp]),
     "cnv_poisson_solve": (C.c_int, [_vp, C.c_int, C.c_double, _vp, C.POINTER(C.c_int), C.POINTER(C.c_double),
                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -93,6 +95,8 @@ CNV_API = {
     "cnv_poisson_peer_push_counts": (None, [_vp, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "cnv_poisson_peer_import": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int)]),
     "cnv_poisson_peer_disable": (None, [_vp]),
+    "cnv_poisson_peer_quiesce": (None, [_vp, _vp]),
+    "cnv_poisson_peer_close": (None, [_vp]),
     "cnv_poisson_peer_enabled": (C.c_int, [_vp]),
     "cnv_poisson_peer_trace": (C.c_int, [_vp, C.c_int]),
     "cnv_poisson_peer_trace_read": (None, [_vp, _vp, C.c_longlong]),

@@ -3,6 +3,8 @@
 // (src/main.c:283-395) on top of the CUDA kernels.
 #include <cmath>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/cnavier_b200.h"
@@ -63,6 +65,82 @@ __global__ void k_l1_distance(const double *__restrict__ a, const double *__rest
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
+
+// ---- pinned host memory pool (cnv_host_alloc / cnv_host_free) ------------------------------------------------
+// The reference hands fields around as caller-owned mtrx storage that is allocated and freed once per call and per time
+// step (allocm / freem, src/linearalg.c:53-99).  Page-locking 134 MB takes longer than solving on it, so large blocks
+// are page-locked once and recycled through size-keyed free lists; small ones are plain heap memory.
+struct HostPool {
+    std::mutex mu;
+    std::unordered_map<void *, std::pair<size_t, bool>> live;   // ptr -> (bytes, pinned)
+    std::unordered_map<size_t, std::vector<void *>> free_pinned; // bytes -> recycled pinned blocks
+    size_t pooled_bytes = 0;
+};
+static HostPool &host_pool()
+{
+    static HostPool *p = new HostPool;  // never destroyed: blocks may outlive static destruction order
+    return *p;
+}
+constexpr size_t kPinThreshold = 1u << 20;        // blocks of >= 1 MiB are page-locked
+constexpr size_t kPoolLimit = (size_t)8 << 30;    // recycled (idle) pinned memory kept at most
+
+static bool device_present()
+{
+    static int n = -1;
+    if (n < 0) {
+        int c = 0;
+        if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+        n = c;
+    }
+    return n > 0;
+}
+
+// ---- solver objects of the host-buffer entry point, kept between calls ---------------------------------------
+// cnv_poisson_host() is what poisson_SOR_log(mtrx ...) of the drop-in library lands on, once per time step with the same
+// grid: creating a PoissonSolver per call costs three cudaMalloc + memset of the field size.  The last two shapes per
+// device stay alive (the pressure recipe alternates two solves); the pass-count predictor carries over between calls.
+struct CachedSolver {
+    int dev, nrows, ncols, T;
+    size_t env;  // fingerprint of the CNV_* environment the solver was planned under (tuning / A-B switches are read at construction)
+    PoissonSolver *s;
+};
+extern "C" char **environ;
+static size_t cnv_env_fingerprint()
+{
+    size_t h = 1469598103934665603ull;  // FNV-1a over every CNV_* variable
+    for (char **e = environ; e && *e; e++) {
+        if (std::strncmp(*e, "CNV_", 4) != 0) continue;
+        for (const char *c = *e; *c; c++) h = (h ^ (unsigned char)*c) * 1099511628211ull;
+        h = (h ^ 0xffu) * 1099511628211ull;
+    }
+    return h;
+}
+static std::vector<CachedSolver> &solver_cache()
+{
+    static std::vector<CachedSolver> *c = new std::vector<CachedSolver>;
+    return *c;
+}
+static PoissonSolver *cached_solver(int nrows, int ncols, int T)
+{
+    int dev = 0;
+    CNV_CUDA_CHECK(cudaGetDevice(&dev));
+    auto &c = solver_cache();
+    const size_t env = cnv_env_fingerprint();
+    for (size_t i = 0; i < c.size(); i++)
+        if (c[i].dev == dev && c[i].nrows == nrows && c[i].ncols == ncols && c[i].T == T && c[i].env == env) {
+            CachedSolver hit = c[i];
+            c.erase(c.begin() + i);
+            c.push_back(hit);  // most recently used last
+            return hit.s;
+        }
+    size_t same_dev = 0;
+    for (const CachedSolver &e : c) same_dev += e.dev == dev;
+    if (same_dev >= 2)
+        for (size_t i = 0; i < c.size(); i++)
+            if (c[i].dev == dev) { delete c[i].s; c.erase(c.begin() + i); break; }
+    c.push_back({dev, nrows, ncols, T, env, new PoissonSolver(nrows, ncols, T)});
+    return c.back().s;
+}
 }  // namespace cnv
 
 using namespace cnv;
@@ -118,6 +196,66 @@ int cnv_get_device(void)
 void cnv_device_synchronize(void) { CNV_CUDA_CHECK(cudaDeviceSynchronize()); }
 
 unsigned long long cnv_launch_count(void) { return (unsigned long long)total_launches(); }
+
+// Host memory for fields: page-locked and recycled when large (see HostPool).  Without a CUDA device it is plain heap
+// memory (this is storage, not compute: nothing here computes on the CPU).  Contents are NOT zeroed.
+void *cnv_host_alloc(size_t bytes)
+{
+    if (bytes == 0) bytes = 8;
+    HostPool &hp = host_pool();
+    const bool pin = bytes >= kPinThreshold && device_present();
+    void *p = nullptr;
+    if (pin) {
+        {
+            std::lock_guard<std::mutex> lk(hp.mu);
+            auto it = hp.free_pinned.find(bytes);
+            if (it != hp.free_pinned.end() && !it->second.empty()) {
+                p = it->second.back();
+                it->second.pop_back();
+                hp.pooled_bytes -= bytes;
+            }
+        }
+        if (!p && cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+    }
+    bool pinned = p != nullptr;
+    if (!p) p = std::malloc(bytes);
+    if (!p) return nullptr;
+    std::lock_guard<std::mutex> lk(hp.mu);
+    hp.live[p] = {bytes, pinned};
+    return p;
+}
+void cnv_host_free(void *p)
+{
+    if (!p) return;
+    HostPool &hp = host_pool();
+    size_t bytes = 0;
+    bool pinned = false, known = false;
+    {
+        std::lock_guard<std::mutex> lk(hp.mu);
+        auto it = hp.live.find(p);
+        if (it != hp.live.end()) {
+            known = true; bytes = it->second.first; pinned = it->second.second;
+            hp.live.erase(it);
+            if (pinned && hp.pooled_bytes + bytes <= kPoolLimit) {
+                hp.free_pinned[bytes].push_back(p);
+                hp.pooled_bytes += bytes;
+                return;
+            }
+        }
+    }
+    if (known && pinned) cudaFreeHost(p);
+    else std::free(p);
+}
+/* 1 if p points into a live page-locked block of cnv_host_alloc */
+int cnv_host_is_pinned(const void *p)
+{
+    HostPool &hp = host_pool();
+    std::lock_guard<std::mutex> lk(hp.mu);
+    for (const auto &kv : hp.live)
+        if (kv.second.second && (const char *)p >= (const char *)kv.first && (const char *)p < (const char *)kv.first + kv.second.first)
+            return 1;
+    return 0;
+}
 
 // src/main.c:134 with the truncated PI of include/poisson.h:9
 double cnv_sor_beta(int nx, int ny) { return 0.5 * (2 / (1 + sin(PI / (nx + 1))) + 2 / (1 + sin(PI / (ny + 1)))); }
@@ -252,10 +390,6 @@ void cnv_poisson_plan_info(const cnv_poisson *p, long long *out)
     out[0] = g.WS; out[1] = g.HX; out[2] = g.Wout; out[3] = g.Hout; out[4] = g.nstrips; out[5] = g.nchunks;
     out[6] = pass_threads(p->s->T(), g.WS); out[7] = (long long)pass_smem_bytes(p->s->T(), g.WS);
     out[8] = p->s->T(); out[9] = p->s->consts().pow2;
-    const TileGeom &t = p->s->tile_geom();
-    out[10] = p->s->tiled() ? 1 : 0;
-    out[11] = t.KP; out[12] = t.M; out[13] = t.NSEG; out[14] = t.OW; out[15] = t.OH; out[16] = t.ntx; out[17] = t.nty;
-    if (p->s->tiled()) { out[6] = round_up(t.KP * t.NSEG, 32); out[7] = (long long)tile_smem_bytes(t); }
 }
 int cnv_poisson_prepare(cnv_poisson *p, const double *f_dev, int ldf, double fsign, void *stream)
 {
@@ -283,6 +417,37 @@ int cnv_poisson_upload(cnv_poisson *p, const double *f_host, double fsign, void 
     p->s->peer_ready(st);
     count_launch(1);
     CNV_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+// Slab solvers: the OWNED rows of f from a host array (own_rows x ncols, dense; page-locked for a true DMA) straight into
+// the right-hand-side array, halo rows from the slab neighbours (the library's NCCL communicator, attached with
+// cnv_poisson_attach_comm), scaling in place, zero iterate -- no staging array, nothing synchronises.
+int cnv_poisson_upload_owned(cnv_poisson *p, const double *f_owned_host, double fsign, void *stream)
+{
+    const PassGeom &g = p->s->geom();
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool slab = g.own_lo > 0 || g.own_hi < g.nrows;
+    if (slab && !p->s->has_comm()) return 1;
+    p->s->peer_quiesce(st);
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(p->s->rhs() + (size_t)g.own_lo * g.ld, sizeof(double) * g.ld, f_owned_host,
+                                     sizeof(double) * g.ncols, sizeof(double) * g.ncols, g.own_hi - g.own_lo,
+                                     cudaMemcpyHostToDevice, st));
+    if (slab) p->s->exchange_halos(p->s->rhs(), g.HY, st);
+    launch_prep_rhs(p->s->rhs(), g.nrows, g.ncols, g.ld, fsign, p->s->consts().pscale, p->s->rhs(), p->s->buffer(0),
+                    p->s->buffer(1), g.ld, st);
+    p->s->zero_extra_buffer(st);
+    p->s->peer_ready(st);
+    count_launch(1);
+    CNV_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+// the owned rows of iterate buffer `which` into a host array (own_rows x ncols); valid once `stream` has drained
+int cnv_poisson_download_owned_async(cnv_poisson *p, int which, double *u_owned_host, void *stream)
+{
+    const PassGeom &g = p->s->geom();
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(u_owned_host, sizeof(double) * g.ncols, p->s->buffer(buf_index(p, which)) + (size_t)g.own_lo * g.ld,
+                                     sizeof(double) * g.ld, sizeof(double) * g.ncols, g.own_hi - g.own_lo, cudaMemcpyDeviceToHost,
+                                     (cudaStream_t)stream));
     return 0;
 }
 int cnv_poisson_solve(cnv_poisson *p, int itmax, double tol, void *stream, int *k, double *e, int *sweeps, int *passes,
@@ -358,6 +523,10 @@ int cnv_poisson_peer_import(cnv_poisson *p, int rank, int world, const unsigned 
     return p->s->peer_import(rank, world, handles, layout);
 }
 void cnv_poisson_peer_disable(cnv_poisson *p) { p->s->peer_disable(); }
+// end of the peer path: enqueue the quiesce wait (every push into this rank has landed) ...
+void cnv_poisson_peer_quiesce(cnv_poisson *p, void *stream) { p->s->peer_quiesce((cudaStream_t)stream); }
+// ... and, after a device synchronisation on every rank and a barrier of all ranks, unmap the peers' buffers
+void cnv_poisson_peer_close(cnv_poisson *p) { p->s->peer_close(); }
 int cnv_poisson_peer_trace(cnv_poisson *p, int passes) { return p->s->peer_trace_enable(passes); }
 void cnv_poisson_peer_trace_read(cnv_poisson *p, unsigned long long *out, long long n) { p->s->peer_trace_read(out, (size_t)n); }
 int cnv_poisson_peer_enabled(cnv_poisson *p) { return p->s->peer_enabled() ? 1 : 0; }
@@ -390,18 +559,34 @@ int cnv_poisson_host(const double *f, int nrows, int ncols, double dx, double dy
                      double *u, int *k, double *e, double *history)
 {
     require_device();
-    PoissonSolver s(nrows, ncols, T);
+    if (nrows < 3 || ncols < 3) {
+        std::printf("** Error: invalid parameter **\n");  // src/linearalg.c:58-62 wording
+        std::exit(1);
+    }
+    // solver object and its device arrays are kept between calls (one call per time step from the drop-in poisson_SOR_log);
+    // f goes straight into the solver's right-hand-side array (one pitched copy, DMA when f is page-locked: cnv_host_alloc /
+    // the drop-in allocm) and is scaled in place; psi comes straight out of the iterate buffer
+    PoissonSolver &s = *cached_solver(nrows, ncols, T);
     s.set_consts(dx, dy, beta);
-    DevArray df(nrows, ncols);
-    df.upload(f);
+    const int ld = s.ld();
+    cudaStream_t st = 0;
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(s.rhs(), sizeof(double) * ld, f, sizeof(double) * ncols, sizeof(double) * ncols, nrows,
+                                     cudaMemcpyHostToDevice, st));
     int buf = 0;
-    PoissonResult r = s.solve_from(df.p, df.ld, 1.0, itmax, tol, 0, &buf, history != nullptr);
-    CNV_CUDA_CHECK(cudaMemcpy2D(u, sizeof(double) * ncols, s.buffer(buf), sizeof(double) * s.ld(), sizeof(double) * ncols, nrows,
-                                cudaMemcpyDeviceToHost));
-    if (history) CNV_CUDA_CHECK(cudaMemcpy(history, s.history(), sizeof(double) * (size_t)r.sweeps, cudaMemcpyDeviceToHost));
+    PoissonResult r = s.solve_from(s.rhs(), ld, 1.0, itmax, tol, st, &buf, history != nullptr);
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(u, sizeof(double) * ncols, s.buffer(buf), sizeof(double) * ld, sizeof(double) * ncols, nrows,
+                                     cudaMemcpyDeviceToHost, st));
+    if (history) CNV_CUDA_CHECK(cudaMemcpyAsync(history, s.history(), sizeof(double) * (size_t)r.sweeps, cudaMemcpyDeviceToHost, st));
+    CNV_CUDA_CHECK(cudaStreamSynchronize(st));
     if (k) *k = r.k;
     if (e) *e = r.e;
     return r.status;
+}
+// drops the solver objects cnv_poisson_host keeps between calls (frees their device memory)
+void cnv_poisson_host_cache_clear(void)
+{
+    for (CachedSolver &c : solver_cache()) delete c.s;
+    solver_cache().clear();
 }
 
 // ---- time stepping -----------------------------------------------------------------------------

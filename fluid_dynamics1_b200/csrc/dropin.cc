@@ -1,35 +1,79 @@
 // dropin.cc -- libcnavier_dropin.so: the reference's C signatures (include/cnavier_dropin.h) on top of
-// the cnv_* C ABI.  Host mtrx arguments are gathered into dense row-major staging buffers, the GPU
-// entry point runs, results are scattered into freshly allocated caller-owned mtrx storage.
+// the cnv_* C ABI.  Host mtrx arguments are passed to the GPU entry points as they lie when they are contiguous (every mtrx
+// this library's allocm / initm creates is: one page-locked, recycled block), gathered into a staging block otherwise;
+// results are written straight into freshly allocated caller-owned mtrx storage.
 // Error behaviour mirrors the reference: message, then exit(1).
 #include <cfloat>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/cnavier_b200.h"
 
 namespace {
 
-std::vector<double> gather(mtrx A)
+// ---- field storage ------------------------------------------------------------------------------------------
+// allocm() below backs every mtrx with ONE contiguous block (rows[i] = block + i*n) from cnv_host_alloc: page-locked and
+// recycled when large.  A field that main.c builds with initm / receives from this library can therefore be handed to the
+// GPU as it lies (one DMA, no row-by-row staging); a mtrx assembled by other means (rows malloc'ed one by one, as the
+// reference's own allocm does, src/linearalg.c:66-79) is still accepted and gathered into a staging block.
+struct Block {
+    double *data;
+    size_t bytes;
+};
+std::mutex g_mu;
+std::unordered_map<double **, Block> &blocks()
 {
-    std::vector<double> h((size_t)A.m * A.n);
-    for (int i = 0; i < A.m; i++) std::memcpy(&h[(size_t)i * A.n], A.M[i], sizeof(double) * A.n);
-    return h;
+    static auto *b = new std::unordered_map<double **, Block>;
+    return *b;
 }
-void scatter(const std::vector<double> &h, mtrx A)
+
+bool contiguous(mtrx A)
 {
-    for (int i = 0; i < A.m; i++) std::memcpy(A.M[i], &h[(size_t)i * A.n], sizeof(double) * A.n);
+    for (int i = 1; i < A.m; i++)
+        if (A.M[i] != A.M[0] + (size_t)i * A.n) return false;
+    return true;
 }
-mtrx from_dense(const std::vector<double> &h, int m, int n)
+
+// dense row-major view of a mtrx: the mtrx's own storage when it is contiguous, a (pooled) staging copy otherwise
+struct Dense {
+    double *p;
+    bool staged;
+    mtrx src;
+    explicit Dense(mtrx A, bool copy_in = true) : p(nullptr), staged(false), src(A)
+    {
+        if (contiguous(A)) { p = A.M[0]; return; }
+        staged = true;
+        p = static_cast<double *>(cnv_host_alloc(sizeof(double) * (size_t)A.m * A.n));
+        if (!p) { std::printf("** Error: insufficient memory **"); std::exit(1); }
+        if (copy_in)
+            for (int i = 0; i < A.m; i++) std::memcpy(p + (size_t)i * A.n, A.M[i], sizeof(double) * A.n);
+    }
+    void copy_back() const
+    {
+        if (staged)
+            for (int i = 0; i < src.m; i++) std::memcpy(src.M[i], p + (size_t)i * src.n, sizeof(double) * src.n);
+    }
+    ~Dense() { if (staged) cnv_host_free(p); }
+    Dense(const Dense &) = delete;
+};
+
+mtrx new_mtrx(int m, int n)
 {
     mtrx A;
     A.M = allocm(m, n);
     A.m = m;
     A.n = n;
-    scatter(h, A);
+    return A;
+}
+mtrx from_dense(const std::vector<double> &h, int m, int n)
+{
+    mtrx A = new_mtrx(m, n);
+    std::memcpy(A.M[0], h.data(), sizeof(double) * (size_t)m * n);
     return A;
 }
 void log_to(FILE *f, const char *fmt, ...)
@@ -48,10 +92,11 @@ const char kItmax[] = "Error: maximum number of iterations achieved for Poisson 
 // to the FILE* only, and stay silent when it is NULL (src/poisson.c:24-32)
 mtrx solve(mtrx f, double dx, double dy, int itmax, double tol, double beta, FILE *log, bool to_stdout)
 {
-    std::vector<double> hf = gather(f), hu(hf.size());
+    Dense hf(f);
+    mtrx U = new_mtrx(f.m, f.n);  // caller-owned result (released with freem), written by the GPU path directly
     int k = 0;
     double e = 0;
-    const int status = cnv_poisson_host(hf.data(), f.m, f.n, dx, dy, itmax, tol, beta, 0, hu.data(), &k, &e, nullptr);
+    const int status = cnv_poisson_host(hf.p, f.m, f.n, dx, dy, itmax, tol, beta, 0, U.M[0], &k, &e, nullptr);
     if (status != 0) {
         if (to_stdout) std::printf("%s", kItmax);
         else log_to(log, "%s", kItmax);
@@ -59,7 +104,7 @@ mtrx solve(mtrx f, double dx, double dy, int itmax, double tol, double beta, FIL
     }
     if (to_stdout) std::printf(kSolved, k, e);
     else log_to(log, kSolved, k, e);
-    return from_dense(hu, f.m, f.n);
+    return U;
 }
 
 mtrx diff(int n, int o, double h, int deriv)
@@ -83,12 +128,16 @@ double **allocm(int m, int n)
         std::printf("** Error: invalid parameter **\n");
         std::exit(1);
     }
+    // one contiguous block behind the row table (see "field storage" above); freem() below is its counterpart.  The
+    // reference's pair (src/linearalg.c:53-99) mallocs and frees row by row; callers only ever go through
+    // allocm / freem and A.M[i][j], so the pair may choose its own backing store.
     double **rows = static_cast<double **>(std::malloc(sizeof(double *) * m));
-    if (!rows) { std::printf("** Error: insufficient memory **"); std::exit(1); }
-    for (int i = 0; i < m; i++) {
-        rows[i] = static_cast<double *>(std::malloc(sizeof(double) * n));  // one allocation per row: freem() contract
-        if (!rows[i]) { std::printf("** Error: insufficient memory **"); std::exit(1); }
-    }
+    const size_t bytes = sizeof(double) * (size_t)m * n;
+    double *data = rows ? static_cast<double *>(cnv_host_alloc(bytes)) : nullptr;
+    if (!rows || !data) { std::printf("** Error: insufficient memory **"); std::exit(1); }
+    for (int i = 0; i < m; i++) rows[i] = data + (size_t)i * n;
+    std::lock_guard<std::mutex> lk(g_mu);
+    blocks()[rows] = {data, bytes};
     return rows;
 }
 double **freem(mtrx A)
@@ -98,7 +147,15 @@ double **freem(mtrx A)
         std::printf("** Error: invalid parameter **\n");
         std::exit(1);
     }
-    for (int i = 0; i < A.m; i++) std::free(A.M[i]);
+    bool ours = false;
+    Block b = {nullptr, 0};
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = blocks().find(A.M);
+        if (it != blocks().end()) { ours = true; b = it->second; blocks().erase(it); }
+    }
+    if (ours) cnv_host_free(b.data);
+    else for (int i = 0; i < A.m; i++) std::free(A.M[i]);  // a mtrx built the reference's way: one malloc per row
     std::free(A.M);
     return nullptr;
 }
@@ -108,11 +165,8 @@ void zerosm(mtrx A)
 }
 mtrx initm(int m, int n)
 {
-    mtrx A;
-    A.M = allocm(m, n);
-    A.m = m;
-    A.n = n;
-    zerosm(A);
+    mtrx A = new_mtrx(m, n);
+    std::memset(A.M[0], 0, sizeof(double) * (size_t)m * n);
     return A;
 }
 mtrx eye(int n)
@@ -137,9 +191,7 @@ mtrx kronecker(mtrx A, mtrx B)
 {
     // the reference sizes the result A.n*B.n square and indexes blocks with A.n (src/linearalg.c:356,367)
     const int n = A.n * B.n;
-    mtrx C;
-    C.M = allocm(n, n);
-    C.m = C.n = n;
+    mtrx C = new_mtrx(n, n);
     for (int i = 0; i < n; i++)
         for (int j = 0; j < n; j++) C.M[i][j] = A.M[i / A.n][j / A.n] * B.M[i % B.n][j % B.n];
     return C;
@@ -197,29 +249,30 @@ mtrx Diff2(int n, int o, double dx) { return diff(n, o, dx, 2); }
 // ---- include/fluiddyn.h ---------------------------------------------------------------------------
 void euler(mtrx w, mtrx dwdx, mtrx dwdy, mtrx d2wdx2, mtrx d2wdy2, mtrx u, mtrx v, double Re, double dt)
 {
-    std::vector<double> hw = gather(w), a = gather(dwdx), b = gather(dwdy), c = gather(d2wdx2), d = gather(d2wdy2),
-                        hu = gather(u), hv = gather(v);
-    cnv_euler_host(hw.data(), a.data(), b.data(), c.data(), d.data(), hu.data(), hv.data(), w.m, w.n, Re, dt);
-    scatter(hw, w);
+    Dense hw(w), a(dwdx), b(dwdy), c(d2wdx2), d(d2wdy2), hu(u), hv(v);
+    cnv_euler_host(hw.p, a.p, b.p, c.p, d.p, hu.p, hv.p, w.m, w.n, Re, dt);
+    hw.copy_back();
 }
 mtrx continuity(mtrx dudx, mtrx dvdy)
 {
-    std::vector<double> a = gather(dudx), b = gather(dvdy), o(a.size());
-    cnv_continuity_host(a.data(), b.data(), dudx.m, dudx.n, o.data());
-    return from_dense(o, dudx.m, dudx.n);
+    Dense a(dudx), b(dvdy);
+    mtrx o = new_mtrx(dudx.m, dudx.n);
+    cnv_continuity_host(a.p, b.p, dudx.m, dudx.n, o.M[0]);
+    return o;
 }
 mtrx vorticity(mtrx first, mtrx second)
 {
-    std::vector<double> a = gather(first), b = gather(second), o(a.size());
-    cnv_vorticity_host(a.data(), b.data(), first.m, first.n, o.data());
-    return from_dense(o, first.m, first.n);
+    Dense a(first), b(second);
+    mtrx o = new_mtrx(first.m, first.n);
+    cnv_vorticity_host(a.p, b.p, first.m, first.n, o.M[0]);
+    return o;
 }
 
 // ---- include/poisson.h ----------------------------------------------------------------------------
 double error(mtrx u1, mtrx u2)
 {
-    std::vector<double> a = gather(u1), b = gather(u2);
-    return cnv_error_host(a.data(), b.data(), u1.m, u1.n);
+    Dense a(u1), b(u2);
+    return cnv_error_host(a.p, b.p, u1.m, u1.n);
 }
 mtrx poisson(mtrx f, double dx, double dy, int itmax, double tol) { return solve(f, dx, dy, itmax, tol, 1.0, nullptr, true); }
 mtrx poisson_SOR(mtrx f, double dx, double dy, int itmax, double tol, double beta)

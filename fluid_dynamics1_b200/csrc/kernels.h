@@ -5,10 +5,10 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "fd_coeffs.h"
 #include "poisson_plan.h"
-#include "poisson_tile.h"
 
 // The reference reports failures with a message and exit(1) (src/poisson.c:280-284,
 // src/linearalg.c:58-79); CUDA errors follow the same convention.
@@ -24,6 +24,9 @@
     } while (0)
 
 namespace cnv {
+
+constexpr int kMaxDevices = 64;
+int current_device_slot();  // cudaGetDevice, clamped to [0, kMaxDevices): index of per-device caches
 
 // A slab of a row-decomposed grid: the local array has nloc rows, local row 0 is global row grow0 of
 // gnrows; rows [own_lo, own_hi) (local) are owned, the others are halo rows.  Single GPU: {n, 0, n, 0, n}.
@@ -68,10 +71,6 @@ bool resident_plan(int nrows, int ncols, int ld, size_t smem_limit, ResidentGeom
 void launch_resident(const ResidentGeom &g, size_t smem, const RelaxConsts &rc, const double *psi0, const double *rhs, double *out,
                      PoissonCtl *ctl, double *hist, int itmax, double tol, cudaStream_t s);
 
-// ---- poisson_tile.cu: stationary-tile pass kernel for grids that fit shared memory / L2 ----
-void launch_tile_pass(const TileGeom &g, const RelaxConsts &rc, double *b0, double *b1, const double *rhs, PoissonCtl *ctl,
-                      double *partials, double *hist, double *norms, int fused, cudaStream_t s, const PeerLinks &L);
-
 // ---- poisson.cu ----
 struct PoissonResult {
     int status;  // 0 converged, 1 itmax reached (the reference exits the process here)
@@ -97,8 +96,6 @@ public:
     int ld() const { return geom_.ld; }
     int T() const { return T_; }
     const PassGeom &geom() const { return geom_; }
-    bool tiled() const { return use_tile_; }  // passes run the stationary-tile kernel (poisson_tile.cu)
-    const TileGeom &tile_geom() const { return tile_; }
     double *rhs() { return rhs_; }                // device, pitch ld(): pscale * f
     double *buffer(int i) { return buf_[i]; }     // the iterate buffers: 0, 1 (and 2 with the lagged peer decision)
     int num_buffers() const { return links_.enabled && links_.lag && buf_[2] ? 3 : 2; }
@@ -146,7 +143,8 @@ public:
     void peer_quiesce(cudaStream_t s);  // before re-initialising the iterate: every push launched so far has landed
     void peer_ready(cudaStream_t s);    // after re-initialising it: the neighbours may push into the new buffers
     bool peer_enabled() const { return links_.enabled != 0; }
-    void peer_disable() { links_.enabled = 0; }
+    void peer_disable() { peer_close(); }
+    void peer_close();  // unmap the peers' buffers (after quiesce + all-rank barrier, see poisson.cu)
     // diagnostics: record per-CTA timestamps of the first `passes` passes after every reset (tools/peer_trace.py)
     int peer_trace_enable(int passes);                       // returns CTAs per pass
     void peer_trace_read(unsigned long long *out, size_t n);  // n = passes * ctas * 6
@@ -154,8 +152,6 @@ public:
 private:
     int T_;
     PassGeom geom_;
-    TileGeom tile_ = {};
-    bool use_tile_ = false;
     RelaxConsts rc_;
     double *buf_[3] = {nullptr, nullptr, nullptr};
     bool lag_ = false;  // CNV_PEER_LAG=1: lagged stop decision on the peer path (three iterate buffers)
@@ -174,6 +170,8 @@ private:
     double *gather_ = nullptr;  // [world][8] norms of every rank
     int dist_passes_ = 0;       // passes enqueued since the last reset (static exchange pattern)
     PeerLinks links_ = {};
+    std::vector<void *> imported_;  // CUDA IPC mappings opened by peer_import
+    void release_imports();
     PeerMailbox *mailbox_ = nullptr;
     PoissonCtl *ctlbuf_ = nullptr;
     unsigned long long peer_gidx_ = 0;  // passes launched since peer_import (global pass index)

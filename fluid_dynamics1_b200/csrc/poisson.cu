@@ -14,12 +14,20 @@
 
 #include "kernels.h"
 #include "nccl_dl.h"
+#include "peer_device.cuh"
 
 namespace cnv {
 
 static size_t g_launches = 0;
 size_t total_launches() { return g_launches; }
 void count_launch(size_t n) { g_launches += n; }
+
+int current_device_slot()
+{
+    int dev = 0;
+    CNV_CUDA_CHECK(cudaGetDevice(&dev));
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
 
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -47,34 +55,11 @@ __device__ __forceinline__ void group_sums(double *sm, double acc, int g, int kk
     __syncthreads();
 }
 
-// ---- peer-memory helpers (multi-GPU): bounded spin-waits on system-scope flags ----
-__device__ __forceinline__ unsigned long long globaltimer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;  // a peer that is 4 s late is dead: never hang the GPU
-__device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned long long want)
-{
-    if (ld_acquire_sys(p) >= want) return true;
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(p) < want) {
-        if (globaltimer_ns() - t0 > kPeerTimeoutNs) return false;
-        __nanosleep(64);
-    }
-    return true;
-}
+// peer-memory helpers (multi-GPU: system-scope flags, bounded spin-waits): peer_device.cuh
+using peerdev::globaltimer_ns;
+using peerdev::report_error;
+using peerdev::st_release_sys;
+using peerdev::wait_ge;
 
 // Sum over the ranks (rank order: identical on every rank) of the norms pass `g` published in this rank's mailbox.
 // Returns false if a rank's flag did not arrive in time.
@@ -82,7 +67,7 @@ __device__ bool gather_norms(const PeerLinks &L, unsigned long long g, double *e
 {
     PeerMailbox *mb = L.mail[L.rank];
     for (int r = 0; r < L.world; r++)
-        if (!wait_ge(&mb->norm_flag[r], g + 1)) return false;  // pass g publishes the value g+1
+        if (!wait_ge(L, &mb->norm_flag[r], g + 1)) return false;  // pass g publishes the value g+1
     const int slot = (int)(g & (kNormSlots - 1));
     for (int i = 0; i < 8; i++) {
         double sum = 0.0;
@@ -104,7 +89,7 @@ __device__ PoissonCtl peer_state(const PeerLinks &L, int T, double *hist)
     if (!L.lag) {
         if (c.state != 0) return c;
         if (!gather_norms(L, L.gidx - 1, e)) {
-            atomicExch(&L.mail[L.rank]->error, 1ull);
+            report_error(L);
             c.state = 3;
             return c;
         }
@@ -122,7 +107,7 @@ __device__ PoissonCtl peer_state(const PeerLinks &L, int T, double *hist)
         if (ok) lag_final(c, L.pidx, e, T, hist);
     }
     if (!ok) {
-        atomicExch(&L.mail[L.rank]->error, 1ull);
+        report_error(L);
         c.state = 3;
     }
     return c;
@@ -169,7 +154,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
         if (need) {
             PeerMailbox *mb = L.mail[L.rank];
             for (int r = tid; r < L.world; r += blockDim.x)
-                if (!wait_ge(&mb->norm_flag[r], L.gidx - lagd + 1)) s_bad = 1;  // pass g publishes the value g+1
+                if (!wait_ge(L, &mb->norm_flag[r], L.gidx - lagd + 1)) s_bad = 1;  // pass g publishes the value g+1
             __syncthreads();
             const int slot = (int)((L.gidx - lagd) & (kNormSlots - 1));
             for (int i = tid; i < 8 * L.world; i += blockDim.x) s_nrm[i >> 3][i & 7] = *(volatile double *)&mb->norms[slot][i >> 3][i & 7];
@@ -184,7 +169,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
                     for (int r = 0; r < L.world; r++) sum = xadd(sum, s_nrm[r][g]);  // rank order: identical on every rank
                 e[g] = sum;
             }
-            if (need && s_bad) atomicExch(&L.mail[L.rank]->error, 1ull);
+            if (need && s_bad) report_error(L);
             const LagAction a = peer_advance(c, e, need, s_bad != 0, L.pidx, L.lag, T, first_cta ? hist : nullptr);
             s_ctl = c;
             s_act = a;
@@ -210,28 +195,34 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
 
     const CtaGeom G = cta_geom(p, blockIdx.x, blockIdx.y);
     if (PEER) {
+        __shared__ int s_inputs_ok;
         if (tid == 0) {
             PeerMailbox *mb = L.mail[L.rank];
             const bool push_down = L.rank > 0 && G.y0 < p.own_lo + p.HY;
             const bool push_up = L.rank < L.world - 1 && G.y1 > p.own_hi - p.HY;
             bool ok = true;
             // first pass of a solve: the neighbour must have finished zeroing the buffer this CTA pushes into
-            if (L.pidx == 0 && push_down) ok &= wait_ge(&mb->ready[0], L.epoch);
-            if (L.pidx == 0 && push_up) ok &= wait_ge(&mb->ready[1], L.epoch);
+            if (L.pidx == 0 && push_down) ok = ok && wait_ge(L, &mb->ready[0], L.epoch);
+            if (L.pidx == 0 && push_up) ok = ok && wait_ge(L, &mb->ready[1], L.epoch);
             // this CTA streams halo rows -> the neighbour's pushes of the previous pass must have landed (a redo
             // pass of the lagged machine re-reads an older buffer whose halos landed passes ago)
             if (s_act.kind == 1) {
-                if (L.rank > 0 && G.ylo < p.own_lo) ok &= wait_ge(&mb->halo_count[0], L.gidx * L.need_low);
-                if (L.rank < L.world - 1 && G.yhi >= p.own_hi) ok &= wait_ge(&mb->halo_count[1], L.gidx * L.need_high);
+                if (L.rank > 0 && G.ylo < p.own_lo) ok = ok && wait_ge(L, &mb->halo_count[0], L.gidx * L.need_low);
+                if (L.rank < L.world - 1 && G.yhi >= p.own_hi) ok = ok && wait_ge(L, &mb->halo_count[1], L.gidx * L.need_high);
             }
-            if (!ok) atomicExch(&mb->error, 1ull);
+            if (!ok) report_error(L);
+            s_inputs_ok = ok ? 1 : 0;
             if (trace) trace[2] = globaltimer_ns();
         }
         __syncthreads();
+        // a wait failed (a peer stopped responding): neither stream stale halos nor store into buffers the neighbour may be
+        // re-initialising.  The error flag is set in every rank's mailbox; the hosts abort at their next state read-back.
+        if (!s_inputs_ok) return;
     }
     StreamThread<T> st;
     stream_init<T>(st, p, G, sm, in, rhs, tid, blockDim.x);
-    if (kLean) { stream_set_sweeps<T>(st, nsw); stream_prezero<T>(st, sm); }
+    stream_set_sweeps<T>(st, nsw);
+    stream_prezero<T>(st, sm);
     const int TPG = p.WS / (2 * kPairs);
     const int kk = tid - st.g * TPG;
 
@@ -336,8 +327,14 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
 // peer path: state after `L.pidx` passes -> ctlbuf[pidx & 1] (what the host reads back); also reports timeouts
 __global__ void k_peer_finalize(const PeerLinks L, int T, double *hist)
 {
-    PoissonCtl c = peer_state(L, T, hist);
-    if (*(volatile unsigned long long *)&L.mail[L.rank]->error) c.state = 3;
+    PoissonCtl c;
+    if (*(volatile unsigned long long *)&L.mail[L.rank]->error) {  // a wait failed somewhere: do not wait for norms that never come
+        c = L.ctlbuf[0];
+        c.state = 3;
+    } else {
+        c = peer_state(L, T, hist);
+        if (*(volatile unsigned long long *)&L.mail[L.rank]->error) c.state = 3;
+    }
     L.ctlbuf[L.lag ? 2 : L.pidx & 1] = c;  // (lagged machine: slots 0/1 carry the chain X_p the passes read)
 }
 // peer path: this rank's iterate buffers are (re-)initialised for solve epoch L.epoch: tell both neighbours
@@ -353,9 +350,9 @@ __global__ void k_peer_quiesce(const PeerLinks L)
 {
     PeerMailbox *mb = L.mail[L.rank];
     bool ok = true;
-    if (L.rank > 0) ok &= wait_ge(&mb->halo_count[0], L.gidx * L.need_low);
-    if (L.rank < L.world - 1) ok &= wait_ge(&mb->halo_count[1], L.gidx * L.need_high);
-    if (!ok) atomicExch(&mb->error, 1ull);
+    if (L.rank > 0) ok = ok && wait_ge(L, &mb->halo_count[0], L.gidx * L.need_low);
+    if (L.rank < L.world - 1) ok = ok && wait_ge(L, &mb->halo_count[1], L.gidx * L.need_high);
+    if (!ok) report_error(L);
 }
 
 // multi-GPU: stopping decision from all-reduced norms (identical on every rank)
@@ -397,11 +394,14 @@ static void launch_pass(const PassGeom &g, const RelaxConsts &rc, double *b0, do
                         double *partials, double *hist, double *norms, int fused, int threads, size_t smem, cudaStream_t s,
                         const PeerLinks &L)
 {
-    static size_t configured = 48 * 1024;  // opt in to large dynamic shared memory (static smem counts against the 227 KB)
-    if (smem > configured) {
+    // opt in to large dynamic shared memory (static smem counts against the 227 KB).  Function attributes belong to the
+    // device context, so the cache is per device (cnv_set_device may switch between solvers of one process).
+    static size_t configured[kMaxDevices] = {};
+    size_t &conf = configured[current_device_slot()];
+    if (smem > 48 * 1024 && smem > conf) {
         CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_pass<T, POW2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_pass<T, POW2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        conf = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.nstrips, g.nchunks);
@@ -422,8 +422,6 @@ static void launch_pass(const PassGeom &g, const RelaxConsts &rc, double *b0, do
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int kTileAutoWaves = 0;  // default use of the tile kernel: grids of up to this many waves of tiles (0 = opt-in only)
-
 static int env_int(const char *name, int dflt)
 {
     const char *e = std::getenv(name);
@@ -463,17 +461,6 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
     }
     threads_ = pass_threads(T, geom_.WS);
     smem_ = pass_smem_bytes(T, geom_.WS);
-    // CNV_POISSON_TILE: 1 = stationary-tile kernel whenever a tile plan exists, 0 = never, default = by size
-    // (the tile kernel wins while the grid fits a few waves of tiles, see profiles/)
-    const int tile_mode = env_int("CNV_POISSON_TILE", -1);
-    if (tile_mode != 0 && T >= 2) {
-        double cost = 0;
-        if (tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, lim.num_sms, lim.smem_per_cta - 2560, &tile_, &cost,
-                      env_int("CNV_TILE_KP", 0), env_int("CNV_TILE_M", 0), env_int("CNV_TILE_NSEG", 0))) {
-            const long tiles = (long)tile_.ntx * tile_.nty;
-            use_tile_ = tile_mode == 1 || tiles <= kTileAutoWaves * lim.num_sms;
-        }
-    }
     std::memset(&rc_, 0, sizeof rc_);
     const size_t bytes = (size_t)nrows * ld * sizeof(double);
     for (int i = 0; i < 2; i++) {
@@ -482,8 +469,7 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
     }
     CNV_CUDA_CHECK(cudaMalloc(&rhs_, bytes));
     CNV_CUDA_CHECK(cudaMemset(rhs_, 0, bytes));
-    size_t npart = (size_t)geom_.nstrips * geom_.nchunks * T;
-    if (use_tile_ && npart < (size_t)tile_.ntx * tile_.nty * 8) npart = (size_t)tile_.ntx * tile_.nty * 8;
+    const size_t npart = (size_t)geom_.nstrips * geom_.nchunks * T;
     CNV_CUDA_CHECK(cudaMalloc(&partials_, sizeof(double) * npart));
     CNV_CUDA_CHECK(cudaMalloc(&norms_, sizeof(double) * 8));
     CNV_CUDA_CHECK(cudaMemset(norms_, 0, sizeof(double) * 8));
@@ -495,6 +481,7 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
 
 PoissonSolver::~PoissonSolver()
 {
+    peer_close();  // (a caller that shares buffers with peers quiesces + synchronises all ranks first, see peer_close)
     cudaFree(buf_[0]); cudaFree(buf_[1]); if (buf_[2]) cudaFree(buf_[2]); cudaFree(rhs_); cudaFree(partials_); cudaFree(norms_); cudaFree(ctl_);
     if (hist_) cudaFree(hist_);
     if (gather_) cudaFree(gather_);
@@ -541,7 +528,8 @@ PoissonCtl PoissonSolver::read_ctl(cudaStream_t s)
     CNV_CUDA_CHECK(cudaEventRecord(ev_, s));
     CNV_CUDA_CHECK(cudaEventSynchronize(ev_));
     if (h_ctl_->state == 3) {
-        std::printf("** Error: multi-GPU peer exchange timed out (a neighbour rank stopped responding) **\n");
+        std::printf("** Error: multi-GPU peer exchange timed out (a rank stopped responding for more than %.0f s; "
+                    "CNV_PEER_TIMEOUT_MS) **\n", links_.timeout_ns * 1e-9);
         std::fflush(stdout);
         std::exit(1);
     }
@@ -578,15 +566,6 @@ void PoissonSolver::peer_export(unsigned char *out256)
 void PoissonSolver::peer_push_counts(int rank, int world, long long *low, long long *high) const
 {
     long long lo = 0, hi = 0;
-    if (use_tile_ && env_int("CNV_TILE_PEER", 0) != 0 && !lag_) {  // tiles whose output rows reach into the boundary band
-        for (int by = 0; by < tile_.nty; by++) {
-            const TileRows r = tile_rows_of(tile_, by);
-            if (rank > 0 && r.pa[0] < r.pb[0]) lo += tile_.ntx;
-            if (rank < world - 1 && r.pa[1] < r.pb[1]) hi += tile_.ntx;
-        }
-        *low = lo; *high = hi;
-        return;
-    }
     for (int by = 0; by < geom_.nchunks; by++) {
         const CtaGeom G = cta_geom(geom_, 0, by);
         if (rank > 0 && G.y0 < geom_.own_lo + geom_.HY) lo += geom_.nstrips;
@@ -604,15 +583,24 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
     links_.lag = lag_ ? 1 : 0;
     links_.buf2 = buf_[2];
     const int nbuf = lag_ ? 3 : 2;
+    // every mapping opened here is remembered, so that the error paths below and peer_close() release it again
     auto open = [&](const unsigned char *h64, void **out) {
         cudaIpcMemHandle_t h;
         std::memcpy(&h, h64, 64);
-        return cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        if (cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
+        imported_.push_back(*out);
+        return true;
+    };
+    auto fail = [&](int code) {
+        cudaGetLastError();
+        release_imports();
+        std::memset(&links_, 0, sizeof links_);
+        return code;
     };
     for (int r = 0; r < world; r++) {
         if (r == rank) { links_.mail[r] = mailbox_; continue; }
         void *ptr = nullptr;
-        if (!open(handles + 256 * r + 128, &ptr)) { cudaGetLastError(); return 2; }
+        if (!open(handles + 256 * r + 128, &ptr)) return fail(2);
         links_.mail[r] = (PeerMailbox *)ptr;
     }
     const int *me = layout + 4 * rank;
@@ -620,7 +608,7 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
         const int *nb = layout + 4 * (rank - 1);
         for (int b = 0; b < nbuf; b++) {
             void *ptr = nullptr;
-            if (!open(handles + 256 * (rank - 1) + 64 * (b == 2 ? 3 : b), &ptr)) { cudaGetLastError(); return 3; }
+            if (!open(handles + 256 * (rank - 1) + 64 * (b == 2 ? 3 : b), &ptr)) return fail(3);
             links_.down_buf[b] = (double *)ptr;
         }
         links_.down_delta = (long long)(nb[1] - me[0]) * geom_.ld;  // my row own_lo + i -> its row own_hi' + i
@@ -630,7 +618,7 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
         const int *nb = layout + 4 * (rank + 1);
         for (int b = 0; b < nbuf; b++) {
             void *ptr = nullptr;
-            if (!open(handles + 256 * (rank + 1) + 64 * (b == 2 ? 3 : b), &ptr)) { cudaGetLastError(); return 4; }
+            if (!open(handles + 256 * (rank + 1) + 64 * (b == 2 ? 3 : b), &ptr)) return fail(4);
             links_.up_buf[b] = (double *)ptr;
         }
         links_.up_delta = (long long)(nb[0] - me[1]) * geom_.ld;    // my row own_hi - HY + i -> its row own_lo'' - HY + i
@@ -638,13 +626,31 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
     }
     links_.push_low = (unsigned long long)me[2];
     links_.push_high = (unsigned long long)me[3];
+    // spin-wait bound: a rank whose host is late (writing output, paused) is not dead; a dead one must not hang the GPU
+    links_.timeout_ns = (unsigned long long)std::max(1, env_int("CNV_PEER_TIMEOUT_MS", 300000)) * 1000000ull;
     links_.enabled = 1;
-    // the in-kernel peer exchange is part of the streaming kernel; the stationary-tile kernel has it as well (plain stop
-    // machine only), opt-in until it has run on hardware: CNV_TILE_PEER=1 together with CNV_POISSON_TILE=1
-    if (!(use_tile_ && env_int("CNV_TILE_PEER", 0) != 0 && !lag_)) use_tile_ = false;
     distributed_ = true;
     peer_gidx_ = 0;
     return 0;
+}
+
+void PoissonSolver::release_imports()
+{
+    for (void *p : imported_) cudaIpcCloseMemHandle(p);
+    imported_.clear();
+    cudaGetLastError();
+}
+
+// End of the peer path for this solver.  Protocol for the caller (SlabPoisson.close, the multi-GPU driver): every rank calls
+// peer_quiesce + a device synchronisation (all pushes INTO this rank have landed, all passes OF this rank -- trailing no-op
+// passes included, which still write flags into every mailbox -- have drained), then a barrier of all ranks, then
+// peer_close(); only after that may any rank free the buffers its peers had mapped.
+void PoissonSolver::peer_close()
+{
+    if (!links_.enabled && imported_.empty()) return;
+    cudaDeviceSynchronize();
+    release_imports();
+    std::memset(&links_, 0, sizeof links_);
 }
 
 int PoissonSolver::peer_trace_enable(int passes)
@@ -696,10 +702,6 @@ void PoissonSolver::enqueue_passes(int npasses, cudaStream_t s)
             L.epoch = peer_epoch_;
         } else if (L.trace) {
             L.pidx = trace_pass_++;  // diagnostics only (tools/peer_trace.py --single)
-        }
-        if (use_tile_) {
-            launch_tile_pass(tile_, rc_, buf_[0], buf_[1], rhs_, ctl_, partials_, hist, norms_, fused, s, L);
-            continue;
         }
 #define CNV_PASS(TT)                                                                                                     \
     if (T_ == TT) {                                                                                                      \

@@ -70,12 +70,9 @@ inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, i
 {
     // rows taken off a boundary chunk whose CTAs exchange with a neighbour slab (see PassGeom::trim_lo)
     if (trim < 0) trim = std::getenv("CNV_POISSON_TRIM") ? std::atoi(std::getenv("CNV_POISSON_TRIM")) : 32;
-    // ... and rows ADDED to a chunk at the domain boundary: it has no halo rows on that side, i.e. 2T fewer rows to stream
-    // than an interior chunk of the same height (per-CTA trace: 3 % shorter at 4096^2); equalising the streamed rows
-    // shortens the longest CTA
-    // (CNV_POISSON_EDGE=<rows> overrides the 2T, 0 switches it off: A/B switch)
-    const int edge = std::getenv("CNV_POISSON_EDGE") ? std::atoi(std::getenv("CNV_POISSON_EDGE")) : 2 * T;
-    const int want_lo = own_lo > 0 ? trim : -edge, want_hi = own_hi < nrows ? trim : -edge;
+    // (Making the chunks at the domain boundary 2T rows TALLER -- they have no halo rows to stream on that side -- was
+    // tried and measured slower on B200: 4.99e11 vs 5.05e11 cell-updates/s at 4096^2, profiles/ab_r2.md; removed.)
+    const int want_lo = own_lo > 0 ? trim : 0, want_hi = own_hi < nrows ? trim : 0;
     PassGeom best;
     std::memset(&best, 0, sizeof best);
     double best_cost = 1e300;
@@ -114,7 +111,7 @@ inline PassGeom make_plan(int nrows, int ncols, int ld, int grow0, int gnrows, i
                     tl = th = 0;
                     Hout = (own + nchunks - 1) / nchunks;
                 }
-                nchunks = (own + tl + (th < 0 ? th : 0) + Hout - 1) / Hout;  // the last chunk absorbs the remainder (it is -th rows taller)
+                nchunks = (own + tl + Hout - 1) / Hout;  // the last chunk absorbs the remainder
                 const long ctas = (long)nstrips * nchunks;
                 const long nwaves = (ctas + slots - 1) / slots;
                 const int steps = Hout + 2 * HY + kSkew * T + 6;  // halo + pipeline fill + fixed per-CTA start-up cost

@@ -222,10 +222,11 @@ template <bool POW2>
 static void launch_resident_t(const ResidentGeom &g, size_t smem, const RelaxConsts &rc, const double *psi0, const double *rhs,
                               double *out, PoissonCtl *ctl, double *hist, int itmax, double tol, cudaStream_t s)
 {
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
+    static size_t configured[kMaxDevices] = {};  // per device: function attributes belong to the device context
+    size_t &conf = configured[current_device_slot()];
+    if (smem > 48 * 1024 && smem > conf) {
         CNV_CUDA_CHECK(cudaFuncSetAttribute(k_poisson_resident<POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        conf = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.C);

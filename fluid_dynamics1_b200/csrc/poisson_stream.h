@@ -37,17 +37,6 @@ constexpr int kLand = kSkew > 4 ? 1 : 0;  // input rows must have landed this ma
 constexpr int kPairs = 2;  // 4 measured slower on B200 (128 registers + spills, 12 warps/SM: 47 vs 36 us/sweep at 4096^2)
 static_assert(kPairs % 2 == 0, "pairs are moved as 16-byte vectors");
 constexpr int ring_rows(int T) { return kSkew * T + kPrefetch - (kSkew > 4 ? 1 : 0); }
-// Experimental leaner step body (build with -DCNV_STREAM_LEAN; `make lean` -> libcnavier_b200_lean.so, selected at run time
-// by CNV_LIB=lean): one range test selects an "interior" body without per-row range checks for the norm and the
-// write-back, and the L1 norm is accumulated as acc += (|d0| + |d1|) per colour (a 2-long dependent chain instead of
-// 4 adds + 2 selects at the end of every step).  The iterate is bit-identical; only the association of the norm sum
-// differs (1e-16 relative).  Not measured yet (profiles/analysis_r1.md, items 2 and 3).
-#ifdef CNV_STREAM_LEAN
-constexpr bool kLean = true;
-#else
-constexpr bool kLean = false;
-#endif
-
 struct PassGeom {
     // local array: nrows x ncols doubles with pitch ld; row 0 is global row grow0 of gnrows
     int nrows, ncols, ld, grow0, gnrows;
@@ -236,7 +225,7 @@ struct StreamThread {
     int vmask;           // bit 2p / 2p+1: even / odd column of pair k0+p updatable
     bool colown, allvalid;
     bool mask_path;      // warp-uniform: some lane of this warp owns a column that must not be updated (see stream_step)
-    int int_lo; unsigned int_span;  // kLean: steps r in [int_lo, int_lo + int_span] have both rows updatable AND inside [y0, y1)
+    int int_lo; unsigned int_span;  // steps r in [int_lo, int_lo + int_span] have both rows updatable AND inside [y0, y1)
     // h[(PH - a) & 3] = N loaded a steps ago, rr[(PH - a) & 3] = red results of a steps ago (a = 0: this step);
     // compile-time indices, so both stay in registers and no register moves are needed to age them
     vecP h[4], rr[4];
@@ -304,7 +293,7 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.acc = 0.0;
 }
 
-// kLean: the steps in which this thread's red row q = r-1-dq and black row q-2 are both updatable and both inside the
+// The steps in which this thread's red row q = r-1-dq and black row q-2 are both updatable and both inside the
 // CTA's output rows [y0, y1) -- there the norm and the write-back need no range checks (nsw = sweeps of this pass)
 template <int T>
 CNV_HD void stream_set_sweeps(StreamThread<T> &s, int nsw)
@@ -327,14 +316,11 @@ CNV_HD void stream_load_row(const StreamThread<T> &s, double *sm, int slot, long
             const double *g = s.lptr[j] - back_elems;
             cp_async8(sm, slot + s.ldE[j], g);
             cp_async8(sm, slot + s.ldO[j], g + 1);
-        } else if (!kLean && s.lzero[j]) {  // (kLean: zero-filled once for all ring slots, stream_prezero)
-            sts1(sm, slot + s.ldE[j], 0.0);
-            sts1(sm, slot + s.ldO[j], 0.0);
-        }
+        }  // (columns outside the array: zero-filled once for all ring slots, stream_prezero)
     }
 }
 
-// kLean: columns outside the local array (strips hanging over the domain edge) hold zeros in every ring slot for the
+// Columns outside the local array (strips hanging over the domain edge) hold zeros in every ring slot for the
 // whole pass -- nobody ever stores anything else there (their update mask is 0, so a store writes back the loaded 0) --
 // so they are filled once here instead of once per streamed row.  Call before stream_prologue; the first CTA barrier of
 // the step loop orders these stores before any read.
@@ -373,6 +359,10 @@ CNV_HD void stream_prologue(const StreamThread<T> &s, double *sm)
 // Loads and arithmetic are unconditional so that the four cell updates of a step interleave; validity
 // (Dirichlet ring, halo edges, pipeline fill/drain) is applied by selects only on the slow path -- threads
 // whose four columns are all updatable take the select-free path whenever both rows are updatable.
+// One range test (int_lo / int_span, stream_set_sweeps) selects the "interior" body: both rows updatable and inside
+// the CTA's output rows, so the norm and the write-back need no per-row checks; the L1 norm is accumulated as
+// acc += (|d0| + |d1|) per colour (a 2-long dependent chain).  Measured on B200 against the per-row-checked body it
+// replaced: 5.20e11 vs 4.99e11 cell-updates/s at 4096^2 (profiles/ab_r2.md).
 constexpr int rot4(int j, int ph) { return (j - ph) & 3; }
 
 template <int T, bool POW2, int PH>
@@ -413,7 +403,7 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         const double Eb = typeR ? bb.v[i] : (i == kPairs - 1 ? xb : bb.v[i + 1]);
         m.v[i] = relax<POW2>(Nb.v[i], Sb.v[i], Eb, Wb, ownb.v[i], Pb.v[i], rc);
     }
-    if (kLean && (unsigned)(r - s.int_lo) <= s.int_span) {
+    if ((unsigned)(r - s.int_lo) <= s.int_span) {
         // interior: both rows updatable and inside the output rows -- no per-row range checks at all
         if (s.mask_path) {
 #pragma unroll
@@ -473,25 +463,15 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         }
         // L1 update norm of this level (non-updated cells contribute exactly 0)
         if (s.colown) {
-            if (kLean) {  // same association as the interior body: acc + (|d0| + |d1|) per colour; acc + 0.0 is exact
-                double dr = 0.0, db = 0.0;
+            // same association as the interior body: acc + (|d0| + |d1|) per colour; acc + 0.0 is exact
+            double dr = 0.0, db = 0.0;
 #pragma unroll
-                for (int i = 0; i < kPairs; i++) {
-                    dr = i == 0 ? fabs(xsub(n.v[i], own.v[i])) : xadd(dr, fabs(xsub(n.v[i], own.v[i])));
-                    db = i == 0 ? fabs(xsub(m.v[i], ownb.v[i])) : xadd(db, fabs(xsub(m.v[i], ownb.v[i])));
-                }
-                s.acc = xadd(s.acc, (q >= s.y0 && q < s.y1) ? dr : 0.0);
-                s.acc = xadd(s.acc, (qb >= s.y0 && qb < s.y1) ? db : 0.0);
-            } else {
-                if (q >= s.y0 && q < s.y1) {
-#pragma unroll
-                    for (int i = 0; i < kPairs; i++) s.acc = xadd(s.acc, fabs(xsub(n.v[i], own.v[i])));
-                }
-                if (qb >= s.y0 && qb < s.y1) {
-#pragma unroll
-                    for (int i = 0; i < kPairs; i++) s.acc = xadd(s.acc, fabs(xsub(m.v[i], ownb.v[i])));
-                }
+            for (int i = 0; i < kPairs; i++) {
+                dr = i == 0 ? fabs(xsub(n.v[i], own.v[i])) : xadd(dr, fabs(xsub(n.v[i], own.v[i])));
+                db = i == 0 ? fabs(xsub(m.v[i], ownb.v[i])) : xadd(db, fabs(xsub(m.v[i], ownb.v[i])));
             }
+            s.acc = xadd(s.acc, (q >= s.y0 && q < s.y1) ? dr : 0.0);
+            s.acc = xadd(s.acc, (qb >= s.y0 && qb < s.y1) ? db : 0.0);
         }
         // ---- write back: the black row of the last level is final; its red cells are r2 ----
         if (s.sact && qb >= s.y0 && qb < s.y1) {
@@ -569,6 +549,7 @@ struct PeerLinks {
     // halos landed, stream done, push done, exit; null in production
     unsigned long long *trace;
     int trace_passes;
+    unsigned long long timeout_ns;  // bound of every spin-wait on a peer flag (CNV_PEER_TIMEOUT_MS)
 };
 
 // ---- solver state machine (one instance per solve, device resident) ---------------------------

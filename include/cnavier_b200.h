@@ -28,6 +28,12 @@ unsigned long long cnv_launch_count(void); /* kernels launched by this library s
 int cnv_set_device(int device);           /* one process per GPU: bind this library to a device */
 int cnv_get_device(void);
 void cnv_device_synchronize(void);
+/* Host memory for fields (what the drop-in allocm / freem of include/linearalg.h:13-15 are backed by; the reference
+ * allocates and frees every field once per call, src/linearalg.c:53-99).  Blocks of >= 1 MiB are page-locked and
+ * recycled through size-keyed free lists (page-locking 134 MB costs more than a solve); contents are not zeroed. */
+void *cnv_host_alloc(size_t bytes);
+void cnv_host_free(void *p);
+int cnv_host_is_pinned(const void *p);
 
 /* ---- scalars of the driver: src/main.c:134 (beta, truncated PI), :162/:276 (step count) ------- */
 double cnv_sor_beta(int nx, int ny);
@@ -64,6 +70,10 @@ int cnv_pressure_rhs_host(const double *u, const double *v, int nrows, int ncols
 int cnv_poisson_host(const double *f, int nrows, int ncols, double dx, double dy, int itmax, double tol, double beta,
                      int T, double *u, int *k, double *e, double *history /* NULL or itmax doubles */);
 
+/* cnv_poisson_host keeps its solver objects (device arrays, launch plan, pass-count predictor) between calls, the last
+ * two grid shapes per device; this releases them. */
+void cnv_poisson_host_cache_clear(void);
+
 /* Device-resident solver object (benchmarks, time stepping, multi-GPU). */
 typedef struct cnv_poisson cnv_poisson;
 cnv_poisson *cnv_poisson_create(int nrows, int ncols, int T);
@@ -77,11 +87,14 @@ double *cnv_poisson_rhs_ptr(cnv_poisson *p);              /* device: prepared ri
 double *cnv_poisson_buf_ptr(cnv_poisson *p, int which);   /* device: iterate buffers 0/1 (2: lagged peer decision) */
 int cnv_poisson_num_buffers(cnv_poisson *p);              /* 2, or 3 once the peer path runs with CNV_PEER_LAG=1 */
 double *cnv_poisson_norms_ptr(cnv_poisson *p);            /* device: T per-sweep norms of the last pass */
-/* out[0..17] = WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, T, pow2-path flag (streaming kernel);
-   tiled (1: passes run the stationary-tile kernel), KP, M, NSEG, OW, OH, ntx, nty (its tile shape) */
+/* out[0..9] = WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, T, pow2-path flag of the streaming kernel's plan */
 void cnv_poisson_plan_info(const cnv_poisson *p, long long *out);
 /* stage a host right-hand side f (nrows x ncols, dense) and zero the iterate; fsign = -1 solves with -f */
 int cnv_poisson_upload(cnv_poisson *p, const double *f_host, double fsign, void *stream);
+/* slab solvers: the OWNED rows (own_rows x ncols, dense, ideally page-locked) into the right-hand-side array, halo rows from
+ * the slab neighbours over the attached communicator, scaled in place, iterate zeroed; returns 1 without a communicator */
+int cnv_poisson_upload_owned(cnv_poisson *p, const double *f_owned_host, double fsign, void *stream);
+int cnv_poisson_download_owned_async(cnv_poisson *p, int which, double *u_owned_host, void *stream);
 /* same from a device array with pitch ldf */
 int cnv_poisson_prepare(cnv_poisson *p, const double *f_dev, int ldf, double fsign, void *stream);
 /* run to convergence / itmax (synchronises).  Returns 0 / 1 as cnv_poisson_host. */
@@ -121,8 +134,8 @@ void cnv_poisson_exchange_halos(cnv_poisson *p, double *field_dev, int depth, vo
  * pushes in the neighbours' mailboxes, publishes its per-sweep norms in every rank's mailbox, and every CTA of the next
  * pass derives the stop decision itself.  Setup: every rank exports 256 bytes (IPC handles of iterate buffers 0 and 1,
  * of its mailbox, and of iterate buffer 2 or zeros) and its push counts; the caller all-gathers them (world x 256 bytes;
- * world x 4 ints: own_lo, own_hi, push_low, push_high) and every rank imports.  All spin-waits time out after 4 s
- * (message + exit(1)).
+ * world x 4 ints: own_lo, own_hi, push_low, push_high) and every rank imports.  All spin-waits are bounded
+ * (CNV_PEER_TIMEOUT_MS, default 300000; message + exit(1) on every rank once one of them gives up).
  * CNV_PEER_LAG=1 (read at export time, must agree on all ranks; opt-in): lagged stop decision -- a pass needs the other
  * ranks' norms of the pass BEFORE the previous one only, so passes no longer rendezvous; three iterate buffers rotate,
  * results are bit-identical (state machine: csrc/poisson_stream.h lag_fold / lag_action).  The result buffer index
@@ -131,6 +144,11 @@ void cnv_poisson_peer_export(cnv_poisson *p, unsigned char *out256);
 void cnv_poisson_peer_push_counts(cnv_poisson *p, int rank, int world, long long *low, long long *high);
 int cnv_poisson_peer_import(cnv_poisson *p, int rank, int world, const unsigned char *handles, const int *layout);
 void cnv_poisson_peer_disable(cnv_poisson *p);
+/* Tear-down, in this order on EVERY rank: cnv_poisson_peer_quiesce(stream); synchronise the device; barrier of all ranks;
+ * cnv_poisson_peer_close() (unmaps the neighbours' buffers); only then cnv_poisson_destroy.  A rank that frees its buffers
+ * while a neighbour's trailing passes still write flags or halo rows into them faults that neighbour. */
+void cnv_poisson_peer_quiesce(cnv_poisson *p, void *stream);
+void cnv_poisson_peer_close(cnv_poisson *p);
 int cnv_poisson_peer_enabled(cnv_poisson *p);
 /* diagnostics of the peer path: per-CTA globaltimer stamps (start, state known, halos landed, stream done, push done,
  * exit) of the first `passes` passes after a reset; returns the CTAs per pass.  Read passes*ctas*6 values back. */

@@ -147,6 +147,23 @@ class Port:
         fail = self.L.orc_run(C.byref(P), cfg["ui"], cfg["vi"], nsteps, u, v, w, psi, ks, es)
         return dict(u=u, v=v, w=w, psi=psi, k=ks, e=es, failed_step=fail)
 
+    def run_diag(self, cfg: dict, nsteps: int, redblack=True):
+        """run() one orc_step at a time, also returning the per-step continuity max / min (src/main.c:387-408)."""
+        shp = (cfg["nx"], cfg["ny"])
+        u, v, w, psi = (np.zeros(shp) for _ in range(4))
+        u[1:-1, 1:-1] = cfg["ui"]
+        v[1:-1, 1:-1] = cfg["vi"]
+        out = dict(k=[], e=[], cont_max=[], cont_min=[], failed_step=0)
+        for t in range(nsteps):
+            r = self.step(cfg, u, v, w, psi, redblack)
+            for key in ("k", "e", "cont_max", "cont_min"):
+                out[key].append(r[key])
+            if r["status"]:
+                out["failed_step"] = t + 1
+                break
+        out.update(u=u, v=v, w=w, psi=psi)
+        return out
+
     def step(self, cfg: dict, u, v, w, psi, redblack=True):
         P = self.params(cfg, redblack)
         k, e, mx, mn = C.c_int(), C.c_double(), C.c_double(), C.c_double()
@@ -288,4 +305,14 @@ def parse_poisson_log(text: str):
         if line.startswith("Poisson equation solved with"):
             parts = line.split()
             out.append((int(parts[4]), parts[-1]))
+    return out
+
+
+def parse_continuity_log(text: str):
+    """[(max_string, min_string)] from the 'Continuity max: X | Continuity min: Y | ...' lines (src/main.c:400-408)."""
+    out = []
+    for line in text.splitlines():
+        if line.startswith("Continuity max:"):
+            parts = line.split()
+            out.append((parts[2], parts[6]))
     return out

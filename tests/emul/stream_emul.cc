@@ -12,7 +12,6 @@
 #include <vector>
 
 #include "../../fluid_dynamics1_b200/csrc/poisson_plan.h"
-#include "../../fluid_dynamics1_b200/csrc/poisson_tile.h"
 
 using namespace cnv;
 
@@ -31,7 +30,7 @@ static void run_pass(const PassGeom &p, const RelaxConsts &rc, const double *in,
             for (auto &x : sm) x = std::nan("");
             const CtaGeom G = cta_geom(p, bx, by);
             for (int t = 0; t < NT; t++) stream_init<T>(st[t], p, G, sm.data(), in, rhs, t, NT);
-            if (kLean) for (int t = 0; t < NT; t++) { stream_set_sweeps<T>(st[t], nsw); stream_prezero<T>(st[t], sm.data()); }
+            for (int t = 0; t < NT; t++) { stream_set_sweeps<T>(st[t], nsw); stream_prezero<T>(st[t], sm.data()); }
             for (int t = 0; t < NT; t++) stream_prologue<T>(st[t], sm.data());
             for (int r = st[0].ybase; r <= st[0].rend; r += 4) {
                 // --- barrier before every step ---
@@ -44,87 +43,7 @@ static void run_pass(const PassGeom &p, const RelaxConsts &rc, const double *in,
         }
 }
 
-// stationary-tile kernel (poisson_tile.h): the same phases as k_poisson_tile, a barrier between them
-template <int M, bool POW2>
-static void run_tile_pass(const TileGeom &g, const RelaxConsts &rc, const double *in, const double *rhs, double *out, int nsw,
-                          double *norms)
-{
-    const int NT = g.KP * g.NSEG;
-    std::vector<double> sm(tile_smem_bytes(g) / sizeof(double));
-    std::vector<TileThread<M>> th(NT);
-    for (int s = 0; s < 8; s++) norms[s] = 0.0;
-    for (int by = 0; by < g.nty; by++)
-        for (int bx = 0; bx < g.ntx; bx++) {
-            for (auto &x : sm) x = std::nan("");
-            for (int t = 0; t < NT; t++) tile_load<M>(th[t], g, bx, by, t, sm.data(), in, rhs);
-            const int par0 = (g.grow0 + g.own_lo + by * g.OH - g.HT) & 1;
-            for (int s = 0; s < nsw; s++) {
-                for (int t = 0; t < NT; t++) {
-                    if (par0 == 0) tile_half_sweep<M, POW2, 0>(th[t], rc, sm.data()); else tile_half_sweep<M, POW2, 1>(th[t], rc, sm.data());
-                }
-                for (int t = 0; t < NT; t++) {
-                    if (par0 == 0) tile_half_sweep<M, POW2, 1>(th[t], rc, sm.data()); else tile_half_sweep<M, POW2, 0>(th[t], rc, sm.data());
-                }
-                for (int t = 0; t < NT; t++) { norms[s] += th[t].acc; th[t].acc = 0.0; }
-            }
-            for (int t = 0; t < NT; t++) tile_store<M>(th[t], out);
-        }
-}
-
 extern "C" {
-
-// tile plan only: KP, M, NSEG, OW, OH, ntx, nty, smem bytes in out[8]; returns 0 if a plan exists
-int emul_tile_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T, int fkp, int fm, int fnseg,
-                   long *out)
-{
-    TileGeom g;
-    double cost = 0;
-    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, &cost, fkp, fm, fnseg)) return -1;
-    out[0] = g.KP; out[1] = g.M; out[2] = g.NSEG; out[3] = g.OW; out[4] = g.OH; out[5] = g.ntx; out[6] = g.nty;
-    out[7] = (long)tile_smem_bytes(g);
-    return 0;
-}
-
-// slab geometry of tile row `by` (poisson_tile.h tile_rows_of, the kernel's own code): y0, y1, rlo, rhi, pa0, pb0, pa1, pb1
-int emul_tile_rows(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T, int by, int *out)
-{
-    TileGeom g;
-    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, nullptr)) return -1;
-    const TileRows r = tile_rows_of(g, by);
-    out[0] = r.y0; out[1] = r.y1; out[2] = r.rlo; out[3] = r.rhi; out[4] = r.pa[0]; out[5] = r.pb[0]; out[6] = r.pa[1]; out[7] = r.pb[1];
-    return 0;
-}
-
-// the tile planner's cost estimate per sweep (arbitrary units), < 0 if no plan exists
-double emul_tile_cost(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T)
-{
-    TileGeom g;
-    double cost = 0;
-    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, &cost)) return -1.0;
-    return cost;
-}
-
-// one pass of the tile kernel's schedule (see emul_pass for the arguments); fkp/fm/fnseg pin the tile shape
-int emul_tile_pass(int T, int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int fkp, int fm, int fnseg,
-                   double dx, double dy, double beta, int mode, const double *in, const double *f, double *out, int nsw,
-                   double *norms)
-{
-    TileGeom g;
-    if (!tile_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, T, 148, 224 * 1024, &g, nullptr, fkp, fm, fnseg)) return -1;
-    RelaxConsts rc = make_relax_consts(dx, dy, beta);
-    if (mode == 1) { rc.pow2 = 0; rc.pscale = rc.cf; }
-    std::vector<double> rhs((size_t)nrows * ld);
-    for (size_t i = 0; i < rhs.size(); i++) rhs[i] = rc.pscale * f[i];
-#define RUNT(MM)                                                                          \
-    if (g.M == MM) {                                                                      \
-        if (rc.pow2) run_tile_pass<MM, true>(g, rc, in, rhs.data(), out, nsw, norms);     \
-        else run_tile_pass<MM, false>(g, rc, in, rhs.data(), out, nsw, norms);            \
-        return 0;                                                                         \
-    }
-    RUNT(6) RUNT(8) RUNT(10) RUNT(12) RUNT(14) RUNT(16)
-#undef RUNT
-    return -2;
-}
 
 // plan only: returns WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, trim_lo, trim_hi in out[10]
 void emul_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int T, int force_ws,
@@ -227,7 +146,6 @@ int emul_pass_sweeps(int sweeps, int redo, int itmax, int T)
     return pass_sweeps(c, T);
 }
 
-int emul_is_lean() { return kLean ? 1 : 0; }
 
 // Markstein division vs hardware division: returns the number of mismatches
 long emul_check_div(double d, const double *a, long n)

@@ -4,8 +4,8 @@ container (needs /root/reference and oracle/_ref built by `make -C oracle`):
     python tests/golden/make_golden.py
 
 Outputs (all small, committed):
-  ref_logs.json            per-step Poisson sweep counts (logged k = sweeps-1) and 7-digit residual
-                           strings parsed from the reference's shipped run logs
+  ref_logs.json            per-step Poisson sweep counts (logged k = sweeps-1), 7-digit residual strings and the
+                           7-digit "Continuity max / min" strings parsed from the reference's shipped run logs
                            (/root/reference/output/logs/testRun{NOOMP,OMP,NOOMPHIGHRES,OMPHIGHRES}.txt)
   fields_default_rb.npz    psi,w,u,v (raw fp64) after steps 0, 10, 20 of config_default.txt run by the
                            unmodified reference built with -DOPENMP_ENABLED (red-black SOR), + its k/e log
@@ -36,8 +36,11 @@ def logs():
     for name in ("testRunNOOMP", "testRunOMP", "testRunNOOMPHIGHRES", "testRunOMPHIGHRES"):
         with open(os.path.join(REFLOGS, name + ".txt")) as f:
             pl = api.parse_poisson_log(f.read())
-        res[name] = {"k": [k for k, _ in pl], "e": [e for _, e in pl]}
-        print(name, len(pl), "poisson lines")
+        with open(os.path.join(REFLOGS, name + ".txt")) as f:
+            cl = api.parse_continuity_log(f.read())
+        res[name] = {"k": [k for k, _ in pl], "e": [e for _, e in pl],
+                     "cont_max": [a for a, _ in cl], "cont_min": [b for _, b in cl]}
+        print(name, len(pl), "poisson lines,", len(cl), "continuity lines")
     with open(os.path.join(OUT, "ref_logs.json"), "w") as f:
         json.dump(res, f)
 
@@ -73,6 +76,8 @@ def sine():
 
 if __name__ == "__main__":
     logs()
+    if sys.argv[1:] == ["logs"]:
+        sys.exit(0)
     sine()
     fields(dict(api.CONFIG_DEFAULT), 21, "fields_default_rb.npz")
     fields(dict(api.CONFIG_DEFAULT, poisson_tol=1e-11, poisson_max_it=100000, output_interval=2), 3,

@@ -84,20 +84,3 @@ def test_lagged_peer_time_stepping_and_repeated_solves(world):
     assert "SLAB SIM CHECK PASSED" in _torchrun("slab_sim_gpu_check.py", [128, 4], world, 29770 + world, "peer", LAG)
     assert "STRESS PASSED" in _torchrun("slab_stress.py", [world * 100, 96, 4, 12], world, 29780 + world, "peer", LAG)
     assert "STRESS PASSED" in _torchrun("slab_stress.py", [1024, 1024, 8, 4], world, 29790 + world, "peer", LAG)
-
-
-# The peer exchange inside the stationary-tile kernel (CNV_POISSON_TILE=1 + CNV_TILE_PEER=1) was also written after the round's
-# GPU budget was spent (CPU evidence: tests/test_lag_protocol.py::test_plain_peer_machine_with_tile_kernel).  Opt-in like the
-# lagged decision: CNV_TEST_TILE_PEER=1.
-_tile_peer = pytest.mark.skipif(os.environ.get("CNV_TEST_TILE_PEER", "0") != "1", reason="tile kernel + peer exchange: opt-in (CNV_TEST_TILE_PEER=1)")
-TILE_PEER = {"CNV_POISSON_TILE": "1", "CNV_TILE_PEER": "1"}
-
-
-@_tile_peer
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_tile_peer_poisson_bitwise(world):
-    if _ngpus() < world:
-        pytest.skip(f"needs {world} GPUs")
-    assert "SLAB CHECK PASSED" in _torchrun("slab_gpu_check.py", [world * 64, 96, 2], world, 29850 + world, "peer", TILE_PEER)
-    assert "SLAB CHECK PASSED" in _torchrun("slab_gpu_check.py", [1024, 1024, 4], world, 29860 + world, "peer", TILE_PEER)
-    assert "STRESS PASSED" in _torchrun("slab_stress.py", [1024, 1024, 4, 4], world, 29870 + world, "peer", TILE_PEER)

@@ -17,32 +17,27 @@ ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _EMUL = {}
 
 
-def _load_emul(variant):
-    """The schedule emulator, compiled from the kernel's own header; "lean" = the experimental step body
-    (-DCNV_STREAM_LEAN, csrc/poisson_stream.h kLean; libcnavier_b200_lean.so on the GPU side)."""
-    if variant in _EMUL:
-        return _EMUL[variant]
-    so = os.path.join(ROOT, "tests", "emul", "libstream_emul.so" if variant == "default" else "libstream_emul_lean.so")
+def _load_emul():
+    """The schedule emulator, compiled from the kernel's own header (csrc/poisson_stream.h)."""
+    if "e" in _EMUL:
+        return _EMUL["e"]
+    so = os.path.join(ROOT, "tests", "emul", "libstream_emul.so")
     src = os.path.join(ROOT, "tests", "emul", "stream_emul.cc")
     hdrs = [os.path.join(ROOT, "fluid_dynamics1_b200", "csrc", h) for h in ("poisson_stream.h", "poisson_plan.h", "exact.h")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(x) for x in [src] + hdrs):
-        subprocess.run(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17"] +
-                       (["-DCNV_STREAM_LEAN"] if variant == "lean" else []) + [src, "-o", so], check=True)
+        subprocess.run(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", src, "-o", so], check=True)
     E = C.CDLL(so)
-    assert E.emul_is_lean() == (1 if variant == "lean" else 0)
-    _EMUL[variant] = E
+    _EMUL["e"] = E
     return E
 
 
-@pytest.fixture(scope="module", params=["default", "lean"])
-def emul(request):
-    E = _load_emul(request.param)
+@pytest.fixture(scope="module")
+def emul():
+    E = _load_emul()
     E.emul_pass.argtypes = [C.c_int] * 10 + [C.c_double] * 3 + [C.c_int, dp, dp, dp, C.c_int, dp]
     E.emul_plan.argtypes = [C.c_int] * 10 + [np.ctypeslib.ndpointer(dtype=np.int64)]
     E.emul_decide.argtypes = [ip, dp, dp, C.c_int, C.c_void_p]
     E.emul_pass_sweeps.argtypes = [C.c_int] * 4
-    E.emul_tile_pass.argtypes = [C.c_int] * 11 + [C.c_double] * 3 + [C.c_int, dp, dp, dp, C.c_int, dp]
-    E.emul_tile_plan.argtypes = [C.c_int] * 11 + [np.ctypeslib.ndpointer(dtype=np.int64)]
     E.emul_check_div.restype = C.c_long
     E.emul_check_div.argtypes = [C.c_double, dp, C.c_long]
     return E
@@ -81,60 +76,6 @@ def test_stream_schedule_bitwise_vs_oracle(emul, port, shape, T):
             got, want, gn, on = _emul_sweeps(emul, port, n, m, T, 3, mode, ws, ch)
             assert got.tobytes() == want.tobytes(), (shape, T, mode, ws, ch)
             np.testing.assert_allclose(gn, on, rtol=1e-13)
-
-
-def _emul_tile_sweeps(E, port, n, m, T, npass, mode, shape=(0, 0, 0), dx=None, dy=None, seed=0, last_nsw=None):
-    rng = np.random.default_rng(seed)
-    dx = dx or 1.0 / n
-    dy = dy or 1.0 / m
-    beta = port.beta(n, m)
-    f = rng.standard_normal((n, m))
-    ld = (m + 15) // 16 * 16
-    fp = np.zeros((n, ld))
-    fp[:, :m] = f
-    a, b = np.zeros((n, ld)), np.zeros((n, ld))
-    got_norms, total = [], 0
-    for ip in range(npass):
-        nsw = last_nsw if (last_nsw and ip == npass - 1) else T
-        norms = np.zeros(8)
-        assert E.emul_tile_pass(T, n, m, ld, 0, n, 0, n, *shape, dx, dy, beta, mode, a, fp, b, nsw, norms) == 0
-        a, b = b, a
-        got_norms += list(norms[:nsw])
-        total += nsw
-    u, onorms = port.poisson_sweeps(f, dx, dy, total, beta)
-    return a[:, :m], u, np.array(got_norms), onorms
-
-
-@pytest.mark.parametrize("T", [2, 4, 6, 8])
-@pytest.mark.parametrize("shape", [(64, 64), (40, 72), (100, 100), (33, 47), (131, 90)])
-def test_tile_schedule_bitwise_vs_oracle(emul, port, shape, T):
-    """The stationary-tile kernel's schedule (register-resident thread columns, 2T-cell halo on all four sides,
-    one barrier per half-sweep) == T plain red-black sweeps of the oracle, bit for bit; automatic and pinned tile
-    shapes (several tiles in x and y, odd and even tile origins), both arithmetic paths, short last pass."""
-    n, m = shape
-    for mode in (0, 1):
-        for tshape in ((0, 0, 0), (2 * T + 6, 6, 0), (2 * T + 9, 8, 0), (2 * T + 5, 10, 0), (2 * T + 8, 12, 0), (2 * T + 4, 14, 0), (2 * T + 4, 16, 0)):
-            got, want, gn, on = _emul_tile_sweeps(emul, port, n, m, T, 3, mode, tshape, last_nsw=max(1, T - 1))
-            assert got.tobytes() == want.tobytes(), (shape, T, mode, tshape)
-            np.testing.assert_allclose(gn, on, rtol=1e-13)
-
-
-def test_tile_schedule_nonuniform_spacing(emul, port):
-    got, want, gn, on = _emul_tile_sweeps(emul, port, 50, 38, 4, 2, 0, dx=0.013, dy=0.02)
-    assert got.tobytes() == want.tobytes()
-    np.testing.assert_allclose(gn, on, rtol=1e-13)
-
-
-def test_tile_planner_properties(emul):
-    for nrows, ncols in [(64, 64), (128, 128), (256, 256), (1024, 1024), (544, 4096), (2048, 2048), (33, 47)]:
-        for T in (2, 4, 6, 8):
-            o = np.zeros(8, dtype=np.int64)
-            assert emul.emul_tile_plan(nrows, ncols, (ncols + 15) // 16 * 16, 0, nrows, 0, nrows, T, 0, 0, 0, o) == 0
-            KP, M, NSEG, OW, OH, ntx, nty, smem = (int(x) for x in o)
-            assert M % 2 == 0 and OW == 2 * KP - 4 * T and OH == NSEG * M - 4 * T and OW > 0 and OH > 0
-            assert (KP * NSEG + 31) // 32 * 32 <= (640 if M <= 10 else 448)
-            assert smem <= 224 * 1024
-            assert ntx * OW >= ncols and nty * OH >= nrows
 
 
 @pytest.mark.parametrize("trim", [0, 8, 11])
@@ -226,14 +167,8 @@ def test_schedules_fuzz_vs_oracle(emul, port, seed, monkeypatch):
         a[:, :cols] = u0[g0:g0 + nloc]
         fp[:, :cols] = f[g0:g0 + nloc]
         norms = np.zeros(8)
-        tile = T >= 2 and rng.integers(0, 3) == 0
-        if tile:
-            rc = emul.emul_tile_pass(T, nloc, cols, ld, g0, gn, hlo, hlo + own, 0, 0, 0, dx, dy, beta, mode, a, fp, b, nsw, norms)
-            if rc != 0:
-                continue                                 # grids too small for any tile plan use the streaming kernel
-        else:
-            assert emul.emul_pass(T, nloc, cols, ld, g0, gn, hlo, hlo + own, ws, ch, dx, dy, beta, mode, a, fp, b, nsw, norms) == 0
-        where = dict(case=case, tile=bool(tile), T=T, own=own, cols=cols, lower=lower, upper=upper, ws=ws, ch=ch, mode=mode, nsw=nsw)
+        assert emul.emul_pass(T, nloc, cols, ld, g0, gn, hlo, hlo + own, ws, ch, dx, dy, beta, mode, a, fp, b, nsw, norms) == 0
+        where = dict(case=case, T=T, own=own, cols=cols, lower=lower, upper=upper, ws=ws, ch=ch, mode=mode, nsw=nsw)
         assert b[hlo:hlo + own, :cols].tobytes() == want[g0 + hlo:g0 + hlo + own].tobytes(), where
         if not (lower or upper):
             np.testing.assert_allclose(norms[:nsw], wn, rtol=1e-12, err_msg=str(where))
@@ -258,7 +193,7 @@ def test_planner_properties(emul):
             # chunks tile the rows: first = Hout - trim_lo, interior = Hout, the last one takes the remainder
             last = nrows - ((nchunks - 1) * Hout - tlo) if nchunks > 1 else nrows
             assert Hout - tlo >= 1 and 1 <= last <= Hout - thi + nchunks, (nrows, ncols, T, Hout, nchunks, tlo, thi)
-            assert tlo in (0, -2 * T) and thi in (0, -2 * T)   # whole domain: boundary chunks are 2T rows taller or untouched
+            assert tlo == 0 and thi == 0                       # whole domain: no chunk next to a neighbour slab
             assert threads == T * WS // 4 and threads <= (640 if T >= 6 else 320)
             assert smem <= 227 * 1024 - 1024
 
@@ -336,12 +271,6 @@ def test_cabi_exports_every_declared_symbol():
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert dropin_decl <= exported, dropin_decl - exported
     assert L.cnv_device_count() >= 0 and b"sm_100a" in L.cnv_version()
-    # the experimental build variant (CNV_LIB=lean) exports the same ABI
-    lean = os.path.join(os.path.dirname(_lib.LIB_PATH), "libcnavier_b200_lean.so")
-    if os.path.exists(lean):
-        out = subprocess.run(["nm", "-D", "--defined-only", lean], capture_output=True, text=True).stdout
-        exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
-        assert declared <= exported, declared - exported
 
 
 def test_cabi_scalars_and_coefficients_on_cpu(port):

@@ -30,17 +30,13 @@ def E():
     lib.emul_lag_final.argtypes = [ip, dp, C.c_int, dp, C.c_int, C.c_void_p]
     lib.emul_peer_needs_norms.argtypes = [ip, dp, C.c_int, C.c_int]
     lib.emul_peer_advance.argtypes = [ip, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip]
-    lib.emul_tile_pass.argtypes = [C.c_int] * 11 + [C.c_double] * 3 + [C.c_int, dp, dp, dp, C.c_int, dp]
-    lib.emul_tile_plan.argtypes = [C.c_int] * 11 + [np.ctypeslib.ndpointer(dtype=np.int64)]
-    lib.emul_tile_rows.argtypes = [C.c_int] * 9 + [ip]
     return lib
 
 
 class Rank:
-    def __init__(self, E, r, world, rows, cols, T, f, itmax, tol, lag=1, tile=False):
+    def __init__(self, E, r, world, rows, cols, T, f, itmax, tol, lag=1):
         self.E, self.r, self.world, self.T = E, r, world, T
         self.lag, self.lagd, self.nbuf = lag, (2 if lag else 1), (3 if lag else 2)
-        self.tile = tile  # passes by the stationary-tile kernel, pushes with ITS per-tile-row geometry (tile_rows_of)
         self.rows, self.cols = rows, cols
         self.grow0, self.nloc, self.own_lo, self.own_hi, _, _ = slab_layout(rows, world, r, T)
         self.ld = (cols + 15) // 16 * 16
@@ -120,41 +116,15 @@ class Rank:
                 if 0 <= nb < self.world and kind == 1:
                     assert ranks[nb].p >= p - self.lagd + 1, "push into a buffer the neighbour has not finished reading"
             geo = (self.nloc, self.cols, self.ld, self.grow0, self.rows, self.own_lo, self.own_hi)
-            if self.tile:
-                rc = self.E.emul_tile_pass(T, *geo, 0, 0, 0, dx, dy, beta, 0, self.bufs[bi], self.floc, self.bufs[bo], nsw, norms)
-            else:
-                rc = self.E.emul_pass(T, *geo, 0, int(os.environ.get("CNV_TEST_CHUNKS", "0")), dx, dy, beta, 0, self.bufs[bi],
-                                      self.floc, self.bufs[bo], nsw, norms)
+            rc = self.E.emul_pass(T, *geo, 0, int(os.environ.get("CNV_TEST_CHUNKS", "0")), dx, dy, beta, 0, self.bufs[bi],
+                                  self.floc, self.bufs[bo], nsw, norms)
             assert rc == 0
-            if self.tile:
-                # the kernel's pushes, tile row by tile row: rows [pa, pb) of side 0 go to the lower neighbour's high halo
-                # (my row own_lo + i -> its row own_hi' + i), of side 1 to the upper neighbour's low halo
-                plan = np.zeros(8, dtype=np.int64)
-                assert self.E.emul_tile_plan(*geo, T, 0, 0, 0, plan) == 0
-                ntx, nty, ow = int(plan[5]), int(plan[6]), int(plan[3])
-                c1 = min(ntx * ow, self.ld)
-                pushed = [0, 0]
-                for by in range(nty):
-                    tr = np.zeros(8, dtype=np.int32)
-                    assert self.E.emul_tile_rows(*geo, T, by, tr) == 0
-                    if self.r > 0 and tr[4] < tr[5]:
-                        nb = ranks[self.r - 1]
-                        d = nb.own_hi - self.own_lo
-                        nb.bufs[bo][tr[4] + d:tr[5] + d, :c1] = self.bufs[bo][tr[4]:tr[5], :c1]
-                        pushed[0] += int(tr[5] - tr[4])
-                    if self.r < self.world - 1 and tr[6] < tr[7]:
-                        nb = ranks[self.r + 1]
-                        d = (nb.own_lo - H) - (self.own_hi - H)
-                        nb.bufs[bo][tr[6] + d:tr[7] + d, :c1] = self.bufs[bo][tr[6]:tr[7], :c1]
-                        pushed[1] += int(tr[7] - tr[6])
-                assert pushed[0] == (H if self.r > 0 else 0) and pushed[1] == (H if self.r < self.world - 1 else 0)
-            else:
-                if self.r > 0:                     # my first owned rows -> the lower neighbour's high halo
-                    nb = ranks[self.r - 1]
-                    nb.bufs[bo][nb.own_hi:nb.own_hi + H] = self.bufs[bo][self.own_lo:self.own_lo + H]
-                if self.r < self.world - 1:        # my last owned rows -> the upper neighbour's low halo
-                    nb = ranks[self.r + 1]
-                    nb.bufs[bo][nb.own_lo - H:nb.own_lo] = self.bufs[bo][self.own_hi - H:self.own_hi]
+            if self.r > 0:                     # my first owned rows -> the lower neighbour's high halo
+                nb = ranks[self.r - 1]
+                nb.bufs[bo][nb.own_hi:nb.own_hi + H] = self.bufs[bo][self.own_lo:self.own_lo + H]
+            if self.r < self.world - 1:        # my last owned rows -> the upper neighbour's low halo
+                nb = ranks[self.r + 1]
+                nb.bufs[bo][nb.own_lo - H:nb.own_lo] = self.bufs[bo][self.own_hi - H:self.own_hi]
         if self.r > 0:
             ranks[self.r - 1].halo_passes[1] += 1
         if self.r < self.world - 1:
@@ -180,14 +150,14 @@ class Rank:
         return st[0], st[1]
 
 
-def lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed, ranks=None, fseed=11, lag=1, tile=False):
+def lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed, ranks=None, fseed=11, lag=1):
     rng = np.random.default_rng(seed)
     f = np.random.default_rng(fseed).standard_normal((rows, cols))
     dx, dy = 1.0 / cols, 1.0 / rows
     port = api.port()
     beta = port.beta(rows, cols)
     if ranks is None:
-        ranks = [Rank(E, r, world, rows, cols, T, f, itmax, tol, lag, tile) for r in range(world)]
+        ranks = [Rank(E, r, world, rows, cols, T, f, itmax, tol, lag) for r in range(world)]
     else:
         for k in ranks:
             k.new_solve(f, itmax, tol)
@@ -353,39 +323,22 @@ def test_plain_peer_machine_same_simulation(E, world, T):
     assert ints[0] == 2 and int(ints[2]) == 7 and full.tobytes() == want["u"].tobytes()
 
 
-@pytest.mark.parametrize("world,T", [(2, 2), (3, 2), (2, 4)])
-def test_plain_peer_machine_with_tile_kernel(E, world, T):
-    """The stationary-tile kernel inside the peer protocol (CNV_POISSON_TILE=1 + CNV_TILE_PEER=1): passes by the tile kernel's
-    own per-thread code, boundary rows pushed tile row by tile row with the kernel's own geometry (tile_rows_of): exactly the
-    2T boundary rows reach each neighbour, and field, iteration count and residual equal the single-domain oracle."""
-    rows, cols = 56 * world, 72
-    f = np.random.default_rng(11).standard_normal((rows, cols))
-    port = api.port()
-    for ksweep in range(2 * T, 3 * T + 1):
-        tol = port.poisson(f, 1.0 / cols, 1.0 / rows, ksweep + 1, 0.0, port.beta(rows, cols), redblack=True)["e"] * (1 + 1e-9)
-        ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, 5000, tol, [2], seed=ksweep, lag=0, tile=True)
-        assert ints[0] == 1 and int(ints[5]) == want["k"]
-        assert full.tobytes() == want["u"].tobytes()
-
-
 def test_peer_protocol_random_configurations(E):
-    """Seeded sweep over the whole protocol simulation: 2-4 ranks, T = 2/4/8, plain and lagged machine, streaming and tile
-    kernel passes, random tolerance (converging anywhere or hitting itmax) and random host batch sizes."""
+    """Seeded sweep over the whole protocol simulation: 2-4 ranks, T = 2/4/8, plain and lagged machine,
+    random tolerance (converging anywhere or hitting itmax) and random host batch sizes."""
     rng = np.random.default_rng(77)
     for case in range(24):
         world = int(rng.integers(2, 5))
         T = int(rng.choice([2, 4, 8]))
         lag = int(rng.integers(0, 2))
-        tile = bool(lag == 0 and T <= 4 and rng.integers(0, 3) == 0)
+        rng.integers(0, 3)                       # (keeps the seeded sequence of the cases below unchanged)
         rows = int(rng.integers(max(4 * T + 2, 24), 70)) * world
         cols = int(rng.integers(40, 90))
-        if tile:
-            rows, cols = max(rows, 56 * world), max(cols, 64)
         tol = float(10 ** rng.uniform(-3, 0.5))
         itmax = int(rng.choice([5000, 5000, 17, 40]))
         batches = [int(x) for x in rng.integers(1, 7, size=3)]
-        ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed=case, lag=lag, tile=tile, fseed=case)
-        where = dict(case=case, world=world, T=T, lag=lag, tile=tile, rows=rows, cols=cols, tol=tol, itmax=itmax, batches=batches)
+        ints, dbls, full, want, P = lagged_solve(E, rows, cols, T, world, itmax, tol, batches, seed=case, lag=lag, fseed=case)
+        where = dict(case=case, world=world, T=T, lag=lag, rows=rows, cols=cols, tol=tol, itmax=itmax, batches=batches)
         assert int(ints[0]) == (1 if want["status"] == 0 else 2), where
         assert full.tobytes() == want["u"].tobytes(), where
         if want["status"] == 0:

@@ -1,7 +1,7 @@
 """Device-time probe of the Poisson pass kernels: fixed sweeps on an nrows x ncols grid for several temporal block
 depths and plans.  Prints cell-updates/s and the fraction of the 24 B/cell HBM roofline.
 python tools/probe_poisson.py NROWS NCOLS "SPEC,SPEC,..." [sweeps]
-SPEC = T:WS:CHUNKS (streaming kernel; 0 = planner's choice) or tT:KP:M:NSEG (stationary-tile kernel)"""
+SPEC = T:WS:CHUNKS (streaming kernel; 0 = planner's choice)"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -15,11 +15,8 @@ except Exception:
     pass
 
 
-def run(nr, nc, T, ws=0, chunks=0, sweeps=256, reps=3, tile=None):
+def run(nr, nc, T, ws=0, chunks=0, sweeps=256, reps=3):
     os.environ["CNV_POISSON_WS"] = str(ws); os.environ["CNV_POISSON_CHUNKS"] = str(chunks)
-    os.environ["CNV_POISSON_TILE"] = "1" if tile else "0"
-    for k, v in zip(("KP", "M", "NSEG"), tile or (0, 0, 0)):
-        os.environ["CNV_TILE_" + k] = str(v)
     s = fd.PoissonSolver(nr, nc, T)
     s.set_consts(1.0 / nc, 1.0 / nc, fd.sor_beta(nc, nc))
     rng = np.random.default_rng(0)
@@ -36,11 +33,6 @@ def run(nr, nc, T, ws=0, chunks=0, sweeps=256, reps=3, tile=None):
     assert st["sweeps"] == sweeps, st
     cu = (nr - 2) * (nc - 2) * sweeps / best
     p = s.plan
-    if p["tiled"]:
-        print(f"{nr}x{nc} T={T} tile KP={p['KP']} M={p['M']} NSEG={p['NSEG']} out={p['OH']}x{p['OW']} ctas={p['ntx']}x{p['nty']} "
-              f"thr={p['threads']} smem={p['smem']//1024}K {best/sweeps*1e6:8.2f} us/sweep {cu:.3e} cu/s frac={cu*24/peak:.3f}", flush=True)
-        s.close()
-        return
     print(f"{nr}x{nc} T={T} WS={p['WS']} Hout={p['Hout']} ctas={p['nstrips']}x{p['nchunks']} thr={p['threads']} smem={p['smem']//1024}K "
           f"{best/sweeps*1e6:8.2f} us/sweep {cu:.3e} cu/s frac={cu*24/peak:.3f}", flush=True)
     s.close()
@@ -52,10 +44,6 @@ if __name__ == "__main__":
     sweeps = int(sys.argv[4]) if len(sys.argv) > 4 else 256
     for spec in specs.split(","):
         try:
-            if spec.startswith("t"):
-                T, kp, m, nseg = (int(x) for x in spec[1:].split(":"))
-                run(nr, nc, T, sweeps=sweeps, tile=(kp, m, nseg))
-                continue
             T, ws, ch = (int(x) for x in spec.split(":"))
             run(nr, nc, T, ws, ch, sweeps)
         except Exception as e:

@@ -7,9 +7,8 @@ import fluid_dynamics1_b200 as fd
 
 rng = np.random.default_rng(0)
 only = sys.argv[1] if len(sys.argv) > 1 else None
-for path, env in (("resident", dict(CNV_POISSON_RESIDENT="2", CNV_POISSON_TILE="0")),
-                  ("stream", dict(CNV_POISSON_RESIDENT="0", CNV_POISSON_TILE="0")),
-                  ("tile", dict(CNV_POISSON_RESIDENT="0", CNV_POISSON_TILE="1"))):
+for path, env in (("resident", dict(CNV_POISSON_RESIDENT="2")),
+                  ("stream", dict(CNV_POISSON_RESIDENT="0"))):
     if only and path != only:
         continue
     os.environ.update(env)
@@ -19,12 +18,12 @@ for path, env in (("resident", dict(CNV_POISSON_RESIDENT="2", CNV_POISSON_TILE="
     p = sim.pressure()
     print(path, "steps k =", list(r["k"]), "pressure k =", p["k"], flush=True)
     sim.close()
-    # a non-square general-arithmetic grid with several strips / chunks / tiles, fixed sweeps
+    # a non-square general-arithmetic grid with several strips / chunks, fixed sweeps
     for T in (4, 8):
         s = fd.PoissonSolver(150, 330, T)
         s.set_consts(0.01, 0.013, 1.7)
         s.upload(rng.standard_normal((150, 330)))
         res = s.solve(2 * T + 3, 0.0)
-        print(path, "T", T, "plan", {k: s.plan[k] for k in ("tiled", "WS", "nstrips", "nchunks", "ntx", "nty")}, "sweeps", res["sweeps"], flush=True)
+        print(path, "T", T, "plan", {k: s.plan[k] for k in ("WS", "nstrips", "nchunks")}, "sweeps", res["sweeps"], flush=True)
         s.close()
 print("SANITIZE WORKLOAD DONE")
