@@ -1,15 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the cnavier hot path on B200.
 
-Metric (BASELINE.json): Poisson cell-updates/s (and sweeps/s) against the HBM roofline.
-Workload at N GPUs: the 4096^2 Re=1000 lid-driven cavity grid (BASELINE config 4, the configuration
-the north_star target is quoted on; it fits one GPU), slab-decomposed over N GPUs by rows with a
-fixed 4096 x 4096 slab per GPU (weak scaling; `--scaling strong` keeps the total at 4096^2).
-A "step" = one fixed-sweep red-black SOR solve (`--sweeps`, default 1024) of lap(psi) = -w from a zero
-initial guess on a synthetic cavity-like vorticity field (zero guess + state reset are inside the
-timed region; no convergence exit: tol = 0, so no work is ever skipped).
+Metric (BASELINE.json): Poisson cell-updates/s (and sweeps/s) against the HBM roofline at 1/2/4/8 B200.
+A "step" = one fixed-sweep red-black SOR solve (`--sweeps`, default 1024) of lap(psi) = -w from a zero initial guess on a
+synthetic cavity-like vorticity field (zero guess + state reset are inside the timed region; tol = 0, so no work is ever
+skipped).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+Workloads (`--series auto`, the default):
+  N = 1   the 4096^2 Re=1000 cavity grid (BASELINE config 4, the configuration the north_star target is quoted on).
+  N > 1   headline `value`: the WEAK series on BASELINE config 5's per-GPU shape -- 2048 x 16384 rows per GPU, i.e. a
+          (2048 N) x 16384 grid that is exactly 16384^2 at N = 8;
+          `strong`: BASELINE config 4 itself, 4096^2 split over the N GPUs (strong scaling);
+          `weak_4096_rows_per_gpu`: a 4096 x 4096 slab per GPU (the series round 1 reported), side key only;
+          `weak_base_1gpu`: every rank alone on a 2048 x 16384 grid in the same run (the weak series' denominator).
+Every workload is verified after its timed loop (`parity_check`): a 24-sweep solve (3 passes) on the same data, every
+rank's owned rows bitwise against the oracle (oracle/liboracle.so, test infrastructure, outside every timed region).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (N > 1: under torch.distributed.run)
     python bench.py --impl reference ...                     # the reference's own CPU code (oracle/_ref)
 
 One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for the definitions.
@@ -32,17 +39,22 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 ALGO_BYTES_PER_CELL_SWEEP = 24.0  # read psi + read f + write psi
+NOISE_BLOCK = 256                 # rows per independently seeded noise block (any rank can regenerate any row range)
+PARITY_SWEEPS = 24
 
 
 def synthetic_vorticity(nrows, ncols, row0=0, total_rows=None, seed=1234):
-    """Deterministic cavity-like vorticity: strong near the moving lid (last row), smooth bulk, plus
-    small-scale noise so that no cell is trivially zero."""
+    """Deterministic cavity-like vorticity for global rows [row0, row0 + nrows) of a total_rows x ncols grid: strong near
+    the moving lid (last row), smooth bulk, plus small-scale noise so that no cell is trivially zero.  The noise is drawn
+    per block of 256 global rows, so a slab (or a slab plus neighbouring rows) sees exactly the values of the whole grid."""
     total_rows = total_rows or nrows
-    rng = np.random.default_rng(seed + row0)
     i = (np.arange(row0, row0 + nrows) / total_rows)[:, None]
     j = (np.arange(ncols) / ncols)[None, :]
     w = -40.0 * np.exp(-((1 - i) * 30.0)) * np.sin(np.pi * j) + 4.0 * np.sin(2 * np.pi * i) * np.sin(3 * np.pi * j)
-    w += 0.05 * rng.standard_normal((nrows, ncols))
+    for b in range(row0 // NOISE_BLOCK, (row0 + nrows - 1) // NOISE_BLOCK + 1):
+        blk = np.random.default_rng([seed, b, ncols]).standard_normal((NOISE_BLOCK, ncols))
+        lo, hi = max(row0, b * NOISE_BLOCK), min(row0 + nrows, (b + 1) * NOISE_BLOCK)
+        w[lo - row0:hi - row0] += 0.05 * blk[lo - b * NOISE_BLOCK:hi - b * NOISE_BLOCK]
     return np.ascontiguousarray(w)
 
 
@@ -54,6 +66,23 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def measured_traffic(nrows, ncols, T):
+    """DRAM bytes per pass launch from the committed ncu capture of exactly this shape and depth, else None."""
+    tp = os.path.join(ROOT, "profiles", "poisson_pass_traffic.json")
+    try:
+        d = json.load(open(tp))
+        return d.get("by_shape", {}).get(f"{nrows}x{ncols}:T{T}")
+    except Exception:
+        return None
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -110,237 +139,480 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def _config_name(n):
-    return {1024: "BASELINE config 3", 4096: "BASELINE config 4", 16384: "BASELINE config 5"}.get(n, "custom")
+def headline_shape(args, world):
+    """(total_rows, ncols, rows_per_gpu, scaling, description) of the workload `value` is measured on."""
+    if args.series == "auto" and world > 1:
+        return 2048 * world, 16384, 2048, "weak", (
+            f"{2048 * world}x16384 Re=5000 lid-driven cavity, red-black SOR Poisson solve (BASELINE config 5 grid: 2048 x 16384 rows "
+            f"per GPU, 16384^2 at 8 GPUs)")
+    n = args.n
+    name = {1024: "BASELINE config 3", 4096: "BASELINE config 4", 16384: "BASELINE config 5"}.get(n, "custom")
+    if args.scaling == "weak":
+        return n * world, n, n, "weak", (f"{n * world}x{n} Re={5000 if n == 16384 else 1000} lid-driven cavity, red-black SOR Poisson "
+                                         f"solve ({name} grid{' per GPU' if world > 1 else ''})")
+    return n, n, n // world, "strong", f"{n}x{n} Re={5000 if n == 16384 else 1000} lid-driven cavity, red-black SOR Poisson solve ({name} grid)"
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line: identical for both arms (--impl b200 / reference)."""
+    total_rows, ncols, rows_per, scaling, desc = headline_shape(args, world)
+    return {"workload": desc, "grid": [total_rows, ncols], "rows_per_gpu": rows_per, "sweeps_per_step": args.sweeps,
+            "gpus": world, "scaling": scaling,
+            "l2": ("inputs larger than L2 (3 x %.0f MB resident arrays per GPU vs 126 MB L2), no flush" if
+                   3 * rows_per * ncols * 8 > 126e6 else
+                   "arrays fit L2 at this slab size (3 x %.0f MB per GPU vs 126 MB L2): L2-resident run, no flush") %
+                  (rows_per * ncols * 8 / 1e6)}
+
+
+class Ctx:
+    """Per-process plumbing: torch for streams / events / torch.distributed, ctypes for the C ABI."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        import fluid_dynamics1_b200 as fd
+        from fluid_dynamics1_b200 import parallel
+        self.torch, self.dist, self.fd, self.parallel = torch, dist, fd, parallel
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+        fd.require_gpu()
+        torch.cuda.set_device(self.local_rank)
+        self.L = fd.lib()
+        self.L.cnv_set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.stream = torch.cuda.current_stream()
+        self.sp = C.c_void_p(self.stream.cuda_stream)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def max_over_ranks(self, vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def gather_floats(self, v):
+        if self.world == 1:
+            return [float(v)]
+        t = self.torch.zeros(self.world, device="cuda", dtype=self.torch.float64)
+        t[self.rank] = v
+        self.dist.all_reduce(t)
+        return t.tolist()
+
+    def all_ok(self, ok):
+        if self.world == 1:
+            return bool(ok)
+        t = self.torch.tensor([1 if ok else 0], device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+
+class PoissonRun:
+    """One Poisson workload: total_rows x ncols, slab-decomposed over ctx.world GPUs (world = 1: the whole grid), or --
+    `single=True` -- this rank alone on the whole grid while the other ranks do the same (weak-scaling denominator)."""
+
+    def __init__(self, ctx, total_rows, ncols, T, single=False):
+        fd = ctx.fd
+        self.ctx, self.total_rows, self.ncols = ctx, total_rows, ncols
+        self.world = 1 if single else ctx.world
+        self.dx = self.dy = 1.0 / ncols
+        self.beta = fd.sor_beta(ncols, ncols)
+        if self.world > 1:
+            self.slab = ctx.parallel.SlabPoisson(total_rows, ncols, T, ctx.rank, ctx.world, stream=ctx.sp)
+            self.slab.set_consts(self.dx, self.dy, self.beta)
+            self.solver = self.slab.solver
+            self.row0, self.own_rows = self.slab.row0, self.slab.own_rows
+        else:
+            self.slab = None
+            self.solver = fd.PoissonSolver(total_rows, ncols, T)
+            self.solver.set_consts(self.dx, self.dy, self.beta)
+            self.row0, self.own_rows = 0, total_rows
+        self.T = self.solver.T
+        self.plan = dict(self.solver.plan)
+        self.w_host = synthetic_vorticity(self.own_rows, ncols, self.row0, total_rows)
+        self.interior_cells = (total_rows - 2) * (ncols - 2)
+        self.pin_in = self.pin_out = None
+
+    # ---- resident-input steps (the `value` measurement) ----
+    def upload(self, host):
+        if self.slab is None:
+            self.solver.upload(host, -1.0, self.ctx.sp)  # f = -w (src/main.c:348)
+        else:
+            self.slab.upload_owned(host, -1.0)
+
+    def zero_and_run(self, sweeps, events=None):
+        """zero guess, reset the state machine, `sweeps` sweeps (tol = 0)."""
+        npass = (sweeps + self.T - 1) // self.T
+        sp, stream = self.ctx.sp, self.ctx.stream
+        if self.slab is None:
+            self.solver.L.cnv_poisson_prepare(self.solver.h, None, 0, 1.0, sp)  # f == NULL: only zero the iterate buffers
+            self.solver.reset(sweeps, 0.0, sp)
+        else:
+            self.slab.zero_iterate()
+            self.slab.reset(sweeps, 0.0)
+        if events is not None:
+            events[0].record(stream)
+        self.enqueue(npass)
+        if events is not None:
+            events[1].record(stream)
+        return npass
+
+    def enqueue(self, npass):
+        if self.slab is None:
+            self.solver.enqueue(npass, self.ctx.sp)
+        else:
+            self.slab.enqueue(npass)
+
+    def state(self):
+        return self.solver.state(self.ctx.sp) if self.slab is None else self.slab.state()
+
+    def result_buf(self, npass):
+        return npass & 1 if self.slab is None else self.slab.buf_after(npass)
+
+    def download_owned(self, which, out):
+        if self.slab is None:
+            self.solver.L.cnv_poisson_download(self.solver.h, which, out, self.ctx.sp)
+        else:
+            self.slab.download_owned(which, out)
+        return out
+
+    def timed(self, sweeps, steps, warmup, clocks=None):
+        """-> dict(ms, pass_ms, npass, launches, clocks).  CUDA events on the launching stream, barrier + synchronize on both
+        sides, max over ranks."""
+        ctx = self.ctx
+        self.upload(self.w_host)
+        for _ in range(warmup):
+            self.zero_and_run(sweeps)
+        ctx.barrier()
+        launches0 = ctx.L.cnv_launch_count()
+        ev0, ev1 = ctx.event(), ctx.event()
+        pass_ev = [(ctx.event(), ctx.event()) for _ in range(steps)]
+        ctx.barrier()
+        wall0 = time.time()
+        ev0.record(ctx.stream)
+        npass = 0
+        for k in range(steps):
+            npass = self.zero_and_run(sweeps, pass_ev[k])
+        ev1.record(ctx.stream)
+        ctx.barrier()
+        wall1 = time.time()
+        launches = ctx.L.cnv_launch_count() - launches0
+        ms = ev0.elapsed_time(ev1)
+        pass_ms = sum(a.elapsed_time(b) for a, b in pass_ev)
+        st = self.state()   # verify the work really happened
+        assert st["sweeps"] == sweeps and st["state"] == 2, st
+        if self.world > 1:
+            ms, pass_ms = ctx.max_over_ranks([ms, pass_ms])
+        return dict(ms=ms, pass_ms=pass_ms, npass=npass, launches=launches, wall=(wall0, wall1))
+
+    # ---- parity: the workload's own data, every rank's owned rows bitwise against the oracle ----
+    def parity_check(self, sweeps=PARITY_SWEEPS):
+        from oracle import api   # the checker; never inside a timed region
+        port = api.port()
+        ctx = self.ctx
+        self.upload(self.w_host)
+        npass = self.zero_and_run(sweeps)
+        st = self.state()
+        got = np.empty((self.own_rows, self.ncols))
+        self.download_owned(self.result_buf(npass), got)
+        # oracle on the owned rows plus enough neighbouring rows that the artificial zero ring cannot reach them: a sweep
+        # moves information by 2 rows, and the first row must keep the global (i + j) colouring (even row offset)
+        reach = 2 * sweeps + 2
+        g0 = max(0, self.row0 - reach)
+        g0 -= g0 & 1
+        g1 = min(self.total_rows, self.row0 + self.own_rows + reach)
+        f = -synthetic_vorticity(g1 - g0, self.ncols, g0, self.total_rows)
+        want, norms = port.poisson_sweeps(f, self.dx, self.dy, sweeps, self.beta)
+        want = want[self.row0 - g0:self.row0 - g0 + self.own_rows]
+        ok = st["sweeps"] == sweeps and got.tobytes() == want.tobytes()
+        return ctx.all_ok(ok) if self.world > 1 else ok
+
+    # ---- end to end: host buffers in, host psi out, through the C ABI, copies inside the timed region ----
+    def e2e(self, sweeps, steps):
+        ctx, torch = self.ctx, self.ctx.torch
+        if self.pin_in is None:
+            self.pin_in = torch.from_numpy(self.w_host).pin_memory()
+            self.pin_out = torch.empty_like(self.pin_in).pin_memory()
+        in_np, out_np = self.pin_in.numpy(), self.pin_out.numpy()
+        npass = (sweeps + self.T - 1) // self.T
+
+        def step():
+            self.upload(in_np)                                  # H2D of w + rhs preparation (+ halo exchange) + zero guess
+            if self.slab is None:
+                self.solver.reset(sweeps, 0.0, ctx.sp)
+            else:
+                self.slab.reset(sweeps, 0.0)
+            self.enqueue(npass)
+            self.download_owned(self.result_buf(npass), out_np)  # D2H of psi, synchronised: one solve at a time
+
+        step()
+        ctx.barrier()
+        e0, e1 = ctx.event(), ctx.event()
+        e0.record(ctx.stream)
+        for _ in range(steps):
+            step()
+        e1.record(ctx.stream)
+        ctx.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            ms = ctx.max_over_ranks([ms])[0]
+        return ms, out_np
+
+    def close(self):
+        if self.slab is not None:
+            self.slab.close()
+        else:
+            self.solver.close()
+
+
+def pipelined_e2e(ctx, run, sweeps, steps):
+    """Single GPU, side figure: two solver objects on two streams keep two INDEPENDENT solves in flight, so the host copies
+    of one overlap the sweeps of the other (every solve still pays its own H2D, preparation, sweeps and D2H inside the
+    timed region).  A time-stepping caller has one dependent solve per step and sees the sequential figure."""
+    torch, fd = ctx.torch, ctx.fd
+    stream2 = torch.cuda.Stream()
+    sp2 = C.c_void_p(stream2.cuda_stream)
+    solver2 = fd.PoissonSolver(run.total_rows, run.ncols, run.T)
+    solver2.set_consts(run.dx, run.dy, run.beta)
+    in_np = run.pin_in.numpy()
+    pin_out2 = torch.empty_like(run.pin_in).pin_memory()
+    lanes = [(run.solver, ctx.sp, run.pin_out.numpy()), (solver2, sp2, pin_out2.numpy())]
+    npass = (sweeps + run.T - 1) // run.T
+    count = [0]
+
+    def step():
+        sv, spx, outx = lanes[count[0] & 1]
+        count[0] += 1
+        sv.upload(in_np, -1.0, spx)
+        sv.reset(sweeps, 0.0, spx)
+        sv.enqueue(npass, spx)
+        sv.L.cnv_poisson_download_async(sv.h, npass & 1, outx, spx)
+
+    step(); step()
+    ctx.barrier()
+    e0, e1 = ctx.event(), ctx.event()
+    e0.record(ctx.stream)
+    stream2.wait_stream(ctx.stream)                  # both lanes start after e0
+    for _ in range(steps):
+        step()
+    ctx.stream.wait_stream(stream2)                  # e1 after the last solve of either lane
+    e1.record(ctx.stream)
+    ctx.barrier()
+    ms = e0.elapsed_time(e1)
+    same = np.array_equal(lanes[0][2], lanes[1][2])
+    solver2.close()
+    return ms, same
+
+
+def dropin_e2e(ctx, run, reps=3):
+    """The call a C user of the reference makes: poisson_SOR_log(mtrx f, dx, dy, itmax, tol, beta, FILE*) of
+    libcnavier_dropin.so (include/poisson.h:16 of the reference) on the 4096^2 grid, host mtrx in, caller-owned host mtrx
+    out, solved to the reference's tolerance (1e-3).  Timed with the host clock around the call; beside it the same solve
+    through the pinned-buffer solver object (upload + solve + download), one at a time."""
+    fd = ctx.fd
+    D = fd.dropin()
+    n, m = run.total_rows, run.ncols
+    tol, itmax = 1e-3, 400000
+    f = -run.w_host
+    F = D.initm(n, m)
+    C.memmove(F.M[0], f.ctypes.data, f.nbytes)       # the drop-in allocm backs a mtrx with one contiguous (page-locked) block
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        logp = os.path.join(td, "log.txt")
+        times, k = [], None
+        U = None
+        for i in range(reps + 1):
+            fh = libc.fopen(logp.encode(), b"w")
+            t0 = time.perf_counter()
+            U2 = D.poisson_SOR_log(F, run.dx, run.dy, itmax, tol, run.beta, fh)
+            t1 = time.perf_counter()
+            libc.fclose(fh)
+            if U is not None:
+                D.freem(U)
+            U = U2
+            if i > 0:
+                times.append(t1 - t0)
+            k = int(open(logp).read().split()[4])
+        psi_dropin = np.ctypeslib.as_array(U.M[0], shape=(n * m,)).reshape(n, m).copy()
+        D.freem(U)
+        D.freem(F)
+    t_dropin = float(np.mean(times))
+    # the same solve through the solver object with page-locked buffers
+    s = run.solver
+    pin_f = ctx.torch.from_numpy(np.ascontiguousarray(f)).pin_memory()
+    pin_u = ctx.torch.empty_like(pin_f).pin_memory()
+    times2, k2 = [], None
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        s.upload(pin_f.numpy(), 1.0, ctx.sp)
+        r = s.solve(itmax, tol, ctx.sp)
+        s.L.cnv_poisson_download(s.h, r["buf"], pin_u.numpy(), ctx.sp)
+        t1 = time.perf_counter()
+        if i > 0:
+            times2.append(t1 - t0)
+        k2 = r["k"]
+    t_obj = float(np.mean(times2))
+    cells = (n - 2) * (m - 2)
+    out = {"call": "poisson_SOR_log(mtrx f, dx, dy, itmax, tol = 1e-3, beta, FILE*) of libcnavier_dropin.so, host mtrx in / caller-owned host mtrx out",
+           "sweeps": k + 1, "ms_per_call": t_dropin * 1e3, "value": cells * (k + 1) / t_dropin, "unit": "cell-updates/s",
+           "solver_object_pinned_ms_per_call": t_obj * 1e3, "solver_object_pinned_value": cells * (k2 + 1) / t_obj,
+           "dropin_over_solver_object_time": t_dropin / t_obj,
+           "same_result": bool(k == k2 and np.array_equal(psi_dropin, pin_u.numpy()))}
+    return out
+
+
+def series_entry(ctx, run, args, steps, peak, with_e2e=True):
+    """Measure one workload: timed loop, parity check, (optionally) e2e."""
+    t = run.timed(args.sweeps, steps, args.warmup)
+    parity = run.parity_check()
+    per_gpu_cells = run.interior_cells / run.world
+    launch_s = t["pass_ms"] * 1e-3 / (t["npass"] * steps)
+    achieved = ALGO_BYTES_PER_CELL_SWEEP * per_gpu_cells * run.T / launch_s / 1e9
+    out = {"grid": [run.total_rows, run.ncols], "value": run.interior_cells * args.sweeps * steps / (t["ms"] * 1e-3),
+           "unit": "cell-updates/s", "ms_per_step": t["ms"] / steps, "steps": steps,
+           "sweeps_per_s": args.sweeps * steps / (t["ms"] * 1e-3), "pass_launch_us": launch_s * 1e6,
+           "frac": achieved / peak, "achieved_gbs_per_gpu": achieved,
+           "parity_check": "bitwise-ok" if parity else "MISMATCH",
+           "plan": {"temporal_block_T": run.T, "strip_width": run.plan["WS"], "rows_per_chunk": run.plan["Hout"],
+                    "ctas": run.plan["nstrips"] * run.plan["nchunks"], "arith_path": "pow2-exact" if run.plan["pow2"] else "general"}}
+    if run.slab is not None:
+        out["plan"]["exchange"] = ("peer" if run.slab.peer else "nccl" if run.slab.comm else "torch") + \
+                                  ("+lagged-decision" if run.slab.peer and len(run.slab.bufs) == 3 else "")
+    if with_e2e:
+        ms, _ = run.e2e(args.sweeps, steps)
+        out["e2e"] = {"value": run.interior_cells * args.sweeps * steps / (ms * 1e-3), "ms_per_step": ms / steps}
+    out["_timed"] = t
+    return out
 
 
 def run_gpu(args):
-    import torch
-    import torch.distributed as dist
-
-    import fluid_dynamics1_b200 as fd
-    from fluid_dynamics1_b200 import parallel
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
-    fd.require_gpu()
-    torch.cuda.set_device(local_rank)
-    L = fd.lib()
-    L.cnv_set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    ncols = args.n
-    if args.scaling == "weak":
-        total_rows, rows_per = args.n * world, args.n
-    else:
-        total_rows, rows_per = args.n, args.n // world
-    T, S = args.T, args.sweeps
-    dx = dy = 1.0 / ncols
-    beta = fd.sor_beta(ncols, ncols)
-    stream = torch.cuda.current_stream()
-    sp = C.c_void_p(stream.cuda_stream)
-
-    slab = parallel.SlabPoisson(total_rows, ncols, T, rank, world, stream=sp) if world > 1 else None
-    if slab is None:
-        solver = fd.PoissonSolver(rows_per, ncols, T)
-        solver.set_consts(dx, dy, beta)
-        w_host = synthetic_vorticity(rows_per, ncols)
-        solver.upload(w_host, -1.0, sp)  # f = -w (src/main.c:348)
-        T = solver.T
-        plan = solver.plan
-    else:
-        slab.set_consts(dx, dy, beta)
-        w_host = synthetic_vorticity(slab.own_rows, ncols, slab.row0, total_rows)
-        slab.upload_owned(w_host, -1.0)
-        T = slab.T
-        plan = slab.solver.plan
-    npass = (S + T - 1) // T
-    interior_cells = (total_rows - 2) * (ncols - 2)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def one_step(pass_events=None):
-        """resident-input step: zero guess, reset state machine, S sweeps."""
-        if slab is None:
-            solver.L.cnv_poisson_prepare(solver.h, None, 0, 1.0, sp)  # f == NULL: only zero the iterate buffers
-            solver.reset(S, 0.0, sp)
-            if pass_events is not None:
-                pass_events[0].record(stream)
-            solver.enqueue(npass, sp)
-            if pass_events is not None:
-                pass_events[1].record(stream)
-        else:
-            slab.zero_iterate()
-            slab.reset(S, 0.0)
-            if pass_events is not None:
-                pass_events[0].record(stream)
-            slab.enqueue(npass)
-            if pass_events is not None:
-                pass_events[1].record(stream)
-
-    sampler = ClockSampler(local_rank)
+    ctx = Ctx(args)
+    rank, world = ctx.rank, ctx.world
+    # the oracle is only the checker of parity_check(); give it this rank's share of the host cores (torchrun exports
+    # OMP_NUM_THREADS=1)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, host_cores() // world))
+    peak, peak_src = peaks()
+    total_rows, ncols, rows_per, scaling, _ = headline_shape(args, world)
+    sampler = ClockSampler(ctx.local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
-    launches0 = L.cnv_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pass_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    wall0 = time.time()
-    ev0.record(stream)
-    for k in range(args.steps):
-        one_step(pass_ev[k])
-    ev1.record(stream)
-    barrier()
-    wall1 = time.time()
-    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    launches = L.cnv_launch_count() - launches0
-    ms = ev0.elapsed_time(ev1)
-    pass_ms = sum(a.elapsed_time(b) for a, b in pass_ev)
-    # verify the work really happened
-    st = solver.state(sp) if slab is None else slab.state()
-    assert st["sweeps"] == S and st["state"] == 2, st
 
-    # ---- e2e: host buffers in, host psi out, through the C ABI, copies inside the timed region ----
-    pin_in = torch.from_numpy(w_host).pin_memory()
-    pin_out = torch.empty_like(pin_in).pin_memory()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    in_np, out_np = pin_in.numpy(), pin_out.numpy()
-
-    # Single GPU: two solver objects on two streams keep two solves in flight, so the host copies of one solve
-    # overlap the sweeps of the other (every solve still pays its own H2D, preparation, sweeps and D2H inside the
-    # timed region).  Slabs: one solve at a time.
-    if slab is None:
-        stream2 = torch.cuda.Stream()
-        sp2 = C.c_void_p(stream2.cuda_stream)
-        solver2 = fd.PoissonSolver(rows_per, ncols, T)
-        solver2.set_consts(dx, dy, beta)
-        pin_out2 = torch.empty_like(pin_in).pin_memory()
-        lanes = [(solver, sp, out_np), (solver2, sp2, pin_out2.numpy())]
-    e2e_count = [0]
-
-    def e2e_step():
-        if slab is None:
-            sv, spx, outx = lanes[e2e_count[0] & 1]
-            e2e_count[0] += 1
-            sv.upload(in_np, -1.0, spx)               # H2D + rhs preparation + zero guess
-            sv.reset(S, 0.0, spx)
-            sv.enqueue(npass, spx)
-            sv.L.cnv_poisson_download_async(sv.h, npass & 1, outx, spx)   # D2H of psi
-        else:
-            slab.upload_owned(in_np, -1.0)
-            slab.reset(S, 0.0)
-            slab.enqueue(npass)
-            slab.download_owned(slab.buf_after(npass), out_np)
-
-    e2e_step()
-    if slab is None:
-        e2e_step()
-    barrier()
-    e0.record(stream)
-    if slab is None:
-        stream2.wait_stream(stream)                  # both lanes start after e0
-    for _ in range(args.steps):
-        e2e_step()
-    if slab is None:
-        stream.wait_stream(stream2)                  # e1 after the last solve of either lane
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    e2e_seq_ms = None
-    if slab is None:
-        # for transparency also one solve at a time (a single lane, D2H synchronised before the next H2D)
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nseq = max(2, args.steps // 4)
-        s0.record(stream)
-        for _ in range(nseq):
-            solver.upload(in_np, -1.0, sp)
-            solver.reset(S, 0.0, sp)
-            solver.enqueue(npass, sp)
-            solver.L.cnv_poisson_download(solver.h, npass & 1, out_np, sp)
-        s1.record(stream)
-        torch.cuda.synchronize()
-        e2e_seq_ms = s0.elapsed_time(s1) / nseq
-        # both lanes produced the field of the resident-input run (same input, same sweeps)
-        chk = solver.download(npass & 1)
-        assert np.array_equal(out_np, chk) and np.array_equal(lanes[1][2], chk), "e2e result differs from the device-resident run"
-        solver2.close()
-
+    run = PoissonRun(ctx, total_rows, ncols, args.T)
+    head = series_entry(ctx, run, args, args.steps, peak, with_e2e=True)
+    t = head.pop("_timed")
+    clocks = sampler.stop(*t["wall"]) if rank == 0 else None
+    launches = t["launches"]
     if world > 1:
-        t = torch.tensor([ms, pass_ms, e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, pass_ms, e2e_ms = t.tolist()
-        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        lt = ctx.torch.tensor([launches], device="cuda", dtype=ctx.torch.int64)
+        ctx.dist.all_reduce(lt)
         launches = int(lt.item())
+    T = run.T
+    per_gpu_cells = run.interior_cells / world
+    out = {
+        "metric": "poisson_cell_updates_per_s", "value": head["value"], "unit": "cell-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "plan": head["plan"],
+        "sweeps_per_s": head["sweeps_per_s"],
+        "parity_check": head["parity_check"],
+        "parity_check_what": f"{PARITY_SWEEPS} sweeps ({(PARITY_SWEEPS + T - 1) // T} passes) on the benchmark's own data after the timed loop: every "
+                             f"rank's owned rows bitwise against oracle/liboracle.so (red-black restatement of src/poisson.c:238-262)",
+        "roofline": {"bound": "hbm", "achieved": head["achieved_gbs_per_gpu"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
+                     "traffic": measured_traffic(run.solver.nrows, ncols, T), "peak_source": peak_src,
+                     "kernel": f"k_poisson_pass<T={T}>",
+                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_SWEEP * per_gpu_cells * T,
+                     "launch_us": head["pass_launch_us"],
+                     "note": "per GPU; temporal blocking: T sweeps per HBM pass, so algorithmic GB/s may exceed the HBM peak; traffic = ncu "
+                             "dram bytes per launch for exactly this slab shape (null where not captured)"},
+        "e2e": {"value": head["e2e"]["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": int(run.w_host.nbytes * world),
+                "d2h_bytes_per_step": int(run.w_host.nbytes * world), "ms_per_step": head["e2e"]["ms_per_step"],
+                "pipeline": "one solve at a time per GPU through the C ABI: pinned host w -> H2D + rhs preparation"
+                            + (" + halo exchange" if world > 1 else "") + " -> sweeps -> D2H of psi, synchronised before the next solve"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    ok = head["parity_check"] == "bitwise-ok"
+
+    if world == 1:
+        # side figures on one GPU
+        ms, same = pipelined_e2e(ctx, run, args.sweeps, args.steps)
+        out["e2e"]["pipelined_value"] = run.interior_cells * args.sweeps * args.steps / (ms * 1e-3)
+        out["e2e"]["pipelined_note"] = ("two independent solves in flight (two solver objects, two streams): copies of one overlap the "
+                                        "sweeps of the other; not available to a time-stepping caller")
+        ok = ok and same
+        if args.series == "auto":
+            out["e2e"]["dropin"] = dropin_e2e(ctx, run)
+            ok = ok and out["e2e"]["dropin"]["same_result"]
+        run.close()
+        if args.series == "auto":
+            base = PoissonRun(ctx, 2048, 16384, args.T)
+            e = series_entry(ctx, base, args, max(3, args.steps // 2), peak, with_e2e=False)
+            e.pop("_timed")
+            out["weak_base_config5_shape"] = e
+            ok = ok and e["parity_check"] == "bitwise-ok"
+            base.close()
+        out["stencil_phase"] = stencil_phase(ctx.fd, ctx.torch, args.n, ctx.sp, ctx.stream, peak)
+        out["timestep_1024"] = timestep_1024(ctx.fd, peak, cpu=not args.no_cpu)
+        if args.n == 4096:
+            out["timestep_4096"] = timestep_4096(ctx.fd, peak)
+        if not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(args.n, args.cpu_seconds)
+    else:
+        run.close()
+        if args.series == "auto":
+            side_steps = max(3, args.steps // 2)
+            # the weak series' denominator: every rank alone on one config-5 slab shape, all GPUs of the box busy at once
+            base = PoissonRun(ctx, 2048, 16384, args.T, single=True)
+            tb = base.timed(args.sweeps, side_steps, args.warmup)
+            vals = ctx.gather_floats(base.interior_cells * args.sweeps * side_steps / (tb["ms"] * 1e-3))
+            pb = ctx.all_ok(base.parity_check())
+            base.close()
+            out["weak_base_1gpu"] = {"grid": [2048, 16384], "value_mean": float(np.mean(vals)), "value_min": float(np.min(vals)),
+                                     "value_max": float(np.max(vals)), "parity_check": "bitwise-ok" if pb else "MISMATCH",
+                                     "note": "each of the N ranks alone on a 2048 x 16384 grid, all N GPUs running at the same time"}
+            out["weak_efficiency_vs_base"] = out["value"] / (world * float(np.mean(vals)))
+            ok = ok and pb
+            # BASELINE config 4 under strong scaling
+            srun = PoissonRun(ctx, 4096, 4096, args.T)
+            e = series_entry(ctx, srun, args, args.steps, peak, with_e2e=True)
+            e.pop("_timed")
+            srun.close()
+            e["workload"] = "4096x4096 Re=1000 lid-driven cavity (BASELINE config 4), slab-decomposed over the N GPUs: strong scaling"
+            out["strong"] = e
+            ok = ok and e["parity_check"] == "bitwise-ok"
+            # round 1's series
+            wrun = PoissonRun(ctx, 4096 * world, 4096, args.T)
+            e = series_entry(ctx, wrun, args, side_steps, peak, with_e2e=False)
+            e.pop("_timed")
+            wrun.close()
+            out["weak_4096_rows_per_gpu"] = e
+            ok = ok and e["parity_check"] == "bitwise-ok"
+            out["timestep_slab"] = timestep_slab(ctx, peak)
+            ok = ok and out["timestep_slab"].get("parity_check", "bitwise-ok") == "bitwise-ok"
 
     if rank == 0:
-        peak, peak_src = peaks()
-        value = interior_cells * S * args.steps / (ms * 1e-3)
-        e2e_val = interior_cells * S * args.steps / (e2e_ms * 1e-3)
-        # dominant kernel: k_poisson_pass<T>.  Algorithmic bytes per launch = 24 B x interior cells of this
-        # GPU's slab x sweeps per launch (T); duration = CUDA-event time around the pass launches / count.
-        per_gpu_cells = interior_cells / world
-        launch_s = pass_ms * 1e-3 / (npass * args.steps)
-        achieved = ALGO_BYTES_PER_CELL_SWEEP * per_gpu_cells * T / launch_s / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "poisson_pass_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        out = {
-            "metric": "poisson_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{total_rows}x{ncols} Re={5000 if ncols == 16384 else 1000} lid-driven cavity, red-black SOR Poisson solve "
-                                   f"({_config_name(args.n)} grid{' per GPU' if args.scaling == 'weak' and world > 1 else ''})",
-                       "grid": [total_rows, ncols], "slab_rows_per_gpu": rows_per, "sweeps_per_step": S,
-                       "temporal_block_T": T, "strip_width": plan["WS"], "rows_per_chunk": plan["Hout"],
-                       "ctas": plan["nstrips"] * plan["nchunks"], "arith_path": "pow2-exact" if plan["pow2"] else "general",
-                       "parallelism": f"slab{world}" if world > 1 else "single",
-                       **({"exchange": ("peer" if slab.peer else "nccl" if slab.comm else "torch") +
-                                       ("+lagged-decision" if slab.peer and len(slab.bufs) == 3 else "") +
-                                       ("+tile-kernel" if plan.get("tiled") else "")} if slab is not None else {}),
-                       "l2": ("inputs larger than L2 (3 x %.0f MB resident arrays per GPU vs 126 MB L2), no flush" if
-                              3 * rows_per * ncols * 8 > 126e6 else
-                              "arrays fit L2 at this slab size (3 x %.0f MB per GPU vs 126 MB L2): L2-resident run, no flush") %
-                             (rows_per * ncols * 8 / 1e6)},
-            "sweeps_per_s": S * args.steps / (ms * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic if not plan.get("tiled") else None, "peak_source": peak_src,
-                         "kernel": (f"k_poisson_tile<M={plan['M']}> (T={T})" if plan.get("tiled") else f"k_poisson_pass<T={T}>"),
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_SWEEP * per_gpu_cells * T,
-                         "launch_us": launch_s * 1e6,
-                         "note": "temporal blocking: T sweeps per HBM pass, so algorithmic GB/s may exceed the HBM peak"},
-            "e2e": {"value": e2e_val, "unit": "cell-updates/s", "h2d_bytes_per_step": int(w_host.nbytes * world),
-                    "d2h_bytes_per_step": int(w_host.nbytes * world), "ms_per_step": e2e_ms / args.steps,
-                    "sequential_value": (interior_cells * S / (e2e_seq_ms * 1e-3) if e2e_seq_ms else None),
-                    "pipeline": ("2 solves in flight: two solver objects on two streams, pinned host buffers; each solve = H2D of w, "
-                                 "rhs preparation, sweeps, D2H of psi" if world == 1 else "one solve at a time per slab")},
-            "gpu_launches": int(launches), "clocks": clocks,
-        }
-        if world == 1:
-            out["stencil_phase"] = stencil_phase(fd, torch, args.n, sp, stream, peak)
-            out["timestep_1024"] = timestep_1024(fd, peak, cpu=not args.no_cpu)
-            if args.n == 4096:
-                out["timestep_4096"] = timestep_4096(fd, peak)
-        if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(args.n, args.cpu_seconds)
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("bench.py: a parity check FAILED (see parity_check keys)")
 
 
 def stencil_phase(fd, torch, n, sp, stream, peak, reps=20):
@@ -378,7 +650,7 @@ def timestep_1024(fd, peak, steps=4, cpu=True):
     sweeps = float(np.mean(r["k"])) + 1
     sim.close()
     out = {"grid": [n, n], "steps": steps, "ms_per_step": dt * 1e3, "cell_steps_per_s": n * n / dt,
-           "poisson_sweeps_per_step": sweeps, "algorithmic_gbs": (72 + 24 * sweeps) * n * n / dt / 1e9,
+           "poisson_sweeps_per_step": sweeps, "us_per_sweep": dt * 1e6 / sweeps, "algorithmic_gbs": (72 + 24 * sweeps) * n * n / dt / 1e9,
            "frac_of_hbm_peak": (72 + 24 * sweeps) * n * n / dt / 1e9 / peak,
            "note": "8 MB fields: L2-resident, launch/latency bound rather than HBM bound"}
     if cpu:
@@ -411,6 +683,27 @@ def timestep_4096(fd, peak, steps=2):
             "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
 
 
+def timestep_slab(ctx, peak, steps=2):
+    """BASELINE config 4 (4096^2, Re 1000) as WHOLE time steps slab-decomposed over the N GPUs (SlabSimulation: stencil phases
+    with 3-row halo exchanges, distributed Poisson solve to the reference's tolerance, continuity all-reduce).  The sweep
+    counts of the steps must equal those of the single-GPU run (they are a function of the bits of the fields)."""
+    n = 4096
+    cfg = dict(nx=n, ny=n, Re=1000.0, dt=5e-6, poisson_max_it=100000, poisson_tol=1e-3)
+    sim = ctx.parallel.SlabSimulation(cfg, ctx.rank, ctx.world, stream=ctx.sp)
+    sim.step(1)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    r = sim.step(steps)
+    ctx.barrier()
+    dt = ctx.max_over_ranks([(time.perf_counter() - t0) / steps])[0]
+    sweeps = float(np.mean(r["k"])) + 1
+    sim.close()
+    gbs = (72 + 24 * sweeps) * n * n / dt / 1e9
+    return {"grid": [n, n], "gpus": ctx.world, "steps": steps, "ms_per_step": dt * 1e3, "cell_steps_per_s": n * n / dt,
+            "poisson_sweeps_per_step": sweeps, "poisson_k": [int(k) for k in r["k"]],
+            "poisson_cell_updates_per_s": (n - 2) ** 2 * sweeps / dt, "algorithmic_gbs": gbs, "frac_of_hbm_peak_per_gpu": gbs / peak / ctx.world}
+
+
 # ------------------------------------------------------------------------------------------------
 _CHILD = r"""
 import sys, time, numpy as np
@@ -426,11 +719,21 @@ R.poisson(f, 1.0 / n, 1.0 / n, k, 0.0, beta, sor=True)   # never converges (tol 
 """
 
 
+def cpu_env():
+    """Environment of the CPU arm: all host cores (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(host_cores())
+    env["OMP_PROC_BIND"] = "false"
+    env.pop("OMP_PLACES", None)
+    return env
+
+
 def ref_sweeps_time(n, k):
     """Wall time of k red-black sweeps of the UNMODIFIED poisson_SOR_log (oracle/_ref): run in a child
     process with itmax = k, tol = 0 -- it performs exactly k sweeps and then exit(1)s (src/poisson.c:280-284)."""
     with tempfile.TemporaryDirectory() as td:
-        p = subprocess.Popen([sys.executable, "-c", _CHILD.format(root=ROOT, n=n, k=k)], stdout=subprocess.PIPE, text=True, cwd=td)
+        p = subprocess.Popen([sys.executable, "-c", _CHILD.format(root=ROOT, n=n, k=k)], stdout=subprocess.PIPE, text=True, cwd=td,
+                             env=cpu_env())
         start = None
         for line in p.stdout:
             if line.startswith("START"):
@@ -442,58 +745,71 @@ def ref_sweeps_time(n, k):
     return end - start
 
 
+_CALIB = r"""
+import sys, time, numpy as np
+sys.path.insert(0, {root!r})
+from oracle import api
+from bench import synthetic_vorticity
+n, k = {n}, {k}
+port = api.port()
+f = -synthetic_vorticity(n, n)
+t0 = time.time()
+port.poisson_sweeps(f, 1.0 / n, 1.0 / n, k, port.beta(n, n))
+print("PER_SWEEP", (time.time() - t0) / k, port.max_threads(), flush=True)
+"""
+
+
 def cpu_sweep_rate(n, seconds, prefer_ref=True):
-    """(cell-updates/s, kind, cores, sample description) of the CPU reference path on this box."""
+    """(cell-updates/s, kind, threads, sample description, sample seconds) of the CPU reference path on this box."""
     from oracle import api
-    cores = os.cpu_count() or 1
-    port = api.port()
-    f = -synthetic_vorticity(n, n)
-    beta = port.beta(n, n)
-    t0 = time.time()
-    port.poisson_sweeps(f, 1.0 / n, 1.0 / n, 2, beta)
-    per_sweep = (time.time() - t0) / 2
+    cores = host_cores()
+    # calibrate the sample size in a child as well, so that it runs with all host cores whatever this process' OpenMP state
+    c = subprocess.run([sys.executable, "-c", _CALIB.format(root=ROOT, n=n, k=2)], capture_output=True, text=True, env=cpu_env())
+    per_sweep, threads = 1.0, cores
+    for line in c.stdout.splitlines():
+        if line.startswith("PER_SWEEP"):
+            per_sweep, threads = float(line.split()[1]), int(line.split()[2])
     k = int(max(2, min(2000, seconds / max(per_sweep, 1e-6))))
     if prefer_ref and api.ref() is not None:
         t = ref_sweeps_time(n, k)
         kind = "reference"
         what = "unmodified poisson_SOR_log (oracle/_ref, -O2 -fopenmp -DOPENMP_ENABLED, red-black)"
     else:
-        t0 = time.time()
-        port.poisson_sweeps(f, 1.0 / n, 1.0 / n, k, beta)
-        t = time.time() - t0
+        c = subprocess.run([sys.executable, "-c", _CALIB.format(root=ROOT, n=n, k=k)], capture_output=True, text=True, env=cpu_env())
+        t = [float(x.split()[1]) for x in c.stdout.splitlines() if x.startswith("PER_SWEEP")][0] * k
         kind = "port"
         what = "oracle/cnavier_oracle.c orc_poisson_sweeps (OpenMP red-black)"
-    threads = port.max_threads()
-    return (n - 2) ** 2 * k / t, kind, threads, f"{k} sweeps of the {n}x{n} grid, {what}, {threads} OpenMP threads on {cores} host cores"
+    return ((n - 2) ** 2 * k / t, kind, threads,
+            f"{k} sweeps of the {n}x{n} grid, {what}, {threads} OpenMP threads on {cores} host cores", t)
 
 
 def cpu_baseline(n, seconds):
-    v, kind, threads, sample = cpu_sweep_rate(n, seconds)
+    v, kind, threads, sample, _ = cpu_sweep_rate(n, seconds)
     return {"value": v, "unit": "cell-updates/s", "cores": threads, "kind": kind, "sample": sample}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.  Each step is a bounded
+    sample of sweeps (the rate per cell is size independent; the sample runs on the 4096-wide BASELINE config 4 grid)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = args.gpus
     per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
+    vals, secs = [], []
     kind = threads = sample = None
     for i in range(args.warmup + args.steps):
-        v, kind, threads, sample = cpu_sweep_rate(args.n, per_step)
+        v, kind, threads, sample, t = cpu_sweep_rate(args.n, per_step)
         if i >= args.warmup:
-            vals.append(v)
+            vals.append(v); secs.append(t)
     value = float(len(vals) / sum(1.0 / v for v in vals))  # total work / total time
-    total_rows = args.n * args.gpus if args.scaling == "weak" else args.n
-    # time one full step (args.sweeps sweeps of the whole grid) would take at the sampled rate
-    ms_equiv = (total_rows - 2) * (args.n - 2) * args.sweeps / value * 1e3
+    total_rows, ncols, _, scaling, _ = headline_shape(args, world)
     out = {"impl": "reference", "metric": "poisson_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_equiv, "higher_is_better": True,
-           "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{total_rows}x{args.n} Re={5000 if args.n == 16384 else 1000} lid-driven cavity, red-black SOR Poisson solve ({_config_name(args.n)} grid)",
-                      "note": "CPU arm: each step is a bounded sample of sweeps on the 4096x4096 grid; rate is size-independent per cell; "
-                              "ms_per_step is the time one full step would take at that rate"},
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
+           "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, world),
+           "step_is": "a bounded sample of sweeps of the same solve (see cpu_baseline.sample); ms_per_step is its measured wall time",
+           "ms_per_full_step_equiv": (total_rows - 2) * (ncols - 2) * args.sweeps / value * 1e3,
            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": threads, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -505,14 +821,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--series", default="auto", choices=["auto", "single"],
+                    help="auto: the BASELINE workloads (see the module docstring); single: only the grid given by --grid / --scaling")
     ap.add_argument("--n", "--grid", dest="n", type=int, default=4096,
-                    help="grid columns (and rows per GPU under weak scaling); use --grid under torchrun, whose own parser trips over --n")
+                    help="grid columns (and rows per GPU under weak scaling) of --series single; use --grid under torchrun, whose own "
+                         "parser trips over --n")
     ap.add_argument("--sweeps", type=int, default=1024, help="red-black SOR sweeps per step")
     ap.add_argument("--T", type=int, default=0, help="temporal block depth (0 = library default)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="--series single at N > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
+    if args.n != 4096 or args.scaling != "weak":
+        args.series = "single"
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 3)   # timing rule: W >= 3
     if args.impl == "reference":

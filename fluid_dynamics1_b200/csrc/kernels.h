@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "fd_coeffs.h"
+#include "poisson_onchip.h"
 #include "poisson_plan.h"
 
 // The reference reports failures with a message and exit(1) (src/poisson.c:280-284,
@@ -71,6 +72,10 @@ bool resident_plan(int nrows, int ncols, int ld, size_t smem_limit, ResidentGeom
 void launch_resident(const ResidentGeom &g, size_t smem, const RelaxConsts &rc, const double *psi0, const double *rhs, double *out,
                      PoissonCtl *ctl, double *hist, int itmax, double tol, cudaStream_t s);
 
+// ---- poisson_onchip.cu: the whole solve in one persistent launch, iterate resident in registers (<= ~1.5 M cells) ----
+void launch_onchip(const OnchipGeom &g, const RelaxConsts &rc, double *b0, double *b1, double *b2, const double *rhs, PoissonCtl *ctl,
+                   unsigned long long *flags, double *partials, double *hist, cudaStream_t s);
+
 // ---- poisson.cu ----
 struct PoissonResult {
     int status;  // 0 converged, 1 itmax reached (the reference exits the process here)
@@ -96,9 +101,11 @@ public:
     int ld() const { return geom_.ld; }
     int T() const { return T_; }
     const PassGeom &geom() const { return geom_; }
+    bool onchip() const { return use_onchip_; }  // solve() runs the persistent on-chip kernel (poisson_onchip.cu)
+    const OnchipGeom &onchip_geom() const { return oc_; }
     double *rhs() { return rhs_; }                // device, pitch ld(): pscale * f
-    double *buffer(int i) { return buf_[i]; }     // the iterate buffers: 0, 1 (and 2 with the lagged peer decision)
-    int num_buffers() const { return links_.enabled && links_.lag && buf_[2] ? 3 : 2; }
+    double *buffer(int i) { return buf_[i]; }     // the iterate buffers: 0, 1 (and 2 with a lagged stop decision: peer path, on-chip kernel)
+    int num_buffers() const { return ((links_.enabled && links_.lag) || use_onchip_) && buf_[2] ? 3 : 2; }
     void zero_extra_buffer(cudaStream_t s)  // third buffer of the lagged peer decision: same initial state as 0 and 1
     {
         if (buf_[2]) CNV_CUDA_CHECK(cudaMemsetAsync(buf_[2], 0, (size_t)geom_.nrows * geom_.ld * sizeof(double), s));
@@ -152,6 +159,10 @@ public:
 private:
     int T_;
     PassGeom geom_;
+    OnchipGeom oc_ = {};
+    bool use_onchip_ = false;
+    unsigned long long *oc_flags_ = nullptr;
+    double *oc_partials_ = nullptr;
     RelaxConsts rc_;
     double *buf_[3] = {nullptr, nullptr, nullptr};
     bool lag_ = false;  // CNV_PEER_LAG=1: lagged stop decision on the peer path (three iterate buffers)

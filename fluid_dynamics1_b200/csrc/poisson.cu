@@ -422,6 +422,8 @@ static void launch_pass(const PassGeom &g, const RelaxConsts &rc, double *b0, do
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int kOnchipDefault = 0;  // default use of the on-chip kernel where a plan exists (CNV_POISSON_ONCHIP overrides)
+
 static int env_int(const char *name, int dflt)
 {
     const char *e = std::getenv(name);
@@ -461,8 +463,21 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
     }
     threads_ = pass_threads(T, geom_.WS);
     smem_ = pass_smem_bytes(T, geom_.WS);
+    // CNV_POISSON_ONCHIP: 1 = the persistent on-chip kernel whenever a plan exists (whole-domain solvers only), 0 = never
+    const int oc_mode = env_int("CNV_POISSON_ONCHIP", kOnchipDefault);
+    if (oc_mode != 0 && grow0 == 0 && gnrows == nrows && own_lo == 0 && own_hi == nrows)
+        use_onchip_ = onchip_plan(nrows, ncols, ld, grow0, gnrows, own_lo, own_hi, lim.num_sms, &oc_, env_int("CNV_ONCHIP_T", 0),
+                                  env_int("CNV_ONCHIP_NTX", 0), env_int("CNV_ONCHIP_NTY", 0));
     std::memset(&rc_, 0, sizeof rc_);
     const size_t bytes = (size_t)nrows * ld * sizeof(double);
+    if (use_onchip_) {  // three iterate buffers rotate (lagged stop decision), per-CTA flags, per-pass norm partials
+        CNV_CUDA_CHECK(cudaMalloc(&buf_[2], bytes));
+        CNV_CUDA_CHECK(cudaMemset(buf_[2], 0, bytes));
+        const size_t ncta = (size_t)oc_.ntx * oc_.nty;
+        CNV_CUDA_CHECK(cudaMalloc(&oc_flags_, sizeof(unsigned long long) * (ncta + 1)));
+        CNV_CUDA_CHECK(cudaMalloc(&oc_partials_, sizeof(double) * kOcNormSlots * ncta * 8));
+        CNV_CUDA_CHECK(cudaMemset(oc_partials_, 0, sizeof(double) * kOcNormSlots * ncta * 8));
+    }
     for (int i = 0; i < 2; i++) {
         CNV_CUDA_CHECK(cudaMalloc(&buf_[i], bytes));
         CNV_CUDA_CHECK(cudaMemset(buf_[i], 0, bytes));
@@ -488,6 +503,8 @@ PoissonSolver::~PoissonSolver()
     if (mailbox_) cudaFree(mailbox_);
     if (trace_) cudaFree(trace_);
     if (ctlbuf_) cudaFree(ctlbuf_);
+    if (oc_flags_) cudaFree(oc_flags_);
+    if (oc_partials_) cudaFree(oc_partials_);
     cudaFreeHost(h_ctl_);
     cudaEventDestroy(ev_);
 }
@@ -527,6 +544,11 @@ PoissonCtl PoissonSolver::read_ctl(cudaStream_t s)
     CNV_CUDA_CHECK(cudaMemcpyAsync(h_ctl_, src, sizeof(PoissonCtl), cudaMemcpyDeviceToHost, s));
     CNV_CUDA_CHECK(cudaEventRecord(ev_, s));
     CNV_CUDA_CHECK(cudaEventSynchronize(ev_));
+    if (h_ctl_->state == 3 && !links_.enabled) {
+        std::printf("** Error: the on-chip Poisson kernel timed out waiting for a neighbour tile (CNV_ONCHIP_TIMEOUT_MS) **\n");
+        std::fflush(stdout);
+        std::exit(1);
+    }
     if (h_ctl_->state == 3) {
         std::printf("** Error: multi-GPU peer exchange timed out (a rank stopped responding for more than %.0f s; "
                     "CNV_PEER_TIMEOUT_MS) **\n", links_.timeout_ns * 1e-9);
@@ -817,6 +839,23 @@ PoissonResult PoissonSolver::solve(int itmax, double tol, cudaStream_t s, int *r
         r.sweeps = c.sweeps;
         r.passes = c.passes;
         r.e = c.result_e;
+        return r;
+    }
+    // Grids whose iterate fits the register files: the whole solve in one persistent cooperative launch
+    // (poisson_onchip.cu).  Same arithmetic, same red-black order -> same bits.
+    if (use_onchip_ && !distributed_ && itmax > 0) {
+        k_reset_ctl<<<1, 1, 0, s>>>(ctl_, itmax, tol, 3);  // (three buffers in rotation)
+        launch_onchip(oc_, rc_, buf_[0], buf_[1], buf_[2], rhs_, ctl_, oc_flags_, oc_partials_, use_hist_ ? hist_ : nullptr, s);
+        launches_ += 1;
+        count_launch(2);
+        PoissonCtl c = read_ctl(s);
+        if (result_buf) *result_buf = c.cur;
+        PoissonResult r;
+        r.status = c.state == 1 ? 0 : 1;
+        r.k = c.result_k;
+        r.sweeps = c.sweeps;
+        r.passes = c.passes;
+        r.e = c.state == 1 ? c.result_e : c.last_e;
         return r;
     }
     // Sweep counts drift slowly from one time step to the next (the shipped logs move by <= ~10

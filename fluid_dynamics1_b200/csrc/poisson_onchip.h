@@ -1,0 +1,299 @@
+// poisson_onchip.h -- the whole Poisson solve in ONE persistent launch with the iterate resident ON CHIP (registers),
+// for grids that fit the GPU's register files (<= ~1.5 M cells: BASELINE config 3, 1024^2, and everything below it).
+// Shared between the CUDA kernel (poisson_onchip.cu) and the host-side schedule checker (tests/emul/stream_emul.cc).
+//
+// Why.  At 1024^2 the fields (2 x 8 MB) live in L2 and the streaming pass kernel (poisson_stream.h) is bound by what
+// it pays per PASS, not per cell: 98 streamed row-steps per CTA for 31 useful rows, one launch + one grid-wide
+// reduction per 8 sweeps (6.4 us per sweep, 0.55 of the 24 B/cell HBM roofline).  Here a CTA per SM keeps one tile of
+// psi and of the right-hand side in REGISTERS for the whole solve (src/poisson.c:234-279: all sweeps and the
+// convergence test), and only tile-boundary data ever moves:
+//   * thread (px, py) owns a patch of kOcPW = 4 columns x kOcPM = 8 rows (32 cells of psi + their 32 right-hand sides);
+//     a half-sweep updates its 16 cells of one colour, all independent of each other; of their 64 operands 52 are the
+//     thread's own registers, 12 belong to the four adjacent threads and come from shared memory, where every thread
+//     publishes the 24 perimeter cells of its patch (arrays indexed [slot][thread]: unit stride across a warp for the
+//     owner AND for all four neighbours, so conflict-free for any tile shape); one __syncthreads per half-sweep;
+//   * the tile carries a halo of 2T cells on all four sides; T sweeps ("a pass") run without any communication (the
+//     stale halo edge spreads one cell per half-sweep and stays inside the halo, whose results are discarded);
+//   * after a pass the CTA stores its output cells to the pass' global iterate buffer (L2), raises its flag
+//     (release, gpu scope), waits for the flags of its <= 8 neighbour tiles and reloads ONLY its halo cells;
+//   * the stop decision lags one pass behind (lag_fold / lag_action of poisson_stream.h, three iterate buffers in
+//     rotation): a pass starts knowing the global norms of the pass before the previous one, which every CTA sums
+//     itself from all CTAs' partials in a fixed order, so there is no grid-wide barrier on the critical path;
+//     if the first sweep below `tol` was not the last sweep of its pass, the tiles are reloaded from that pass' (still
+//     intact) input and exactly the converged number of sweeps is recomputed.
+// Same sweeps, same operand values, same separately rounded operations (exact.h::relax) as the reference's red-black
+// loop: the field is bit-identical; the L1 norm differs only in summation order (as for the other kernels).
+#pragma once
+#include "poisson_plan.h"
+
+namespace cnv {
+
+constexpr int kOcPW = 4;           // patch columns per thread
+constexpr int kOcPM = 8;           // patch rows per thread
+constexpr int kOcMaxThreads = 384; // registers: 64 (psi) + 64 (rhs) + temporaries per thread, one CTA per SM
+constexpr int kOcPad = 64;         // published arrays are addressable for thread ids -kOcPad .. kOcMaxThreads + kOcPad - 1
+constexpr int kOcPitch = kOcMaxThreads + 2 * kOcPad;  // doubles per slot
+constexpr int kOcSlots = 2 * kOcPM + 2 * kOcPW;       // ColLo[PM], ColHi[PM], RowLo[PW], RowHi[PW]
+constexpr int kOcNormSlots = 4;    // rings of per-pass norm partials
+static_assert(kOcPM % 2 == 0 && kOcPW == 4, "colour pattern of a patch is static");
+
+CNV_HD int oc_slot_col_lo(int i) { return i; }                        // cell (i, 0)
+CNV_HD int oc_slot_col_hi(int i) { return kOcPM + i; }                // cell (i, PW-1)
+CNV_HD int oc_slot_row_lo(int j) { return 2 * kOcPM + j; }            // cell (0, j)
+CNV_HD int oc_slot_row_hi(int j) { return 2 * kOcPM + kOcPW + j; }    // cell (PM-1, j)
+inline size_t oc_smem_bytes() { return (size_t)kOcSlots * kOcPitch * sizeof(double); }
+
+struct OnchipGeom {
+    // local array: nrows x ncols doubles with pitch ld; row 0 is global row grow0 of gnrows; rows [own_lo, own_hi) are produced
+    int nrows, ncols, ld, grow0, gnrows, own_lo, own_hi;
+    int T;         // sweeps per pass
+    int H;         // halo cells on every side = 2T (a multiple of 4)
+    int OW, OH;    // output columns / rows per tile (even)
+    int NPX, NPY;  // patches per tile; tile = (4 NPX) x (8 NPY) cells, threads per CTA = NPX * NPY
+    int ntx, nty;  // tiles
+};
+
+CNV_HD int oc_threads(const OnchipGeom &g) { return g.NPX * g.NPY; }
+
+struct OcTile {
+    int tx0, ty0;  // array column / row of tile cell (0, 0) (may be negative)
+    int x0, x1;    // output columns [x0, x1)
+    int y0, y1;    // output rows [y0, y1)
+    int par0;      // colour of tile cell (0, 0): (global row + column) & 1
+};
+
+CNV_HD OcTile oc_tile(const OnchipGeom &g, int bx, int by)
+{
+    OcTile t;
+    t.x0 = bx * g.OW;
+    t.x1 = t.x0 + g.OW < g.ld ? t.x0 + g.OW : g.ld;
+    t.y0 = g.own_lo + by * g.OH;
+    t.y1 = t.y0 + g.OH < g.own_hi ? t.y0 + g.OH : g.own_hi;
+    t.tx0 = t.x0 - g.H;
+    t.ty0 = t.y0 - g.H;
+    t.par0 = (g.grow0 + t.ty0 + t.tx0) & 1;
+    return t;
+}
+
+// Per-thread state.  p / f: the patch of psi and of the (pre-scaled) right-hand side, row i = 0..7 bottom-up, column j = 0..3.
+// Masks: bit (4 i + j) per cell, bit (2 i + j/2) per column pair (global loads / stores move pairs).
+struct OcThread {
+    double p[kOcPM][kOcPW];
+    double f[kOcPM][kOcPW];
+    unsigned upd;       // cell may be updated: inside the array, off the Dirichlet ring, off the array's first / last row
+    unsigned ownp;      // pair belongs to the tile's output region (stored after a pass, counted in the norm)
+    unsigned halop;     // pair is in the array but not in the output region: reloaded after every pass
+    unsigned inp;       // pair exists in the array
+    bool fast;          // all 32 cells updatable
+    int dist;           // distance (cells) of the patch from the output region: 0 if it touches it
+    long long gofs;     // element offset of cell (0, 0) in the global arrays
+    int ld;
+    int own, west, east, south, north;  // byte offsets of slot 0 for this thread and its four neighbours
+};
+
+CNV_HD void oc_thread_init(OcThread &t, const OnchipGeom &g, const OcTile &tl, int tid, const double *sm)
+{
+    const int px = tid % g.NPX, py = tid / g.NPX;
+    const int c0 = tl.tx0 + kOcPW * px, r0 = tl.ty0 + kOcPM * py;  // array coordinates of patch cell (0, 0)
+    t.upd = t.ownp = t.halop = t.inp = 0;
+    int dmin = 1 << 30;
+    for (int i = 0; i < kOcPM; i++)
+        for (int j = 0; j < kOcPW; j++) {
+            const int ar = r0 + i, ac = c0 + j, gr = g.grow0 + ar;
+            const bool in = ar >= 0 && ar < g.nrows && ac >= 0 && ac < g.ld;
+            const bool own = in && ar >= tl.y0 && ar < tl.y1 && ac >= tl.x0 && ac < tl.x1;
+            if (in && ar >= 1 && ar <= g.nrows - 2 && gr >= 1 && gr <= g.gnrows - 2 && ac >= 1 && ac <= g.ncols - 2) t.upd |= 1u << (4 * i + j);
+            if ((j & 1) == 0) {
+                if (in) t.inp |= 1u << (2 * i + j / 2);
+                if (own) t.ownp |= 1u << (2 * i + j / 2);
+                if (in && !own) t.halop |= 1u << (2 * i + j / 2);
+            }
+            // distance to the output region (Chebyshev: information moves one cell per half-sweep in either direction)
+            const int dr = ar < tl.y0 ? tl.y0 - ar : (ar >= tl.y1 ? ar - tl.y1 + 1 : 0);
+            const int dc = ac < tl.x0 ? tl.x0 - ac : (ac >= tl.x1 ? ac - tl.x1 + 1 : 0);
+            const int d = dr > dc ? dr : dc;
+            if (d < dmin) dmin = d;
+        }
+    t.fast = t.upd == 0xffffffffu;
+    t.dist = dmin;
+    t.gofs = (long long)r0 * g.ld + c0;
+    t.ld = g.ld;
+    const int base = smem_base(sm) + kOcPad * 8;
+    t.own = base + tid * 8;
+    t.west = t.own - 8;
+    t.east = t.own + 8;
+    t.south = t.own - g.NPX * 8;
+    t.north = t.own + g.NPX * 8;
+    for (int i = 0; i < kOcPM; i++)
+        for (int j = 0; j < kOcPW; j++) t.p[i][j] = t.f[i][j] = 0.0;
+}
+
+constexpr int kOcSlotBytes = kOcPitch * 8;
+
+// publish the perimeter cells of the patch (all of them, both colours)
+CNV_HD void oc_publish_all(const OcThread &t, double *sm)
+{
+#pragma unroll
+    for (int i = 0; i < kOcPM; i++) {
+        sts1(sm, t.own + oc_slot_col_lo(i) * kOcSlotBytes, t.p[i][0]);
+        sts1(sm, t.own + oc_slot_col_hi(i) * kOcSlotBytes, t.p[i][kOcPW - 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < kOcPW; j++) {
+        sts1(sm, t.own + oc_slot_row_lo(j) * kOcSlotBytes, t.p[0][j]);
+        sts1(sm, t.own + oc_slot_row_hi(j) * kOcSlotBytes, t.p[kOcPM - 1][j]);
+    }
+}
+
+// (re)load pairs of psi selected by `mask` (pair bits) from `in`; all loads are issued before the first use
+CNV_HD void oc_load_psi(OcThread &t, const double *in, unsigned mask)
+{
+#pragma unroll
+    for (int i = 0; i < kOcPM; i++)
+#pragma unroll
+        for (int jp = 0; jp < 2; jp++)
+            if ((mask >> (2 * i + jp)) & 1u) {
+                const dbl2 v = ldg2(in + t.gofs + (long long)i * t.ld + 2 * jp);
+                t.p[i][2 * jp] = v.x;
+                t.p[i][2 * jp + 1] = v.y;
+            }
+}
+CNV_HD void oc_load_rhs(OcThread &t, const double *rhs)
+{
+#pragma unroll
+    for (int i = 0; i < kOcPM; i++)
+#pragma unroll
+        for (int jp = 0; jp < 2; jp++)
+            if ((t.inp >> (2 * i + jp)) & 1u) {
+                const dbl2 v = ldg2(rhs + t.gofs + (long long)i * t.ld + 2 * jp);
+                t.f[i][2 * jp] = v.x;
+                t.f[i][2 * jp + 1] = v.y;
+            }
+}
+CNV_HD void oc_store(const OcThread &t, double *out)
+{
+#pragma unroll
+    for (int i = 0; i < kOcPM; i++)
+#pragma unroll
+        for (int jp = 0; jp < 2; jp++)
+            if ((t.ownp >> (2 * i + jp)) & 1u) stg2(out + t.gofs + (long long)i * t.ld + 2 * jp, t.p[i][2 * jp], t.p[i][2 * jp + 1]);
+}
+
+// One half-sweep.  PH = (i + j) & 1 of the cells updated (patch coordinates; the patch origin has even tile coordinates, so
+// PH = colour ^ tile.par0 for every thread of the CTA).  The 16 updates only read cells of the other colour, which nobody
+// writes during this half-sweep: they are independent, the in-place update is safe, and the neighbours' published cells
+// read here were written in an earlier half-sweep (one barrier per half-sweep).
+// SEL: apply the per-cell update mask.  NORM: 0 = no output cell, 1 = all cells are output cells, 2 = per-pair test.
+template <bool POW2, int PH, bool SEL, int NORM>
+CNV_HD void oc_half_sweep_body(OcThread &t, const RelaxConsts &rc, double *sm, double &acc)
+{
+    constexpr int PM = kOcPM, PW = kOcPW;
+    // operands that belong to the adjacent threads: column 0 cells (rows with i & 1 == PH) need W, column 3 cells (the other
+    // rows) need E, row 0 cells (columns with j & 1 == PH) need S, row PM-1 cells (the other columns) need N
+    double wv[PM / 2], ev[PM / 2], sv[PW / 2], nv[PW / 2];
+#pragma unroll
+    for (int h = 0; h < PM / 2; h++) {
+        wv[h] = lds1(sm, t.west + oc_slot_col_hi(2 * h + PH) * kOcSlotBytes);
+        ev[h] = lds1(sm, t.east + oc_slot_col_lo(2 * h + (PH ^ 1)) * kOcSlotBytes);
+    }
+#pragma unroll
+    for (int h = 0; h < PW / 2; h++) {
+        sv[h] = lds1(sm, t.south + oc_slot_row_hi(2 * h + PH) * kOcSlotBytes);
+        nv[h] = lds1(sm, t.north + oc_slot_row_lo(2 * h + (PH ^ 1)) * kOcSlotBytes);
+    }
+#pragma unroll
+    for (int i = 0; i < PM; i++) {
+#pragma unroll
+        for (int h = 0; h < PW / 2; h++) {
+            const int j = 2 * h + ((i + PH) & 1);
+            const double N = i + 1 < PM ? t.p[i + 1 < PM ? i + 1 : i][j] : nv[h];
+            const double S = i > 0 ? t.p[i > 0 ? i - 1 : 0][j] : sv[h];
+            const double E = j + 1 < PW ? t.p[i][j + 1 < PW ? j + 1 : j] : ev[i / 2];
+            const double W = j > 0 ? t.p[i][j > 0 ? j - 1 : 0] : wv[i / 2];
+            const double old = t.p[i][j];
+            double v = relax<POW2>(N, S, E, W, old, t.f[i][j], rc);
+            if (SEL) v = ((t.upd >> (4 * i + j)) & 1u) ? v : old;
+            t.p[i][j] = v;
+            if (j == 0) sts1(sm, t.own + oc_slot_col_lo(i) * kOcSlotBytes, v);
+            if (j == PW - 1) sts1(sm, t.own + oc_slot_col_hi(i) * kOcSlotBytes, v);
+            if (i == 0) sts1(sm, t.own + oc_slot_row_lo(j) * kOcSlotBytes, v);
+            if (i == PM - 1) sts1(sm, t.own + oc_slot_row_hi(j) * kOcSlotBytes, v);
+            // L1 update norm over the output cells (cells that were not updated contribute exactly 0)
+            if (NORM == 1) acc = xadd(acc, fabs(xsub(v, old)));
+            else if (NORM == 2 && ((t.ownp >> (2 * i + j / 2)) & 1u)) acc = xadd(acc, fabs(xsub(v, old)));
+        }
+    }
+}
+
+template <bool POW2, int PH>
+CNV_HD void oc_half_sweep(OcThread &t, const RelaxConsts &rc, double *sm, double &acc)
+{
+    const bool allown = t.ownp == 0xffffu, noown = t.ownp == 0;
+    if (t.fast && allown) oc_half_sweep_body<POW2, PH, false, 1>(t, rc, sm, acc);
+    else if (t.fast && noown) oc_half_sweep_body<POW2, PH, false, 0>(t, rc, sm, acc);
+    else if (noown) oc_half_sweep_body<POW2, PH, true, 0>(t, rc, sm, acc);
+    else oc_half_sweep_body<POW2, PH, true, 2>(t, rc, sm, acc);
+}
+
+// ---- planner -----------------------------------------------------------------------------------------------------
+// One tile per CTA, all CTAs co-resident (ntx * nty <= SMs: the kernel is launched cooperatively and spins on its
+// neighbours' flags).  Cost per sweep (clock cycles, fitted to the B200 measurements in profiles/): the tile's patches
+// share the SM's fp64 pipe / shared-memory port at ~6 cycles per warp-wide cell update, two barriers per sweep, and the
+// exchange after every pass (flags through L2 + halo reload) is amortised over T sweeps.
+inline bool onchip_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int num_sms, OnchipGeom *best,
+                        int force_T = 0, int force_ntx = 0, int force_nty = 0)
+{
+    OnchipGeom b;
+    std::memset(&b, 0, sizeof b);
+    double bc = 1e300;
+    const int own = own_hi - own_lo;
+    for (int T = 2; T <= 8; T += 2) {
+        if (force_T && T != force_T) continue;
+        const int H = 2 * T;
+        for (int ntx = 1; ntx <= num_sms; ntx++) {
+            if (force_ntx && ntx != force_ntx) continue;
+            int OW = (ncols + ntx - 1) / ntx;
+            OW += OW & 1;
+            if (ntx > 1 && OW < H) break;  // a tile's halo must come from its direct neighbours only
+            if ((ncols + OW - 1) / OW != ntx) continue;  // (same tiling as a smaller ntx)
+            const int NPX = (OW + 2 * H + kOcPW - 1) / kOcPW;
+            if (NPX > kOcPad - 1) continue;
+            for (int nty = 1; ntx * nty <= num_sms; nty++) {
+                if (force_nty && nty != force_nty) continue;
+                int OH = (own + nty - 1) / nty;
+                OH += OH & 1;
+                if (nty > 1 && OH < H) break;
+                if ((own + OH - 1) / OH != nty) continue;
+                const int NPY = (OH + 2 * H + kOcPM - 1) / kOcPM;
+                const int NT = NPX * NPY;
+                if (NT > kOcMaxThreads) continue;
+                const double warps = (NT + 31) / 32;
+                const double sweep = warps * 32.0 * 6.0 + 2 * 200.0;       // 32 cell updates per thread and sweep
+                const double cost = sweep + 4500.0 / T;
+                if (cost < bc) {
+                    bc = cost;
+                    b.T = T; b.H = H; b.OW = OW; b.OH = OH; b.NPX = NPX; b.NPY = NPY; b.ntx = ntx; b.nty = nty;
+                }
+            }
+        }
+    }
+    if (bc >= 1e300) return false;
+    b.nrows = nrows; b.ncols = ncols; b.ld = ld; b.grow0 = grow0; b.gnrows = gnrows; b.own_lo = own_lo; b.own_hi = own_hi;
+    *best = b;
+    return true;
+}
+
+// neighbour tiles whose output a tile's halo comes from: (bx + dx, by + dy), dx, dy in {-1, 0, 1}, inside the tile grid
+CNV_HD int oc_neighbours(const OnchipGeom &g, int bx, int by, int *out /* 8 */)
+{
+    int n = 0;
+    for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+            if (!dx && !dy) continue;
+            const int x = bx + dx, y = by + dy;
+            if (x >= 0 && x < g.ntx && y >= 0 && y < g.nty) out[n++] = y * g.ntx + x;
+        }
+    return n;
+}
+
+}  // namespace cnv

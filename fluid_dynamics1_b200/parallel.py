@@ -166,14 +166,18 @@ class SlabPoisson:
                 w.wait()
 
     def upload_owned(self, f_owned, fsign=1.0):
-        """Owned rows of the right-hand side from a host array; halo rows come from the neighbours."""
-        torch = self.torch
+        """Owned rows of the right-hand side from a host array (page-locked for a true DMA); halo rows come from the
+        neighbours.  One library call: pitched H2D straight into the solver's right-hand-side array, halo exchange on
+        the library's communicator, scaling in place, zero iterate -- no staging array, nothing synchronises."""
         f_owned = np.ascontiguousarray(f_owned, dtype=np.float64)
         assert f_owned.shape == (self.own_rows, self.ncols)
-        src = torch.from_numpy(f_owned)
-        stage = torch.empty((self.nrows, self.ncols), dtype=torch.float64, device=self.rhs.device)
-        stage.zero_()
-        stage[self.own_lo:self.own_hi].copy_(src, non_blocking=True)
+        if self.comm or self.world == 1:
+            if self.L.cnv_poisson_upload_owned(self.h, f_owned, fsign, self.stream) == 0:
+                self._src = f_owned  # keep alive until the stream has consumed it
+                return
+        torch = self.torch       # CNV_DIST_BACKEND=torch (no native communicator): stage through a device array
+        stage = torch.zeros((self.nrows, self.ncols), dtype=torch.float64, device=self.rhs.device)
+        stage[self.own_lo:self.own_hi].copy_(torch.from_numpy(f_owned), non_blocking=True)
         self.exchange_halos(stage)
         self.L.cnv_poisson_prepare(self.h, C.c_void_p(stage.data_ptr()), self.ncols, fsign, self.stream)
         self._stage = stage  # keep alive until the stream has consumed it
@@ -185,10 +189,31 @@ class SlabPoisson:
         """Index of the buffer holding the iterate after `npasses` full passes of a solve that did not stop early."""
         return npasses % len(self.bufs)
 
-    def download_owned(self, which, out):
-        t = self.bufs[which % len(self.bufs)][self.own_lo:self.own_hi, :self.ncols]
-        self.torch.from_numpy(out).copy_(t)  # synchronising D2H
+    def download_owned(self, which, out, sync=True):
+        """Owned rows of iterate buffer `which` into the host array `out` (own_rows x ncols, page-locked for a true DMA)."""
+        assert out.shape == (self.own_rows, self.ncols) and out.flags.c_contiguous
+        self.L.cnv_poisson_download_owned_async(self.h, which % len(self.bufs), out, self.stream)
+        if sync:
+            self.torch.cuda.synchronize()
         return out
+
+    def close(self):
+        """Tear-down in the order the peer path needs (include/cnavier_b200.h): quiesce, synchronise, barrier of all
+        ranks, unmap the neighbours' buffers, barrier, and only then free this rank's own buffers."""
+        if getattr(self, "h", None) is None:
+            return
+        if self.peer:
+            self.L.cnv_poisson_peer_quiesce(self.h, self.stream)
+        self.torch.cuda.synchronize()
+        if self.world > 1 and self.dist.is_initialized():
+            self.dist.barrier()
+            self.L.cnv_poisson_peer_close(self.h)
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+        self.peer = False
+        self.bufs, self.rhs, self.norms = [], None, None
+        self.solver.close()
+        self.h = None
 
     # ---- solve ----------------------------------------------------------------------------------
     def reset(self, itmax, tol):
@@ -216,8 +241,12 @@ class SlabPoisson:
     def state(self):
         return self.solver.state(self.stream)
 
-    def solve(self, itmax, tol, first_batch=16):
+    def solve(self, itmax, tol, first_batch=16, rendezvous=False):
         """Run to convergence / itmax with the reference's stopping rule; every rank returns the same dict."""
+        if self.peer and rendezvous:
+            # host-level rendezvous before the first pass: the in-kernel waits of the peer path then only ever span the skew
+            # WITHIN a solve, not whatever the hosts did in between (output files, garbage collection, ...)
+            self.dist.barrier()
         self.zero_iterate()
         self.reset(itmax, tol)
         max_passes = (itmax + self.T - 1) // self.T + 2 + (3 if len(self.bufs) == 3 else 0)  # lagged decision: speculative passes
@@ -289,7 +318,7 @@ class SlabSimulation:
 
     def close(self):
         if self.h:
-            self.poisson.solver.close()
+            self.poisson.close()
             self.L.cnv_sim_destroy(self.h)
             self.h = None
 

@@ -38,6 +38,7 @@ def main():
         slab.upload_owned(f[slab.row0:slab.row0 + slab.own_rows], 1.0)
         res = slab.solve(itmax, tol)
         full = slab.gather_result(res["buf"])
+        slab.close()   # quiesce + barrier + unmap the neighbours' buffers before anybody frees its own
         if rank == 0:
             single = fd.poisson_sor(f, dx, dy, itmax, tol, beta, T=T, raise_on_itmax=False)
             same_k = res["k"] == single["k"] and res["status"] == single["status"]

@@ -38,5 +38,6 @@ for it in range(reps):
         bad += 0 if same else 1
         print(f"rep {it}: k={res['k']} (single {single['k']}) passes={res['passes']} same={same} first_dev_sweep={first}"
               + (f" rel={rel[first]:.2e} pass={first // slab.T}" if first >= 0 else ""), flush=True)
+slab.close()
 if rank == 0: print("STRESS", "PASSED" if bad == 0 else f"FAILED ({bad}/{reps})", flush=True)
 dist.destroy_process_group()
