@@ -70,6 +70,7 @@ CNV_API = {
     "cnv_poisson_num_buffers": (C.c_int, [_vp]),
     "cnv_poisson_norms_ptr": (_vp, [_vp]),
     "cnv_poisson_plan_info": (None, [_vp, C.POINTER(C.c_longlong)]),
+    "cnv_poisson_onchip_profile": (C.c_int, [_vp, _vp, C.c_int]),
     "cnv_poisson_upload": (C.c_int, [_vp, _dp, C.c_double, _vp]),
     "cnv_poisson_upload_owned": (C.c_int, [_vp, _dp, C.c_double, _vp]),
     "cnv_poisson_download_owned_async": (C.c_int, [_vp, C.c_int, _dp, _vp]),

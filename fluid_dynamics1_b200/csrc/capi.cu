@@ -390,7 +390,14 @@ void cnv_poisson_plan_info(const cnv_poisson *p, long long *out)
     out[0] = g.WS; out[1] = g.HX; out[2] = g.Wout; out[3] = g.Hout; out[4] = g.nstrips; out[5] = g.nchunks;
     out[6] = pass_threads(p->s->T(), g.WS); out[7] = (long long)pass_smem_bytes(p->s->T(), g.WS);
     out[8] = p->s->T(); out[9] = p->s->consts().pow2;
+    const OnchipGeom &o = p->s->onchip_geom();
+    out[10] = p->s->onchip() ? 1 : 0;
+    out[11] = o.T; out[12] = o.ntx; out[13] = o.nty; out[14] = o.NPX; out[15] = o.NPY; out[16] = o.OW; out[17] = o.OH;
 }
+// CNV_ONCHIP_PROF=1 (read when the solver is created): clock ticks thread 0 of every CTA of the on-chip kernel spent in the
+// phases of its pass loop during the last solve -- out[cta][8]: 0 wait for all norms, 1 fold + decide, 2 sweeps, 3 store + flag,
+// 4 wait for the neighbours, 5 halo reload.  Returns the number of CTAs written (0 = profiling off).
+int cnv_poisson_onchip_profile(cnv_poisson *p, unsigned long long *out, int max_ctas) { return p->s->onchip_profile(out, max_ctas); }
 int cnv_poisson_prepare(cnv_poisson *p, const double *f_dev, int ldf, double fsign, void *stream)
 {
     const PassGeom &g = p->s->geom();
@@ -774,6 +781,85 @@ int cnv_sim_step(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, do
         s->steps++;
     }
     CNV_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// One time step of a slab simulation (world > 1), entirely inside the library: the loop body of src/main.c:283-395 with the halo
+// exchanges of the slab decomposition on the library's NCCL communicator (attach it to cnv_sim_poisson() first) and the
+// distributed Poisson solve (peer-memory path if it was set up, the NCCL group per pass otherwise).  Every rank calls it
+// with the same arguments and gets the same k / e / continuity values.  Returns 0, or (index of the step whose Poisson solve
+// hit itmax) + 1 on every rank, or -1 without a communicator.
+int cnv_sim_step_slab(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, double *cont_min)
+{
+    if (!s->ps->has_comm()) {
+        std::printf("** Error: slab time stepping needs the communicator (cnv_poisson_attach_comm) **\n");
+        return -1;
+    }
+    const Config &c = s->cfg;
+    const double bc[8] = {c.u1, c.u2, c.u3, c.u4, c.v1, c.v2, c.v3, c.v4};
+    cudaStream_t st = s->stream;
+    PoissonSolver &P = *s->ps;
+    const int H3 = 3;  // reach of the order-6 stencils (orders 2 and 4 need less)
+    for (int t = 0; t < nsteps; t++) {
+        launch_ring_bc_vorticity(s->u, s->v, s->w, s->map, s->ncols, s->ld, bc, s->d1x, s->d1y, st);
+        P.exchange_halos(s->w, H3, st);
+        launch_euler_fused(s->w, s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->d2x, s->d2y, s->inv_re, c.dt,
+                           P.consts().pscale, s->w2, P.rhs(), st);
+        std::swap(s->w, s->w2);
+        count_launch(2);
+        P.exchange_halos(P.rhs(), P.geom().HY, st);  // 2T rows: the solver recomputes its halo rows
+        // zero initial guess every step (fresh initm in the reference, src/poisson.c:229), peer-safe
+        P.peer_quiesce(st);
+        launch_prep_rhs(nullptr, s->nrows, s->ncols, 0, 1.0, P.consts().pscale, P.rhs(), P.buffer(0), P.buffer(1), s->ld, st);
+        P.zero_extra_buffer(st);
+        P.peer_ready(st);
+        count_launch(1);
+        PoissonResult r = P.solve(c.poisson_max_it, c.poisson_tol, st, &s->psi_buf, false);
+        s->sweeps += r.sweeps;
+        s->passes += r.passes;
+        if (k) k[t] = r.k;
+        if (e) e[t] = r.e;
+        if (r.status != 0) return t + 1;
+        P.exchange_halos(P.buffer(s->psi_buf), H3, st);  // (a "redo" pass leaves the result's halo rows stale)
+        launch_velocity(P.buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
+        count_launch(1);
+        P.exchange_halos(s->u, H3, st);
+        P.exchange_halos(s->v, H3, st);
+        if (s->diag && (cont_max || cont_min)) {
+            launch_continuity(s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket, s->cont_result, st);
+            count_launch(1);
+            P.allreduce_max_min(s->cont_result, st);
+            CNV_CUDA_CHECK(cudaMemcpyAsync(s->h_cont, s->cont_result, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+            CNV_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (cont_max) cont_max[t] = s->h_cont[0];
+            if (cont_min) cont_min[t] = s->h_cont[1];
+        }
+        s->steps++;
+    }
+    CNV_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// Whole fields of a slab simulation on rank 0 (host arrays of nx*ny doubles there, ignored elsewhere; NULL to skip a field --
+// identically on every rank): every rank sends its owned rows over the communicator.
+int cnv_sim_gather_fields_slab(cnv_sim *s, double *psi, double *w, double *u, double *v)
+{
+    if (!s->ps->has_comm()) return -1;
+    const int world = s->ps->comm().world, rank = s->ps->comm().rank;
+    const double *src[4] = {s->ps->buffer(s->psi_buf), s->w, s->u, s->v};
+    double *dst[4] = {psi, w, u, v};
+    double *stage = nullptr;
+    if (rank == 0) {
+        const int rows = (s->map.gnrows + world - 1) / world;
+        CNV_CUDA_CHECK(cudaMalloc(&stage, sizeof(double) * (size_t)rows * s->ld));
+    }
+    for (int i = 0; i < 4; i++)
+        if (dst[i] || rank != 0) {
+            if (rank != 0 && !dst[i]) continue;
+            s->ps->gather_field_to_root(src[i], stage, dst[i], s->stream);
+        }
+    CNV_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    if (stage) cudaFree(stage);
     return 0;
 }
 

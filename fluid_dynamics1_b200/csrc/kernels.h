@@ -74,7 +74,7 @@ void launch_resident(const ResidentGeom &g, size_t smem, const RelaxConsts &rc, 
 
 // ---- poisson_onchip.cu: the whole solve in one persistent launch, iterate resident in registers (<= ~1.5 M cells) ----
 void launch_onchip(const OnchipGeom &g, const RelaxConsts &rc, double *b0, double *b1, double *b2, const double *rhs, PoissonCtl *ctl,
-                   unsigned long long *flags, double *partials, double *hist, cudaStream_t s);
+                   unsigned long long *flags, double *partials, double *hist, cudaStream_t s, unsigned long long *prof = nullptr);
 
 // ---- poisson.cu ----
 struct PoissonResult {
@@ -101,7 +101,8 @@ public:
     int ld() const { return geom_.ld; }
     int T() const { return T_; }
     const PassGeom &geom() const { return geom_; }
-    bool onchip() const { return use_onchip_; }  // solve() runs the persistent on-chip kernel (poisson_onchip.cu)
+    bool onchip() const { return use_onchip_; }
+    int onchip_profile(unsigned long long *out, int max_ctas);  // CNV_ONCHIP_PROF=1: 8 phase counters per CTA of the last solve  // solve() runs the persistent on-chip kernel (poisson_onchip.cu)
     const OnchipGeom &onchip_geom() const { return oc_; }
     double *rhs() { return rhs_; }                // device, pitch ld(): pscale * f
     double *buffer(int i) { return buf_[i]; }     // the iterate buffers: 0, 1 (and 2 with a lagged stop decision: peer path, on-chip kernel)
@@ -140,6 +141,9 @@ public:
     bool has_comm() const { return comm_.comm != nullptr; }
     void enqueue_passes_dist(int npasses, cudaStream_t s);
     void exchange_halos(double *field, int depth, cudaStream_t s);  // any slab-local field with this solver's layout
+    void allreduce_max_min(double *two_dev, cudaStream_t s);        // two[0] <- max, two[1] <- min over the ranks
+    void gather_field_to_root(const double *field, double *stage_dev, double *host_out, cudaStream_t s);
+    const SlabComm &comm() const { return comm_; }
     void restart_pass_counter() { dist_passes_ = 0; }
     // Peer-memory path (CUDA IPC over NVLink): boundary rows are stored into the neighbours' halos by the pass
     // kernel itself, norms are published in every rank's mailbox, each CTA derives the stop decision: one kernel
@@ -162,6 +166,7 @@ private:
     OnchipGeom oc_ = {};
     bool use_onchip_ = false;
     unsigned long long *oc_flags_ = nullptr;
+    unsigned long long *oc_prof_ = nullptr;   // CNV_ONCHIP_PROF=1: per-CTA phase counters of the last solve
     double *oc_partials_ = nullptr;
     RelaxConsts rc_;
     double *buf_[3] = {nullptr, nullptr, nullptr};

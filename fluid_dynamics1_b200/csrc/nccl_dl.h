@@ -1,6 +1,6 @@
 // nccl_dl.h -- NCCL entry points resolved at run time (dlopen), so that libcnavier_b200.so carries no link-time
 // dependency on NCCL and binds to whichever libnccl.so.2 the process already holds (torch's bundled one when the
-// Python layer is in use).  Only the calls of the slab halo exchange are needed.
+// Python layer is in use).  Only the calls of the slab halo exchange and of the continuity max / min all-reduce are needed.
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
@@ -17,6 +17,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -38,9 +39,10 @@ inline const NcclApi &nccl_api()
     CNV_SYM(GroupEnd, "ncclGroupEnd");
     CNV_SYM(Send, "ncclSend");
     CNV_SYM(Recv, "ncclRecv");
+    CNV_SYM(AllReduce, "ncclAllReduce");
     CNV_SYM(GetErrorString, "ncclGetErrorString");
 #undef CNV_SYM
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send && api.Recv;
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send && api.Recv && api.AllReduce;
     return api;
 }
 

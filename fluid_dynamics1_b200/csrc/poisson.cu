@@ -422,7 +422,8 @@ static void launch_pass(const PassGeom &g, const RelaxConsts &rc, double *b0, do
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int kOnchipDefault = 0;  // default use of the on-chip kernel where a plan exists (CNV_POISSON_ONCHIP overrides)
+constexpr int kOnchipDefault = 1;  // the on-chip kernel wherever it has a plan: measured faster than the streaming kernel on every
+                                   // grid it fits (1.8 vs 3.3 us per sweep at 64^2 ... 2.7 vs 6.1 at 1024^2, profiles/onchip_r2.md)
 
 static int env_int(const char *name, int dflt)
 {
@@ -474,9 +475,13 @@ PoissonSolver::PoissonSolver(int nrows, int ncols, int T, int grow0, int gnrows,
         CNV_CUDA_CHECK(cudaMalloc(&buf_[2], bytes));
         CNV_CUDA_CHECK(cudaMemset(buf_[2], 0, bytes));
         const size_t ncta = (size_t)oc_.ntx * oc_.nty;
-        CNV_CUDA_CHECK(cudaMalloc(&oc_flags_, sizeof(unsigned long long) * (ncta + 1)));
-        CNV_CUDA_CHECK(cudaMalloc(&oc_partials_, sizeof(double) * kOcNormSlots * ncta * 8));
-        CNV_CUDA_CHECK(cudaMemset(oc_partials_, 0, sizeof(double) * kOcNormSlots * ncta * 8));
+        CNV_CUDA_CHECK(cudaMalloc(&oc_flags_, sizeof(unsigned long long) * kOcFlagStride * (ncta + 2 * kOcNormSlots + 1)));
+        CNV_CUDA_CHECK(cudaMalloc(&oc_partials_, sizeof(double) * kOcNormSlots * (ncta + 1) * 8));
+        CNV_CUDA_CHECK(cudaMemset(oc_partials_, 0, sizeof(double) * kOcNormSlots * (ncta + 1) * 8));
+        if (env_int("CNV_ONCHIP_PROF", 0)) {
+            CNV_CUDA_CHECK(cudaMalloc(&oc_prof_, sizeof(unsigned long long) * ncta * 8));
+            CNV_CUDA_CHECK(cudaMemset(oc_prof_, 0, sizeof(unsigned long long) * ncta * 8));
+        }
     }
     for (int i = 0; i < 2; i++) {
         CNV_CUDA_CHECK(cudaMalloc(&buf_[i], bytes));
@@ -505,8 +510,18 @@ PoissonSolver::~PoissonSolver()
     if (ctlbuf_) cudaFree(ctlbuf_);
     if (oc_flags_) cudaFree(oc_flags_);
     if (oc_partials_) cudaFree(oc_partials_);
+    if (oc_prof_) cudaFree(oc_prof_);
     cudaFreeHost(h_ctl_);
     cudaEventDestroy(ev_);
+}
+
+int PoissonSolver::onchip_profile(unsigned long long *out, int max_ctas)
+{
+    if (!oc_prof_) return 0;
+    const int ncta = std::min(max_ctas, oc_.ntx * oc_.nty);
+    CNV_CUDA_CHECK(cudaDeviceSynchronize());
+    CNV_CUDA_CHECK(cudaMemcpy(out, oc_prof_, sizeof(unsigned long long) * 8 * (size_t)ncta, cudaMemcpyDeviceToHost));
+    return ncta;
 }
 
 void PoissonSolver::set_consts(double dx, double dy, double beta) { rc_ = make_relax_consts(dx, dy, beta); }
@@ -807,6 +822,40 @@ void PoissonSolver::enqueue_passes_dist(int npasses, cudaStream_t s)
     CNV_CUDA_CHECK(cudaGetLastError());
 }
 
+// continuity diagnostic of a slab run (src/main.c:407-408, maxel / minel): two[0] <- max over the ranks, two[1] <- min
+void PoissonSolver::allreduce_max_min(double *two, cudaStream_t s)
+{
+    const NcclApi &n = nccl_api();
+    ncclComm_t comm = (ncclComm_t)comm_.comm;
+    CNV_NCCL_CHECK(n.GroupStart());
+    CNV_NCCL_CHECK(n.AllReduce(two, two, 1, ncclFloat64, ncclMax, comm, s));
+    CNV_NCCL_CHECK(n.AllReduce(two + 1, two + 1, 1, ncclFloat64, ncclMin, comm, s));
+    CNV_NCCL_CHECK(n.GroupEnd());
+}
+
+// owned rows of a slab-local field -> rank 0 (device to device over NCCL), which assembles the whole field on the host:
+// rank 0 passes host_out (gnrows x ncols) and a device staging array of at least (largest slab) x ld doubles
+void PoissonSolver::gather_field_to_root(const double *field, double *stage, double *host_out, cudaStream_t s)
+{
+    const NcclApi &n = nccl_api();
+    ncclComm_t comm = (ncclComm_t)comm_.comm;
+    const int world = comm_.world, rank = comm_.rank, ld = geom_.ld, gn = geom_.gnrows;
+    const int base = gn / world, rem = gn % world;
+    if (rank != 0) {
+        CNV_NCCL_CHECK(n.Send(field + (size_t)geom_.own_lo * ld, (size_t)(geom_.own_hi - geom_.own_lo) * ld, ncclFloat64, 0, comm, s));
+        return;
+    }
+    CNV_CUDA_CHECK(cudaMemcpy2DAsync(host_out, sizeof(double) * geom_.ncols, field + (size_t)geom_.own_lo * ld, sizeof(double) * ld,
+                                     sizeof(double) * geom_.ncols, geom_.own_hi - geom_.own_lo, cudaMemcpyDeviceToHost, s));
+    for (int r = 1; r < world; r++) {
+        const int r0 = r * base + (r < rem ? r : rem), rows = base + (r < rem ? 1 : 0);
+        CNV_NCCL_CHECK(n.Recv(stage, (size_t)rows * ld, ncclFloat64, r, comm, s));
+        CNV_CUDA_CHECK(cudaMemcpy2DAsync(host_out + (size_t)r0 * geom_.ncols, sizeof(double) * geom_.ncols, stage, sizeof(double) * ld,
+                                         sizeof(double) * geom_.ncols, rows, cudaMemcpyDeviceToHost, s));
+    }
+    CNV_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
 void PoissonSolver::enqueue_decide(cudaStream_t s)
 {
     k_decide<<<1, 1, 0, s>>>(ctl_, norms_, T_, use_hist_ ? hist_ : nullptr);
@@ -845,7 +894,7 @@ PoissonResult PoissonSolver::solve(int itmax, double tol, cudaStream_t s, int *r
     // (poisson_onchip.cu).  Same arithmetic, same red-black order -> same bits.
     if (use_onchip_ && !distributed_ && itmax > 0) {
         k_reset_ctl<<<1, 1, 0, s>>>(ctl_, itmax, tol, 3);  // (three buffers in rotation)
-        launch_onchip(oc_, rc_, buf_[0], buf_[1], buf_[2], rhs_, ctl_, oc_flags_, oc_partials_, use_hist_ ? hist_ : nullptr, s);
+        launch_onchip(oc_, rc_, buf_[0], buf_[1], buf_[2], rhs_, ctl_, oc_flags_, oc_partials_, use_hist_ ? hist_ : nullptr, s, oc_prof_);
         launches_ += 1;
         count_launch(2);
         PoissonCtl c = read_ctl(s);
@@ -867,9 +916,18 @@ PoissonResult PoissonSolver::solve(int itmax, double tol, cudaStream_t s, int *r
     const int max_passes = (itmax + T_ - 1) / T_ + 2 + (links_.enabled && links_.lag ? 3 : 0);
     int enq = 0;
     PoissonCtl c;
+    // slab solvers: the peer path exchanges inside the pass kernel; without it every pass is followed by the NCCL group
+    // (halo rows + norm all-gather) and the decide kernel
+    const bool nccl_path = distributed_ && !links_.enabled;
+    if (nccl_path && !comm_.comm) {
+        std::printf("** Error: slab solver without a communicator: attach one (cnv_poisson_attach_comm) or set up the peer path **\n");
+        std::exit(1);
+    }
     for (;;) {
         batch = std::max(1, std::min(batch, max_passes + 1 - enq));
-        enqueue_passes(batch, s);
+        if (nccl_path) batch = std::min(batch, 32);  // a surplus (no-op) pass still costs its NCCL group on this path
+        if (nccl_path) enqueue_passes_dist(batch, s);
+        else enqueue_passes(batch, s);
         enq += batch;
         c = read_ctl(s);
         if (c.state != 0) break;

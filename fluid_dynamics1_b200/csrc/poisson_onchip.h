@@ -30,11 +30,20 @@ namespace cnv {
 
 constexpr int kOcPW = 4;           // patch columns per thread
 constexpr int kOcPM = 8;           // patch rows per thread
-constexpr int kOcMaxThreads = 384; // registers: 64 (psi) + 64 (rhs) + temporaries per thread, one CTA per SM
+#ifndef CNV_OC_OCC
+#define CNV_OC_OCC 1
+#endif
+// CTAs per SM.  Two half-size CTAs per SM (so that one computes while the other sits in the latency chain between two passes)
+// were measured SLOWER at 1024^2: 4.2-4.6 vs 3.9 us per sweep (more tiles = more halo cells to recompute, and the sweeps of the
+// two CTAs share the fp64 pipe, which is already half busy); profiles/onchip_r2.md.
+constexpr int kOcOcc = CNV_OC_OCC;
+constexpr int kOcMaxThreads = 384 / kOcOcc - 32;  // compute threads; + one service warp = 384 x 168 registers = 64512 per SM
+constexpr int kOcMaxCtas = 148 * kOcOcc;     // (the kernel gathers all CTAs' norm partials in a fixed-size shared array)
 constexpr int kOcPad = 64;         // published arrays are addressable for thread ids -kOcPad .. kOcMaxThreads + kOcPad - 1
 constexpr int kOcPitch = kOcMaxThreads + 2 * kOcPad;  // doubles per slot
 constexpr int kOcSlots = 2 * kOcPM + 2 * kOcPW;       // ColLo[PM], ColHi[PM], RowLo[PW], RowHi[PW]
 constexpr int kOcNormSlots = 4;    // rings of per-pass norm partials
+constexpr int kOcFlagStride = 16;  // one 128-byte line per CTA flag: pollers of different flags hit different L2 lines
 static_assert(kOcPM % 2 == 0 && kOcPW == 4, "colour pattern of a patch is static");
 
 CNV_HD int oc_slot_col_lo(int i) { return i; }                        // cell (i, 0)
@@ -47,8 +56,8 @@ struct OnchipGeom {
     // local array: nrows x ncols doubles with pitch ld; row 0 is global row grow0 of gnrows; rows [own_lo, own_hi) are produced
     int nrows, ncols, ld, grow0, gnrows, own_lo, own_hi;
     int T;         // sweeps per pass
-    int H;         // halo cells on every side = 2T (a multiple of 4)
-    int OW, OH;    // output columns / rows per tile (even)
+    int HX, HY;    // halo columns / rows on either side: 2T rounded up to whole patches (multiples of 4 / 8)
+    int OW, OH;    // output columns / rows per tile (multiples of 4 / 8): a patch is all output or all halo
     int NPX, NPY;  // patches per tile; tile = (4 NPX) x (8 NPY) cells, threads per CTA = NPX * NPY
     int ntx, nty;  // tiles
 };
@@ -69,61 +78,63 @@ CNV_HD OcTile oc_tile(const OnchipGeom &g, int bx, int by)
     t.x1 = t.x0 + g.OW < g.ld ? t.x0 + g.OW : g.ld;
     t.y0 = g.own_lo + by * g.OH;
     t.y1 = t.y0 + g.OH < g.own_hi ? t.y0 + g.OH : g.own_hi;
-    t.tx0 = t.x0 - g.H;
-    t.ty0 = t.y0 - g.H;
+    t.tx0 = t.x0 - g.HX;
+    t.ty0 = t.y0 - g.HY;
     t.par0 = (g.grow0 + t.ty0 + t.tx0) & 1;
     return t;
 }
 
 // Per-thread state.  p / f: the patch of psi and of the (pre-scaled) right-hand side, row i = 0..7 bottom-up, column j = 0..3.
-// Masks: bit (4 i + j) per cell, bit (2 i + j/2) per column pair (global loads / stores move pairs).
+// Output regions are aligned to patches, so a thread is an OUTPUT thread (all its cells inside the array belong to the tile's
+// output region: stored after a pass, counted in the norm) or a HALO thread (reloaded after every pass, norm discarded).
 struct OcThread {
     double p[kOcPM][kOcPW];
     double f[kOcPM][kOcPW];
-    unsigned upd;       // cell may be updated: inside the array, off the Dirichlet ring, off the array's first / last row
-    unsigned ownp;      // pair belongs to the tile's output region (stored after a pass, counted in the norm)
-    unsigned halop;     // pair is in the array but not in the output region: reloaded after every pass
-    unsigned inp;       // pair exists in the array
+    unsigned upd;       // bit 4 i + j: cell may be updated (inside the array, off the Dirichlet ring, off the array's first / last row)
+    unsigned inr;       // bit i: patch row i exists in the array (global loads / stores move whole 32-byte patch rows)
+    bool band;          // output thread whose patch lies in the boundary band of the output region (a neighbour's halo)
+    bool own;           // output thread
+    int src;            // halo thread: the tile (CTA index) whose output region its patch lies in, -1 if outside the array
     bool fast;          // all 32 cells updatable
-    int dist;           // distance (cells) of the patch from the output region: 0 if it touches it
+    int dist;           // distance (cells) of the patch from the output region: 0 for output threads
     long long gofs;     // element offset of cell (0, 0) in the global arrays
     int ld;
-    int own, west, east, south, north;  // byte offsets of slot 0 for this thread and its four neighbours
+    int self, west, east, south, north;  // byte offsets of slot 0 for this thread and its four neighbours
 };
 
 CNV_HD void oc_thread_init(OcThread &t, const OnchipGeom &g, const OcTile &tl, int tid, const double *sm)
 {
     const int px = tid % g.NPX, py = tid / g.NPX;
     const int c0 = tl.tx0 + kOcPW * px, r0 = tl.ty0 + kOcPM * py;  // array coordinates of patch cell (0, 0)
-    t.upd = t.ownp = t.halop = t.inp = 0;
-    int dmin = 1 << 30;
+    t.upd = t.inr = 0;
     for (int i = 0; i < kOcPM; i++)
         for (int j = 0; j < kOcPW; j++) {
             const int ar = r0 + i, ac = c0 + j, gr = g.grow0 + ar;
-            const bool in = ar >= 0 && ar < g.nrows && ac >= 0 && ac < g.ld;
-            const bool own = in && ar >= tl.y0 && ar < tl.y1 && ac >= tl.x0 && ac < tl.x1;
+            const bool in = ar >= 0 && ar < g.nrows && ac >= 0 && ac < g.ld;  // (c0 and ld are multiples of 4: a row is in or out)
             if (in && ar >= 1 && ar <= g.nrows - 2 && gr >= 1 && gr <= g.gnrows - 2 && ac >= 1 && ac <= g.ncols - 2) t.upd |= 1u << (4 * i + j);
-            if ((j & 1) == 0) {
-                if (in) t.inp |= 1u << (2 * i + j / 2);
-                if (own) t.ownp |= 1u << (2 * i + j / 2);
-                if (in && !own) t.halop |= 1u << (2 * i + j / 2);
-            }
-            // distance to the output region (Chebyshev: information moves one cell per half-sweep in either direction)
-            const int dr = ar < tl.y0 ? tl.y0 - ar : (ar >= tl.y1 ? ar - tl.y1 + 1 : 0);
-            const int dc = ac < tl.x0 ? tl.x0 - ac : (ac >= tl.x1 ? ac - tl.x1 + 1 : 0);
-            const int d = dr > dc ? dr : dc;
-            if (d < dmin) dmin = d;
+            if (in && j == 0) t.inr |= 1u << i;
         }
+    // patch-aligned regions: the patch origin decides (x0, y0, OW, OH, HX, HY are multiples of the patch size)
+    t.own = r0 >= tl.y0 && r0 < tl.y1 && c0 >= tl.x0 && c0 < tl.x1;
+    // the part of the output region the neighbour tiles read as their halo: stored before the flag is raised
+    t.band = t.own && (r0 < tl.y0 + g.HY || r0 + kOcPM > tl.y1 - g.HY || c0 < tl.x0 + g.HX || c0 + kOcPW > tl.x1 - g.HX);
+    t.src = -1;
+    // (pad columns beyond the last tile's output region belong to nobody: they hold zeros for ever)
+    if (!t.own && r0 >= g.own_lo && r0 < g.own_hi && c0 >= 0 && c0 < g.ld && c0 / g.OW < g.ntx)
+        t.src = ((r0 - g.own_lo) / g.OH) * g.ntx + c0 / g.OW;
+    // distance to the output region (Chebyshev: information moves one cell per half-sweep in either direction)
+    const int dr = r0 + kOcPM - 1 < tl.y0 ? tl.y0 - (r0 + kOcPM - 1) : (r0 >= tl.y1 ? r0 - tl.y1 + 1 : 0);
+    const int dc = c0 + kOcPW - 1 < tl.x0 ? tl.x0 - (c0 + kOcPW - 1) : (c0 >= tl.x1 ? c0 - tl.x1 + 1 : 0);
+    t.dist = dr > dc ? dr : dc;
     t.fast = t.upd == 0xffffffffu;
-    t.dist = dmin;
     t.gofs = (long long)r0 * g.ld + c0;
     t.ld = g.ld;
     const int base = smem_base(sm) + kOcPad * 8;
-    t.own = base + tid * 8;
-    t.west = t.own - 8;
-    t.east = t.own + 8;
-    t.south = t.own - g.NPX * 8;
-    t.north = t.own + g.NPX * 8;
+    t.self = base + tid * 8;
+    t.west = t.self - 8;
+    t.east = t.self + 8;
+    t.south = t.self - g.NPX * 8;
+    t.north = t.self + g.NPX * 8;
     for (int i = 0; i < kOcPM; i++)
         for (int j = 0; j < kOcPW; j++) t.p[i][j] = t.f[i][j] = 0.0;
 }
@@ -135,57 +146,50 @@ CNV_HD void oc_publish_all(const OcThread &t, double *sm)
 {
 #pragma unroll
     for (int i = 0; i < kOcPM; i++) {
-        sts1(sm, t.own + oc_slot_col_lo(i) * kOcSlotBytes, t.p[i][0]);
-        sts1(sm, t.own + oc_slot_col_hi(i) * kOcSlotBytes, t.p[i][kOcPW - 1]);
+        sts1(sm, t.self + oc_slot_col_lo(i) * kOcSlotBytes, t.p[i][0]);
+        sts1(sm, t.self + oc_slot_col_hi(i) * kOcSlotBytes, t.p[i][kOcPW - 1]);
     }
 #pragma unroll
     for (int j = 0; j < kOcPW; j++) {
-        sts1(sm, t.own + oc_slot_row_lo(j) * kOcSlotBytes, t.p[0][j]);
-        sts1(sm, t.own + oc_slot_row_hi(j) * kOcSlotBytes, t.p[kOcPM - 1][j]);
+        sts1(sm, t.self + oc_slot_row_lo(j) * kOcSlotBytes, t.p[0][j]);
+        sts1(sm, t.self + oc_slot_row_hi(j) * kOcSlotBytes, t.p[kOcPM - 1][j]);
     }
 }
 
-// (re)load pairs of psi selected by `mask` (pair bits) from `in`; all loads are issued before the first use
-CNV_HD void oc_load_psi(OcThread &t, const double *in, unsigned mask)
+// (re)load the patch of psi from `in` (the rows that exist in the array); all loads are issued before the first use
+CNV_HD void oc_load_psi(OcThread &t, const double *in)
 {
 #pragma unroll
     for (int i = 0; i < kOcPM; i++)
-#pragma unroll
-        for (int jp = 0; jp < 2; jp++)
-            if ((mask >> (2 * i + jp)) & 1u) {
-                const dbl2 v = ldg2(in + t.gofs + (long long)i * t.ld + 2 * jp);
-                t.p[i][2 * jp] = v.x;
-                t.p[i][2 * jp + 1] = v.y;
-            }
+        if ((t.inr >> i) & 1u) {
+            const dbl4 v = ldg4(in + t.gofs + (long long)i * t.ld);
+            t.p[i][0] = v.x; t.p[i][1] = v.y; t.p[i][2] = v.z; t.p[i][3] = v.w;
+        }
 }
 CNV_HD void oc_load_rhs(OcThread &t, const double *rhs)
 {
 #pragma unroll
     for (int i = 0; i < kOcPM; i++)
-#pragma unroll
-        for (int jp = 0; jp < 2; jp++)
-            if ((t.inp >> (2 * i + jp)) & 1u) {
-                const dbl2 v = ldg2(rhs + t.gofs + (long long)i * t.ld + 2 * jp);
-                t.f[i][2 * jp] = v.x;
-                t.f[i][2 * jp + 1] = v.y;
-            }
+        if ((t.inr >> i) & 1u) {
+            const dbl4 v = ldg4(rhs + t.gofs + (long long)i * t.ld);
+            t.f[i][0] = v.x; t.f[i][1] = v.y; t.f[i][2] = v.z; t.f[i][3] = v.w;
+        }
 }
 CNV_HD void oc_store(const OcThread &t, double *out)
 {
 #pragma unroll
     for (int i = 0; i < kOcPM; i++)
-#pragma unroll
-        for (int jp = 0; jp < 2; jp++)
-            if ((t.ownp >> (2 * i + jp)) & 1u) stg2(out + t.gofs + (long long)i * t.ld + 2 * jp, t.p[i][2 * jp], t.p[i][2 * jp + 1]);
+        if ((t.inr >> i) & 1u) stg4(out + t.gofs + (long long)i * t.ld, t.p[i][0], t.p[i][1], t.p[i][2], t.p[i][3]);
 }
 
 // One half-sweep.  PH = (i + j) & 1 of the cells updated (patch coordinates; the patch origin has even tile coordinates, so
 // PH = colour ^ tile.par0 for every thread of the CTA).  The 16 updates only read cells of the other colour, which nobody
 // writes during this half-sweep: they are independent, the in-place update is safe, and the neighbours' published cells
 // read here were written in an earlier half-sweep (one barrier per half-sweep).
-// SEL: apply the per-cell update mask.  NORM: 0 = no output cell, 1 = all cells are output cells, 2 = per-pair test.
-template <bool POW2, int PH, bool SEL, int NORM>
-CNV_HD void oc_half_sweep_body(OcThread &t, const RelaxConsts &rc, double *sm, double &acc)
+// SEL: apply the per-cell update mask (threads next to the Dirichlet ring or the array edge; chosen per WARP by the caller so
+// that a warp never runs both bodies).  `acc` collects |new - old| of ALL 16 cells; halo threads discard theirs.
+template <bool POW2, int PH, bool SEL>
+CNV_HD void oc_half_sweep(OcThread &t, const RelaxConsts &rc, double *sm, double &acc)
 {
     constexpr int PM = kOcPM, PW = kOcPW;
     // operands that belong to the adjacent threads: column 0 cells (rows with i & 1 == PH) need W, column 3 cells (the other
@@ -214,31 +218,18 @@ CNV_HD void oc_half_sweep_body(OcThread &t, const RelaxConsts &rc, double *sm, d
             double v = relax<POW2>(N, S, E, W, old, t.f[i][j], rc);
             if (SEL) v = ((t.upd >> (4 * i + j)) & 1u) ? v : old;
             t.p[i][j] = v;
-            if (j == 0) sts1(sm, t.own + oc_slot_col_lo(i) * kOcSlotBytes, v);
-            if (j == PW - 1) sts1(sm, t.own + oc_slot_col_hi(i) * kOcSlotBytes, v);
-            if (i == 0) sts1(sm, t.own + oc_slot_row_lo(j) * kOcSlotBytes, v);
-            if (i == PM - 1) sts1(sm, t.own + oc_slot_row_hi(j) * kOcSlotBytes, v);
-            // L1 update norm over the output cells (cells that were not updated contribute exactly 0)
-            if (NORM == 1) acc = xadd(acc, fabs(xsub(v, old)));
-            else if (NORM == 2 && ((t.ownp >> (2 * i + j / 2)) & 1u)) acc = xadd(acc, fabs(xsub(v, old)));
+            if (j == 0) sts1(sm, t.self + oc_slot_col_lo(i) * kOcSlotBytes, v);
+            if (j == PW - 1) sts1(sm, t.self + oc_slot_col_hi(i) * kOcSlotBytes, v);
+            if (i == 0) sts1(sm, t.self + oc_slot_row_lo(j) * kOcSlotBytes, v);
+            if (i == PM - 1) sts1(sm, t.self + oc_slot_row_hi(j) * kOcSlotBytes, v);
+            acc = xadd(acc, fabs(xsub(v, old)));  // (a cell that was not updated contributes exactly 0)
         }
     }
 }
 
-template <bool POW2, int PH>
-CNV_HD void oc_half_sweep(OcThread &t, const RelaxConsts &rc, double *sm, double &acc)
-{
-    const bool allown = t.ownp == 0xffffu, noown = t.ownp == 0;
-    if (t.fast && allown) oc_half_sweep_body<POW2, PH, false, 1>(t, rc, sm, acc);
-    else if (t.fast && noown) oc_half_sweep_body<POW2, PH, false, 0>(t, rc, sm, acc);
-    else if (noown) oc_half_sweep_body<POW2, PH, true, 0>(t, rc, sm, acc);
-    else oc_half_sweep_body<POW2, PH, true, 2>(t, rc, sm, acc);
-}
-
 // ---- planner -----------------------------------------------------------------------------------------------------
-// One tile per CTA, all CTAs co-resident (ntx * nty <= SMs: the kernel is launched cooperatively and spins on its
-// neighbours' flags).  Cost per sweep (clock cycles, fitted to the B200 measurements in profiles/): the tile's patches
-// share the SM's fp64 pipe / shared-memory port at ~6 cycles per warp-wide cell update, two barriers per sweep, and the
+// One tile per CTA, all CTAs co-resident (ntx * nty <= SMs: the kernel is launched cooperatively and waits on its
+// neighbours' flags).  The cost per sweep (clock cycles) is fitted to the B200 measurements in profiles/onchip_r2.md; the
 // exchange after every pass (flags through L2 + halo reload) is amortised over T sweeps.
 inline bool onchip_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int own_lo, int own_hi, int num_sms, OnchipGeom *best,
                         int force_T = 0, int force_ntx = 0, int force_nty = 0)
@@ -249,30 +240,29 @@ inline bool onchip_plan(int nrows, int ncols, int ld, int grow0, int gnrows, int
     const int own = own_hi - own_lo;
     for (int T = 2; T <= 8; T += 2) {
         if (force_T && T != force_T) continue;
-        const int H = 2 * T;
-        for (int ntx = 1; ntx <= num_sms; ntx++) {
+        const int HX = round_up(2 * T, kOcPW), HY = round_up(2 * T, kOcPM);
+        for (int ntx = 1; ntx <= num_sms * kOcOcc; ntx++) {
             if (force_ntx && ntx != force_ntx) continue;
-            int OW = (ncols + ntx - 1) / ntx;
-            OW += OW & 1;
-            if (ntx > 1 && OW < H) break;  // a tile's halo must come from its direct neighbours only
+            const int OW = round_up((ncols + ntx - 1) / ntx, kOcPW);
+            if (ntx > 1 && OW < HX) break;               // a tile's halo must come from its direct neighbours only
             if ((ncols + OW - 1) / OW != ntx) continue;  // (same tiling as a smaller ntx)
-            const int NPX = (OW + 2 * H + kOcPW - 1) / kOcPW;
+            const int NPX = (OW + 2 * HX) / kOcPW;
             if (NPX > kOcPad - 1) continue;
-            for (int nty = 1; ntx * nty <= num_sms; nty++) {
+            for (int nty = 1; ntx * nty <= num_sms * kOcOcc && ntx * nty <= kOcMaxCtas; nty++) {
                 if (force_nty && nty != force_nty) continue;
-                int OH = (own + nty - 1) / nty;
-                OH += OH & 1;
-                if (nty > 1 && OH < H) break;
+                const int OH = round_up((own + nty - 1) / nty, kOcPM);
+                if (nty > 1 && OH < HY) break;
                 if ((own + OH - 1) / OH != nty) continue;
-                const int NPY = (OH + 2 * H + kOcPM - 1) / kOcPM;
+                const int NPY = (OH + 2 * HY) / kOcPM;
                 const int NT = NPX * NPY;
                 if (NT > kOcMaxThreads) continue;
+                // measured (profiles/onchip_r2.md): a sweep costs ~2800 cycles + 80 per compute warp (latency of the two
+                // half-sweeps, then the fp64 pipe), the exchange between two passes ~6000 cycles
                 const double warps = (NT + 31) / 32;
-                const double sweep = warps * 32.0 * 6.0 + 2 * 200.0;       // 32 cell updates per thread and sweep
-                const double cost = sweep + 4500.0 / T;
+                const double cost = 2800.0 + 80.0 * warps + 6000.0 / T;
                 if (cost < bc) {
                     bc = cost;
-                    b.T = T; b.H = H; b.OW = OW; b.OH = OH; b.NPX = NPX; b.NPY = NPY; b.ntx = ntx; b.nty = nty;
+                    b.T = T; b.HX = HX; b.HY = HY; b.OW = OW; b.OH = OH; b.NPX = NPX; b.NPY = NPY; b.ntx = ntx; b.nty = nty;
                 }
             }
         }

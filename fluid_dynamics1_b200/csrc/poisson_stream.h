@@ -141,7 +141,22 @@ __device__ __forceinline__ dbl2 ldg2(const double *p)
     const double2 v = __ldcg(reinterpret_cast<const double2 *>(p));  // L2 only: the other buffer is written every pass
     return {v.x, v.y};
 }
+// 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): four consecutive doubles, 32-byte aligned
+struct dbl4 { double x, y, z, w; };
+__device__ __forceinline__ dbl4 ldg4(const double *p)
+{
+    dbl4 v;
+    asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg4(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 #else
+struct dbl4 { double x, y, z, w; };
+inline dbl4 ldg4(const double *p) { return {p[0], p[1], p[2], p[3]}; }
+inline void stg4(double *p, double a, double b, double c, double d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 inline int smem_base(const double *) { return 0; }
 inline double *at(const double *sm, int off) { return reinterpret_cast<double *>(reinterpret_cast<char *>(const_cast<double *>(sm)) + off); }
 inline void cp_async8(const double *sm, int dst, const double *src) { *at(sm, dst) = *src; }
@@ -592,38 +607,48 @@ CNV_HD int pass_sweeps(const PoissonCtl &c, int T)
 // e[0..nsw-1]: global L1 update norms of the sweeps of the pass just finished
 CNV_HD void decide(PoissonCtl &c, const double *e, int nsw, double *hist)
 {
+    // (e is only ever indexed by the unrolled loop counter: with a caller's register array nothing here touches local memory --
+    // the on-chip kernel's service warp runs this between two passes)
+    int hit = -1;
+    double ehit = 0.0, elast = 0.0;
+    const bool redo = c.redo > 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        if (s < nsw) {
+            if (s == nsw - 1) elast = e[s];
+            if (!redo && hit < 0) {
+                if (hist) hist[c.sweeps + s] = e[s];
+                if (e[s] < c.tol) { hit = s; ehit = e[s]; }
+            }
+        }
+    }
     c.passes++;
-    if (c.redo > 0) {  // recomputation up to the converged sweep: done
+    if (redo) {  // recomputation up to the converged sweep: done
         c.cur = next_buf(c, c.cur);
         c.sweeps += nsw;
         c.result_k = c.sweeps - 1;
-        c.result_e = e[nsw - 1];
-        c.last_e = e[nsw - 1];
+        c.result_e = elast;
+        c.last_e = elast;
         c.redo = 0;
         c.state = 1;
         return;
-    }
-    int hit = -1;
-    for (int s = 0; s < nsw; s++) {
-        if (hist) hist[c.sweeps + s] = e[s];
-        if (e[s] < c.tol) { hit = s; break; }
     }
     if (hit == nsw - 1) {
         c.cur = next_buf(c, c.cur);
         c.sweeps += nsw;
         c.result_k = c.sweeps - 1;
-        c.result_e = e[hit];
-        c.last_e = e[hit];
+        c.result_e = ehit;
+        c.last_e = ehit;
         c.state = 1;
     } else if (hit >= 0) {
         c.redo = hit + 1;  // `cur` untouched: the pass input is recomputed with hit+1 sweeps
-        c.hit_e = e[hit];
+        c.hit_e = ehit;
     } else {
         c.cur = next_buf(c, c.cur);
         c.sweeps += nsw;
-        c.last_e = e[nsw - 1];
+        c.last_e = elast;
         c.result_k = c.sweeps - 1;
-        c.result_e = e[nsw - 1];
+        c.result_e = elast;
         if (c.sweeps >= c.itmax) c.state = 2;
     }
 }

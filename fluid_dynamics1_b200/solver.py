@@ -131,9 +131,10 @@ class PoissonSolver:
 
     def refresh_plan(self):
         """(Re-)read the launch plan: which pass kernel runs can change when the multi-GPU exchange is set up."""
-        info = (C.c_longlong * 10)()
+        info = (C.c_longlong * 18)()
         self.L.cnv_poisson_plan_info(self.h, info)
-        keys = ("WS", "HX", "Wout", "Hout", "nstrips", "nchunks", "threads", "smem", "T", "pow2")
+        keys = ("WS", "HX", "Wout", "Hout", "nstrips", "nchunks", "threads", "smem", "T", "pow2",
+                "onchip", "oc_T", "oc_ntx", "oc_nty", "oc_NPX", "oc_NPY", "oc_OW", "oc_OH")
         self.plan = dict(zip(keys, list(info)))
 
     def close(self):
@@ -145,7 +146,7 @@ class PoissonSolver:
 
     def set_consts(self, dx, dy, beta):
         self.L.cnv_poisson_set_consts(self.h, dx, dy, beta)
-        info = (C.c_longlong * 10)()
+        info = (C.c_longlong * 18)()
         self.L.cnv_poisson_plan_info(self.h, info)
         self.plan["pow2"] = info[9]
 

@@ -87,8 +87,13 @@ double *cnv_poisson_rhs_ptr(cnv_poisson *p);              /* device: prepared ri
 double *cnv_poisson_buf_ptr(cnv_poisson *p, int which);   /* device: iterate buffers 0/1 (2: lagged peer decision) */
 int cnv_poisson_num_buffers(cnv_poisson *p);              /* 2, or 3 once the peer path runs with CNV_PEER_LAG=1 */
 double *cnv_poisson_norms_ptr(cnv_poisson *p);            /* device: T per-sweep norms of the last pass */
-/* out[0..9] = WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, T, pow2-path flag of the streaming kernel's plan */
+/* out[0..9] = WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, T, pow2-path flag of the streaming kernel's plan;
+   out[10..17] = 1 if cnv_poisson_solve runs the persistent on-chip kernel, then its T, tile grid ntx x nty, patches per tile
+   NPX x NPY, output columns / rows per tile */
 void cnv_poisson_plan_info(const cnv_poisson *p, long long *out);
+/* diagnostics (CNV_ONCHIP_PROF=1 when the solver is created): clock ticks per phase of the on-chip kernel's pass loop in the last
+ * solve, out[cta][8] = wait for all norms, fold + decide, sweeps, store + flag, wait for neighbours, halo reload, -, - */
+int cnv_poisson_onchip_profile(cnv_poisson *p, unsigned long long *out, int max_ctas);
 /* stage a host right-hand side f (nrows x ncols, dense) and zero the iterate; fsign = -1 solves with -f */
 int cnv_poisson_upload(cnv_poisson *p, const double *f_host, double fsign, void *stream);
 /* slab solvers: the OWNED rows (own_rows x ncols, dense, ideally page-locked) into the right-hand-side array, halo rows from

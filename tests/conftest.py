@@ -23,6 +23,8 @@ def pytest_collection_modifyitems(config, items):
         name = item.nodeid
         if "test_gpu_z_multi" in name:
             return 3
+        if "[onchip" in name or "-onchip]" in name or "onchip-" in name:
+            return 2
         if "[resident" in name or "-resident]" in name or "resident-" in name:
             return 1
         return 0

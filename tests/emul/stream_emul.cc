@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../fluid_dynamics1_b200/csrc/poisson_plan.h"
+#include "../../fluid_dynamics1_b200/csrc/poisson_onchip.h"
 
 using namespace cnv;
 
@@ -146,6 +147,93 @@ int emul_pass_sweeps(int sweeps, int redo, int itmax, int T)
     return pass_sweeps(c, T);
 }
 
+
+// ---- the persistent on-chip kernel (poisson_onchip.h): a whole solve with the kernel's own per-thread code, tile geometry,
+// masks and lagged stop machine.  CTAs run one after the other inside a pass (compute + store), then all of them reload
+// their halo cells -- the order the flags of the real kernel enforce.  bufs: 3 x nrows x ld (bufs[0] = initial iterate).
+// plan_out: T, H, OW, OH, NPX, NPY, ntx, nty.  Returns 0, -1 (no plan).
+}  // extern "C"
+template <bool POW2>
+static void run_onchip(const OnchipGeom &g, const RelaxConsts &rc, const double *rhs, double *bufs, PoissonCtl &ctl, double *hist)
+{
+    const int ncta = g.ntx * g.nty, NT = oc_threads(g);
+    const size_t fld = (size_t)g.nrows * g.ld;
+    double *B[3] = {bufs, bufs + fld, bufs + 2 * fld};
+    std::vector<std::vector<double>> sm(ncta, std::vector<double>(kOcSlots * kOcPitch, 0.0));
+    std::vector<std::vector<OcThread>> th(ncta, std::vector<OcThread>(NT));
+    std::vector<OcTile> tiles(ncta);
+    for (int c = 0; c < ncta; c++) {
+        tiles[c] = oc_tile(g, c % g.ntx, c / g.ntx);
+        for (int t = 0; t < NT; t++) {
+            oc_thread_init(th[c][t], g, tiles[c], t, sm[c].data());
+            oc_load_rhs(th[c][t], rhs);
+            oc_load_psi(th[c][t], B[ctl.cur]);
+            oc_publish_all(th[c][t], sm[c].data());
+        }
+    }
+    std::vector<std::vector<double>> norms;  // [pass][8]
+    PoissonCtl X = ctl;
+    int P = 0;
+    for (int p = 0;; p++) {
+        const bool need = p >= 2 && X.state == 0 && X.redo == 0;
+        if (p >= 2) {
+            double e[8];
+            for (int i = 0; i < 8; i++) e[i] = need ? norms[p - 2][i] : 0.0;
+            lag_fold(X, e, g.T, hist);
+        }
+        const LagAction act = lag_action(X, p, g.T);
+        P = p;
+        if (act.kind == 0) break;
+        std::vector<double> e(8, 0.0);
+        for (int c = 0; c < ncta; c++) {
+            double *s = sm[c].data();
+            if (act.kind == 2)
+                for (int t = 0; t < NT; t++) { oc_load_psi(th[c][t], B[act.in]); oc_publish_all(th[c][t], s); }
+            for (int sw = 0; sw < act.nsw; sw++) {
+                const int rem0 = 2 * (act.nsw - sw) - 1;
+                double acc = 0.0;
+                for (int col = 0; col < 2; col++)
+                    for (int t = 0; t < NT; t++) {
+                        if (th[c][t].dist > rem0 - col) continue;
+                        double a = 0.0;
+                        const bool sel = !th[c][t].fast;
+                        if ((tiles[c].par0 ^ col) == 0) { if (sel) oc_half_sweep<POW2, 0, true>(th[c][t], rc, s, a); else oc_half_sweep<POW2, 0, false>(th[c][t], rc, s, a); }
+                        else { if (sel) oc_half_sweep<POW2, 1, true>(th[c][t], rc, s, a); else oc_half_sweep<POW2, 1, false>(th[c][t], rc, s, a); }
+                        if (th[c][t].own) acc += a;
+                    }
+                e[sw] += acc;
+            }
+            for (int t = 0; t < NT; t++) if (th[c][t].own) oc_store(th[c][t], B[act.out]);
+        }
+        norms.push_back(e);
+        if (act.kind == 2) continue;
+        for (int c = 0; c < ncta; c++)
+            for (int t = 0; t < NT; t++)
+                if (!th[c][t].own) { oc_load_psi(th[c][t], B[act.out]); oc_publish_all(th[c][t], sm[c].data()); }
+    }
+    if (lag_final_needs_last(X, P)) lag_final(X, P, norms[P - 1].data(), g.T, hist);
+    ctl = X;
+}
+extern "C" {
+
+int emul_onchip_solve(int nrows, int ncols, int ld, int T, int ntx, int nty, int num_sms, double dx, double dy, double beta, int mode,
+                      const double *f, double *bufs, int itmax, double tol, int *ints, double *dbls, double *hist, long *plan_out)
+{
+    OnchipGeom g;
+    if (!onchip_plan(nrows, ncols, ld, 0, nrows, 0, nrows, num_sms, &g, T, ntx, nty)) return -1;
+    plan_out[0] = g.T; plan_out[1] = g.HX; plan_out[2] = g.OW; plan_out[3] = g.OH; plan_out[4] = g.NPX; plan_out[5] = g.NPY;
+    plan_out[6] = g.ntx; plan_out[7] = g.nty;
+    RelaxConsts rc = make_relax_consts(dx, dy, beta);
+    if (mode == 1) { rc.pow2 = 0; rc.pscale = rc.cf; }
+    std::vector<double> rhs((size_t)nrows * ld);
+    for (size_t i = 0; i < rhs.size(); i++) rhs[i] = rc.pscale * f[i];
+    PoissonCtl c; std::memset(&c, 0, sizeof c);
+    c.state = itmax > 0 ? 0 : 2; c.itmax = itmax; c.result_k = -1; c.tol = tol; c.nbuf = 3;
+    if (rc.pow2) run_onchip<true>(g, rc, rhs.data(), bufs, c, hist);
+    else run_onchip<false>(g, rc, rhs.data(), bufs, c, hist);
+    ctl_to(c, ints, dbls);
+    return 0;
+}
 
 // Markstein division vs hardware division: returns the number of mismatches
 long emul_check_div(double d, const double *a, long n)

@@ -25,11 +25,13 @@ def _gpu():
     fd.require_gpu()
 
 
-@pytest.fixture(params=["resident", "stream"])
+@pytest.fixture(params=["resident", "stream", "onchip"])
 def small_grid_path(request, monkeypatch):
     """The Poisson kernels a small grid can take: the whole-solve cluster kernel (single-CTA grids by default, forced here
-    for every grid it can hold) and the streaming pass kernel."""
+    for every grid it can hold), the streaming pass kernel, and the persistent on-chip kernel (register-resident tiles,
+    forced here for every grid it has a plan for)."""
     monkeypatch.setenv("CNV_POISSON_RESIDENT", "2" if request.param == "resident" else "0")  # 2 = force (clusters too)
+    monkeypatch.setenv("CNV_POISSON_ONCHIP", "1" if request.param == "onchip" else "0")
     return request.param
 
 
@@ -236,6 +238,42 @@ def test_poisson_4096_stop_inside_a_pass_streaming_kernel(port, T, stop):
     assert r["passes"] == (stop + 1 + T - 1) // T + (0 if (stop + 1) % T == 0 else 1)   # + the redo pass
     assert s.download(r["buf"]).tobytes() == want["u"].tobytes()
     assert "%E" % r["e"] == "%E" % want["e"]
+    s.close()
+
+
+@pytest.mark.parametrize("T,ntx,nty", [(0, 0, 0), (4, 12, 12), (4, 9, 16), (2, 16, 9), (2, 12, 12)])
+def test_poisson_onchip_1024_fixed_sweeps_and_converged(port, monkeypatch, T, ntx, nty):
+    """BASELINE config 3 grid on the persistent on-chip kernel: the planner's own tiling and pinned ones (T = 2 .. 8, different
+    tile grids; deeper blocking does not fit 384 threads per tile at this size), 27 sweeps with tol = 0 (itmax stop inside a pass) bitwise against the oracle; then a converging solve with a
+    real stop decision (beta = 1.5: monotone norms, stop inside the third pass -> the pass' input is reloaded and recomputed)."""
+    n = 1024
+    monkeypatch.setenv("CNV_POISSON_ONCHIP", "1")
+    monkeypatch.setenv("CNV_POISSON_RESIDENT", "0")
+    monkeypatch.setenv("CNV_ONCHIP_T", str(T)); monkeypatch.setenv("CNV_ONCHIP_NTX", str(ntx)); monkeypatch.setenv("CNV_ONCHIP_NTY", str(nty))
+    rng = np.random.default_rng(n)
+    f = rng.standard_normal((n, n))
+    beta = port.beta(n, n)
+    s = fd.PoissonSolver(n, n, 0)
+    assert s.plan["onchip"] == 1 and (T == 0 or (s.plan["oc_T"], s.plan["oc_ntx"], s.plan["oc_nty"]) == (T, ntx, nty)), s.plan
+    s.set_consts(1 / n, 1 / n, beta)
+    s.upload(f)
+    want, norms = port.poisson_sweeps(f, 1 / n, 1 / n, 27, beta)
+    r = s.solve(27, 0.0)
+    assert r["status"] == 1 and r["sweeps"] == 27
+    assert s.download(r["buf"]).tobytes() == want.tobytes()
+    assert abs(r["e"] - norms[-1]) <= 1e-11 * norms[-1]
+    beta = 1.5
+    s.set_consts(1 / n, 1 / n, beta)
+    _, norms = port.poisson_sweeps(f, 1 / n, 1 / n, 20, beta)
+    for stop in (18, 15, 9):
+        assert norms[stop] < norms[:stop].min()
+        tol = 0.5 * (norms[stop] + norms[stop - 1])
+        w = port.poisson(f, 1 / n, 1 / n, 1000, tol, beta, redblack=True)
+        s.upload(f)
+        r = s.solve(1000, tol)
+        assert r["status"] == 0 and r["k"] == stop == w["k"]
+        assert s.download(r["buf"]).tobytes() == w["u"].tobytes()
+        assert "%E" % r["e"] == "%E" % w["e"]
     s.close()
 
 

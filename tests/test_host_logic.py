@@ -38,6 +38,8 @@ def emul():
     E.emul_plan.argtypes = [C.c_int] * 10 + [np.ctypeslib.ndpointer(dtype=np.int64)]
     E.emul_decide.argtypes = [ip, dp, dp, C.c_int, C.c_void_p]
     E.emul_pass_sweeps.argtypes = [C.c_int] * 4
+    E.emul_onchip_solve.argtypes = [C.c_int] * 7 + [C.c_double] * 3 + [C.c_int, dp, dp, C.c_int, C.c_double, ip, dp, C.c_void_p,
+                                                                        np.ctypeslib.ndpointer(dtype=np.int64)]
     E.emul_check_div.restype = C.c_long
     E.emul_check_div.argtypes = [C.c_double, dp, C.c_long]
     return E
@@ -76,6 +78,77 @@ def test_stream_schedule_bitwise_vs_oracle(emul, port, shape, T):
             got, want, gn, on = _emul_sweeps(emul, port, n, m, T, 3, mode, ws, ch)
             assert got.tobytes() == want.tobytes(), (shape, T, mode, ws, ch)
             np.testing.assert_allclose(gn, on, rtol=1e-13)
+
+
+# ---- the persistent on-chip kernel (csrc/poisson_onchip.h): its per-thread code, tile geometry, masks and lagged stop
+# machine run as a whole solve on the CPU (tests/emul/stream_emul.cc::run_onchip) ----
+def _onchip(E, port, n, m, T, ntx, nty, itmax, tol, mode=0, dx=None, dy=None, sms=148, seed=0, beta=None, u0=None):
+    rng = np.random.default_rng(seed)
+    f = rng.standard_normal((n, m))
+    dx, dy = dx or 1.0 / m, dy or 1.0 / n
+    beta = beta or port.beta(n, m)
+    ld = (m + 15) // 16 * 16
+    fp = np.zeros((n, ld))
+    fp[:, :m] = f
+    bufs = np.zeros((3, n, ld))
+    ints, dbls, plan = np.zeros(8, dtype=np.int32), np.zeros(4), np.zeros(8, dtype=np.int64)
+    hist = np.zeros(max(itmax, 1))
+    if E.emul_onchip_solve(n, m, ld, T, ntx, nty, sms, dx, dy, beta, mode, fp, bufs, itmax, tol, ints, dbls, hist.ctypes.data, plan) != 0:
+        return None
+    want = port.poisson(f, dx, dy, itmax, tol, beta, redblack=True, history=True)
+    return dict(u=bufs[ints[1]][:, :m], ints=ints, dbls=dbls, plan=[int(x) for x in plan], want=want, hist=hist)
+
+
+@pytest.mark.parametrize("T", [2, 4, 6, 8])
+@pytest.mark.parametrize("shape", [(64, 64), (40, 72), (100, 100), (33, 47), (131, 90), (9, 200)])
+def test_onchip_schedule_bitwise_vs_oracle(emul, port, shape, T):
+    """Register-resident patches, published perimeters, 2T-cell halos reloaded after every pass, three rotating buffers:
+    == plain red-black sweeps of the oracle, bit for bit; one tile and several tiles in x and y (odd and even tile origins),
+    both arithmetic paths, converging solves (redo pass included) and itmax stops."""
+    n, m = shape
+    for mode, dx, dy in ((0, None, None), (1, 0.013, 0.02)):
+        for ntx, nty, itmax, tol in ((0, 0, 5000, 1e-3), (1, 1, 5000, 1e-3), (2, 3, 3 * T + 1, 0.0), (3, 2, 2 * T, 0.0), (2, 2, 1, 0.0)):
+            r = _onchip(emul, port, n, m, T, ntx, nty, itmax, tol, mode, dx, dy, seed=n + T)
+            if r is None:
+                continue                               # (no plan with that many tiles for this grid)
+            w = r["want"]
+            where = (shape, T, mode, ntx, nty, itmax, tol, r["plan"])
+            assert int(r["ints"][0]) == (1 if w["status"] == 0 else 2), where
+            assert int(r["ints"][5]) == w["k"] and int(r["ints"][2]) == w["k"] + 1, where
+            assert r["u"].tobytes() == w["u"].tobytes(), where
+            np.testing.assert_allclose(r["hist"][:w["k"] + 1], w["history"], rtol=1e-12, err_msg=str(where))
+            assert abs(r["dbls"][1] - w["e"]) <= 1e-12 * max(w["e"], 1e-300), where
+
+
+def test_onchip_every_stop_position(emul, port):
+    """The converged sweep at every position inside a pass, for every T: the lagged decision either takes the pass' output
+    (last sweep) or reloads the pass' input and recomputes exactly the converged number of sweeps."""
+    n = 40
+    f_seed = 3
+    base = _onchip(emul, port, n, n, 4, 2, 2, 5000, 1e-9, seed=f_seed)
+    hist = base["want"]["history"]
+    ks = [k for k in range(1, len(hist)) if hist[k] < hist[:k].min()][:18]
+    assert len(ks) >= 16 and len({k % 8 for k in ks}) == 8
+    for T in (2, 4, 6, 8):
+        for k in ks:
+            tol = 0.5 * (hist[k] + hist[:k].min())
+            r = _onchip(emul, port, n, n, T, 2, 2, 5000, tol, seed=f_seed)
+            assert r["want"]["k"] == k
+            assert int(r["ints"][0]) == 1 and int(r["ints"][5]) == k, (T, k)
+            assert r["u"].tobytes() == r["want"]["u"].tobytes(), (T, k)
+
+
+def test_onchip_planner_properties(emul, port):
+    for n, m, sms in [(64, 64, 148), (128, 128, 148), (256, 256, 148), (1024, 1024, 148), (1024, 1024, 132), (512, 2048, 148), (33, 47, 148)]:
+        r = _onchip(emul, port, n, m, 0, 0, 0, 1, 0.0, sms=sms)
+        assert r is not None, (n, m)
+        T, H, OW, OH, NPX, NPY, ntx, nty = r["plan"]
+        assert H == 2 * T and T in (2, 4, 6, 8) and OW % 4 == 0 and OH % 8 == 0
+        assert ntx * nty <= sms and NPX * NPY <= 352                 # compute threads; + one service warp per CTA
+        assert 4 * NPX == OW + 2 * H and 8 * NPY >= OH + 2 * H
+        assert ntx * OW >= m and nty * OH >= n
+        assert (ntx == 1 or OW >= H) and (nty == 1 or OH >= H)
+    assert _onchip(emul, port, 2048, 2048, 0, 0, 0, 1, 0.0) is None      # does not fit the register files: streaming kernel
 
 
 @pytest.mark.parametrize("trim", [0, 8, 11])
