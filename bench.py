@@ -441,12 +441,11 @@ def dropin_e2e(ctx, run, reps=3):
         for i in range(reps + 1):
             fh = libc.fopen(logp.encode(), b"w")
             t0 = time.perf_counter()
-            U2 = D.poisson_SOR_log(F, run.dx, run.dy, itmax, tol, run.beta, fh)
+            if U is not None:
+                D.freem(U)                       # like main.c: psi.M = freem(psi) before psi = poisson_SOR_log(...) (src/main.c:347-355)
+            U = D.poisson_SOR_log(F, run.dx, run.dy, itmax, tol, run.beta, fh)
             t1 = time.perf_counter()
             libc.fclose(fh)
-            if U is not None:
-                D.freem(U)
-            U = U2
             if i > 0:
                 times.append(t1 - t0)
             k = int(open(logp).read().split()[4])

@@ -110,6 +110,8 @@ CNV_API = {
     "cnv_sim_phase": (None, [_vp, C.c_int, _vp]),
     "cnv_sim_destroy": (None, [_vp]),
     "cnv_sim_step": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "cnv_sim_step_slab": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "cnv_sim_gather_fields_slab": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "cnv_sim_get_fields": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "cnv_sim_set_fields": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "cnv_sim_set_diagnostics": (None, [_vp, C.c_int]),

@@ -840,8 +840,8 @@ int cnv_sim_step_slab(cnv_sim *s, int nsteps, int *k, double *e, double *cont_ma
     return 0;
 }
 
-// Whole fields of a slab simulation on rank 0 (host arrays of nx*ny doubles there, ignored elsewhere; NULL to skip a field --
-// identically on every rank): every rank sends its owned rows over the communicator.
+// Whole fields of a slab simulation on rank 0 (host arrays of nx*ny doubles there, ignored on the other ranks; a NULL on rank 0
+// drops that field after receiving it): every rank sends the owned rows of all four fields over the communicator.
 int cnv_sim_gather_fields_slab(cnv_sim *s, double *psi, double *w, double *u, double *v)
 {
     if (!s->ps->has_comm()) return -1;
@@ -853,11 +853,7 @@ int cnv_sim_gather_fields_slab(cnv_sim *s, double *psi, double *w, double *u, do
         const int rows = (s->map.gnrows + world - 1) / world;
         CNV_CUDA_CHECK(cudaMalloc(&stage, sizeof(double) * (size_t)rows * s->ld));
     }
-    for (int i = 0; i < 4; i++)
-        if (dst[i] || rank != 0) {
-            if (rank != 0 && !dst[i]) continue;
-            s->ps->gather_field_to_root(src[i], stage, dst[i], s->stream);
-        }
+    for (int i = 0; i < 4; i++) s->ps->gather_field_to_root(src[i], stage, rank == 0 ? dst[i] : nullptr, s->stream);
     CNV_CUDA_CHECK(cudaStreamSynchronize(s->stream));
     if (stage) cudaFree(stage);
     return 0;

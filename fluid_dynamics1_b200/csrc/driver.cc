@@ -8,7 +8,10 @@
 // copies them out only at output steps.  GPU-only knobs come from the environment so config files
 // stay reference-compatible:  CNV_NO_VTK=1 suppresses VTK files (large grids),
 // CNV_POISSON_T=<1|2|4|8> temporal block depth.
+#include <sys/socket.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -89,6 +92,87 @@ void help_config()
     std::printf("\nBoundary Conditions:\n  ui, vi, u1, u2, u3, u4, v1, v2, v3, v4\n");
 }
 
+// ---- multi-GPU run: one process per GPU (CNV_GPUS=N), forked by cnv_main before its first CUDA call ------------------
+// The ranks only need three host-side collectives to set themselves up (NCCL unique id, CUDA IPC handles of the peer-memory
+// path) and to stay in step at the end: a star of socket pairs between rank 0 (the process the user started) and its children.
+struct Boot {
+    int rank = 0, world = 1;
+    std::vector<int> fd;  // rank 0: fd[r] = socket to rank r (fd[0] unused); rank r > 0: fd[0] = socket to rank 0
+    static void xfer(int f, void *buf, size_t n, bool wr)
+    {
+        char *p = static_cast<char *>(buf);
+        while (n > 0) {
+            const ssize_t k = wr ? ::write(f, p, n) : ::read(f, p, n);
+            if (k <= 0) {
+                std::printf("** Error: a rank of the multi-GPU run stopped responding **\n");
+                std::fflush(stdout);
+                std::_Exit(1);
+            }
+            p += k;
+            n -= (size_t)k;
+        }
+    }
+    // every rank contributes `bytes` bytes; everybody receives all of them in rank order
+    void allgather(const void *mine, size_t bytes, void *all)
+    {
+        char *out = static_cast<char *>(all);
+        if (rank == 0) {
+            std::memcpy(out, mine, bytes);
+            for (int r = 1; r < world; r++) xfer(fd[r], out + (size_t)r * bytes, bytes, false);
+            for (int r = 1; r < world; r++) xfer(fd[r], out, bytes * world, true);
+        } else {
+            xfer(fd[0], const_cast<void *>(mine), bytes, true);
+            xfer(fd[0], out, bytes * world, false);
+        }
+    }
+    void bcast(void *buf, size_t bytes)  // from rank 0
+    {
+        if (rank == 0) { for (int r = 1; r < world; r++) xfer(fd[r], buf, bytes, true); }
+        else xfer(fd[0], buf, bytes, false);
+    }
+    void barrier()
+    {
+        char c = 0;
+        std::vector<char> all(world);
+        allgather(&c, 1, all.data());
+    }
+    bool all_ok(bool ok)
+    {
+        char c = ok ? 1 : 0;
+        std::vector<char> all(world);
+        allgather(&c, 1, all.data());
+        for (char x : all) ok = ok && x;
+        return ok;
+    }
+};
+
+// fork world-1 children (call BEFORE the first CUDA call of the process); returns this process' rank
+Boot boot_fork(int world)
+{
+    Boot b;
+    b.world = world;
+    b.fd.assign(world, -1);
+    std::fflush(stdout);
+    for (int r = 1; r < world; r++) {
+        int sv[2];
+        if (socketpair(AF_UNIX, SOCK_STREAM, 0, sv) != 0) { std::printf("** Error: socketpair failed **\n"); std::exit(1); }
+        const pid_t pid = fork();
+        if (pid < 0) { std::printf("** Error: fork failed **\n"); std::exit(1); }
+        if (pid == 0) {  // child = rank r: keeps its end, drops everything inherited from the parent
+            for (int q = 1; q < r; q++) ::close(b.fd[q]);
+            ::close(sv[0]);
+            b.rank = r;
+            b.fd.assign(world, -1);
+            b.fd[0] = sv[1];
+            if (!std::getenv("CNV_RANK_STDOUT")) (void)!std::freopen("/dev/null", "w", stdout);  // rank 0 does the talking
+            return b;
+        }
+        ::close(sv[1]);
+        b.fd[r] = sv[0];
+    }
+    return b;
+}
+
 double now_s()
 {
     timespec ts;
@@ -134,8 +218,23 @@ extern "C" int cnv_main(int argc, char **argv)
         return 1;
     }
     cnv_config_print(&cfg);
-    std::printf("\n=== Execution Status ===\nBackend: CUDA (sm_100a), %d device(s) visible\n========================\n\n",
-                cnv_device_count());
+    // CNV_GPUS=N (N > 1): slab-decomposed run, one process per GPU.  The children are forked here, before this process makes
+    // its first CUDA call; rank 0 (this process) keeps the terminal, the log file and the VTK output.
+    const int ngpu = std::getenv("CNV_GPUS") ? std::atoi(std::getenv("CNV_GPUS")) : 1;
+    Boot boot;
+    if (ngpu > 1) boot = boot_fork(ngpu);
+    const int rank = boot.rank, world = boot.world;
+    if (world > 1) {
+        const bool enough = cnv_device_count() >= world;
+        if (!boot.all_ok(enough)) {
+            if (rank == 0) std::printf("** Error: CNV_GPUS=%d but only %d CUDA device(s) are visible **\n", world, cnv_device_count());
+            if (rank != 0) std::_Exit(1);
+            return 1;
+        }
+        cnv_set_device(rank);
+    }
+    std::printf("\n=== Execution Status ===\nBackend: CUDA (sm_100a), %d device(s) visible, %d in use\n========================\n\n",
+                cnv_device_count(), world);
 
     const double beta = cnv_sor_beta(cfg.nx, cfg.ny);
     std::printf("Poisson SOR parameter: %lf\n", beta);
@@ -153,7 +252,44 @@ extern "C" int cnv_main(int argc, char **argv)
     }
 
     const char *tenv = std::getenv("CNV_POISSON_T");
-    cnv_sim *sim = cnv_sim_create(&cfg, tenv ? std::atoi(tenv) : 0);
+    cnv_sim *sim = world > 1 ? cnv_sim_create_slab(&cfg, tenv ? std::atoi(tenv) : 0, rank, world) : cnv_sim_create(&cfg, tenv ? std::atoi(tenv) : 0);
+    cnv_comm *comm = nullptr;
+    if (world > 1) {
+        // NCCL communicator of the slab halo exchanges: rank 0 creates the unique id, everybody joins
+        unsigned char id[128] = {0};
+        int ok = rank == 0 ? cnv_comm_unique_id(id) == 0 : 1;
+        boot.bcast(id, sizeof id);
+        if (ok) comm = cnv_comm_create(rank, world, id);
+        if (!boot.all_ok(comm != nullptr)) {
+            if (rank == 0) std::printf("** Error: could not create the NCCL communicator of the %d ranks **\n", world);
+            if (rank != 0) std::_Exit(1);
+            return 1;
+        }
+        cnv_poisson *ps = cnv_sim_poisson(sim);
+        cnv_poisson_attach_comm(ps, comm);
+        // peer-memory path of the Poisson solve: exchange the CUDA IPC handles and push counts
+        const char *be = std::getenv("CNV_DIST_BACKEND");
+        if (!be || std::strcmp(be, "peer") == 0) {
+            struct Rec { unsigned char h[256]; int layout[4]; } mine, *all = new Rec[world];
+            int lay[8];
+            cnv_sim_layout(sim, lay);
+            long long lo = 0, hi = 0;
+            cnv_poisson_peer_export(ps, mine.h);
+            cnv_poisson_peer_push_counts(ps, rank, world, &lo, &hi);
+            mine.layout[0] = lay[2]; mine.layout[1] = lay[3]; mine.layout[2] = (int)lo; mine.layout[3] = (int)hi;
+            boot.allgather(&mine, sizeof mine, all);
+            std::vector<unsigned char> handles((size_t)256 * world);
+            std::vector<int> layout((size_t)4 * world);
+            for (int r = 0; r < world; r++) {
+                std::memcpy(&handles[(size_t)256 * r], all[r].h, 256);
+                std::memcpy(&layout[(size_t)4 * r], all[r].layout, sizeof(int) * 4);
+            }
+            delete[] all;
+            const bool imported = cnv_poisson_peer_import(ps, rank, world, handles.data(), layout.data()) == 0;
+            if (!boot.all_ok(imported)) cnv_poisson_peer_disable(ps);  // all ranks or none: the NCCL group per pass instead
+        }
+        std::printf("Slab decomposition: %d ranks, Poisson exchange: %s\n", world, cnv_poisson_peer_enabled(ps) ? "peer memory (NVLink)" : "NCCL");
+    }
     const bool no_vtk = std::getenv("CNV_NO_VTK") && std::atoi(std::getenv("CNV_NO_VTK"));
 
     // log file ./output/logs/<run>.txt (src/main.c:229-273)
@@ -162,9 +298,11 @@ extern "C" int cnv_main(int argc, char **argv)
     if (output_dir.compare(0, prefix.size(), prefix) == 0 && output_dir.size() > prefix.size())
         run_name = output_dir.substr(prefix.size());
     const std::string log_filename = "./output/logs/" + run_name + ".txt";
-    if (std::system("mkdir -p output/logs") != 0) std::printf("Warning: could not create output/logs\n");
-    FILE *log = std::fopen(log_filename.c_str(), "w");
-    if (!log) {
+    if (rank == 0 && std::system("mkdir -p output/logs") != 0) std::printf("Warning: could not create output/logs\n");
+    FILE *log = rank == 0 ? std::fopen(log_filename.c_str(), "w") : nullptr;
+    if (rank != 0) {
+        // (the other ranks compute their slabs; rank 0 logs and writes the output files)
+    } else if (!log) {
         std::printf("Warning: Could not create log file %s. Logging to console instead.\n", log_filename.c_str());
     } else {
         std::printf("Logging simulation progress to: %s\n", log_filename.c_str());
@@ -186,7 +324,7 @@ extern "C" int cnv_main(int argc, char **argv)
         const double t0 = now_s();
         int k = 0;
         double e = 0, cmax = 0, cmin = 0;
-        const int failed = cnv_sim_step(sim, 1, &k, &e, &cmax, &cmin);
+        const int failed = world > 1 ? cnv_sim_step_slab(sim, 1, &k, &e, &cmax, &cmin) : cnv_sim_step(sim, 1, &k, &e, &cmax, &cmin);
         if (failed) {
             log_line(log, "Error: maximum number of iterations achieved for Poisson equation.\n");  // src/poisson.c:280
             rc = 1;
@@ -208,8 +346,13 @@ extern "C" int cnv_main(int argc, char **argv)
         else log_line(log, "Est. remaining: -- s\n");
         if (!no_vtk && cfg.output_interval != 0 && t % cfg.output_interval == 0) {
             const size_t n = (size_t)cfg.nx * cfg.ny;
-            psi.resize(n); w.resize(n); u.resize(n); v.resize(n);
-            cnv_sim_get_fields(sim, psi.data(), w.data(), u.data(), v.data());
+            if (rank == 0) { psi.resize(n); w.resize(n); u.resize(n); v.resize(n); }
+            if (world > 1) {
+                cnv_sim_gather_fields_slab(sim, psi.data(), w.data(), u.data(), v.data());  // every rank sends its owned rows to rank 0
+                if (rank != 0) continue;
+            } else {
+                cnv_sim_get_fields(sim, psi.data(), w.data(), u.data(), v.data());
+            }
             write_vtk(psi, cfg.nx, cfg.ny, "stream-function", output_dir);
             write_vtk(w, cfg.nx, cfg.ny, "vorticity", output_dir);
             write_vtk(u, cfg.nx, cfg.ny, "x-velocity", output_dir);
@@ -218,7 +361,25 @@ extern "C" int cnv_main(int argc, char **argv)
     }
     long long counters[3];
     cnv_sim_counters(sim, counters);
+    if (world > 1) {
+        // tear-down in the order the peer path needs: no rank frees a buffer a neighbour has mapped or may still write into
+        cnv_poisson *ps = cnv_sim_poisson(sim);
+        cnv_poisson_peer_quiesce(ps, nullptr);
+        cnv_device_synchronize();
+        boot.barrier();
+        cnv_poisson_peer_close(ps);
+        cnv_device_synchronize();
+        boot.barrier();
+    }
     cnv_sim_destroy(sim);
+    if (comm) cnv_comm_destroy(comm);
+    if (world > 1 && rank != 0) std::_Exit(rc);  // children are done; rank 0 reports
+    if (world > 1) {
+        for (int r = 1; r < world; r++) {
+            int st = 0;
+            if (wait(&st) > 0 && (!WIFEXITED(st) || WEXITSTATUS(st) != rc) && rc == 0) rc = 1;
+        }
+    }
     if (rc == 0) std::printf("Simulation complete!\n");
     const double end = now_s();
     log_line(log, "\n=== Timing Summary ===\n");

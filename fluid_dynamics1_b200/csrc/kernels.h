@@ -58,20 +58,6 @@ void launch_velocity_continuity(const double *psi, const RowMap &m, int ncols, i
 void launch_prep_rhs(const double *f, int nrows, int ncols, int ldf, double sign, double pscale, double *rhs, double *psi0,
                      double *psi1, int ld, cudaStream_t s);
 
-// ---- poisson_resident.cu: whole solve in one launch for small grids (thread-block cluster + DSMEM) ----
-struct ResidentGeom {
-    int nrows, ncols, ld;
-    int KP;   // column pairs per row = ceil(ncols / 2)
-    int PK;   // shared row pitch (doubles) = KP + 2 (one pad each side for the k-1 / k+1 neighbour)
-    int RPC;  // rows per CTA
-    int RPB;  // rows covered by one "m" step of the CTA = kResThreads / KP (even)
-    int C;    // cluster size
-};
-
-bool resident_plan(int nrows, int ncols, int ld, size_t smem_limit, ResidentGeom *g, size_t *smem);
-void launch_resident(const ResidentGeom &g, size_t smem, const RelaxConsts &rc, const double *psi0, const double *rhs, double *out,
-                     PoissonCtl *ctl, double *hist, int itmax, double tol, cudaStream_t s);
-
 // ---- poisson_onchip.cu: the whole solve in one persistent launch, iterate resident in registers (<= ~1.5 M cells) ----
 void launch_onchip(const OnchipGeom &g, const RelaxConsts &rc, double *b0, double *b1, double *b2, const double *rhs, PoissonCtl *ctl,
                    unsigned long long *flags, double *partials, double *hist, cudaStream_t s, unsigned long long *prof = nullptr);

@@ -845,13 +845,15 @@ void PoissonSolver::gather_field_to_root(const double *field, double *stage, dou
         CNV_NCCL_CHECK(n.Send(field + (size_t)geom_.own_lo * ld, (size_t)(geom_.own_hi - geom_.own_lo) * ld, ncclFloat64, 0, comm, s));
         return;
     }
-    CNV_CUDA_CHECK(cudaMemcpy2DAsync(host_out, sizeof(double) * geom_.ncols, field + (size_t)geom_.own_lo * ld, sizeof(double) * ld,
-                                     sizeof(double) * geom_.ncols, geom_.own_hi - geom_.own_lo, cudaMemcpyDeviceToHost, s));
+    if (host_out)
+        CNV_CUDA_CHECK(cudaMemcpy2DAsync(host_out, sizeof(double) * geom_.ncols, field + (size_t)geom_.own_lo * ld, sizeof(double) * ld,
+                                         sizeof(double) * geom_.ncols, geom_.own_hi - geom_.own_lo, cudaMemcpyDeviceToHost, s));
     for (int r = 1; r < world; r++) {
         const int r0 = r * base + (r < rem ? r : rem), rows = base + (r < rem ? 1 : 0);
-        CNV_NCCL_CHECK(n.Recv(stage, (size_t)rows * ld, ncclFloat64, r, comm, s));
-        CNV_CUDA_CHECK(cudaMemcpy2DAsync(host_out + (size_t)r0 * geom_.ncols, sizeof(double) * geom_.ncols, stage, sizeof(double) * ld,
-                                         sizeof(double) * geom_.ncols, rows, cudaMemcpyDeviceToHost, s));
+        CNV_NCCL_CHECK(n.Recv(stage, (size_t)rows * ld, ncclFloat64, r, comm, s));  // (always: the sender does not know what rank 0 wants)
+        if (host_out)
+            CNV_CUDA_CHECK(cudaMemcpy2DAsync(host_out + (size_t)r0 * geom_.ncols, sizeof(double) * geom_.ncols, stage, sizeof(double) * ld,
+                                             sizeof(double) * geom_.ncols, rows, cudaMemcpyDeviceToHost, s));
     }
     CNV_CUDA_CHECK(cudaStreamSynchronize(s));
 }
@@ -871,25 +873,6 @@ PoissonResult PoissonSolver::solve(int itmax, double tol, cudaStream_t s, int *r
     }
     use_hist_ = keep_history;
     reset_ctl(itmax, tol, s);
-    // Small grids: the whole solve (all sweeps + the convergence test after each) in one cluster launch with psi
-    // resident in shared memory (poisson_resident.cu).  Same arithmetic, same red-black order -> same bits.
-    ResidentGeom rg;
-    size_t rsmem = 0;
-    if (!distributed_ && geom_.grow0 == 0 && geom_.gnrows == geom_.nrows && geom_.own_lo == 0 && geom_.own_hi == geom_.nrows &&
-        itmax > 0 && resident_plan(geom_.nrows, geom_.ncols, geom_.ld, smem_optin_, &rg, &rsmem)) {
-        launch_resident(rg, rsmem, rc_, buf_[0], rhs_, buf_[1], ctl_, use_hist_ ? hist_ : nullptr, itmax, tol, s);
-        launches_ += 1;
-        count_launch(1);
-        PoissonCtl c = read_ctl(s);
-        if (result_buf) *result_buf = c.cur;
-        PoissonResult r;
-        r.status = c.state == 1 ? 0 : 1;
-        r.k = c.result_k;
-        r.sweeps = c.sweeps;
-        r.passes = c.passes;
-        r.e = c.result_e;
-        return r;
-    }
     // Grids whose iterate fits the register files: the whole solve in one persistent cooperative launch
     // (poisson_onchip.cu).  Same arithmetic, same red-black order -> same bits.
     if (use_onchip_ && !distributed_ && itmax > 0) {

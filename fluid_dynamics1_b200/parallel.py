@@ -330,6 +330,20 @@ class SlabSimulation:
 
     def step(self, nsteps=1, diagnostics=True):
         L, P, H3 = self.L, self.poisson, self.STENCIL_HALO
+        if P.comm:
+            # the library's own slab step (csrc/capi.cu cnv_sim_step_slab: stencil phases, halo exchanges on its NCCL communicator,
+            # distributed Poisson solve, continuity all-reduce) -- what the C driver runs under CNV_GPUS=N
+            k = np.zeros(nsteps, dtype=np.int32)
+            e, cmax, cmin = np.zeros(nsteps), np.zeros(nsteps), np.zeros(nsteps)
+            failed = L.cnv_sim_step_slab(self.h, nsteps, k.ctypes.data, e.ctypes.data,
+                                         cmax.ctypes.data if diagnostics else None, cmin.ctypes.data if diagnostics else None)
+            if failed < 0:
+                raise RuntimeError("cnv_sim_step_slab: no communicator")
+            n = failed if failed else nsteps
+            self.psi_buf = None
+            return dict(failed_step=failed, k=list(k[:n]), e=list(e[:n]), cont_max=list(cmax[:n]) if diagnostics else [],
+                        cont_min=list(cmin[:n]) if diagnostics else [])
+        # CNV_DIST_BACKEND=torch (no native communicator): the same step orchestrated through torch.distributed
         ks, es, cmax, cmin = [], [], [], []
         for _ in range(nsteps):
             L.cnv_sim_phase(self.h, 0, self.stream)
@@ -356,6 +370,12 @@ class SlabSimulation:
 
     def gather_fields(self):
         """psi, w, u, v of the whole grid on rank 0 (None elsewhere)."""
+        if self.poisson.comm and self.psi_buf is None:
+            shape = (self.gnrows, self.ncols)
+            out = {n: np.empty(shape) for n in ("psi", "w", "u", "v")} if self.rank == 0 else None
+            ptr = (lambda n: out[n].ctypes.data) if self.rank == 0 else (lambda n: None)
+            self.L.cnv_sim_gather_fields_slab(self.h, ptr("psi"), ptr("w"), ptr("u"), ptr("v"))
+            return out
         out = {}
         srcs = {"psi": self.poisson.bufs[self.psi_buf], "w": self._field(2), "u": self._field(0), "v": self._field(1)}
         for name, t in srcs.items():

@@ -177,6 +177,14 @@ void cnv_sim_destroy(cnv_sim *s);
 /* Advances nsteps steps.  k/e/cont_max/cont_min: NULL or arrays of nsteps (per-step Poisson log values
  * and continuity diagnostic).  Returns 0, or (index of the step whose Poisson solve hit itmax) + 1. */
 int cnv_sim_step(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, double *cont_min);
+/* Slab simulations (world > 1; attach the NCCL communicator to cnv_sim_poisson() first): whole time steps inside the library
+ * -- the stencil phases with their 3-row halo exchanges, the distributed Poisson solve (peer-memory path if set up, the NCCL
+ * group per pass otherwise), the continuity max / min all-reduce.  Every rank calls it with the same arguments and receives
+ * the same values.  Returns 0, (index of the step whose Poisson solve hit itmax) + 1, or -1 without a communicator. */
+int cnv_sim_step_slab(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, double *cont_min);
+/* whole fields on rank 0 (host arrays of nx*ny there, ignored on the other ranks; a NULL on rank 0 drops that field): every
+ * rank sends the owned rows of all four fields over the communicator */
+int cnv_sim_gather_fields_slab(cnv_sim *s, double *psi, double *w, double *u, double *v);
 int cnv_sim_get_fields(cnv_sim *s, double *psi, double *w, double *u, double *v); /* host, nx*ny each, NULL to skip */
 int cnv_sim_set_fields(cnv_sim *s, const double *psi, const double *w, const double *u, const double *v);
 void cnv_sim_set_diagnostics(cnv_sim *s, int continuity_on);
@@ -192,7 +200,11 @@ int cnv_sim_pressure(cnv_sim *s, int itmax, double tol, double *p_host, int *k, 
 
 /* ---- whole driver: restates src/main.c:27-481 on top of the device-resident path ---------------
  * (same config file, same stdout/log lines, same step order; VTK through printvtk-compatible writer
- * unless CNV_NO_VTK=1).  Returns the process exit code. */
+ * unless CNV_NO_VTK=1).  Returns the process exit code.
+ * CNV_GPUS=N (2..8): the grid is slab-decomposed over N GPUs, one process per GPU -- cnv_main forks N-1 children BEFORE its
+ * first CUDA call (so call it from a process that has not initialised CUDA: the cnavier_b200 executable does), exchanges the
+ * NCCL id and the CUDA IPC handles of the peer-memory path over socket pairs, and rank 0 (the calling process) writes the
+ * same log lines and VTK files as a one-GPU run; fields and Poisson iteration counts are bit-identical to it. */
 int cnv_main(int argc, char **argv);
 /* The driver's VTK writer on its own: replaces printvtk (src/utils.c:38-100) -- ASCII STRUCTURED_POINTS, "%.6lf", file
  * <output_dir>/<title>-1-<count>.vtk opened in append mode, ONE counter across all fields and calls of the process.

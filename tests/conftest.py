@@ -16,17 +16,11 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    """Order under `pytest -x`: the product's default paths first, forced kernel variants after them (the cases
-    parametrised with the forced cluster-resident Poisson kernel of tests/test_gpu_parity.py), the multi-GPU file last.
-    A failure in a forced variant then cannot hide the result of the default path."""
+    """Order under `pytest -x`: the multi-GPU file last (a failure there must not hide the single-GPU parity results)."""
     def rank(item):
         name = item.nodeid
         if "test_gpu_z_multi" in name:
             return 3
-        if "[onchip" in name or "-onchip]" in name or "onchip-" in name:
-            return 2
-        if "[resident" in name or "-resident]" in name or "resident-" in name:
-            return 1
         return 0
     items.sort(key=rank)  # stable: the original order is kept inside each group
 

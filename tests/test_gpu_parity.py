@@ -25,12 +25,10 @@ def _gpu():
     fd.require_gpu()
 
 
-@pytest.fixture(params=["resident", "stream", "onchip"])
+@pytest.fixture(params=["stream", "onchip"])
 def small_grid_path(request, monkeypatch):
-    """The Poisson kernels a small grid can take: the whole-solve cluster kernel (single-CTA grids by default, forced here
-    for every grid it can hold), the streaming pass kernel, and the persistent on-chip kernel (register-resident tiles,
-    forced here for every grid it has a plan for)."""
-    monkeypatch.setenv("CNV_POISSON_RESIDENT", "2" if request.param == "resident" else "0")  # 2 = force (clusters too)
+    """The two Poisson kernels a small grid can take: the streaming pass kernel (one launch per T sweeps) and the persistent
+    on-chip kernel (register-resident tiles, the whole solve in one launch; the default wherever it has a plan)."""
     monkeypatch.setenv("CNV_POISSON_ONCHIP", "1" if request.param == "onchip" else "0")
     return request.param
 
@@ -194,7 +192,7 @@ def test_poisson_every_stop_position(port, small_grid_path):
 
 
 @pytest.mark.parametrize("n,sweeps", [(1024, 24), (4096, 20)])
-def test_poisson_full_size_fixed_sweeps(port, n, sweeps):
+def test_poisson_full_size_fixed_sweeps(port, n, sweeps, monkeypatch):
     """BASELINE sizes: K sweeps of the 1024^2 / 4096^2 cavity grids, bitwise against the oracle
     (OpenMP red-black) and identical for every temporal block depth.  T = 8 at 4096^2 is exactly the plan bench.py
     times (streaming kernel); 20 sweeps = 3 passes, the last one partial (4 of 8 levels active)."""
@@ -202,8 +200,10 @@ def test_poisson_full_size_fixed_sweeps(port, n, sweeps):
     f = rng.standard_normal((n, n))
     beta = port.beta(n, n)
     want, norms = port.poisson_sweeps(f, 1 / n, 1 / n, sweeps, beta)
+    monkeypatch.setenv("CNV_POISSON_ONCHIP", "0")     # the streaming pass kernel (1024^2 takes the on-chip kernel by default)
     for T in (8, 6, 4, 2, 1):
         s = fd.PoissonSolver(n, n, T)
+        assert not s.plan["onchip"]
         s.set_consts(1 / n, 1 / n, beta)
         s.upload(f)
         r = s.solve(sweeps, 0.0)
@@ -248,7 +248,6 @@ def test_poisson_onchip_1024_fixed_sweeps_and_converged(port, monkeypatch, T, nt
     real stop decision (beta = 1.5: monotone norms, stop inside the third pass -> the pass' input is reloaded and recomputed)."""
     n = 1024
     monkeypatch.setenv("CNV_POISSON_ONCHIP", "1")
-    monkeypatch.setenv("CNV_POISSON_RESIDENT", "0")
     monkeypatch.setenv("CNV_ONCHIP_T", str(T)); monkeypatch.setenv("CNV_ONCHIP_NTX", str(ntx)); monkeypatch.setenv("CNV_ONCHIP_NTY", str(nty))
     rng = np.random.default_rng(n)
     f = rng.standard_normal((n, n))

@@ -24,7 +24,7 @@ probe)
     tail -60 gpurun_out/probe_onchip.log
     ;;
 ncuoc)
-    CNV_POISSON_ONCHIP=1 CNV_POISSON_RESIDENT=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_poisson_onchip -c 1 -f -o gpurun_out/ncu_onchip \
+    CNV_POISSON_ONCHIP=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_poisson_onchip -c 1 -f -o gpurun_out/ncu_onchip \
         python tools/prof_onchip.py 1024 64 > gpurun_out/ncu_onchip.log 2>&1
     ;;
 bench)
@@ -36,7 +36,7 @@ ncu)
         python bench.py --steps 2 --warmup 3 --sweeps 128 --no-cpu --series single > gpurun_out/launches.log 2>&1
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_poisson_pass -s 2 -c 1 -f -o gpurun_out/ncu_pass \
         python tools/prof_one.py 4096 8 > gpurun_out/ncu_pass.log 2>&1
-    CNV_POISSON_ONCHIP=1 CNV_POISSON_RESIDENT=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_poisson_onchip -c 1 -f -o gpurun_out/ncu_onchip \
+    CNV_POISSON_ONCHIP=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_poisson_onchip -c 1 -f -o gpurun_out/ncu_onchip \
         python tools/prof_onchip.py 1024 64 > gpurun_out/ncu_onchip.log 2>&1
     ;;
 esac

@@ -39,7 +39,7 @@ def run(nr, nc, T, ws=0, chunks=0, sweeps=256, reps=3):
 
 
 def run_onchip(nr, nc, T, ntx, nty, sweeps=256, reps=3):
-    os.environ.update(CNV_POISSON_ONCHIP="1", CNV_POISSON_RESIDENT="0", CNV_ONCHIP_T=str(T), CNV_ONCHIP_NTX=str(ntx), CNV_ONCHIP_NTY=str(nty))
+    os.environ.update(CNV_POISSON_ONCHIP="1", CNV_ONCHIP_T=str(T), CNV_ONCHIP_NTX=str(ntx), CNV_ONCHIP_NTY=str(nty))
     prof = os.environ.get("CNV_ONCHIP_PROF", "0") == "1"
     s = fd.PoissonSolver(nr, nc, 0)
     os.environ["CNV_POISSON_ONCHIP"] = "0"

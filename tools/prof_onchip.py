@@ -3,7 +3,6 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 os.environ.setdefault("CNV_POISSON_ONCHIP", "1")
-os.environ.setdefault("CNV_POISSON_RESIDENT", "0")
 n, sweeps = int(sys.argv[1]), int(sys.argv[2])
 import fluid_dynamics1_b200 as fd
 s = fd.PoissonSolver(n, n, 0)

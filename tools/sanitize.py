@@ -7,8 +7,8 @@ import fluid_dynamics1_b200 as fd
 
 rng = np.random.default_rng(0)
 only = sys.argv[1] if len(sys.argv) > 1 else None
-for path, env in (("resident", dict(CNV_POISSON_RESIDENT="2")),
-                  ("stream", dict(CNV_POISSON_RESIDENT="0"))):
+for path, env in (("onchip", dict(CNV_POISSON_ONCHIP="1")),
+                  ("stream", dict(CNV_POISSON_ONCHIP="0"))):
     if only and path != only:
         continue
     os.environ.update(env)
@@ -24,6 +24,6 @@ for path, env in (("resident", dict(CNV_POISSON_RESIDENT="2")),
         s.set_consts(0.01, 0.013, 1.7)
         s.upload(rng.standard_normal((150, 330)))
         res = s.solve(2 * T + 3, 0.0)
-        print(path, "T", T, "plan", {k: s.plan[k] for k in ("WS", "nstrips", "nchunks")}, "sweeps", res["sweeps"], flush=True)
+        print(path, "T", T, "plan", {k: s.plan[k] for k in ("onchip", "WS", "nstrips", "nchunks", "oc_T", "oc_ntx", "oc_nty")}, "sweeps", res["sweeps"], flush=True)
         s.close()
 print("SANITIZE WORKLOAD DONE")
