@@ -142,27 +142,33 @@ __device__ __forceinline__ double fd_interior(const double (&c)[7], Load x)
 // Register windows: win[0..6] = the operand at offsets -3..+3 along the differentiated axis.
 // Interior cells (>= HALF away from both walls) use the unrolled interior row on the window; cells within
 // HALF of a wall take the generic closure rows (fd_apply) reading the tile.
-template <int HALF>
+// ZC: the centre coefficient is exactly 0 (interior rows of Diff1, src/finitediff.c:72-145 never set it).  Its term 0 * x = +-0
+// cannot change the running sum: that sum starts at +0.0 and (+0) + (-0) = +0, so it is never -0, and s + (+-0) = s for
+// every s that is not -0.  Skipping the tap is therefore bit-exact (finite operands) and saves 2 of 14 fp64 operations.
+template <int HALF, bool ZC = false>
 __device__ __forceinline__ double win_deriv(const double (&c)[7], const double (&win)[7])
 {
     double sum = 0.0;
 #pragma unroll
-    for (int k = 0; k <= 2 * HALF; k++) sum = xadd(sum, xmul(c[k], win[THALO - HALF + k]));
+    for (int k = 0; k <= 2 * HALF; k++) {
+        if (ZC && k == HALF) continue;
+        sum = xadd(sum, xmul(c[k], win[THALO - HALF + k]));
+    }
     return sum;
 }
-template <int HALF, bool INTERIOR>
+template <int HALF, bool INTERIOR, bool ZC = false>
 __device__ __forceinline__ double tile_dx(const Tile &t, const FdTable &tab, const double (&c)[7], const double (&win)[7],
                                           int li, int j, int j0)
 {
-    if (INTERIOR || (j >= HALF && j < tab.n - HALF)) return win_deriv<HALF>(c, win);
+    if (INTERIOR || (j >= HALF && j < tab.n - HALF)) return win_deriv<HALF, ZC>(c, win);
     return fd_apply(tab, j, [&](int col) { return t.v[li][col - j0 + THALO]; });
 }
 // i = GLOBAL row of the cell, gi0 = global row of the tile's first row
-template <int HALF, bool INTERIOR>
+template <int HALF, bool INTERIOR, bool ZC = false>
 __device__ __forceinline__ double tile_dy(const Tile &t, const FdTable &tab, const double (&c)[7], const double (&win)[7],
                                           int lj, int i, int gi0)
 {
-    if (INTERIOR || (i >= HALF && i < tab.n - HALF)) return win_deriv<HALF>(c, win);
+    if (INTERIOR || (i >= HALF && i < tab.n - HALF)) return win_deriv<HALF, ZC>(c, win);
     return fd_apply(tab, i, [&](int row) { return t.v[row - gi0 + THALO][lj]; });
 }
 // a tile whose cells are all >= 3 away from every wall needs no closure rows at all (uniform per CTA):
@@ -223,8 +229,8 @@ k_euler_fused(const double *__restrict__ w, const double *__restrict__ u, const 
             if (!INTERIOR && i >= m.own_hi) break;
             if (rr > 0) win_y_slide(tw, li, lj, wy);
             win_x(tw, li, lj, wx);
-            const double dwdx = tile_dx<HALF, INTERIOR>(tw, d1x, c1x, wx, li, j, j0);
-            const double dwdy = tile_dy<HALF, INTERIOR>(tw, d1y, c1y, wy, lj, m.grow0 + i, gi0);
+            const double dwdx = tile_dx<HALF, INTERIOR, true>(tw, d1x, c1x, wx, li, j, j0);
+            const double dwdy = tile_dy<HALF, INTERIOR, true>(tw, d1y, c1y, wy, lj, m.grow0 + i, gi0);
             const double d2wdx2 = tile_dx<HALF, INTERIOR>(tw, d2x, c2x, wx, li, j, j0);
             const double d2wdy2 = tile_dy<HALF, INTERIOR>(tw, d2y, c2y, wy, lj, m.grow0 + i, gi0);
             const size_t p = (size_t)i * ld + j;
@@ -285,8 +291,8 @@ k_velocity(const double *__restrict__ psi, RowMap m, int ncols, int ldp, const F
             if (!INTERIOR && i >= m.own_hi) break;
             if (rr > 0) win_y_slide(tp, li, lj, wy);
             win_x(tp, li, lj, wx);
-            const double dpdx = tile_dx<HALF, INTERIOR>(tp, d1x, c1x, wx, li, j, j0);
-            const double dpdy = tile_dy<HALF, INTERIOR>(tp, d1y, c1y, wy, lj, m.grow0 + i, gi0);
+            const double dpdx = tile_dx<HALF, INTERIOR, true>(tp, d1x, c1x, wx, li, j, j0);
+            const double dpdy = tile_dy<HALF, INTERIOR, true>(tp, d1y, c1y, wy, lj, m.grow0 + i, gi0);
             u[(size_t)i * ld + j] = dpdy;
             v[(size_t)i * ld + j] = -dpdx;
         }
@@ -317,8 +323,8 @@ __device__ __forceinline__ void continuity_from_tiles(const Tile &tu, const Tile
             if (!INTERIOR && i >= m.own_hi) break;
             if (rr > 0) win_y_slide(tv, li, lj, wy);
             win_x(tu, li, lj, wx);
-            const double dudx = tile_dx<HALF, INTERIOR>(tu, d1x, c1x, wx, li, j, j0);
-            const double dvdy = tile_dy<HALF, INTERIOR>(tv, d1y, c1y, wy, lj, m.grow0 + i, gi0);
+            const double dudx = tile_dx<HALF, INTERIOR, true>(tu, d1x, c1x, wx, li, j, j0);
+            const double dvdy = tile_dy<HALF, INTERIOR, true>(tv, d1y, c1y, wy, lj, m.grow0 + i, gi0);
             const double c = xadd(dudx, dvdy);
             mx = fmax(mx, c);
             mn = fmin(mn, c);
@@ -373,21 +379,27 @@ __device__ __forceinline__ void minmax_finish(double mx, double mn, double *__re
     }
 }
 
+// Persistent: a CTA walks the tiles bid, bid + grid, ... and keeps its max / min in registers, so the block reduction, the
+// fence and the ticket of minmax_finish are paid once per CTA, not once per 64 x 32 tile (8192 tiles at 4096^2: the per-tile
+// epilogue cost as much as the tile's arithmetic -- 103 us = 39 % of the HBM peak before, see profiles/).
 template <int HALF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)  // (80 registers, 3 CTAs per SM; forcing 64 registers for a fourth CTA measured 135 vs 105 us)
 k_continuity(const double *__restrict__ u, const double *__restrict__ v, RowMap m, int ncols, int ld,
              const FdTable d1x, const FdTable d1y, double *__restrict__ partial, unsigned *__restrict__ ticket,
-             double *__restrict__ result)
+             double *__restrict__ result, const int gx, const int ntiles)
 {
     __shared__ Tile tu, tv;
     double mx = -DBL_MAX, mn = DBL_MAX;  // maxel/minel start values, src/linearalg.c:478,514
-    const int j0 = blockIdx.x * TW, i0 = m.own_lo + blockIdx.y * TH;
-    tile_load(tu, u, i0, j0, m.nloc, ncols, ld);
-    tile_load(tv, v, i0, j0, m.nloc, ncols, ld);
     double c1x[7], c1y[7];
     load_coefs(d1x, c1x); load_coefs(d1y, c1y);
-    __syncthreads();
-    continuity_from_tiles<HALF>(tu, tv, m, ncols, d1x, d1y, c1x, c1y, i0, j0, mx, mn);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int j0 = (tile % gx) * TW, i0 = m.own_lo + (tile / gx) * TH;
+        __syncthreads();  // everybody has finished reading the previous tile
+        tile_load(tu, u, i0, j0, m.nloc, ncols, ld);
+        tile_load(tv, v, i0, j0, m.nloc, ncols, ld);
+        __syncthreads();
+        continuity_from_tiles<HALF>(tu, tv, m, ncols, d1x, d1y, c1x, c1y, i0, j0, mx, mn);
+    }
     minmax_finish(mx, mn, partial, ticket, result);
 }
 
@@ -540,11 +552,11 @@ k_pressure_rhs(const double *__restrict__ u, const double *__restrict__ v, RowMa
             if (!INTERIOR && i >= m.own_hi) break;
             if (rr > 0) { win_y_slide(tu, li, lj, uy); win_y_slide(tv, li, lj, vy); }
             win_x(tu, li, lj, wx);
-            const double dudx = tile_dx<HALF, INTERIOR>(tu, d1x, c1x, wx, li, j, j0);
+            const double dudx = tile_dx<HALF, INTERIOR, true>(tu, d1x, c1x, wx, li, j, j0);
             win_x(tv, li, lj, wx);
-            const double dvdx = tile_dx<HALF, INTERIOR>(tv, d1x, c1x, wx, li, j, j0);
-            const double dudy = tile_dy<HALF, INTERIOR>(tu, d1y, c1y, uy, lj, m.grow0 + i, gi0);
-            const double dvdy = tile_dy<HALF, INTERIOR>(tv, d1y, c1y, vy, lj, m.grow0 + i, gi0);
+            const double dvdx = tile_dx<HALF, INTERIOR, true>(tv, d1x, c1x, wx, li, j, j0);
+            const double dudy = tile_dy<HALF, INTERIOR, true>(tu, d1y, c1y, uy, lj, m.grow0 + i, gi0);
+            const double dvdy = tile_dy<HALF, INTERIOR, true>(tv, d1y, c1y, vy, lj, m.grow0 + i, gi0);
             const double f = xadd(xadd(xmul(dudx, dudx), xmul(dvdy, dvdy)), xmul(xmul(2.0, dudy), dvdx));
             if (f_out) f_out[(size_t)i * ldo + j] = f;
             if (rhs) rhs[(size_t)i * ld + j] = xmul(pscale, -f);
@@ -633,7 +645,16 @@ void launch_continuity(const double *u, const double *v, const RowMap &m, int nc
                        double *partial, unsigned *ticket, double *result, cudaStream_t s)
 {
     const dim3 b(TW, 4), g = tile_grid(m, ncols);
-#define CALL(H) k_continuity<H><<<g, b, 0, s>>>(u, v, m, ncols, ld, d1x, d1y, partial, ticket, result)
+    const int ntiles = (int)(g.x * g.y);
+    static int slots = 0;  // CTAs the device holds at once (3 per SM: 80 registers x 256 threads, two staged tiles of 21.6 KB)
+    if (!slots) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = 3 * sms;
+    }
+    const int grid = ntiles < slots ? ntiles : slots;
+#define CALL(H) k_continuity<H><<<grid, b, 0, s>>>(u, v, m, ncols, ld, d1x, d1y, partial, ticket, result, (int)g.x, ntiles)
     CNV_BY_HALF(d1x.half, CALL);
 #undef CALL
 }
