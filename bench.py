@@ -141,7 +141,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def headline_shape(args, world):
     """(total_rows, ncols, rows_per_gpu, scaling, description) of the workload `value` is measured on."""
-    if args.series == "auto" and world > 1:
+    if args.series in ("auto", "headline") and world > 1:
         return 2048 * world, 16384, 2048, "weak", (
             f"{2048 * world}x16384 Re=5000 lid-driven cavity, red-black SOR Poisson solve (BASELINE config 5 grid: 2048 x 16384 rows "
             f"per GPU, 16384^2 at 8 GPUs)")
@@ -492,8 +492,7 @@ def series_entry(ctx, run, args, steps, peak, with_e2e=True):
            "plan": {"temporal_block_T": run.T, "strip_width": run.plan["WS"], "rows_per_chunk": run.plan["Hout"],
                     "ctas": run.plan["nstrips"] * run.plan["nchunks"], "arith_path": "pow2-exact" if run.plan["pow2"] else "general"}}
     if run.slab is not None:
-        out["plan"]["exchange"] = ("peer" if run.slab.peer else "nccl" if run.slab.comm else "torch") + \
-                                  ("+lagged-decision" if run.slab.peer and len(run.slab.bufs) == 3 else "")
+        out["plan"]["exchange"] = "peer" if run.slab.peer else "nccl" if run.slab.comm else "torch"
     if with_e2e:
         ms, _ = run.e2e(args.sweeps, steps)
         out["e2e"] = {"value": run.interior_cells * args.sweeps * steps / (ms * 1e-3), "ms_per_step": ms / steps}
@@ -820,7 +819,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--series", default="auto", choices=["auto", "single"],
+    ap.add_argument("--series", default="auto", choices=["auto", "headline", "single"],
                     help="auto: the BASELINE workloads (see the module docstring); single: only the grid given by --grid / --scaling")
     ap.add_argument("--n", "--grid", dest="n", type=int, default=4096,
                     help="grid columns (and rows per GPU under weak scaling) of --series single; use --grid under torchrun, whose own "

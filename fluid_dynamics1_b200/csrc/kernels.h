@@ -91,9 +91,9 @@ public:
     int onchip_profile(unsigned long long *out, int max_ctas);  // CNV_ONCHIP_PROF=1: 8 phase counters per CTA of the last solve  // solve() runs the persistent on-chip kernel (poisson_onchip.cu)
     const OnchipGeom &onchip_geom() const { return oc_; }
     double *rhs() { return rhs_; }                // device, pitch ld(): pscale * f
-    double *buffer(int i) { return buf_[i]; }     // the iterate buffers: 0, 1 (and 2 with a lagged stop decision: peer path, on-chip kernel)
-    int num_buffers() const { return ((links_.enabled && links_.lag) || use_onchip_) && buf_[2] ? 3 : 2; }
-    void zero_extra_buffer(cudaStream_t s)  // third buffer of the lagged peer decision: same initial state as 0 and 1
+    double *buffer(int i) { return buf_[i]; }     // the iterate buffers: 0, 1 (and 2 for the on-chip kernel, whose stop decision lags a pass)
+    int num_buffers() const { return use_onchip_ && buf_[2] ? 3 : 2; }
+    void zero_extra_buffer(cudaStream_t s)  // third buffer (on-chip kernel): same initial state as 0 and 1
     {
         if (buf_[2]) CNV_CUDA_CHECK(cudaMemsetAsync(buf_[2], 0, (size_t)geom_.nrows * geom_.ld * sizeof(double), s));
     }
@@ -156,7 +156,6 @@ private:
     double *oc_partials_ = nullptr;
     RelaxConsts rc_;
     double *buf_[3] = {nullptr, nullptr, nullptr};
-    bool lag_ = false;  // CNV_PEER_LAG=1: lagged stop decision on the peer path (three iterate buffers)
     double *rhs_ = nullptr, *partials_ = nullptr, *hist_ = nullptr, *norms_ = nullptr;
     int hist_cap_ = 0;
     PoissonCtl *ctl_ = nullptr, *h_ctl_ = nullptr;

@@ -78,38 +78,19 @@ __device__ bool gather_norms(const PeerLinks &L, unsigned long long g, double *e
 }
 
 // Host-visible state after `L.pidx` passes (peer path), derived by one thread.
-// Plain machine: S_0 is what k_reset_ctl wrote; S_p = decide(S_{p-1}, norms of pass p-1); ctlbuf[p & 1] = S_p.
-// Lagged machine (L.lag): ctlbuf[p & 1] = X_p = lag_fold(X_{p-1}, norms of pass p-2); the host sees
-// lag_final(X_P, norms of pass P-1), see poisson_stream.h.
+// S_0 is what k_reset_ctl wrote; S_p = decide(S_{p-1}, norms of pass p-1); ctlbuf[p & 1] = S_p.
 __device__ PoissonCtl peer_state(const PeerLinks &L, int T, double *hist)
 {
     if (L.pidx == 0) return L.ctlbuf[0];
     PoissonCtl c = L.ctlbuf[(L.pidx - 1) & 1];
     double e[8];
-    if (!L.lag) {
-        if (c.state != 0) return c;
-        if (!gather_norms(L, L.gidx - 1, e)) {
-            report_error(L);
-            c.state = 3;
-            return c;
-        }
-        decide(c, e, pass_sweeps(c, T), hist);
-        return c;
-    }
-    bool ok = true;
-    if (L.pidx >= 2) {  // X_{P-1} -> X_P
-        for (int i = 0; i < 8; i++) e[i] = 0.0;
-        if (c.state == 0 && c.redo == 0) ok = gather_norms(L, L.gidx - 2, e);
-        if (ok) lag_fold(c, e, T, hist);
-    }
-    if (ok && lag_final_needs_last(c, L.pidx)) {
-        ok = gather_norms(L, L.gidx - 1, e);
-        if (ok) lag_final(c, L.pidx, e, T, hist);
-    }
-    if (!ok) {
+    if (c.state != 0) return c;
+    if (!gather_norms(L, L.gidx - 1, e)) {
         report_error(L);
         c.state = 3;
+        return c;
     }
+    decide(c, e, pass_sweeps(c, T), hist);
     return c;
 }
 
@@ -130,11 +111,12 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
+    const int chunk = PEER ? peer_chunk_of(blockIdx.y, gridDim.y, L.edge_first) : (int)blockIdx.y;  // chunk row of this CTA
     const bool first_cta = blockIdx.x == 0 && blockIdx.y == 0;
     __shared__ PoissonCtl s_ctl;
     unsigned long long *trace = nullptr;
     if (L.trace && L.pidx < L.trace_passes && tid == 0) {
-        trace = L.trace + ((size_t)L.pidx * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x) * 6;
+        trace = L.trace + ((size_t)L.pidx * gridDim.x * gridDim.y + chunk * gridDim.x + blockIdx.x) * 6;
         trace[0] = globaltimer_ns();
     }
     __shared__ LagAction s_act;  // (peer path only)
@@ -142,21 +124,19 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
         // peer path: derive this pass' state from the previous state + every rank's published norms.  The whole CTA
         // cooperates -- one thread per rank waits for that rank's flag, 8 x world threads fetch the norms -- so the
         // start-up cost does not grow with the number of GPUs (64 dependent loads by one thread were ~10 us at 8 GPUs).
-        // Plain machine: the norms of pass gidx-1 (a rendezvous of all ranks per pass).  Lagged machine (L.lag): the
-        // norms of pass gidx-2, which have normally long arrived; the pass runs speculatively (poisson_stream.h).
+        // The norms are those of pass gidx-1: ~2 us of flag latency per CTA (profiles/scale_r2.md).
         __shared__ double s_nrm[kMaxRanks][8];
         __shared__ int s_bad;
-        const int lagd = peer_lag_distance(L.lag);  // this pass folds the norms of pass gidx - lagd
         const PoissonCtl prev = L.ctlbuf[L.pidx == 0 ? 0 : (L.pidx - 1) & 1];
-        const bool need = peer_needs_norms(prev, L.pidx, L.lag);  // uniform
+        const bool need = peer_needs_norms(prev, L.pidx);  // uniform
         if (tid == 0) s_bad = 0;
         __syncthreads();
         if (need) {
             PeerMailbox *mb = L.mail[L.rank];
             for (int r = tid; r < L.world; r += blockDim.x)
-                if (!wait_ge(L, &mb->norm_flag[r], L.gidx - lagd + 1)) s_bad = 1;  // pass g publishes the value g+1
+                if (!wait_ge(L, &mb->norm_flag[r], L.gidx)) s_bad = 1;  // pass g publishes the value g+1
             __syncthreads();
-            const int slot = (int)((L.gidx - lagd) & (kNormSlots - 1));
+            const int slot = (int)((L.gidx - 1) & (kNormSlots - 1));
             for (int i = tid; i < 8 * L.world; i += blockDim.x) s_nrm[i >> 3][i & 7] = *(volatile double *)&mb->norms[slot][i >> 3][i & 7];
             __syncthreads();
         }
@@ -170,7 +150,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
                 e[g] = sum;
             }
             if (need && s_bad) report_error(L);
-            const LagAction a = peer_advance(c, e, need, s_bad != 0, L.pidx, L.lag, T, first_cta ? hist : nullptr);
+            const LagAction a = peer_advance(c, e, need, s_bad != 0, T, first_cta ? hist : nullptr);
             s_ctl = c;
             s_act = a;
             if (first_cta && L.pidx > 0) L.ctlbuf[L.pidx & 1] = c;
@@ -190,10 +170,10 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     const int nsw = PEER ? s_act.nsw : pass_sweeps(c0, T);
     const int cur = PEER ? s_act.in : c0.cur;
     const int nxt = PEER ? s_act.out : cur ^ 1;
-    const double *__restrict__ in = cur ? (PEER && cur == 2 ? L.buf2 : buf1) : buf0;
-    double *__restrict__ out = PEER ? (nxt == 0 ? buf0 : nxt == 1 ? buf1 : L.buf2) : (cur ? buf0 : buf1);
+    const double *__restrict__ in = cur ? buf1 : buf0;
+    double *__restrict__ out = nxt ? buf1 : buf0;
 
-    const CtaGeom G = cta_geom(p, blockIdx.x, blockIdx.y);
+    const CtaGeom G = cta_geom(p, blockIdx.x, chunk);
     if (PEER) {
         __shared__ int s_inputs_ok;
         if (tid == 0) {
@@ -204,12 +184,9 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
             // first pass of a solve: the neighbour must have finished zeroing the buffer this CTA pushes into
             if (L.pidx == 0 && push_down) ok = ok && wait_ge(L, &mb->ready[0], L.epoch);
             if (L.pidx == 0 && push_up) ok = ok && wait_ge(L, &mb->ready[1], L.epoch);
-            // this CTA streams halo rows -> the neighbour's pushes of the previous pass must have landed (a redo
-            // pass of the lagged machine re-reads an older buffer whose halos landed passes ago)
-            if (s_act.kind == 1) {
-                if (L.rank > 0 && G.ylo < p.own_lo) ok = ok && wait_ge(L, &mb->halo_count[0], L.gidx * L.need_low);
-                if (L.rank < L.world - 1 && G.yhi >= p.own_hi) ok = ok && wait_ge(L, &mb->halo_count[1], L.gidx * L.need_high);
-            }
+            // this CTA streams halo rows -> the neighbour's pushes of the previous pass must have landed
+            if (L.rank > 0 && G.ylo < p.own_lo) ok = ok && wait_ge(L, &mb->halo_count[0], L.gidx * L.need_low);
+            if (L.rank < L.world - 1 && G.yhi >= p.own_hi) ok = ok && wait_ge(L, &mb->halo_count[1], L.gidx * L.need_high);
             if (!ok) report_error(L);
             s_inputs_ok = ok ? 1 : 0;
             if (trace) trace[2] = globaltimer_ns();
@@ -249,35 +226,41 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     if (PEER) {
         // Slab boundary rows: copy what this CTA has just written (still L2 resident) into the neighbour GPU's halo
         // rows with coalesced 16-byte peer stores over NVLink -- outside the streaming loop, which stays identical to
-        // the single-GPU kernel -- then make them visible system-wide and count the push in the neighbour's mailbox.
+        // the single-GPU kernel.  Only the CTAs of the two edge chunk rows do this (they are launched first, see
+        // peer_chunk_of); ONE thread then orders the CTA's pushes system-wide (the CTA barrier makes them precede its
+        // fence: the pattern of a grid barrier's arrive) and counts the push in the neighbour's mailbox, while the rest
+        // of the CTA goes on with the norms.  Round 2 measured 8 us per CTA (every CTA, 576 threads each) for the
+        // unconditional all-thread __threadfence_system() this replaces (profiles/scale_r2.md).
         const bool push_down = L.rank > 0 && G.y0 < p.own_lo + p.HY;
         const bool push_up = L.rank < L.world - 1 && G.y1 > p.own_hi - p.HY;
-        __syncthreads();  // every write-back of this CTA is done and visible to the CTA
-        const int c0 = G.gx0 + p.HX, c1 = (c0 + p.Wout < p.ld ? c0 + p.Wout : p.ld);  // this strip's output columns
-        const int npair = (c1 - c0) >> 1;
-        for (int side = 0; side < 2; side++) {
-            if (side == 0 ? !push_down : !push_up) continue;
-            const int ra = side == 0 ? (G.y0 > p.own_lo ? G.y0 : p.own_lo) : (G.y0 > p.own_hi - p.HY ? G.y0 : p.own_hi - p.HY);
-            const int rb = side == 0 ? (G.y1 < p.own_lo + p.HY ? G.y1 : p.own_lo + p.HY) : (G.y1 < p.own_hi ? G.y1 : p.own_hi);
-            double *peer = (side == 0 ? L.down_buf[nxt] + L.down_delta : L.up_buf[nxt] + L.up_delta);
-            for (int idx = tid; idx < (rb - ra) * npair; idx += blockDim.x) {
-                const int rr = ra + idx / npair, cc = c0 + 2 * (idx % npair);
-                const size_t off = (size_t)rr * p.ld + cc;
-                const double2 v = __ldcg(reinterpret_cast<const double2 *>(out + off));
-                *reinterpret_cast<double2 *>(peer + off) = v;
+        if (push_down || push_up) {  // uniform over the CTA
+            __syncthreads();  // every write-back of this CTA is done and visible to the CTA
+            const int c0 = G.gx0 + p.HX, c1 = (c0 + p.Wout < p.ld ? c0 + p.Wout : p.ld);  // this strip's output columns
+            const int npair = (c1 - c0) >> 1;
+            for (int side = 0; side < 2; side++) {
+                if (side == 0 ? !push_down : !push_up) continue;
+                const int ra = side == 0 ? (G.y0 > p.own_lo ? G.y0 : p.own_lo) : (G.y0 > p.own_hi - p.HY ? G.y0 : p.own_hi - p.HY);
+                const int rb = side == 0 ? (G.y1 < p.own_lo + p.HY ? G.y1 : p.own_lo + p.HY) : (G.y1 < p.own_hi ? G.y1 : p.own_hi);
+                double *peer = (side == 0 ? L.down_buf[nxt] + L.down_delta : L.up_buf[nxt] + L.up_delta);
+                for (int idx = tid; idx < (rb - ra) * npair; idx += blockDim.x) {
+                    const int rr = ra + idx / npair, cc = c0 + 2 * (idx % npair);
+                    const size_t off = (size_t)rr * p.ld + cc;
+                    const double2 v = __ldcg(reinterpret_cast<const double2 *>(out + off));
+                    *reinterpret_cast<double2 *>(peer + off) = v;
+                }
+            }
+            __syncthreads();  // all pushes of the CTA are issued ...
+            if (tid == 0) {
+                __threadfence_system();  // ... and ordered before the counts below, system-wide (cumulative through the barrier)
+                if (push_down) atomicAdd_system(&L.mail[L.rank - 1]->halo_count[1], 1ull);
+                if (push_up) atomicAdd_system(&L.mail[L.rank + 1]->halo_count[0], 1ull);
             }
         }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            if (push_down) atomicAdd_system(&L.mail[L.rank - 1]->halo_count[1], 1ull);
-            if (push_up) atomicAdd_system(&L.mail[L.rank + 1]->halo_count[0], 1ull);
-            if (trace) trace[4] = globaltimer_ns();
-        }
+        if (trace) trace[4] = globaltimer_ns();
     }
     // per-CTA L1 update norms, one per sweep of the pass (level g <-> sweep g+1)
     group_sums(sm, acc, t.g, kk, TPG, s_e);
-    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    const int ncta = gridDim.x * gridDim.y, cta = chunk * gridDim.x + blockIdx.x;  // geometric index: the order of the sums below
     if (tid < T) {
         partials[(size_t)cta * T + tid] = s_e[tid];
         __threadfence();
@@ -296,13 +279,13 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     group_sums(sm, part, t.g, kk, TPG, s_e);
     if (PEER) {
         // publish this rank's norms of the pass in every rank's mailbox, then raise the flag everywhere: thread
-        // (r, g) stores one norm into rank r's mailbox, then one thread per destination rank releases its flag
+        // (r, g) stores one norm into rank r's mailbox, then -- after the CTA barrier, through which the release below
+        // is cumulative over those stores -- one thread per destination rank releases its flag
         const int slot = (int)(L.gidx & (kNormSlots - 1));
         for (int i = tid; i < 8 * L.world; i += blockDim.x) {
             const int r = i >> 3, g = i & 7;
             L.mail[r]->norms[slot][L.rank][g] = (g < T && g < nsw) ? s_e[g] : 0.0;
         }
-        __threadfence_system();
         __syncthreads();
         for (int r = tid; r < L.world; r += blockDim.x) st_release_sys(&L.mail[r]->norm_flag[L.rank], L.gidx + 1);
         if (tid == 0) {
@@ -335,7 +318,7 @@ __global__ void k_peer_finalize(const PeerLinks L, int T, double *hist)
         c = peer_state(L, T, hist);
         if (*(volatile unsigned long long *)&L.mail[L.rank]->error) c.state = 3;
     }
-    L.ctlbuf[L.lag ? 2 : L.pidx & 1] = c;  // (lagged machine: slots 0/1 carry the chain X_p the passes read)
+    L.ctlbuf[L.pidx & 1] = c;
 }
 // peer path: this rank's iterate buffers are (re-)initialised for solve epoch L.epoch: tell both neighbours
 __global__ void k_peer_ready(const PeerLinks L)
@@ -541,7 +524,7 @@ void PoissonSolver::enable_history(int cap)
 void PoissonSolver::reset_ctl(int itmax, double tol, cudaStream_t s)
 {
     dist_passes_ = 0;
-    k_reset_ctl<<<1, 1, 0, s>>>(links_.enabled ? links_.ctlbuf : ctl_, itmax, tol, links_.enabled && links_.lag ? 3 : 2);
+    k_reset_ctl<<<1, 1, 0, s>>>(links_.enabled ? links_.ctlbuf : ctl_, itmax, tol, 2);
     count_launch(1);
 }
 
@@ -554,7 +537,7 @@ PoissonCtl PoissonSolver::read_ctl(cudaStream_t s)
         L.gidx = peer_gidx_;
         k_peer_finalize<<<1, 1, 0, s>>>(L, T_, use_hist_ ? hist_ : nullptr);
         count_launch(1);
-        src = links_.ctlbuf + (links_.lag ? 2 : dist_passes_ & 1);
+        src = links_.ctlbuf + (dist_passes_ & 1);
     }
     CNV_CUDA_CHECK(cudaMemcpyAsync(h_ctl_, src, sizeof(PoissonCtl), cudaMemcpyDeviceToHost, s));
     CNV_CUDA_CHECK(cudaEventRecord(ev_, s));
@@ -579,22 +562,14 @@ void PoissonSolver::peer_export(unsigned char *out256)
     if (!mailbox_) {
         CNV_CUDA_CHECK(cudaMalloc(&mailbox_, sizeof(PeerMailbox)));
         CNV_CUDA_CHECK(cudaMemset(mailbox_, 0, sizeof(PeerMailbox)));
-        CNV_CUDA_CHECK(cudaMalloc(&ctlbuf_, 3 * sizeof(PoissonCtl)));
-        CNV_CUDA_CHECK(cudaMemset(ctlbuf_, 0, 3 * sizeof(PoissonCtl)));
+        CNV_CUDA_CHECK(cudaMalloc(&ctlbuf_, 2 * sizeof(PoissonCtl)));
+        CNV_CUDA_CHECK(cudaMemset(ctlbuf_, 0, 2 * sizeof(PoissonCtl)));
     }
-    // CNV_PEER_LAG=1: lagged stop decision (poisson_stream.h) -- a third iterate buffer joins the rotation
-    lag_ = env_int("CNV_PEER_LAG", 0) != 0;
-    if (lag_ && !buf_[2]) {
-        const size_t bytes = (size_t)geom_.nrows * geom_.ld * sizeof(double);
-        CNV_CUDA_CHECK(cudaMalloc(&buf_[2], bytes));
-        CNV_CUDA_CHECK(cudaMemset(buf_[2], 0, bytes));
-    }
-    cudaIpcMemHandle_t h[4];
+    cudaIpcMemHandle_t h[4];  // (the fourth slot of the 256-byte record is reserved, zero)
     std::memset(h, 0, sizeof h);
     CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[0], buf_[0]));
     CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[1], buf_[1]));
     CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[2], mailbox_));
-    if (lag_) CNV_CUDA_CHECK(cudaIpcGetMemHandle(&h[3], buf_[2]));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     std::memcpy(out256, h, 256);
 }
@@ -611,15 +586,14 @@ void PoissonSolver::peer_push_counts(int rank, int world, long long *low, long l
     *low = lo; *high = hi;
 }
 
-// handles: world x 256 bytes (peer_export of every rank: buffer 0, buffer 1, mailbox, buffer 2 or zeros); layout: world x 4 ints (own_lo, own_hi, push_low, push_high)
+// handles: world x 256 bytes (peer_export of every rank: buffer 0, buffer 1, mailbox, 64 reserved bytes); layout: world x 4 ints (own_lo, own_hi, push_low, push_high)
 int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles, const int *layout)
 {
     if (world > kMaxRanks || !mailbox_) return 1;
     std::memset(&links_, 0, sizeof links_);
     links_.rank = rank; links_.world = world; links_.ctlbuf = ctlbuf_;
-    links_.lag = lag_ ? 1 : 0;
-    links_.buf2 = buf_[2];
-    const int nbuf = lag_ ? 3 : 2;
+    links_.edge_first = env_int("CNV_PEER_EDGE_FIRST", 1) != 0;
+    const int nbuf = 2;
     // every mapping opened here is remembered, so that the error paths below and peer_close() release it again
     auto open = [&](const unsigned char *h64, void **out) {
         cudaIpcMemHandle_t h;
@@ -645,7 +619,7 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
         const int *nb = layout + 4 * (rank - 1);
         for (int b = 0; b < nbuf; b++) {
             void *ptr = nullptr;
-            if (!open(handles + 256 * (rank - 1) + 64 * (b == 2 ? 3 : b), &ptr)) return fail(3);
+            if (!open(handles + 256 * (rank - 1) + 64 * b, &ptr)) return fail(3);
             links_.down_buf[b] = (double *)ptr;
         }
         links_.down_delta = (long long)(nb[1] - me[0]) * geom_.ld;  // my row own_lo + i -> its row own_hi' + i
@@ -655,7 +629,7 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
         const int *nb = layout + 4 * (rank + 1);
         for (int b = 0; b < nbuf; b++) {
             void *ptr = nullptr;
-            if (!open(handles + 256 * (rank + 1) + 64 * (b == 2 ? 3 : b), &ptr)) return fail(4);
+            if (!open(handles + 256 * (rank + 1) + 64 * b, &ptr)) return fail(4);
             links_.up_buf[b] = (double *)ptr;
         }
         links_.up_delta = (long long)(nb[0] - me[1]) * geom_.ld;    // my row own_hi - HY + i -> its row own_lo'' - HY + i
@@ -894,9 +868,8 @@ PoissonResult PoissonSolver::solve(int itmax, double tol, cudaStream_t s, int *r
     // sweeps per step), so the first batch covers the previous solve's pass count plus one and is
     // followed by small batches.  Passes enqueued after convergence exit immediately.
     int batch = predicted_passes_ > 0 ? predicted_passes_ + 1 : 16;
-    // (+2: the redo pass and the slack of the batching; the lagged peer decision adds a speculative pass and may
-    // waste one more at a batch boundary)
-    const int max_passes = (itmax + T_ - 1) / T_ + 2 + (links_.enabled && links_.lag ? 3 : 0);
+    // (+2: the redo pass and the slack of the batching)
+    const int max_passes = (itmax + T_ - 1) / T_ + 2;
     int enq = 0;
     PoissonCtl c;
     // slab solvers: the peer path exchanges inside the pass kernel; without it every pass is followed by the NCCL group

@@ -530,11 +530,11 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
 //                    pass 0 of a solve must not push into a buffer the neighbour is still about to zero
 //   norm_flag[r]     g+1 once rank r has published the per-sweep norms of pass g into norms[g % kNormSlots][r][*]
 //                    (a no-op pass raises the flag without touching the norms)
-// Norm slots.  Within a solve a rank that reads the norms of pass g-2 (lagged decision) can see remote publications of
-// passes g-1, g and g+1 at most (a working pass g+2 needs this rank's flag of pass g): four slots.  Across solves a
-// rank that is two hops away from a finished rank may still be reading slot g-2 of the old solve while the finished
-// rank's first pass of the NEXT solve (global index g+2) publishes; its later passes need the neighbours'
-// re-initialisation, which in turn waits for everybody's old passes.  Eight slots keep those apart as well.
+// Norm slots.  A rank that reads the norms of pass g-1 can see remote publications of passes g and g+1 at most (a working
+// pass g+2 needs this rank's flag of pass g+1).  Across solves a rank that is two hops away from a finished rank may still
+// be reading the last slot of the old solve while the finished rank's first pass of the NEXT solve publishes; its later
+// passes need the neighbours' re-initialisation, which in turn waits for everybody's old passes.  Eight slots keep all of
+// those apart with room to spare.
 constexpr int kMaxRanks = 8;
 constexpr int kNormSlots = 8;
 struct PeerMailbox {
@@ -553,19 +553,29 @@ struct PeerLinks {
     unsigned long long gidx;   // global pass index
     unsigned long long epoch;  // number of (re-)initialisations of the iterate so far (identical on every rank)
     PeerMailbox *mail[kMaxRanks];
-    int lag;                   // 1: lagged stop decision (three iterate buffers, see lag_fold / lag_action)
-    double *buf2;              // this rank's third iterate buffer (lagged decision only)
-    double *down_buf[3], *up_buf[3];   // neighbours' iterate buffers (peer mappings), null at the ends
+    double *down_buf[2], *up_buf[2];   // neighbours' iterate buffers (peer mappings), null at the ends
     long long down_delta, up_delta;    // element offset: my row -> its halo copy in the neighbour's array
     unsigned long long need_low, need_high;  // pushes per pass arriving in my low / high halo
     unsigned long long push_low, push_high;  // pushes per pass I make downwards / upwards
-    PoissonCtl *ctlbuf;        // [3]: ctlbuf[p & 1] = state used by pass p; [2] = host-visible state of the lagged machine
+    PoissonCtl *ctlbuf;        // [2]: ctlbuf[p & 1] = state used by pass p
     // optional trace (tools/peer_trace.py): [pass][cta][6] globaltimer stamps of thread 0 -- start, state known,
     // halos landed, stream done, push done, exit; null in production
     unsigned long long *trace;
     int trace_passes;
     unsigned long long timeout_ns;  // bound of every spin-wait on a peer flag (CNV_PEER_TIMEOUT_MS)
+    int edge_first;            // 1: the two slab-edge chunk rows of CTAs are scheduled first (peer_chunk_of)
 };
+
+// Launch order of the chunk rows on the peer path.  CTAs are dispatched in blockIdx order (x fastest); with the natural
+// order the top chunk row -- whose last rows are the neighbour's low halo -- finishes at the very end of pass p, and the
+// neighbour's chunk row 0, which streams that halo first, starts at the very beginning of pass p+1: no slack, so every
+// pass is a rendezvous with the slower neighbour.  Edge rows first (0, n-1, 1, 2, ...) puts both producers into the
+// first wave of CTAs; their consumers of the next pass then have the rest of the pass as slack.
+CNV_HD int peer_chunk_of(int by, int nchunks, int edge_first)
+{
+    if (!edge_first || nchunks < 3) return by;
+    return by == 0 ? 0 : by == 1 ? nchunks - 1 : by - 1;
+}
 
 // ---- solver state machine (one instance per solve, device resident) ---------------------------
 // Reference semantics (src/poisson.c:234-284): for k = 0..itmax-1 { sweep; e = sum|u-u0|;
@@ -653,9 +663,9 @@ CNV_HD void decide(PoissonCtl &c, const double *e, int nsw, double *hist)
     }
 }
 
-// ---- lagged stop decision (multi-GPU peer path, opt-in) ---------------------------------------------
-// With the plain machine pass p needs every rank's norms of pass p-1 before it can start: each pass is a
-// rendezvous of all ranks.  The lagged machine lets pass p start knowing only the norms of passes <= p-2 and run
+// ---- lagged stop decision (persistent on-chip kernel, poisson_onchip.cu) -----------------------------------
+// With the plain machine pass p needs the grid-wide norms of pass p-1 before it can start: each pass would be a
+// rendezvous of all CTAs.  The lagged machine lets pass p start knowing only the norms of passes <= p-2 and run
 // SPECULATIVELY as if pass p-1 did not converge.  Three iterate buffers rotate (pass p reads B[p%3], writes
 // B[(p+1)%3]) so that whatever the late decision turns out to be, the data it needs is still intact:
 //   * pass h holds the first sweep with e < tol, at its LAST sweep: the answer is its output B[(h+1)%3]; the
@@ -664,8 +674,8 @@ CNV_HD void decide(PoissonCtl &c, const double *e, int nsw, double *hist)
 //     pass h+1 wrote B[(h+2)%3]), into B[(h+2)%3], and is final -- its norms need not be awaited: they equal those
 //     pass h reported (same input, same arithmetic, same summation order), so result_e = e_h[s].
 // X_p below is the chain state a pass derives at its start: X_0 = X_1 = reset state, X_p = lag_fold(X_{p-1}, e_{p-2}).
-// Write-after-read safety of the peer pushes: pass p pushes into the neighbours' B[(p+1)%3], which they last read
-// in pass p-2; every CTA of pass p has seen every rank's norm flag of pass p-2, published after that rank's last read.
+// (Round 2 also ran this machine on the multi-GPU peer path: bit-identical, but no faster at 2 or 8 GPUs -- the per-pass
+// norm wait it removes is ~2 us of a 530 us pass, profiles/scale_r2.md -- so the peer path keeps the plain machine.)
 
 // X_{p-1}, norms of pass p-2 (ignored when the solve is finished or pass p-1 was the redo pass) -> X_p
 CNV_HD void lag_fold(PoissonCtl &c, const double *e, int T, double *hist)
@@ -710,25 +720,15 @@ CNV_HD LagAction lag_action(const PoissonCtl &c, int pidx, int T)
 }
 
 // ---- what a pass of the peer path does at its start (shared by the kernel and the CPU protocol simulation) ----
-// `prev` = chain state the previous pass stored (ctlbuf[(pidx-1) & 1]; the reset state for pidx == 0).
-// lag == 0: plain machine, the pass folds the norms of pass pidx-1; lag == 1: lagged machine, those of pass pidx-2.
-CNV_HD int peer_lag_distance(int lag) { return lag ? 2 : 1; }
-CNV_HD bool peer_needs_norms(const PoissonCtl &prev, int pidx, int lag)
-{
-    return pidx >= peer_lag_distance(lag) && prev.state == 0 && (!lag || prev.redo == 0);
-}
+// `prev` = state the previous pass stored (ctlbuf[(pidx-1) & 1]; the reset state for pidx == 0); the pass folds the norms
+// of pass pidx-1.
+CNV_HD bool peer_needs_norms(const PoissonCtl &prev, int pidx) { return pidx >= 1 && prev.state == 0; }
 // c (in: prev, out: the state of this pass, stored for the next one) and the pass' action.  e = the needed norms summed
 // over the ranks in rank order (ignored unless `need`); bad = a rank's norm flag timed out.
-CNV_HD LagAction peer_advance(PoissonCtl &c, const double *e, bool need, bool bad, int pidx, int lag, int T, double *hist)
+CNV_HD LagAction peer_advance(PoissonCtl &c, const double *e, bool need, bool bad, int T, double *hist)
 {
-    if (need && bad) {
-        c.state = 3;
-    } else if (lag) {
-        if (pidx >= 2) lag_fold(c, e, T, hist);
-    } else if (need) {
-        decide(c, e, pass_sweeps(c, T), hist);
-    }
-    if (lag) return lag_action(c, pidx, T);
+    if (need && bad) c.state = 3;
+    else if (need) decide(c, e, pass_sweeps(c, T), hist);
     LagAction a;
     a.kind = c.state == 0 ? 1 : 0;
     a.in = c.cur; a.out = next_buf(c, c.cur); a.nsw = pass_sweeps(c, T);

@@ -115,7 +115,7 @@ class SlabPoisson:
         if self.comm:
             self.L.cnv_poisson_attach_comm(self.h, self.comm)
         self.peer = backend == "peer" and world <= 8 and self._setup_peer()
-        self._map_bufs()  # (the lagged peer decision, CNV_PEER_LAG=1, adds a third iterate buffer)
+        self._map_bufs()
         self.solver.refresh_plan()
 
     def _map_bufs(self):
@@ -249,12 +249,14 @@ class SlabPoisson:
             self.dist.barrier()
         self.zero_iterate()
         self.reset(itmax, tol)
-        max_passes = (itmax + self.T - 1) // self.T + 2 + (3 if len(self.bufs) == 3 else 0)  # lagged decision: speculative passes
+        max_passes = (itmax + self.T - 1) // self.T + 2   # (+2: the redo pass and the slack of the batching)
         # like PoissonSolver::solve: sweep counts drift slowly from one time step to the next, so the first batch covers the
-        # previous solve's pass count (+ the speculative / redo passes of the lagged machine) and is followed by small ones
+        # previous solve's pass count (+ the redo pass) and is followed by small ones
         # -- every read-back of the state is a host synchronisation and, on the peer path, a rendezvous of all ranks
         predicted = getattr(self, "_predicted_passes", 0)
-        batch = predicted + (3 if len(self.bufs) == 3 else 1) if predicted > 0 else first_batch
+        batch = predicted + 1 if predicted > 0 else first_batch
+        if not self.peer:
+            batch = min(batch, 32)   # a surplus (no-op) pass still costs its halo exchange + norm collective on these paths
         while True:
             self.enqueue(min(batch, max_passes + 1 - self.passes_enqueued))
             st = self.state()

@@ -84,7 +84,7 @@ void cnv_poisson_destroy(cnv_poisson *p);
 void cnv_poisson_set_consts(cnv_poisson *p, double dx, double dy, double beta);
 int cnv_poisson_ld(const cnv_poisson *p);                 /* pitch (doubles) of the device arrays */
 double *cnv_poisson_rhs_ptr(cnv_poisson *p);              /* device: prepared right-hand side */
-double *cnv_poisson_buf_ptr(cnv_poisson *p, int which);   /* device: iterate buffers 0/1 (2: lagged peer decision) */
+double *cnv_poisson_buf_ptr(cnv_poisson *p, int which);   /* device: iterate buffers 0/1 (2: on-chip kernel) */
 int cnv_poisson_num_buffers(cnv_poisson *p);              /* 2, or 3 once the peer path runs with CNV_PEER_LAG=1 */
 double *cnv_poisson_norms_ptr(cnv_poisson *p);            /* device: T per-sweep norms of the last pass */
 /* out[0..9] = WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, T, pow2-path flag of the streaming kernel's plan;
@@ -138,13 +138,10 @@ void cnv_poisson_exchange_halos(cnv_poisson *p, double *field_dev, int depth, vo
  * no collective at all: the pass kernel stores its boundary rows straight into the neighbours' halo rows, counts its
  * pushes in the neighbours' mailboxes, publishes its per-sweep norms in every rank's mailbox, and every CTA of the next
  * pass derives the stop decision itself.  Setup: every rank exports 256 bytes (IPC handles of iterate buffers 0 and 1,
- * of its mailbox, and of iterate buffer 2 or zeros) and its push counts; the caller all-gathers them (world x 256 bytes;
+ * of its mailbox, 64 reserved bytes) and its push counts; the caller all-gathers them (world x 256 bytes;
  * world x 4 ints: own_lo, own_hi, push_low, push_high) and every rank imports.  All spin-waits are bounded
  * (CNV_PEER_TIMEOUT_MS, default 300000; message + exit(1) on every rank once one of them gives up).
- * CNV_PEER_LAG=1 (read at export time, must agree on all ranks; opt-in): lagged stop decision -- a pass needs the other
- * ranks' norms of the pass BEFORE the previous one only, so passes no longer rendezvous; three iterate buffers rotate,
- * results are bit-identical (state machine: csrc/poisson_stream.h lag_fold / lag_action).  The result buffer index
- * reported by cnv_poisson_state is then 0..2. */
+ */
 void cnv_poisson_peer_export(cnv_poisson *p, unsigned char *out256);
 void cnv_poisson_peer_push_counts(cnv_poisson *p, int rank, int world, long long *low, long long *high);
 int cnv_poisson_peer_import(cnv_poisson *p, int rank, int world, const unsigned char *handles, const int *layout);

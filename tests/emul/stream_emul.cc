@@ -119,15 +119,26 @@ void emul_lag_action(const int *ints, const double *dbls, int pidx, int T, int *
     const LagAction a = lag_action(ctl_from(ints, dbls), pidx, T);
     out[0] = a.kind; out[1] = a.in; out[2] = a.out; out[3] = a.nsw;
 }
-// start of a pass of the peer path (the kernel's own decision code): does it need norms, and what does it do
+// start of a pass in the protocol simulation (tests/test_lag_protocol.py).  lag == 0: the peer kernel's own preamble code
+// (peer_needs_norms / peer_advance, plain machine: the pass folds the norms of pass pidx-1).  lag == 1: the lagged machine
+// as the on-chip kernel drives it (lag_fold with the norms of pass pidx-2, then lag_action).
 int emul_peer_needs_norms(const int *ints, const double *dbls, int pidx, int lag)
 {
-    return peer_needs_norms(ctl_from(ints, dbls), pidx, lag) ? 1 : 0;
+    const PoissonCtl c = ctl_from(ints, dbls);
+    if (!lag) return peer_needs_norms(c, pidx) ? 1 : 0;
+    return pidx >= 2 && c.state == 0 && c.redo == 0 ? 1 : 0;
 }
 void emul_peer_advance(int *ints, double *dbls, const double *e, int need, int bad, int pidx, int lag, int T, int *out)
 {
     PoissonCtl c = ctl_from(ints, dbls);
-    const LagAction a = peer_advance(c, e, need != 0, bad != 0, pidx, lag, T, nullptr);
+    LagAction a;
+    if (!lag) {
+        a = peer_advance(c, e, need != 0, bad != 0, T, nullptr);
+    } else {
+        if (need && bad) c.state = 3;
+        else if (pidx >= 2) lag_fold(c, e, T, nullptr);
+        a = lag_action(c, pidx, T);
+    }
     ctl_to(c, ints, dbls);
     out[0] = a.kind; out[1] = a.in; out[2] = a.out; out[3] = a.nsw;
 }

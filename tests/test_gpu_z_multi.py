@@ -59,33 +59,6 @@ def test_slab_peer_repeated_solves(world):
     assert "STRESS PASSED" in _torchrun("slab_stress.py", [1024, 1024, 8, 4], world, 29740 + world, "peer")
 
 
-# The lagged stop decision (CNV_PEER_LAG=1, csrc/poisson_stream.h lag_fold/lag_action) was written after the round's GPU
-# budget was spent: its state machine and protocol are covered on the CPU (tests/test_lag_protocol.py), its device code has
-# not run on hardware yet.  It is opt-in in the product and its GPU tests are opt-in here (CNV_TEST_LAG=1) so that an
-# unverified variant cannot stop the suite; tools/round2_gpu.sh runs them.
-_lag = pytest.mark.skipif(os.environ.get("CNV_TEST_LAG", "0") != "1", reason="lagged peer decision: opt-in (CNV_TEST_LAG=1)")
-LAG = {"CNV_PEER_LAG": "1"}
-
-
-@_lag
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_lagged_peer_poisson_bitwise(world):
-    if _ngpus() < world:
-        pytest.skip(f"needs {world} GPUs")
-    assert "SLAB CHECK PASSED" in _torchrun("slab_gpu_check.py", [world * 40, 96, 4], world, 29750 + world, "peer", LAG)
-    assert "SLAB CHECK PASSED" in _torchrun("slab_gpu_check.py", [1024, 1024, 8], world, 29760 + world, "peer", LAG)
-
-
-@_lag
-@pytest.mark.parametrize("world", [2, 4])
-def test_lagged_peer_time_stepping_and_repeated_solves(world):
-    if _ngpus() < world:
-        pytest.skip(f"needs {world} GPUs")
-    assert "SLAB SIM CHECK PASSED" in _torchrun("slab_sim_gpu_check.py", [128, 4], world, 29770 + world, "peer", LAG)
-    assert "STRESS PASSED" in _torchrun("slab_stress.py", [world * 100, 96, 4, 12], world, 29780 + world, "peer", LAG)
-    assert "STRESS PASSED" in _torchrun("slab_stress.py", [1024, 1024, 8, 4], world, 29790 + world, "peer", LAG)
-
-
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_c_driver_multi_gpu_matches_single_gpu(world, tmp_path):
     """`CNV_GPUS=N cnavier_b200 cfg run` (csrc/driver.cc: one forked process per GPU, NCCL id and CUDA IPC handles exchanged in

@@ -1,11 +1,16 @@
-"""Lagged stop decision of the multi-GPU peer path (CNV_PEER_LAG=1; csrc/poisson_stream.h lag_fold / lag_action /
-lag_final), checked on the CPU: the ranks of a slab decomposition are simulated in ONE process, each pass executed
-by the schedule emulator (tests/emul, the kernel's own per-thread code), with exactly the waits the kernel performs
--- norm flags of pass p-2 from every rank, halo pushes of pass p-1 from the neighbours -- and a RANDOM interleaving
-of the ranks within those constraints (a rank runs as far ahead as the protocol lets it).  Three iterate buffers
-rotate, norms travel through the mailbox slots (indexed by the GLOBAL pass number, which keeps counting across solves), pushes land in the neighbours' halo rows.  The result must be the
-single-domain oracle's field, iteration count and residual, bit for bit, for every position of the converged sweep
-inside a pass and every position of the host's batch boundary."""
+"""The stop-decision state machines of csrc/poisson_stream.h under a multi-domain protocol simulation, on the CPU.
+  * plain machine (lag = 0): the peer path's own start-of-pass code (peer_needs_norms / peer_advance) -- a pass folds the
+    norms of the previous pass, two iterate buffers;
+  * lagged machine (lag = 1: lag_fold / lag_action / lag_final, the decision of the persistent on-chip kernel, where the
+    domains are the tiles of one GPU; round 2 also ran it between GPUs, see profiles/scale_r2.md) -- a pass folds the
+    norms of the pass before the previous one and runs speculatively, three iterate buffers.
+The domains of a slab decomposition are simulated in ONE process, each pass executed by the schedule emulator (tests/emul,
+the kernel's own per-thread code), with exactly the waits of the protocol -- norm flags from every domain, halo pushes of
+pass p-1 from the neighbours -- and a RANDOM interleaving of the domains within those constraints (each runs as far ahead
+as the protocol lets it).  Norms travel through mailbox slots indexed by the GLOBAL pass number (which keeps counting
+across solves), pushes land in the neighbours' halo rows.  The result must be the single-domain oracle's field, iteration
+count and residual, bit for bit, for every position of the converged sweep inside a pass and every position of the host's
+batch boundary."""
 import ctypes as C
 import os
 
