@@ -111,12 +111,11 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
-    const int chunk = PEER ? peer_chunk_of(blockIdx.y, gridDim.y, L.edge_first) : (int)blockIdx.y;  // chunk row of this CTA
     const bool first_cta = blockIdx.x == 0 && blockIdx.y == 0;
     __shared__ PoissonCtl s_ctl;
     unsigned long long *trace = nullptr;
     if (L.trace && L.pidx < L.trace_passes && tid == 0) {
-        trace = L.trace + ((size_t)L.pidx * gridDim.x * gridDim.y + chunk * gridDim.x + blockIdx.x) * 6;
+        trace = L.trace + ((size_t)L.pidx * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x) * 6;
         trace[0] = globaltimer_ns();
     }
     __shared__ LagAction s_act;  // (peer path only)
@@ -173,7 +172,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     const double *__restrict__ in = cur ? buf1 : buf0;
     double *__restrict__ out = nxt ? buf1 : buf0;
 
-    const CtaGeom G = cta_geom(p, blockIdx.x, chunk);
+    const CtaGeom G = cta_geom(p, blockIdx.x, blockIdx.y);
     if (PEER) {
         __shared__ int s_inputs_ok;
         if (tid == 0) {
@@ -226,11 +225,11 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     if (PEER) {
         // Slab boundary rows: copy what this CTA has just written (still L2 resident) into the neighbour GPU's halo
         // rows with coalesced 16-byte peer stores over NVLink -- outside the streaming loop, which stays identical to
-        // the single-GPU kernel.  Only the CTAs of the two edge chunk rows do this (they are launched first, see
-        // peer_chunk_of); ONE thread then orders the CTA's pushes system-wide (the CTA barrier makes them precede its
-        // fence: the pattern of a grid barrier's arrive) and counts the push in the neighbour's mailbox, while the rest
-        // of the CTA goes on with the norms.  Round 2 measured 8 us per CTA (every CTA, 576 threads each) for the
-        // unconditional all-thread __threadfence_system() this replaces (profiles/scale_r2.md).
+        // the single-GPU kernel.  Only the CTAs of the two edge chunk rows do this; ONE thread then orders the CTA's
+        // pushes system-wide (the CTA barrier makes them precede its fence: the pattern of a grid barrier's arrive) and
+        // counts the push in the neighbour's mailbox, while the rest of the CTA goes on with the norms.  Round 2
+        // measured 8 us per CTA (every CTA, 576 threads each) for the unconditional all-thread __threadfence_system()
+        // this replaces (profiles/scale_r2.md).
         const bool push_down = L.rank > 0 && G.y0 < p.own_lo + p.HY;
         const bool push_up = L.rank < L.world - 1 && G.y1 > p.own_hi - p.HY;
         if (push_down || push_up) {  // uniform over the CTA
@@ -260,7 +259,7 @@ k_poisson_pass(const PassGeom p, const RelaxConsts rc, double *__restrict__ buf0
     }
     // per-CTA L1 update norms, one per sweep of the pass (level g <-> sweep g+1)
     group_sums(sm, acc, t.g, kk, TPG, s_e);
-    const int ncta = gridDim.x * gridDim.y, cta = chunk * gridDim.x + blockIdx.x;  // geometric index: the order of the sums below
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
     if (tid < T) {
         partials[(size_t)cta * T + tid] = s_e[tid];
         __threadfence();
@@ -592,7 +591,6 @@ int PoissonSolver::peer_import(int rank, int world, const unsigned char *handles
     if (world > kMaxRanks || !mailbox_) return 1;
     std::memset(&links_, 0, sizeof links_);
     links_.rank = rank; links_.world = world; links_.ctlbuf = ctlbuf_;
-    links_.edge_first = env_int("CNV_PEER_EDGE_FIRST", 1) != 0;
     const int nbuf = 2;
     // every mapping opened here is remembered, so that the error paths below and peer_close() release it again
     auto open = [&](const unsigned char *h64, void **out) {

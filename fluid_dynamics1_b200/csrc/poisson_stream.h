@@ -563,19 +563,7 @@ struct PeerLinks {
     unsigned long long *trace;
     int trace_passes;
     unsigned long long timeout_ns;  // bound of every spin-wait on a peer flag (CNV_PEER_TIMEOUT_MS)
-    int edge_first;            // 1: the two slab-edge chunk rows of CTAs are scheduled first (peer_chunk_of)
 };
-
-// Launch order of the chunk rows on the peer path.  CTAs are dispatched in blockIdx order (x fastest); with the natural
-// order the top chunk row -- whose last rows are the neighbour's low halo -- finishes at the very end of pass p, and the
-// neighbour's chunk row 0, which streams that halo first, starts at the very beginning of pass p+1: no slack, so every
-// pass is a rendezvous with the slower neighbour.  Edge rows first (0, n-1, 1, 2, ...) puts both producers into the
-// first wave of CTAs; their consumers of the next pass then have the rest of the pass as slack.
-CNV_HD int peer_chunk_of(int by, int nchunks, int edge_first)
-{
-    if (!edge_first || nchunks < 3) return by;
-    return by == 0 ? 0 : by == 1 ? nchunks - 1 : by - 1;
-}
 
 // ---- solver state machine (one instance per solve, device resident) ---------------------------
 // Reference semantics (src/poisson.c:234-284): for k = 0..itmax-1 { sweep; e = sum|u-u0|;
