@@ -164,7 +164,6 @@ struct cnv_sim {
     double *cont_partial = nullptr, *cont_result = nullptr, *h_cont = nullptr;
     unsigned *cont_ticket = nullptr;
     bool diag = true;
-    bool split_velocity = true;   // CNV_FUSED_VELOCITY=1: one pass over psi for u, v and the continuity diagnostic (measured slower)
     long long sweeps = 0, passes = 0, steps = 0;
     cudaStream_t stream = 0;
 };
@@ -634,7 +633,6 @@ static cnv_sim *sim_create(const Config *cfg, int T, int rank, int world)
     s->map.own_lo = hlo;
     s->map.own_hi = hlo + (r1 - r0);
     s->nrows = s->map.nloc;
-    s->split_velocity = !(std::getenv("CNV_FUSED_VELOCITY") && std::atoi(std::getenv("CNV_FUSED_VELOCITY")));
     s->ps = new PoissonSolver(s->map.nloc, s->ncols, T, s->map.grow0, gn, s->map.own_lo, s->map.own_hi);
     s->ps->set_consts(s->dx, s->dy, cfg->poisson_type == 2 ? s->beta : 1.0);
     s->ps->set_distributed(world > 1);
@@ -756,23 +754,16 @@ int cnv_sim_step(cnv_sim *s, int nsteps, int *k, double *e, double *cont_max, do
         if (k) k[t] = r.k;
         if (e) e[t] = r.e;
         if (r.status != 0) return t + 1;  // reference: log the error and exit(1), src/poisson.c:280-284
-        // velocities from the streamfunction on all points (:366-383) and the continuity diagnostic (:387-408);
-        // one fused pass over psi on a whole-domain map, separate kernels otherwise
+        // velocities from the streamfunction on all points (:366-383) and the continuity diagnostic (:387-408).  (A fused
+        // form that recomputed the halo velocities from a psi tile with a 6-cell halo -- 56 instead of 72 bytes per cell -- was
+        // bit-identical but slower, 203 vs 164 us at 4096^2: both kernels are bound by fp64 issue, not HBM.  Removed in round 2.)
         const bool want_cont = s->diag && (cont_max || cont_min);
-        const bool fused = want_cont && s->map.nloc == s->map.gnrows && !s->split_velocity;
-        if (fused) {
-            launch_velocity_continuity(s->ps->buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld,
-                                       s->cont_partial, s->cont_ticket, s->cont_result, st);
-        } else {
-            launch_velocity(s->ps->buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
-        }
+        launch_velocity(s->ps->buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
         count_launch(1);
         if (want_cont) {
-            if (!fused) {
-                launch_continuity(s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
-                                  s->cont_result, st);
-                count_launch(1);
-            }
+            launch_continuity(s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
+                              s->cont_result, st);
+            count_launch(1);
             CNV_CUDA_CHECK(cudaMemcpyAsync(s->h_cont, s->cont_result, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
             CNV_CUDA_CHECK(cudaStreamSynchronize(st));
             if (cont_max) cont_max[t] = s->h_cont[0];
@@ -871,16 +862,10 @@ void cnv_sim_stencil_phase(cnv_sim *s, int reps, void *stream)
         launch_euler_fused(s->w, s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->d2x, s->d2y, s->inv_re, c.dt,
                            s->ps->consts().pscale, s->w2, s->ps->rhs(), st);
         std::swap(s->w, s->w2);
-        if (s->map.nloc == s->map.gnrows && !s->split_velocity) {
-            launch_velocity_continuity(s->ps->buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld,
-                                       s->cont_partial, s->cont_ticket, s->cont_result, st);
-            count_launch(3);
-        } else {
-            launch_velocity(s->ps->buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
-            launch_continuity(s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
-                              s->cont_result, st);
-            count_launch(4);
-        }
+        launch_velocity(s->ps->buffer(s->psi_buf), s->map, s->ncols, s->ld, s->d1x, s->d1y, s->u, s->v, s->ld, st);
+        launch_continuity(s->u, s->v, s->map, s->ncols, s->ld, s->d1x, s->d1y, s->cont_partial, s->cont_ticket,
+                          s->cont_result, st);
+        count_launch(4);
     }
     CNV_CUDA_CHECK(cudaGetLastError());
 }

@@ -53,8 +53,6 @@ void launch_pressure_rhs(const double *u, const double *v, const RowMap &m, int 
 int continuity_blocks(int nrows, int ncols);
 void launch_continuity(const double *u, const double *v, const RowMap &m, int ncols, int ld, const FdTable &d1x, const FdTable &d1y,
                        double *partial, unsigned *ticket, double *result, cudaStream_t s);
-void launch_velocity_continuity(const double *psi, const RowMap &m, int ncols, int ldp, const FdTable &d1x, const FdTable &d1y,
-                                double *u, double *v, int ld, double *partial, unsigned *ticket, double *result, cudaStream_t s);
 void launch_prep_rhs(const double *f, int nrows, int ncols, int ldf, double sign, double pscale, double *rhs, double *psi0,
                      double *psi1, int ld, cudaStream_t s);
 

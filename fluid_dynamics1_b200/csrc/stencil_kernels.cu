@@ -404,123 +404,6 @@ k_continuity(const double *__restrict__ u, const double *__restrict__ v, RowMap 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Velocity recovery + continuity diagnostic in one pass over psi (opt-in, CNV_FUSED_VELOCITY=1; measured SLOWER than
-// the two separate kernels at 4096^2, 203 vs 164 us: both are bound by fp64 issue, not by HBM, and the fused form
-// recomputes the halo velocities -- kept as a bit-identical alternative for grids whose u, v do not fit the L2):
-// u = DY psi, v = -(DX psi) are evaluated on the tile PLUS a 3-cell halo from a psi tile with a 6-cell halo,
-// kept in shared memory, written to HBM for the tile's own cells, and DX u + DY v is reduced from the shared
-// copies -- u and v are never read back from HBM (56 instead of 72 algorithmic bytes per cell per time step,
-// SURVEY.md section 8d).  Every value is computed by the same expression as in k_velocity / k_continuity
-// (closures by global index, ascending accumulation), so the results are bit-identical to the separate kernels.
-constexpr int BHALO = 2 * THALO;
-constexpr int BPITCH = TW + 2 * BHALO + 1;
-struct BigTile {
-    double v[TH + 2 * BHALO][BPITCH];
-};
-static_assert(sizeof(BigTile) % 16 == 0, "the u/v tiles behind it stay 16-byte aligned");
-
-template <int HALF, class Load>
-__device__ __forceinline__ double deriv_at(const FdTable &tab, const double (&c)[7], int g, Load x)
-{
-    if (g >= HALF && g < tab.n - HALF) {
-        double sum = 0.0;
-#pragma unroll
-        for (int k = 0; k <= 2 * HALF; k++) sum = xadd(sum, xmul(c[k], x(g - HALF + k)));
-        return sum;
-    }
-    return fd_apply(tab, g, x);
-}
-
-template <int HALF>
-__global__ void __launch_bounds__(256)
-k_velocity_continuity(const double *__restrict__ psi, RowMap m, int ncols, int ldp, const FdTable d1x, const FdTable d1y,
-                      double *__restrict__ u, double *__restrict__ v, int ld, double *__restrict__ partial,
-                      unsigned *__restrict__ ticket, double *__restrict__ result)
-{
-    extern __shared__ double4 dyn_smem[];
-    BigTile &tp = *reinterpret_cast<BigTile *>(dyn_smem);
-    Tile &tu = *reinterpret_cast<Tile *>(reinterpret_cast<char *>(dyn_smem) + sizeof(BigTile));
-    Tile &tv = *reinterpret_cast<Tile *>(reinterpret_cast<char *>(dyn_smem) + sizeof(BigTile) + sizeof(Tile));
-    const int j0 = blockIdx.x * TW, i0 = m.own_lo + blockIdx.y * TH, gi0 = m.grow0 + i0;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {   // psi tile with a 6-cell halo: all of a thread's loads in flight before the first shared store
-        constexpr int NR = (TH + 2 * BHALO + 7) / 8, NC = (TW + 2 * BHALO + 31) / 32;
-        double buf[NR][NC];
-#pragma unroll
-        for (int a = 0; a < NR; a++) {
-            const int li = warp + 8 * a, gi = i0 - BHALO + li;
-            const bool rowok = li < TH + 2 * BHALO && gi >= 0 && gi < m.nloc;
-            const double *row = psi + (size_t)(rowok ? gi : 0) * ldp + (j0 - BHALO);
-#pragma unroll
-            for (int b = 0; b < NC; b++) {
-                const int lj = lane + 32 * b, gj = j0 - BHALO + lj;
-                buf[a][b] = (rowok && lj < TW + 2 * BHALO && gj >= 0 && gj < ncols) ? row[lj] : 0.0;
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < NR; a++) {
-            const int li = warp + 8 * a;
-#pragma unroll
-            for (int b = 0; b < NC; b++) {
-                const int lj = lane + 32 * b;
-                if (li < TH + 2 * BHALO && lj < TW + 2 * BHALO) tp.v[li][lj] = buf[a][b];
-            }
-        }
-    }
-    double c1x[7], c1y[7];
-    load_coefs(d1x, c1x); load_coefs(d1y, c1y);
-    __syncthreads();
-    // u, v on the tile + 3-cell halo (zero outside the domain, like tile_load).  All of a thread's cells are evaluated
-    // into registers before the first shared store, so their operand loads and fp64 chains overlap.
-    constexpr int EW = TW + 2 * THALO, EH = TH + 2 * THALO, NQ = (EW * EH + 255) / 256;
-    const bool interior = tile_is_interior(i0, j0, m, ncols) && gi0 >= BHALO && j0 >= BHALO &&
-                          gi0 + TH + BHALO <= m.gnrows && j0 + TW + BHALO <= ncols;  // no closure row anywhere in the halo
-    double uu[NQ], vv[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        const int idx = tid + 256 * q;
-        const int li = idx / EW, lj = idx - li * EW;
-        const int i = i0 - THALO + li, j = j0 - THALO + lj;
-        const int bi = li + THALO, bj = lj + THALO;  // the cell's position in the psi tile
-        uu[q] = vv[q] = 0.0;
-        if (idx < EW * EH) {
-            if (interior) {
-                double su = 0.0, sv = 0.0;
-#pragma unroll
-                for (int k = 0; k <= 2 * HALF; k++) {
-                    su = xadd(su, xmul(c1y[k], tp.v[bi - HALF + k][bj]));
-                    sv = xadd(sv, xmul(c1x[k], tp.v[bi][bj - HALF + k]));
-                }
-                uu[q] = su; vv[q] = -sv;
-            } else if (i >= 0 && i < m.nloc && j >= 0 && j < ncols) {
-                uu[q] = deriv_at<HALF>(d1y, c1y, m.grow0 + i, [&](int row) { return tp.v[row - gi0 + BHALO][bj]; });
-                vv[q] = -deriv_at<HALF>(d1x, c1x, j, [&](int col) { return tp.v[bi][col - j0 + BHALO]; });
-            }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        const int idx = tid + 256 * q;
-        const int li = idx / EW, lj = idx - li * EW;
-        if (idx < EW * EH) { tu.v[li][lj] = uu[q]; tv.v[li][lj] = vv[q]; }
-    }
-    __syncthreads();
-    const int j = j0 + threadIdx.x, lj = threadIdx.x + THALO;
-    if (j < ncols) {
-#pragma unroll
-        for (int rr = 0; rr < TROWS; rr++) {
-            const int i = i0 + threadIdx.y * TROWS + rr, li = threadIdx.y * TROWS + rr + THALO;
-            if (i >= m.own_hi) break;
-            u[(size_t)i * ld + j] = tu.v[li][lj];
-            v[(size_t)i * ld + j] = tv.v[li][lj];
-        }
-    }
-    double mx = -DBL_MAX, mn = DBL_MAX;
-    continuity_from_tiles<HALF>(tu, tv, m, ncols, d1x, d1y, c1x, c1y, i0, j0, mx, mn);
-    minmax_finish(mx, mn, partial, ticket, result);
-}
-
-// ---------------------------------------------------------------------------------------------
 // Pressure-Poisson right-hand side, the recipe the reference leaves commented out (src/main.c:421-427, declared
 // as pressure() in include/fluiddyn.h:11 but never defined):
 //     f = dudx**2 + dvdy**2 + 2*dudy*dvdx          p = poisson(-f)
@@ -655,23 +538,6 @@ void launch_continuity(const double *u, const double *v, const RowMap &m, int nc
     }
     const int grid = ntiles < slots ? ntiles : slots;
 #define CALL(H) k_continuity<H><<<grid, b, 0, s>>>(u, v, m, ncols, ld, d1x, d1y, partial, ticket, result, (int)g.x, ntiles)
-    CNV_BY_HALF(d1x.half, CALL);
-#undef CALL
-}
-// single-GPU maps only (the halo cells' velocities are recomputed from psi, which needs 6 rows of psi around a tile)
-void launch_velocity_continuity(const double *psi, const RowMap &m, int ncols, int ldp, const FdTable &d1x, const FdTable &d1y,
-                                double *u, double *v, int ld, double *partial, unsigned *ticket, double *result, cudaStream_t s)
-{
-    const dim3 b(TW, 4), g = tile_grid(m, ncols);
-    constexpr size_t smem = sizeof(BigTile) + 2 * sizeof(Tile);
-    static bool configured = false;
-    if (!configured) {
-        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_velocity_continuity<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_velocity_continuity<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CNV_CUDA_CHECK(cudaFuncSetAttribute(k_velocity_continuity<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-#define CALL(H) k_velocity_continuity<H><<<g, b, smem, s>>>(psi, m, ncols, ldp, d1x, d1y, u, v, ld, partial, ticket, result)
     CNV_BY_HALF(d1x.half, CALL);
 #undef CALL
 }

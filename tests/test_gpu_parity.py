@@ -353,25 +353,6 @@ def test_steps_vs_oracle_other_orders_and_solver_types(port, order, ptype, n, sm
         assert np.array_equal(f[name], want[name]), (name, rel_l2(f[name], want[name]))
 
 
-@pytest.mark.parametrize("order,nx,ny", [(2, 40, 72), (4, 72, 40), (6, 64, 64), (6, 130, 67)])
-def test_fused_velocity_continuity_equals_split_kernels(order, nx, ny, monkeypatch):
-    """CNV_FUSED_VELOCITY=1 recovers u, v and the continuity diagnostic in one pass over psi (k_velocity_continuity);
-    it must give the same bits as the default separate k_velocity + k_continuity kernels."""
-    cfg = dict(api.CONFIG_DEFAULT, nx=nx, ny=ny, order=order, dt=0.002)
-    runs = []
-    for fused in ("1", "0"):
-        monkeypatch.setenv("CNV_FUSED_VELOCITY", fused)
-        sim = fd.Simulation(dict(cfg))
-        r = sim.step(4)
-        runs.append((r, sim.fields()))
-        sim.close()
-    (ra, fa), (rb, fb) = runs
-    assert list(ra["k"]) == list(rb["k"])
-    assert ra["cont_max"].tobytes() == rb["cont_max"].tobytes() and ra["cont_min"].tobytes() == rb["cont_min"].tobytes()
-    for name in fa:
-        assert fa[name].tobytes() == fb[name].tobytes(), name
-
-
 SMALL = dict(api.CONFIG_DEFAULT, nx=32, ny=32, dt=0.004, u1=0.05, u2=-0.03, v3=0.02, v4=0.01, output_interval=1)
 
 
