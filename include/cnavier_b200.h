@@ -85,7 +85,7 @@ void cnv_poisson_set_consts(cnv_poisson *p, double dx, double dy, double beta);
 int cnv_poisson_ld(const cnv_poisson *p);                 /* pitch (doubles) of the device arrays */
 double *cnv_poisson_rhs_ptr(cnv_poisson *p);              /* device: prepared right-hand side */
 double *cnv_poisson_buf_ptr(cnv_poisson *p, int which);   /* device: iterate buffers 0/1 (2: on-chip kernel) */
-int cnv_poisson_num_buffers(cnv_poisson *p);              /* 2, or 3 once the peer path runs with CNV_PEER_LAG=1 */
+int cnv_poisson_num_buffers(cnv_poisson *p);              /* 2, or 3 when the on-chip kernel is in use */
 double *cnv_poisson_norms_ptr(cnv_poisson *p);            /* device: T per-sweep norms of the last pass */
 /* out[0..9] = WS, HX, Wout, Hout, nstrips, nchunks, threads, smem bytes, T, pow2-path flag of the streaming kernel's plan;
    out[10..17] = 1 if cnv_poisson_solve runs the persistent on-chip kernel, then its T, tile grid ntx x nty, patches per tile
