@@ -99,34 +99,56 @@ struct Tile {
     double v[TH + 2 * THALO][TPITCH];
 };
 
+__device__ __forceinline__ bool tile_inside(int i0, int j0, int nrows, int ncols);
 // Each of the 8 warps takes tile rows warp, warp+8, ...; a lane takes columns lane, lane+32, lane+64.  All
 // (up to 15) global loads of a thread are issued before the first shared-memory store, so they are in flight
 // together (the loop is fully unrolled; out-of-domain elements read as 0 without touching memory).
+// A tile whose halo lies entirely inside the local array (uniform per CTA; all but the perimeter tiles) takes a path
+// without per-element bounds tests: the general path spends 4 compares + address arithmetic per element, 13 instructions
+// per element in SASS, which was ~40 % of all instructions k_continuity issued (profiles/ncu_stencil_r2.md).
 __device__ __forceinline__ void tile_load(Tile &t, const double *__restrict__ A, int i0, int j0, int nrows, int ncols, int ld)
 {
     constexpr int NR = (TH + 2 * THALO + 7) / 8, NC = (TW + 2 * THALO + 31) / 32;
+    constexpr int LASTR = TH + 2 * THALO - 8 * (NR - 1), LASTC = TW + 2 * THALO - 32 * (NC - 1);  // warps / lanes of the last round
     const int lane = threadIdx.x & 31, warp = (threadIdx.y * blockDim.x + threadIdx.x) >> 5;
     double buf[NR][NC];
+    if (tile_inside(i0, j0, nrows, ncols)) {
+        const double *base = A + (size_t)(i0 - THALO + warp) * ld + (j0 - THALO + lane);
 #pragma unroll
-    for (int a = 0; a < NR; a++) {
-        const int li = warp + 8 * a, gi = i0 - THALO + li;
-        const bool rowok = li < TH + 2 * THALO && gi >= 0 && gi < nrows;
-        const double *row = A + (size_t)(rowok ? gi : 0) * ld + (j0 - THALO);
+        for (int a = 0; a < NR; a++) {
+            const double *row = base + (size_t)(8 * a) * ld;
 #pragma unroll
-        for (int b = 0; b < NC; b++) {
-            const int lj = lane + 32 * b, gj = j0 - THALO + lj;
-            buf[a][b] = (rowok && lj < TW + 2 * THALO && gj >= 0 && gj < ncols) ? row[lj] : 0.0;
+            for (int b = 0; b < NC; b++) {
+                const bool ok = (a < NR - 1 || warp < LASTR) && (b < NC - 1 || lane < LASTC);
+                buf[a][b] = ok ? row[32 * b] : 0.0;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < NR; a++) {
+            const int li = warp + 8 * a, gi = i0 - THALO + li;
+            const bool rowok = li < TH + 2 * THALO && gi >= 0 && gi < nrows;
+            const double *row = A + (size_t)(rowok ? gi : 0) * ld + (j0 - THALO);
+#pragma unroll
+            for (int b = 0; b < NC; b++) {
+                const int lj = lane + 32 * b, gj = j0 - THALO + lj;
+                buf[a][b] = (rowok && lj < TW + 2 * THALO && gj >= 0 && gj < ncols) ? row[lj] : 0.0;
+            }
         }
     }
 #pragma unroll
     for (int a = 0; a < NR; a++) {
-        const int li = warp + 8 * a;
 #pragma unroll
         for (int b = 0; b < NC; b++) {
-            const int lj = lane + 32 * b;
-            if (li < TH + 2 * THALO && lj < TW + 2 * THALO) t.v[li][lj] = buf[a][b];
+            if ((a < NR - 1 || warp < LASTR) && (b < NC - 1 || lane < LASTC)) t.v[warp + 8 * a][lane + 32 * b] = buf[a][b];
         }
     }
+}
+
+// true when the tile's halo lies entirely inside the local array
+__device__ __forceinline__ bool tile_inside(int i0, int j0, int nrows, int ncols)
+{
+    return i0 >= THALO && i0 + TH + THALO <= nrows && j0 >= THALO && j0 + TW + THALO <= ncols;
 }
 
 // interior row: sum_k c[k] * x(k - HALF), ascending
@@ -380,10 +402,20 @@ __device__ __forceinline__ void minmax_finish(double mx, double mn, double *__re
 }
 
 // Persistent: a CTA walks the tiles bid, bid + grid, ... and keeps its max / min in registers, so the block reduction, the
-// fence and the ticket of minmax_finish are paid once per CTA, not once per 64 x 32 tile (8192 tiles at 4096^2: the per-tile
-// epilogue cost as much as the tile's arithmetic -- 103 us = 39 % of the HBM peak before, see profiles/).
+// fence and the ticket of minmax_finish are paid once per CTA, not once per 64 x 32 tile.
+// Interior tiles (no closure row, halo inside the array: all but the perimeter) take a lean path: DX u needs neighbours
+// along x only, DY v along y only, so u is staged WITHOUT its y halo (32 x 70 instead of 38 x 70 values) and v is not
+// staged at all -- a thread walks 8 rows of one column, so its 14 values of v come straight from global memory into the
+// register window (coalesced across the warp, issued before the barrier so that they overlap the staging of u).  Per thread
+// and tile that is 12 + 14 loads, 12 shared stores and 48 shared loads instead of 30 / 30 / 62.  Same operations on the same
+// values in the same order as the general path, so the bits do not depend on the path.
+struct TileX {
+    double v[TH][TW + 2 * THALO];
+};
+static_assert(sizeof(TileX) <= sizeof(Tile), "TileX aliases the u tile");
+
 template <int HALF>
-__global__ void __launch_bounds__(256)  // (80 registers, 3 CTAs per SM; forcing 64 registers for a fourth CTA measured 135 vs 105 us)
+__global__ void __launch_bounds__(256)
 k_continuity(const double *__restrict__ u, const double *__restrict__ v, RowMap m, int ncols, int ld,
              const FdTable d1x, const FdTable d1y, double *__restrict__ partial, unsigned *__restrict__ ticket,
              double *__restrict__ result, const int gx, const int ntiles)
@@ -392,13 +424,44 @@ k_continuity(const double *__restrict__ u, const double *__restrict__ v, RowMap 
     double mx = -DBL_MAX, mn = DBL_MAX;  // maxel/minel start values, src/linearalg.c:478,514
     double c1x[7], c1y[7];
     load_coefs(d1x, c1x); load_coefs(d1y, c1y);
+    const int lane = threadIdx.x & 31, warp = (threadIdx.y * blockDim.x + threadIdx.x) >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int j0 = (tile % gx) * TW, i0 = m.own_lo + (tile / gx) * TH;
         __syncthreads();  // everybody has finished reading the previous tile
-        tile_load(tu, u, i0, j0, m.nloc, ncols, ld);
-        tile_load(tv, v, i0, j0, m.nloc, ncols, ld);
-        __syncthreads();
-        continuity_from_tiles<HALF>(tu, tv, m, ncols, d1x, d1y, c1x, c1y, i0, j0, mx, mn);
+        if (tile_is_interior(i0, j0, m, ncols) && tile_inside(i0, j0, m.nloc, ncols)) {
+            TileX &tx = reinterpret_cast<TileX &>(tu);
+            constexpr int NC = (TW + 2 * THALO + 31) / 32, LASTC = TW + 2 * THALO - 32 * (NC - 1);
+            double win[TROWS + 2 * THALO], ub[TH / 8][NC];
+            const double *vp = v + (size_t)(i0 + threadIdx.y * TROWS - THALO) * ld + (j0 + threadIdx.x);
+#pragma unroll
+            for (int k = 0; k < TROWS + 2 * THALO; k++) win[k] = vp[(size_t)k * ld];
+            const double *up = u + (size_t)(i0 + warp) * ld + (j0 - THALO + lane);
+#pragma unroll
+            for (int a = 0; a < TH / 8; a++)
+#pragma unroll
+                for (int b = 0; b < NC; b++) ub[a][b] = (b < NC - 1 || lane < LASTC) ? up[(size_t)(8 * a) * ld + 32 * b] : 0.0;
+#pragma unroll
+            for (int a = 0; a < TH / 8; a++)
+#pragma unroll
+                for (int b = 0; b < NC; b++)
+                    if (b < NC - 1 || lane < LASTC) tx.v[warp + 8 * a][lane + 32 * b] = ub[a][b];
+            __syncthreads();
+#pragma unroll
+            for (int rr = 0; rr < TROWS; rr++) {
+                const int li = threadIdx.y * TROWS + rr;
+                double wx[7], wy[7];
+#pragma unroll
+                for (int d = 0; d < 7; d++) { wx[d] = tx.v[li][threadIdx.x + d]; wy[d] = win[rr + d]; }
+                const double c = xadd(win_deriv<HALF, true>(c1x, wx), win_deriv<HALF, true>(c1y, wy));
+                mx = fmax(mx, c);
+                mn = fmin(mn, c);
+            }
+        } else {
+            tile_load(tu, u, i0, j0, m.nloc, ncols, ld);
+            tile_load(tv, v, i0, j0, m.nloc, ncols, ld);
+            __syncthreads();
+            continuity_from_tiles<HALF>(tu, tv, m, ncols, d1x, d1y, c1x, c1y, i0, j0, mx, mn);
+        }
     }
     minmax_finish(mx, mn, partial, ticket, result);
 }
@@ -529,14 +592,16 @@ void launch_continuity(const double *u, const double *v, const RowMap &m, int nc
 {
     const dim3 b(TW, 4), g = tile_grid(m, ncols);
     const int ntiles = (int)(g.x * g.y);
-    static int slots = 0;  // CTAs the device holds at once (3 per SM: 80 registers x 256 threads, two staged tiles of 21.6 KB)
-    if (!slots) {
-        int dev = 0, sms = 148;
+    static int slots[kMaxDevices] = {0};  // CTAs the device holds at once (registers and the two staged tiles decide)
+    const int dslot = current_device_slot();
+    if (!slots[dslot]) {
+        int dev = 0, sms = 148, per_sm = 3;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        slots = 3 * sms;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_continuity<3>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
+        slots[dslot] = per_sm * sms;
     }
-    const int grid = ntiles < slots ? ntiles : slots;
+    const int grid = ntiles < slots[dslot] ? ntiles : slots[dslot];
 #define CALL(H) k_continuity<H><<<grid, b, 0, s>>>(u, v, m, ncols, ld, d1x, d1y, partial, ticket, result, (int)g.x, ntiles)
     CNV_BY_HALF(d1x.half, CALL);
 #undef CALL
