@@ -83,7 +83,7 @@ template <bool POW2>
 __global__ void __launch_bounds__(kOcMaxThreads + 32, kOcOcc)
 k_poisson_onchip(const OnchipGeom g, const RelaxConsts rc, double *__restrict__ buf0, double *__restrict__ buf1,
                  double *__restrict__ buf2, const double *__restrict__ rhs, PoissonCtl *ctl, unsigned long long *flags,
-                 double *partials, double *hist, const unsigned long long timeout_ns, unsigned long long *prof, const int dbg)
+                 double *partials, double *hist, const unsigned long long timeout_ns, unsigned long long *prof)
 {
     extern __shared__ double4 sm4[];
     double *sm = reinterpret_cast<double *>(sm4);
@@ -175,7 +175,7 @@ k_poisson_onchip(const OnchipGeom g, const RelaxConsts rc, double *__restrict__ 
             }
             // the rest of the output region is only read back by this CTA itself (a "redo" pass two passes from now) or by the
             // host at the end: stored off the critical path
-            if (active && t.own && !t.band && !(dbg & 1)) oc_store(t, out);  // (dbg: timing experiments only)
+            if (active && t.own && !t.band) oc_store(t, out);
             lap(2);
             __syncthreads();  // (D) the next action is known, the neighbours' bands have landed
             if (act.kind != 2 && s_act.kind == 1) {
@@ -268,7 +268,7 @@ k_poisson_onchip(const OnchipGeom g, const RelaxConsts rc, double *__restrict__ 
         // ---- while the compute warps sweep: this CTA's partials of pass p-1 (s_part is complete since barrier D), then the
         // decision for pass p+1: X_{p+1} = lag_fold(X_p, norms of pass p-1) ----
         if (p >= 1) publish_partials(p - 1, nsw_prev);
-        const bool need = p >= 1 && c.state == 0 && c.redo == 0 && !(dbg & 2);
+        const bool need = p >= 1 && c.state == 0 && c.redo == 0;
         double e[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) e[i] = 0.0;
@@ -334,8 +334,6 @@ static void launch_onchip_t(const OnchipGeom &g, const RelaxConsts &rc, double *
         const char *e = std::getenv("CNV_ONCHIP_TIMEOUT_MS");
         return (unsigned long long)(e ? std::atoi(e) : 10000) * 1000000ull;
     }();
-    // CNV_ONCHIP_DEBUG (timing experiments, results are WRONG): 1 = skip the interior stores, 2 = skip the norm gather
-    static const int dbg = std::getenv("CNV_ONCHIP_DEBUG") ? std::atoi(std::getenv("CNV_ONCHIP_DEBUG")) : 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.ntx, g.nty);
     cfg.blockDim = dim3(round_up(oc_threads(g), 32) + 32);  // compute warps + the service warp
@@ -346,7 +344,7 @@ static void launch_onchip_t(const OnchipGeom &g, const RelaxConsts &rc, double *
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_poisson_onchip<POW2>, g, rc, b0, b1, b2, rhs, ctl, flags, partials, hist, timeout_ns, prof, dbg));
+    CNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_poisson_onchip<POW2>, g, rc, b0, b1, b2, rhs, ctl, flags, partials, hist, timeout_ns, prof));
 }
 
 void launch_onchip(const OnchipGeom &g, const RelaxConsts &rc, double *b0, double *b1, double *b2, const double *rhs, PoissonCtl *ctl,
