@@ -175,6 +175,14 @@ __device__ __forceinline__ bool warp_any(bool x) { return __any_sync(__activemas
 #else
 inline bool warp_any(bool x) { return x; }
 #endif
+// The value `v` of the lane `delta` above (+1) / below (-1) this one.  Device only: the host schedule checker runs one
+// thread at a time and takes the shared-memory form of the same load (stream_step).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double lane_shift(unsigned mask, double v, int up)
+{
+    return up ? __shfl_down_sync(mask, v, 1) : __shfl_up_sync(mask, v, 1);
+}
+#endif
 
 // kPairs doubles of one parity array (pairs k0 .. k0+kPairs-1), moved as 16-byte vectors
 struct vecP { double v[kPairs]; };
@@ -246,6 +254,10 @@ struct StreamThread {
     vecP h[4], rr[4];
     vecP pf_N, pf_own, pf_Pr, pf_Pb;  // operands of THIS step, loaded during the previous step (software pipelining)
     double pf_x, pf_xb;
+    // the two cells beside the thread's columns come from the adjacent lane's registers (stream_step); lanes whose
+    // neighbour sits in another warp or another level group load them from shared memory as before
+    unsigned wmask;          // the lanes of this warp that exist
+    bool nb_lo_far, nb_hi_far;
     double acc;
 };
 
@@ -298,6 +310,16 @@ CNV_HD void stream_init(StreamThread<T> &s, const PassGeom &p, const CtaGeom &G,
     s.allvalid = t.vmask == (1 << (2 * kPairs)) - 1;
     s.mask_path = warp_any(!s.allvalid);
     s.colown = t.colown;
+    {
+        const int TPG = p.WS / (2 * kPairs), kk = tid - t.g * TPG;
+#if defined(__CUDA_ARCH__)
+        s.wmask = __activemask();
+#else
+        s.wmask = 0;
+#endif
+        s.nb_lo_far = kk == 0 || (tid & 31) == 0;
+        s.nb_hi_far = kk == TPG - 1 || (tid & 31) == 31;
+    }
     s.int_lo = 0x7fffffff; s.int_span = 0;
     const int gc4 = G.gx0 + 2 * t.k0;  // first of this thread's columns
     s.sact = t.g == T - 1 && t.colown && gc4 >= 0 && gc4 < p.ld;
@@ -514,9 +536,22 @@ CNV_HD void stream_step(StreamThread<T> &s, const RelaxConsts &rc, double *sm, d
         if (kSkew > 4) s.pf_N = ldsP(sm, s.o[N0] + nA);
         s.pf_own = ldsP(sm, s.o[N1] + nA);
         s.pf_Pr = ldsP(sm, s.o[N1] + nPA);
-        s.pf_x = lds1(sm, s.o[N1] + nB + (tN ? 8 * kPairs : -8));
         s.pf_Pb = ldsP(sm, s.o[N3] + nPB);
+        // The cell beside the thread's columns, in the next red row (x) and the next black row (xb).  Both are values the
+        // ADJACENT thread of this level holds in registers: x = its N of this step (row qtop, same array, nobody writes it
+        // during this step), xb = its red results of the previous step (row q-1; what it stored is what it kept, masks
+        // included).  Two shuffles each instead of a shared-memory load whose 16-byte lane stride costs two extra
+        // wavefronts per warp -- 8.0 M of the 53.6 M wavefronts per launch on the pipe that bounds the kernel
+        // (profiles/ncu_pass_r2.md).  Lanes at a warp or level-group boundary take the load.
+#if defined(__CUDA_ARCH__)
+        s.pf_x = lane_shift(s.wmask, tN ? N.v[0] : N.v[kPairs - 1], tN);
+        s.pf_xb = lane_shift(s.wmask, tN ? s.rr[A1].v[kPairs - 1] : s.rr[A1].v[0], !tN);
+        if (tN ? s.nb_hi_far : s.nb_lo_far) s.pf_x = lds1(sm, s.o[N1] + nB + (tN ? 8 * kPairs : -8));
+        if (tN ? s.nb_lo_far : s.nb_hi_far) s.pf_xb = lds1(sm, s.o[N3] + nA + (tN ? -8 : 8 * kPairs));
+#else
+        s.pf_x = lds1(sm, s.o[N1] + nB + (tN ? 8 * kPairs : -8));
         s.pf_xb = lds1(sm, s.o[N3] + nA + (tN ? -8 : 8 * kPairs));
+#endif
     }
 }
 
