@@ -68,9 +68,9 @@ __device__ __forceinline__ void oc_run_sweeps(OcThread &t, const RelaxConsts &rc
 }
 
 // One CTA = the compute warps (one thread per patch) + ONE SERVICE WARP that owns everything which is latency rather than
-// work.  While the compute warps run the sweeps of pass p it publishes the CTA's norm partials of pass p-1, gathers all CTAs'
-// partials of that pass (one counter to poll, one asynchronous copy into shared memory, fixed-order sums) and folds them into the
-// action of pass p+1, so the stop decision never sits between two passes.  Between the passes it releases the CTA's band flag
+// work.  While the compute warps run the sweeps of pass p it publishes the CTA's norm partials of pass p-1 and counts the CTA
+// in; the CTA that counts in last sums all records in a fixed order and publishes the totals; every service warp then reads
+// those 64 bytes and folds them into the action of pass p+1, so the stop decision never sits between two passes.  Between the passes it releases the CTA's band flag
 // (a release is a fence: 1-2.5 k cycles during which the issuing warp stands still -- tools/ubench/fp64_lat.cu) and polls the
 // neighbour tiles' flags, while the compute warps reduce their norms and store the interior.  The compute warps only ever wait
 // at CTA barriers.  Critical path between two passes: band stores -> barrier -> release -> neighbours' flags -> barrier -> halo
