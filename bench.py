@@ -212,6 +212,9 @@ class Ctx:
         self.dist.all_reduce(t)
         return t.tolist()
 
+    def gather_ints(self, v):
+        return [int(round(x)) for x in self.gather_floats(float(v))]
+
     def all_ok(self, ok):
         if self.world == 1:
             return bool(ok)
@@ -343,10 +346,11 @@ class PoissonRun:
     # ---- end to end: host buffers in, host psi out, through the C ABI, copies inside the timed region ----
     def e2e(self, sweeps, steps):
         ctx, torch = self.ctx, self.ctx.torch
-        if self.pin_in is None:
-            self.pin_in = torch.from_numpy(self.w_host).pin_memory()
-            self.pin_out = torch.empty_like(self.pin_in).pin_memory()
-        in_np, out_np = self.pin_in.numpy(), self.pin_out.numpy()
+        if self.pin_in is None:   # the library's own host allocator: page-locked, on the GPU's NUMA node (what allocm() hands out)
+            self.pin_in = ctx.fd.host_empty(self.w_host.shape)
+            self.pin_in[...] = self.w_host
+            self.pin_out = ctx.fd.host_empty(self.w_host.shape)
+        in_np, out_np = self.pin_in, self.pin_out
         npass = (sweeps + self.T - 1) // self.T
 
         def step():
@@ -369,6 +373,7 @@ class PoissonRun:
         ms = e0.elapsed_time(e1)
         if self.world > 1:
             ms = ctx.max_over_ranks([ms])[0]
+        self.host_numa_node = int(ctx.fd.lib().cnv_host_numa_node())
         return ms, out_np
 
     def close(self):
@@ -387,9 +392,9 @@ def pipelined_e2e(ctx, run, sweeps, steps):
     sp2 = C.c_void_p(stream2.cuda_stream)
     solver2 = fd.PoissonSolver(run.total_rows, run.ncols, run.T)
     solver2.set_consts(run.dx, run.dy, run.beta)
-    in_np = run.pin_in.numpy()
-    pin_out2 = torch.empty_like(run.pin_in).pin_memory()
-    lanes = [(run.solver, ctx.sp, run.pin_out.numpy()), (solver2, sp2, pin_out2.numpy())]
+    in_np = run.pin_in
+    pin_out2 = fd.host_empty(run.pin_in.shape)
+    lanes = [(run.solver, ctx.sp, run.pin_out), (solver2, sp2, pin_out2)]
     npass = (sweeps + run.T - 1) // run.T
     count = [0]
 
@@ -455,14 +460,15 @@ def dropin_e2e(ctx, run, reps=3):
     t_dropin = float(np.mean(times))
     # the same solve through the solver object with page-locked buffers
     s = run.solver
-    pin_f = ctx.torch.from_numpy(np.ascontiguousarray(f)).pin_memory()
-    pin_u = ctx.torch.empty_like(pin_f).pin_memory()
+    pin_f = ctx.fd.host_empty(f.shape)
+    pin_f[...] = f
+    pin_u = ctx.fd.host_empty(f.shape)
     times2, k2 = [], None
     for i in range(reps + 1):
         t0 = time.perf_counter()
-        s.upload(pin_f.numpy(), 1.0, ctx.sp)
+        s.upload(pin_f, 1.0, ctx.sp)
         r = s.solve(itmax, tol, ctx.sp)
-        s.L.cnv_poisson_download(s.h, r["buf"], pin_u.numpy(), ctx.sp)
+        s.L.cnv_poisson_download(s.h, r["buf"], pin_u, ctx.sp)
         t1 = time.perf_counter()
         if i > 0:
             times2.append(t1 - t0)
@@ -473,7 +479,7 @@ def dropin_e2e(ctx, run, reps=3):
            "sweeps": k + 1, "ms_per_call": t_dropin * 1e3, "value": cells * (k + 1) / t_dropin, "unit": "cell-updates/s",
            "solver_object_pinned_ms_per_call": t_obj * 1e3, "solver_object_pinned_value": cells * (k2 + 1) / t_obj,
            "dropin_over_solver_object_time": t_dropin / t_obj,
-           "same_result": bool(k == k2 and np.array_equal(psi_dropin, pin_u.numpy()))}
+           "same_result": bool(k == k2 and np.array_equal(psi_dropin, pin_u))}
     return out
 
 
@@ -543,7 +549,9 @@ def run_gpu(args):
         "e2e": {"value": head["e2e"]["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": int(run.w_host.nbytes * world),
                 "d2h_bytes_per_step": int(run.w_host.nbytes * world), "ms_per_step": head["e2e"]["ms_per_step"],
                 "pipeline": "one solve at a time per GPU through the C ABI: pinned host w -> H2D + rhs preparation"
-                            + (" + halo exchange" if world > 1 else "") + " -> sweeps -> D2H of psi, synchronised before the next solve"},
+                            + (" + halo exchange" if world > 1 else "") + " -> sweeps -> D2H of psi, synchronised before the next solve",
+                "host_buffers": "cnv_host_alloc (page-locked, pooled; placed on the GPU's NUMA node where sysfs names it)",
+                "host_numa_nodes": ctx.gather_ints(getattr(run, "host_numa_node", -1)) if world > 1 else [getattr(run, "host_numa_node", -1)]},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     ok = head["parity_check"] == "bitwise-ok"

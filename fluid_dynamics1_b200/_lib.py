@@ -48,6 +48,7 @@ CNV_API = {
     "cnv_host_alloc": (_vp, [C.c_size_t]),
     "cnv_host_free": (None, [_vp]),
     "cnv_host_is_pinned": (C.c_int, [_vp]),
+    "cnv_host_numa_node": (C.c_int, []),
     "cnv_sor_beta": (C.c_double, [C.c_int, C.c_int]),
     "cnv_num_steps": (C.c_int, [C.c_double, C.c_double]),
     "cnv_diff_dense": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp]),

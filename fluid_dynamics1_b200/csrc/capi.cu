@@ -1,9 +1,14 @@
 // capi.cu -- extern "C" surface of libcnavier_b200.so (declared in include/cnavier_b200.h) and the
 // device-resident time stepper that restates the loop body of the reference driver
 // (src/main.c:283-395) on top of the CUDA kernels.
+#include <cctype>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <unordered_map>
 #include <vector>
 
@@ -74,6 +79,7 @@ struct HostPool {
     std::mutex mu;
     std::unordered_map<void *, std::pair<size_t, bool>> live;   // ptr -> (bytes, pinned)
     std::unordered_map<size_t, std::vector<void *>> free_pinned; // bytes -> recycled pinned blocks
+    std::unordered_map<void *, size_t> registered;              // pinned blocks that are mmap + cudaHostRegister (ptr -> mapped bytes)
     size_t pooled_bytes = 0;
 };
 static HostPool &host_pool()
@@ -93,6 +99,56 @@ static bool device_present()
         n = c;
     }
     return n > 0;
+}
+
+// NUMA node of the current device (sysfs entry of its PCI function), -1 if unknown.  On a two-socket box every GPU hangs off
+// one socket; page-locked memory on the other socket makes every H2D / D2H cross the socket interconnect, which caps the
+// copies of the far GPUs when all GPUs of the box copy at once (8 GPUs: 14 GB/s per GPU against 45 GB/s at 2 GPUs,
+// profiles/scale_r2.md).
+static int device_numa_node()
+{
+    static int node[kMaxDevices];
+    static bool known[kMaxDevices] = {};
+    const int slot = current_device_slot();
+    if (known[slot]) return node[slot];
+    int dev = 0, n = -1;
+    char bus[64] = {0};
+    if (const char *e = std::getenv("CNV_HOST_NUMA_NODE")) {  // platforms whose sysfs does not say (-1): name the node by hand
+        n = std::atoi(e);
+    } else if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetPCIBusId(bus, sizeof bus, dev) == cudaSuccess) {
+        for (char *c = bus; *c; c++) *c = (char)std::tolower((unsigned char)*c);
+        char path[160];
+        std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+        if (FILE *f = std::fopen(path, "r")) {
+            if (std::fscanf(f, "%d", &n) != 1) n = -1;
+            std::fclose(f);
+        }
+    } else {
+        cudaGetLastError();
+    }
+    node[slot] = n; known[slot] = true;
+    return n;
+}
+// `bytes` of page-locked memory whose pages live on the current device's NUMA node: anonymous mapping, preferred-node policy
+// on the range (mbind; a failure -- no permission, one node only -- just leaves the default placement), first touch, then
+// cudaHostRegister.  nullptr if any step fails; the caller then takes cudaHostAlloc.
+static void *numa_local_pinned(size_t bytes)
+{
+    const int node = device_numa_node();
+    if (node < 0 || node >= 1024) return nullptr;
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+    unsigned long mask[16] = {0};
+    mask[node / 64] |= 1ul << (node % 64);
+    (void)syscall(SYS_mbind, p, bytes, 1 /* MPOL_PREFERRED */, mask, 1024ul, 0u);
+    (void)madvise(p, bytes, MADV_HUGEPAGE);
+    std::memset(p, 0, bytes);
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(p, bytes);
+        return nullptr;
+    }
+    return p;
 }
 
 // ---- solver objects of the host-buffer entry point, kept between calls ---------------------------------------
@@ -214,6 +270,14 @@ void *cnv_host_alloc(size_t bytes)
                 hp.pooled_bytes -= bytes;
             }
         }
+        if (!p) {
+            const size_t mapped = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);  // whole 2 MiB pages
+            p = numa_local_pinned(mapped);
+            if (p) {
+                std::lock_guard<std::mutex> lk(hp.mu);
+                hp.registered[p] = mapped;
+            }
+        }
         if (!p && cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
     }
     bool pinned = p != nullptr;
@@ -242,9 +306,20 @@ void cnv_host_free(void *p)
             }
         }
     }
-    if (known && pinned) cudaFreeHost(p);
-    else std::free(p);
+    if (known && pinned) {
+        size_t mapped = 0;
+        {
+            std::lock_guard<std::mutex> lk(hp.mu);
+            auto it = hp.registered.find(p);
+            if (it != hp.registered.end()) { mapped = it->second; hp.registered.erase(it); }
+        }
+        if (mapped) { cudaHostUnregister(p); munmap(p, mapped); }
+        else cudaFreeHost(p);
+    } else {
+        std::free(p);
+    }
 }
+int cnv_host_numa_node(void) { return device_present() ? device_numa_node() : -1; }
 /* 1 if p points into a live page-locked block of cnv_host_alloc */
 int cnv_host_is_pinned(const void *p)
 {

@@ -223,3 +223,30 @@ class Simulation:
         c = (C.c_longlong * 3)()
         self.L.cnv_sim_counters(self.h, c)
         return dict(sweeps=c[0], passes=c[1], steps=c[2])
+
+
+class _HostBlock:
+    """A block of cnv_host_alloc memory (page-locked, on the current device's NUMA node, recycled through the library's pool)."""
+
+    def __init__(self, nbytes):
+        self.L = _lib.lib()
+        self.ptr = self.L.cnv_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError(f"cnv_host_alloc({nbytes})")
+
+    def __del__(self):
+        try:
+            self.L.cnv_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def host_empty(shape, dtype=np.float64):
+    """numpy array over the library's host allocator (csrc/capi.cu cnv_host_alloc): what allocm() of the drop-in library hands
+    to main.c -- blocks of >= 1 MiB are page-locked, so the host-buffer entry points copy them with one DMA each way."""
+    shape = tuple(int(x) for x in (shape if hasattr(shape, "__len__") else (shape,)))
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    blk = _HostBlock(max(nbytes, 8))
+    buf = (C.c_char * max(nbytes, 8)).from_address(blk.ptr)
+    buf._block = blk  # the array keeps the buffer alive, the buffer keeps the block alive
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

@@ -30,10 +30,14 @@ int cnv_get_device(void);
 void cnv_device_synchronize(void);
 /* Host memory for fields (what the drop-in allocm / freem of include/linearalg.h:13-15 are backed by; the reference
  * allocates and frees every field once per call, src/linearalg.c:53-99).  Blocks of >= 1 MiB are page-locked and
- * recycled through size-keyed free lists (page-locking 134 MB costs more than a solve); contents are not zeroed. */
+ * recycled through size-keyed free lists (page-locking 134 MB costs more than a solve); contents are not zeroed.  Where
+ * the platform tells which NUMA node the current device hangs off (sysfs), a page-locked block is placed on that node, so
+ * that the copies of a GPU on the second socket do not cross the socket interconnect; cnv_host_numa_node() = that node
+ * or -1. */
 void *cnv_host_alloc(size_t bytes);
 void cnv_host_free(void *p);
 int cnv_host_is_pinned(const void *p);
+int cnv_host_numa_node(void);
 
 /* ---- scalars of the driver: src/main.c:134 (beta, truncated PI), :162/:276 (step count) ------- */
 double cnv_sor_beta(int nx, int ny);

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import load_golden, rel_l2, sine_rhs
+from conftest import ROOT, load_golden, rel_l2, sine_rhs
 
 pytestmark = pytest.mark.gpu
 
@@ -549,3 +549,60 @@ def test_poisson_weak_scaling_slab_shape_fixed_sweeps(port):
     assert r["sweeps"] == sweeps and got.tobytes() == want.tobytes()
     assert abs(r["e"] - norms[-1]) <= 1e-11 * norms[-1]
     s.close()
+
+
+def test_host_allocator_is_page_locked_and_recycled(port):
+    """fd.host_empty / cnv_host_alloc (what allocm() of the drop-in library is built on): blocks of >= 1 MiB are page-locked
+    (on the GPU's NUMA node where the platform says which one that is), a freed block is recycled for the next request of the
+    same size, small blocks stay ordinary heap memory, and a field goes through upload / solve / download from such a block."""
+    import gc
+
+    L = fd.lib()
+    a = fd.host_empty((1024, 1024))
+    assert L.cnv_host_is_pinned(a.ctypes.data) == 1
+    small = fd.host_empty((64, 64))
+    assert L.cnv_host_is_pinned(small.ctypes.data) == 0
+    addr = a.ctypes.data
+    del a
+    gc.collect()
+    b = fd.host_empty((1024, 1024))
+    assert b.ctypes.data == addr and L.cnv_host_is_pinned(b.ctypes.data) == 1   # recycled, still page-locked
+    n = 520   # 2.2 MB: a page-locked block
+    f = fd.host_empty((n, n))
+    f[...] = np.random.default_rng(5).standard_normal((n, n))
+    assert L.cnv_host_is_pinned(f.ctypes.data) == 1
+    beta = port.beta(n, n)
+    want = port.poisson(np.array(f), 1.0 / n, 1.0 / n, 20000, 1e-3, beta, redblack=True, sor=True)
+    got = fd.poisson_sor(f, 1.0 / n, 1.0 / n, 20000, 1e-3, beta)
+    assert got["k"] == want["k"] and np.array_equal(got["u"], want["u"])
+
+
+def test_host_allocator_numa_placement_path():
+    """The NUMA-local form of cnv_host_alloc (anonymous mapping + preferred-node policy + cudaHostRegister), forced onto node 0
+    so that it runs on every box: the block is page-locked, survives recycling and release, and a solve from / into such
+    blocks gives the bits of a solve from ordinary arrays."""
+    import subprocess
+    import sys
+
+    code = """
+import gc, numpy as np, fluid_dynamics1_b200 as fd
+L = fd.lib()
+assert L.cnv_host_numa_node() == 0
+n = 600
+f = fd.host_empty((n, n)); f[...] = np.random.default_rng(3).standard_normal((n, n))
+assert L.cnv_host_is_pinned(f.ctypes.data) == 1
+beta = fd.sor_beta(n, n)
+a = fd.poisson_sor(f, 1.0 / n, 1.0 / n, 64, 0.0, beta, raise_on_itmax=False)
+b = fd.poisson_sor(np.array(f), 1.0 / n, 1.0 / n, 64, 0.0, beta, raise_on_itmax=False)
+assert np.array_equal(a["u"], b["u"]) and np.isfinite(a["u"]).all() and np.abs(a["u"]).max() > 0
+addr = f.ctypes.data
+del f; gc.collect()
+g = fd.host_empty((n, n)); assert g.ctypes.data == addr and L.cnv_host_is_pinned(g.ctypes.data) == 1
+big = [fd.host_empty((4096, 4096)) for _ in range(3)]   # beyond what the pool keeps idle only when freed: exercise release
+del big; gc.collect()
+print("NUMA PATH OK")
+"""
+    env = dict(os.environ, CNV_HOST_NUMA_NODE="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and "NUMA PATH OK" in r.stdout, r.stdout + r.stderr
+

@@ -600,3 +600,27 @@ print("returned")
             res.append((r.returncode, r.stdout.strip()))
         assert res[0] == res[1], res
         assert res[0][0] == 1 and "returned" not in res[0][1] and "rror" in res[0][1]
+
+
+def test_host_allocator_semantics_without_a_device():
+    """cnv_host_alloc / cnv_host_free / fd.host_empty are storage, not compute: without a GPU they hand out plain heap memory
+    (not page-locked), any size, freed exactly once when the last array over a block dies."""
+    import gc
+
+    import fluid_dynamics1_b200 as fd
+
+    L = fd.lib()
+    a = fd.host_empty((300, 200))
+    a[...] = 3.0
+    big = fd.host_empty((1024, 513))
+    big[...] = 1.0
+    assert a.shape == (300, 200) and a.flags.c_contiguous and a.sum() == 180000.0 and big.sum() == 1024 * 513
+    assert L.cnv_host_is_pinned(a.ctypes.data) == 0 and L.cnv_host_is_pinned(big.ctypes.data) == 0
+    view = big[10:20]          # a view keeps the block alive
+    del big
+    gc.collect()
+    assert view.sum() == 10 * 513
+    p = L.cnv_host_alloc(0)    # zero bytes: still a valid, freeable block
+    assert p
+    L.cnv_host_free(p)
+    L.cnv_host_free(None)
