@@ -120,6 +120,7 @@ CNV_API = {
     "cnv_sim_counters": (None, [_vp, C.POINTER(C.c_longlong)]),
     "cnv_sim_pressure": (C.c_int, [_vp, C.c_int, C.c_double, _vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "cnv_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
+    "cnv_boot_selftest": (C.c_int, [C.c_int]),
     "cnv_vtk_write": (C.c_int, [_dp, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
     "cnv_config_default": (None, [C.POINTER(Config)]),
     "cnv_config_from_file": (None, [C.c_char_p, C.POINTER(Config)]),

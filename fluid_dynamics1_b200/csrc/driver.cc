@@ -196,6 +196,38 @@ extern "C" int cnv_vtk_write(const double *values, int m, int n, const char *tit
     return used;
 }
 
+// Self-test of the bootstrap layer behind CNV_GPUS=N (no CUDA): forks world-1 children and runs the exchanges cnv_main uses --
+// all-gather of 256-byte records (the IPC handle exchange), broadcast (the NCCL id), barrier, all_ok with one dissenting rank.
+// Returns 0 in the parent if every rank saw what it should; the children exit with their own verdict and are waited for.
+extern "C" int cnv_boot_selftest(int world)
+{
+    if (world < 1 || world > 64) return 2;
+    Boot b = boot_fork(world);
+    bool ok = true;
+    std::vector<unsigned char> mine(256), all(256 * (size_t)world);
+    for (int i = 0; i < 256; i++) mine[i] = (unsigned char)(b.rank * 7 + i);
+    b.allgather(mine.data(), 256, all.data());
+    for (int r = 0; r < world; r++)
+        for (int i = 0; i < 256; i++) ok = ok && all[(size_t)r * 256 + i] == (unsigned char)(r * 7 + i);
+    unsigned char id[128];
+    for (int i = 0; i < 128; i++) id[i] = b.rank == 0 ? (unsigned char)(i ^ 0x5a) : 0;
+    b.bcast(id, sizeof id);
+    for (int i = 0; i < 128; i++) ok = ok && id[i] == (unsigned char)(i ^ 0x5a);
+    b.barrier();
+    ok = ok && b.all_ok(true);
+    const bool verdict = b.all_ok(b.rank != world - 1);  // the last rank dissents: everybody must see a failure
+    ok = ok && !verdict;
+    ok = b.all_ok(ok);
+    if (b.rank != 0) std::_Exit(ok ? 0 : 1);
+    int rc = ok ? 0 : 1;
+    for (int r = 1; r < world; r++) {
+        int st = 0;
+        if (::wait(&st) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) rc = 1;
+    }
+    for (int r = 1; r < world; r++) ::close(b.fd[r]);
+    return rc;
+}
+
 extern "C" int cnv_main(int argc, char **argv)
 {
     Config cfg;

@@ -207,6 +207,9 @@ int cnv_sim_pressure(cnv_sim *s, int itmax, double tol, double *p_host, int *k, 
  * NCCL id and the CUDA IPC handles of the peer-memory path over socket pairs, and rank 0 (the calling process) writes the
  * same log lines and VTK files as a one-GPU run; fields and Poisson iteration counts are bit-identical to it. */
 int cnv_main(int argc, char **argv);
+/* CPU-only self-test of the fork + socket-pair bootstrap cnv_main uses for CNV_GPUS=N (all-gather, broadcast, barrier,
+ * agreement on a failure): 0 = every one of `world` processes saw the expected bytes. */
+int cnv_boot_selftest(int world);
 /* The driver's VTK writer on its own: replaces printvtk (src/utils.c:38-100) -- ASCII STRUCTURED_POINTS, "%.6lf", file
  * <output_dir>/<title>-1-<count>.vtk opened in append mode, ONE counter across all fields and calls of the process.
  * `values` is row-major m x n (the reference's A.M[i][j]).  Returns the counter value used.  Host only. */

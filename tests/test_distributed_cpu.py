@@ -42,3 +42,16 @@ def test_slab_protocol_gloo_trimmed_boundary_chunks():
 @pytest.mark.parametrize("world,T,tol,itmax", [(2, 4, 1e-3, 5000), (2, 2, 0.0, 9), (3, 1, 1e-2, 5000)])
 def test_slab_protocol_gloo(world, T, tol, itmax):
     _run(world, 60, 40, T, tol, itmax, 29600 + world * 10 + T)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_c_driver_bootstrap_layer(world):
+    """The fork + socket-pair bootstrap of `CNV_GPUS=N ./cnavier_b200` (csrc/driver.cc Boot: all-gather of the 256-byte IPC
+    records, broadcast of the NCCL id, barrier, agreement on a failure) with `world` real processes and no GPU.  Run in a
+    child interpreter: the self-test forks, which a pytest process full of threads should not do."""
+    import subprocess
+    import sys
+
+    code = f"import fluid_dynamics1_b200 as fd, sys; sys.exit(fd.lib().cnv_boot_selftest({world}))"
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
